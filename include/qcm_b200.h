@@ -1,0 +1,150 @@
+/*
+ * qcm_b200.h -- C ABI of the B200 (sm_100a) execution layer behind QCMaquis's contraction::Engine.
+ *
+ * Plain pointers and sizes only. The C++ host (qcmaquis_b200/csrc/qcm/engine_gpu.hpp, the mirror of
+ * contraction::Engine) flattens one (site, direction) contraction into task arrays ONCE, hands them to
+ * qcm_plan_create, and then calls qcm_site_hamil2 for every Davidson / Jacobi-Davidson iteration and
+ * qcm_boundary_step once per site.  Boundaries live in HBM as qcm_array handles.
+ *
+ * Conventions follow the reference's own C interface (dmrg/lib/maquis_dmrg/maquis_cinterface.h): global
+ * library state, out-arrays of doubles, no callbacks into host code.  Unlike that interface every call
+ * returns a status (0 = ok) and qcm_last_error() describes the failure; the C++ Engine mirror turns a
+ * non-zero status into std::runtime_error, the reference's error convention on this path
+ * (contractions/common/move_boundary.hpp:29, non-abelian/site_hamil.hpp:202).
+ *
+ * All matrices are column-major FP64 (alps::numeric::matrix<double>, alps/numeric/matrix/matrix.hpp:66).
+ */
+#ifndef QCM_B200_H
+#define QCM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- buffer slots a plan's tasks may reference (Ref.buf) ------------------------------------------- */
+enum {
+    QCM_BUF_KET_LP = 0,  /* ket, left-paired  [(phys,left),right]   (MPSTensor::make_left_paired,  mpstensor.hpp:155-168) */
+    QCM_BUF_KET_RP = 1,  /* ket, right-paired [left,(-phys,right)]  (MPSTensor::make_right_paired, mpstensor.hpp:170-183) */
+    QCM_BUF_LEFT   = 2,  /* left boundary,  Boundary::operator[] flattened over b then block (boundary.h:20-145) */
+    QCM_BUF_RIGHT  = 3,  /* right boundary */
+    QCM_BUF_T      = 4,  /* step-1 products of single-use bonds (BoundaryMPSProduct::at, boundary_times_mps.hpp:163-182) */
+    QCM_BUF_TP     = 5,  /* step-1 products of multi-use bonds  (populateData, boundary_times_mps.hpp:188-209) */
+    QCM_BUF_Y      = 6,  /* W-applied panels (lbtm/rbtm kernel outputs, abelian/apply_op.hpp, non-abelian/apply_op.hpp) */
+    QCM_BUF_OUT    = 7,  /* sigma (left-paired) or the new boundary */
+    QCM_BUF_BRA_LP = 8,
+    QCM_BUF_BRA_RP = 9,
+    QCM_BUF_COUNT  = 10
+};
+
+typedef struct { int32_t buf; int32_t pad; int64_t off; } qcm_ref;                       /* element offset inside a slot */
+
+/* panel copy (pairing reshapes: reshapes.h:177-223,289-335; alps_detail.hpp:128-152) */
+typedef struct { qcm_ref src, dst; int32_t rows, cols, lds, ldd; } qcm_copy_task;
+
+/* one K-segment of a grouped GEMM: C(+)= alpha * op(A)[m x k] * op(B)[k x n]
+ * (block_matrix_algorithms.h:48-162 gemm/gemm_trim_left/right; non-abelian/gemm.hpp:48-204) */
+typedef struct { qcm_ref A, B; int32_t lda, ldb, m, n, k, ta, tb, pad; double alpha; } qcm_gemm_seg;
+/* one output block = a list of K-segments (the sum over MPO bond terms b that hit the same sector) */
+typedef struct { qcm_ref C; int32_t ldc, m, n, seg_begin, seg_end, pad; } qcm_gemm_out;
+
+/* W application as gather-axpy: dst panel = sum_i coef_i * src panel_i
+ * (lb_tensor_mpo/rb_tensor_mpo alps_detail.hpp:189-224; SU2 detail::lbtm/rbtm/task_axpy micro_kernels.hpp:19-198;
+ *  coef = W entry * scale * Wigner-9j coupling (gsl_coupling.h:177-204) * Hermitian phase) */
+typedef struct { qcm_ref src; int32_t lds, pad; double coef; } qcm_axpy_src;
+typedef struct { qcm_ref dst; int32_t ldd, rows, cols, src_begin, src_end, pad; } qcm_axpy_dst;
+
+typedef struct {
+    const qcm_gemm_out* t_outs;     int64_t n_t_outs;      /* step 1 for this wave -> QCM_BUF_T   */
+    const qcm_gemm_seg* t_segs;     int64_t n_t_segs;
+    const qcm_axpy_dst* w_dsts;     int64_t n_w_dsts;      /* step 2 -> QCM_BUF_Y                 */
+    const qcm_axpy_src* w_srcs;     int64_t n_w_srcs;
+    const qcm_gemm_out* c_outs;     int64_t n_c_outs;      /* step 3 -> QCM_BUF_OUT (accumulating) */
+    const qcm_gemm_seg* c_segs;     int64_t n_c_segs;
+    int64_t y_elems, t_elems;
+} qcm_wave_desc;
+
+typedef struct {
+    int32_t kind;                    /* 0 sigma (site_hamil2), 1 overlap_mpo_left_step, 2 overlap_mpo_right_step */
+    int32_t n_waves;
+    const qcm_copy_task* pre_copies; int64_t n_pre_copies;
+    const qcm_gemm_out* p_outs;      int64_t n_p_outs;     /* multi-use step-1 products -> QCM_BUF_TP */
+    const qcm_gemm_seg* p_segs;      int64_t n_p_segs;
+    const qcm_wave_desc* waves;
+    int64_t elems[QCM_BUF_COUNT];    /* required size (elements) of every slot; inputs are checked, workspaces grown */
+    double flops;                    /* algorithmic FLOPs of one execution (schedule-derived) */
+    int64_t bytes;                   /* algorithmic bytes of one execution */
+} qcm_plan_desc;
+
+typedef struct qcm_array_s* qcm_array_t;   /* a device-resident FP64 array */
+typedef struct qcm_plan_s*  qcm_plan_t;
+
+/* ---- library state --------------------------------------------------------------------------------- */
+int         qcm_init(int device);                 /* selects the device, creates the stream; idempotent */
+int         qcm_finalize(void);
+const char* qcm_last_error(void);
+int         qcm_device_count(int* n);
+int         qcm_device_name(char* buf, int len);
+int         qcm_sync(void);
+void*       qcm_stream(void);                     /* the cudaStream_t every kernel of the library is launched on */
+int64_t     qcm_launch_count(void);               /* kernels launched by this library so far */
+
+/* ---- device arrays (HBM-resident boundaries and solver vectors; replaces storage::disk, utils/storage.h) */
+int qcm_array_alloc(int64_t n_elems, qcm_array_t* out);
+int qcm_array_free(qcm_array_t a);
+int qcm_array_size(qcm_array_t a, int64_t* n_elems);
+int qcm_array_upload(qcm_array_t a, int64_t off, const double* host, int64_t n);
+int qcm_array_download(qcm_array_t a, int64_t off, double* host, int64_t n);
+int qcm_array_zero(qcm_array_t a);
+void* qcm_array_devptr(qcm_array_t a);
+
+/* ---- plans ----------------------------------------------------------------------------------------- */
+int qcm_plan_create(const qcm_plan_desc* desc, qcm_plan_t* out);
+int qcm_plan_destroy(qcm_plan_t p);
+int qcm_plan_stats(qcm_plan_t p, double* flops, int64_t* bytes, int64_t* n_launches, int64_t* workspace_bytes);
+
+/* ---- the three Engine calls -------------------------------------------------------------------------
+ * qcm_site_hamil2        replaces contraction::Engine<..>::site_hamil2 (abelian/engine.hpp:196-209,
+ *                        non-abelian/engine.hpp:197-207; bodies abelian/site_hamil.hpp:23-90,
+ *                        non-abelian/site_hamil.hpp:28-204).  psi/sigma are HOST buffers holding the
+ *                        left-paired blocks back to back in DualIndex order; the host<->device copies are
+ *                        part of the call.  With a communicator the partial sigma of every rank is summed
+ *                        (NCCL allreduce) before the download, so every rank returns the full sigma.
+ * qcm_site_hamil2_dev    same on device-resident psi/sigma (solver vectors kept in HBM).
+ * qcm_boundary_step      replaces Engine::overlap_mpo_left_step / overlap_mpo_right_step
+ *                        (abelian/engine.hpp:102-122; common/move_boundary.hpp:128-229); `in` is the old
+ *                        boundary, `out` the new one (device resident, zeroed and filled by the call);
+ *                        bra/ket are host buffers (left-paired blocks). */
+int qcm_site_hamil2(qcm_plan_t p, qcm_array_t left, qcm_array_t right, const double* psi, double* sigma);
+int qcm_site_hamil2_dev(qcm_plan_t p, qcm_array_t left, qcm_array_t right, qcm_array_t psi, qcm_array_t sigma);
+int qcm_boundary_step(qcm_plan_t p, qcm_array_t in, const double* bra, const double* ket, qcm_array_t out);
+
+/* device time (ms, CUDA events on the library stream) of the kernels of the last plan execution, by phase:
+ * [0] reshapes, [1] step-1 GEMMs, [2] W application, [3] closing GEMMs, [4] allreduce, [5] total */
+int qcm_last_timing(double ms[6]);
+int qcm_set_timing(int enabled);
+
+/* ---- solver-side vector algebra on device arrays (MPSTensor::scalar_overlap / scalar_norm / += / *=,
+ *      mpstensor.hpp:346-395,458-522; used by ietl::dot/two_norm, ietl_lanczos_solver.h:67-102) ---------- */
+int qcm_vec_dot(qcm_array_t x, qcm_array_t y, int64_t n, double* result);
+int qcm_vec_axpy(double a, qcm_array_t x, qcm_array_t y, int64_t n);       /* y += a x */
+int qcm_vec_scal(double a, qcm_array_t x, int64_t n);
+int qcm_vec_copy(qcm_array_t src, qcm_array_t dst, int64_t n);
+
+/* ---- multi-GPU: one process per GPU, work sharded over the MPO bond index b (the reference's omp_for axis,
+ *      abelian/site_hamil.hpp:74); sigma is combined by one allreduce per call -------------------------- */
+int qcm_comm_unique_id(char id[128]);
+int qcm_comm_init(int rank, int world, const char id[128]);
+int qcm_comm_destroy(void);
+int qcm_comm_allreduce(qcm_array_t a, int64_t n);
+
+/* ---- measured FP64 peaks (roofline denominators; not part of the contraction path) ------------------ */
+int qcm_measure_fp64_fma_peak(double* tflops);     /* register-resident DFMA chains on all SMs */
+int qcm_measure_fp64_dmma_peak(double* tflops);    /* register-resident mma.sync m8n8k4 f64 chains */
+int qcm_measure_hbm_copy(double* gbs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

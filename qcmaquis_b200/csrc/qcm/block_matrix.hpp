@@ -21,6 +21,8 @@ struct Matrix
     std::vector<double> v;
     Matrix() {}
     Matrix(size_t r, size_t c, double init = 0.) : rows(r), cols(c), v(r * c, init) {}
+    // shape without storage (device-resident block whose values have not been fetched)
+    static Matrix shell(size_t r, size_t c) { Matrix m; m.rows = r; m.cols = c; return m; }
     double& operator()(size_t i, size_t j) { return v[i + j * rows]; }
     double const& operator()(size_t i, size_t j) const { return v[i + j * rows]; }
     double* data() { return v.data(); }

@@ -1,0 +1,273 @@
+// qcm::GpuEngine -- the B200 implementation of the reference's contraction::Engine calls on the sweep hot path
+// (abelian/engine.hpp:102-122,196-209; non-abelian/engine.hpp:197-207).  Same call signatures and value
+// semantics as the reference (ket by value, boundaries by const reference, results returned by value), so the
+// sweep drivers (BoundaryPropagator.h:98-122, SiteProblem / ietl::mult, ietl_lanczos_solver.h:108-115) keep
+// working unchanged.  What differs is where the work happens:
+//   * the block loops of site_hamil2 / overlap_mpo_{left,right}_step are walked once by plan::Planner and the
+//     resulting task arrays are handed to the C ABI (include/qcm_b200.h); the plan is cached per
+//     (MPO tensor, boundaries, tensor structure) and reused by every Davidson iteration at that site,
+//   * boundaries returned by the boundary steps stay in HBM (Boundary::device_mirror); the host object carries
+//     the symmetry-block structure only until download() is called,
+//   * with a communicator (one process per GPU) every rank executes its share of the MPO bond index and the
+//     library sums the partial results.
+// There is no CPU fallback: every failure of the device layer surfaces as std::runtime_error.
+#pragma once
+#include "../../../include/qcm_b200.h"
+#include "engine_iface.hpp"
+#include "plan.hpp"
+#include <list>
+
+namespace qcm {
+
+inline void qcm_check(int status, const char* what)
+{
+    if (status != 0) throw std::runtime_error(std::string(what) + ": " + qcm_last_error());
+}
+
+struct DeviceBoundary
+{
+    qcm_array_t arr = nullptr;
+    plan::BoundaryLayout layout;
+    ~DeviceBoundary() { if (arr) qcm_array_free(arr); }
+};
+
+struct CompiledPlan
+{
+    qcm_plan_t handle = nullptr;
+    plan::Layout out_tensor;
+    plan::BoundaryLayout out_boundary;
+    int64_t ket_elems = 0, bra_elems = 0, out_elems = 0;
+    double flops = 0, flops_t = 0, flops_w = 0, flops_close = 0;
+    int64_t bytes = 0;
+    size_t n_gemm_tasks = 0, n_axpy_tasks = 0, n_waves = 0;
+    int64_t workspace_elems = 0;
+    ~CompiledPlan() { if (handle) qcm_plan_destroy(handle); }
+};
+
+class GpuEngine : public EngineIface
+{
+public:
+    explicit GpuEngine(SymmKind s, int device = 0, int rank_ = 0, int world_ = 1, int64_t ws_budget_elems = (int64_t)1 << 29)
+        : symm(s), rank(rank_), world(world_), budget(ws_budget_elems)
+    {
+        qcm_check(qcm_init(device), "qcm_init");
+    }
+
+    // ---- Engine::site_hamil2 ----------------------------------------------------------------------------
+    MPSTensor site_hamil2(MPSTensor ket_tensor, Boundary const& left, Boundary const& right, MPOTensor const& mpo,
+                          bool isHermitian = true) override
+    {
+        ket_tensor.make_left_paired();
+        std::shared_ptr<DeviceBoundary> dl = mirror(left), dr = mirror(right);
+        std::shared_ptr<CompiledPlan> cp = sigma_plan(ket_tensor, dl, dr, mpo, isHermitian);
+        std::vector<double> psi = flatten(ket_tensor.data(), cp->ket_elems), sigma((size_t)cp->out_elems);
+        qcm_check(qcm_site_hamil2(cp->handle, dl->arr, dr->arr, psi.data(), sigma.data()), "qcm_site_hamil2");
+        return MPSTensor(ket_tensor.site_dim(), ket_tensor.row_dim(), ket_tensor.col_dim(), unflatten(cp->out_tensor, sigma), LeftPaired, true);
+    }
+
+    std::shared_ptr<CompiledPlan> sigma_plan(MPSTensor const& ket_tensor, std::shared_ptr<DeviceBoundary> const& dl,
+                                             std::shared_ptr<DeviceBoundary> const& dr, MPOTensor const& mpo, bool isHermitian = true)
+    {
+        ket_tensor.make_left_paired();
+        PlanKey key{&mpo, dl.get(), dr.get(), structure_hash(ket_tensor), isHermitian ? 0 : 3, dl, dr};
+        for (auto& e : cache) if (e.first == key) return e.second;
+        plan::Planner planner(symm, mpo, isHermitian, rank, world, budget);
+        plan::Plan P = planner.plan_sigma(desc_of(ket_tensor), dl->layout, dr->layout);
+        std::shared_ptr<CompiledPlan> cp = compile(P, dl->layout.total, dr->layout.total);
+        remember(key, cp);
+        return cp;
+    }
+
+    // ---- Engine::overlap_mpo_left_step / overlap_mpo_right_step -------------------------------------------
+    Boundary overlap_mpo_left_step(MPSTensor const& bra_tensor, MPSTensor const& ket_tensor, Boundary const& left, MPOTensor const& mpo,
+                                   bool isHermitian = true) override
+    {
+        return boundary_step(1, bra_tensor, ket_tensor, left, mpo, isHermitian);
+    }
+    Boundary overlap_mpo_right_step(MPSTensor const& bra_tensor, MPSTensor const& ket_tensor, Boundary const& right, MPOTensor const& mpo,
+                                    bool isHermitian = true) override
+    {
+        return boundary_step(2, bra_tensor, ket_tensor, right, mpo, isHermitian);
+    }
+
+    // ---- HBM-resident boundary store ----------------------------------------------------------------------
+    // device mirror of a boundary (uploaded on first use; boundaries produced by this engine already have one)
+    std::shared_ptr<DeviceBoundary> mirror(Boundary const& b)
+    {
+        if (b.device_mirror) return std::static_pointer_cast<DeviceBoundary>(b.device_mirror);
+        if (!b.host_valid) throw std::runtime_error("GpuEngine: boundary has neither host data nor a device mirror");
+        std::shared_ptr<DeviceBoundary> d(new DeviceBoundary());
+        std::vector<DualIndex> bases(b.aux_dim());
+        for (size_t k = 0; k < b.aux_dim(); ++k) bases[k] = b[k].basis();
+        d->layout.assign(bases);
+        qcm_check(qcm_array_alloc(d->layout.total, &d->arr), "qcm_array_alloc");
+        std::vector<double> flat((size_t)d->layout.total);
+        for (size_t k = 0; k < b.aux_dim(); ++k)
+            for (size_t j = 0; j < b[k].n_blocks(); ++j)
+                std::copy(b[k][j].v.begin(), b[k][j].v.end(), flat.begin() + d->layout.b[k].off[j]);
+        qcm_check(qcm_array_upload(d->arr, 0, flat.data(), d->layout.total), "qcm_array_upload");
+        b.device_mirror = d;
+        return d;
+    }
+    // fetch the dense blocks of a device-resident boundary into the host object
+    void download(Boundary& b)
+    {
+        if (b.host_valid) return;
+        std::shared_ptr<DeviceBoundary> d = std::static_pointer_cast<DeviceBoundary>(b.device_mirror);
+        if (!d) throw std::runtime_error("GpuEngine::download: no device mirror");
+        std::vector<double> flat((size_t)d->layout.total);
+        qcm_check(qcm_array_download(d->arr, 0, flat.data(), d->layout.total), "qcm_array_download");
+        for (size_t k = 0; k < b.aux_dim(); ++k)
+            for (size_t j = 0; j < b.raw(k).n_blocks(); ++j) {
+                Matrix& m = b.raw(k)[j];
+                m.v.assign(flat.begin() + d->layout.b[k].off[j], flat.begin() + d->layout.b[k].off[j] + m.rows * m.cols);
+            }
+        b.host_valid = true;
+    }
+    void clear_cache() { cache.clear(); }
+    std::shared_ptr<CompiledPlan> last_plan() const { return last; }
+
+    static std::vector<double> flatten(block_matrix const& m, int64_t expect)
+    {
+        std::vector<double> flat; flat.reserve((size_t)expect);
+        for (size_t k = 0; k < m.n_blocks(); ++k) flat.insert(flat.end(), m[k].v.begin(), m[k].v.end());
+        if ((int64_t)flat.size() != expect) throw std::runtime_error("GpuEngine: tensor data does not match the planned structure");
+        return flat;
+    }
+    static block_matrix unflatten(plan::Layout const& L, std::vector<double> const& flat)
+    {
+        block_matrix r;
+        for (size_t k = 0; k < L.basis.size(); ++k) {
+            Matrix m(L.basis[k].ls, L.basis[k].rs);
+            std::copy(flat.begin() + L.off[k], flat.begin() + L.off[k] + m.v.size(), m.v.begin());
+            r.insert_block(std::move(m), L.basis[k].lc, L.basis[k].rc);
+        }
+        return r;
+    }
+    static plan::TensorDesc desc_of(MPSTensor const& t)
+    {
+        t.make_left_paired();
+        return plan::TensorDesc{t.site_dim(), t.row_dim(), t.col_dim(), t.data().basis()};
+    }
+
+private:
+    struct PlanKey
+    {
+        const void *mpo, *a, *b; uint64_t h; int kind;
+        std::shared_ptr<void> keep_a, keep_b;   // the boundaries stay alive while their plan is cached (no address reuse)
+        bool operator==(PlanKey const& o) const { return mpo == o.mpo && a == o.a && b == o.b && h == o.h && kind == o.kind; }
+    };
+
+    Boundary boundary_step(int kind, MPSTensor const& bra_tensor, MPSTensor const& ket_tensor, Boundary const& in, MPOTensor const& mpo, bool isHermitian)
+    {
+        bra_tensor.make_left_paired(); ket_tensor.make_left_paired();
+        std::shared_ptr<DeviceBoundary> din = mirror(in);
+        plan::Planner planner(symm, mpo, isHermitian, rank, world, budget);
+        plan::Plan P = kind == 1 ? planner.plan_left_step(desc_of(bra_tensor), desc_of(ket_tensor), din->layout)
+                                 : planner.plan_right_step(desc_of(bra_tensor), desc_of(ket_tensor), din->layout);
+        std::shared_ptr<CompiledPlan> cp = compile(P, kind == 1 ? din->layout.total : 0, kind == 2 ? din->layout.total : 0);
+        last = cp;
+        std::shared_ptr<DeviceBoundary> dout(new DeviceBoundary());
+        dout->layout = cp->out_boundary;
+        qcm_check(qcm_array_alloc(dout->layout.total, &dout->arr), "qcm_array_alloc");
+        std::vector<double> bra = flatten(bra_tensor.data(), cp->bra_elems), ket = flatten(ket_tensor.data(), cp->ket_elems);
+        qcm_check(qcm_boundary_step(cp->handle, din->arr, bra.data(), ket.data(), dout->arr), "qcm_boundary_step");
+        Boundary ret; ret.resize(dout->layout.aux_dim());
+        for (size_t b = 0; b < ret.aux_dim(); ++b) {
+            DualIndex const& basis = dout->layout.b[b].basis;
+            for (size_t k = 0; k < basis.size(); ++k) ret.raw(b).insert_block(Matrix::shell(basis[k].ls, basis[k].rs), basis[k].lc, basis[k].rc);
+        }
+        ret.device_mirror = dout;
+        ret.host_valid = false;
+        return ret;
+    }
+
+    static void cvt(plan::GemmList const& g, std::vector<qcm_gemm_out>& outs, std::vector<qcm_gemm_seg>& segs)
+    {
+        outs.resize(g.outs.size()); segs.resize(g.segs.size());
+        for (size_t i = 0; i < g.outs.size(); ++i) {
+            plan::Out const& o = g.outs[i];
+            outs[i] = qcm_gemm_out{qcm_ref{o.C.buf, 0, o.C.off}, o.ldc, o.m, o.n, o.seg_begin, o.seg_end, 0};
+        }
+        for (size_t i = 0; i < g.segs.size(); ++i) {
+            plan::Seg const& s = g.segs[i];
+            segs[i] = qcm_gemm_seg{qcm_ref{s.A.buf, 0, s.A.off}, qcm_ref{s.B.buf, 0, s.B.off}, s.lda, s.ldb, s.m, s.n, s.k, s.ta, s.tb, 0, s.alpha};
+        }
+    }
+
+    std::shared_ptr<CompiledPlan> compile(plan::Plan const& P, int64_t left_elems, int64_t right_elems)
+    {
+        struct WaveStore { std::vector<qcm_gemm_out> to, co; std::vector<qcm_gemm_seg> ts, cs; std::vector<qcm_axpy_dst> wd; std::vector<qcm_axpy_src> wsrc; };
+        std::vector<WaveStore> store(P.waves.size());
+        std::vector<qcm_wave_desc> waves(P.waves.size());
+        for (size_t w = 0; w < P.waves.size(); ++w) {
+            plan::Wave const& W = P.waves[w];
+            WaveStore& S = store[w];
+            cvt(W.t_gemm, S.to, S.ts);
+            cvt(W.close_gemm, S.co, S.cs);
+            S.wd.resize(W.w_apply.dsts.size()); S.wsrc.resize(W.w_apply.srcs.size());
+            for (size_t i = 0; i < S.wd.size(); ++i) {
+                plan::AxpyDst const& d = W.w_apply.dsts[i];
+                S.wd[i] = qcm_axpy_dst{qcm_ref{d.dst.buf, 0, d.dst.off}, d.ldd, d.rows, d.cols, d.src_begin, d.src_end, 0};
+            }
+            for (size_t i = 0; i < S.wsrc.size(); ++i) {
+                plan::AxpySrc const& s = W.w_apply.srcs[i];
+                S.wsrc[i] = qcm_axpy_src{qcm_ref{s.src.buf, 0, s.src.off}, s.lds, 0, s.coef};
+            }
+            waves[w] = qcm_wave_desc{S.to.data(), (int64_t)S.to.size(), S.ts.data(), (int64_t)S.ts.size(),
+                                     S.wd.data(), (int64_t)S.wd.size(), S.wsrc.data(), (int64_t)S.wsrc.size(),
+                                     S.co.data(), (int64_t)S.co.size(), S.cs.data(), (int64_t)S.cs.size(), W.y_elems, W.t_elems};
+        }
+        std::vector<qcm_gemm_out> po; std::vector<qcm_gemm_seg> ps;
+        cvt(P.persistent_t, po, ps);
+        std::vector<qcm_copy_task> copies(P.pre_copies.size());
+        for (size_t i = 0; i < copies.size(); ++i) {
+            plan::CopyTask const& c = P.pre_copies[i];
+            copies[i] = qcm_copy_task{qcm_ref{c.src.buf, 0, c.src.off}, qcm_ref{c.dst.buf, 0, c.dst.off}, c.rows, c.cols, c.lds, c.ldd};
+        }
+        qcm_plan_desc d;
+        std::memset(&d, 0, sizeof(d));
+        d.kind = P.kind; d.n_waves = (int32_t)waves.size();
+        d.pre_copies = copies.data(); d.n_pre_copies = (int64_t)copies.size();
+        d.p_outs = po.data(); d.n_p_outs = (int64_t)po.size(); d.p_segs = ps.data(); d.n_p_segs = (int64_t)ps.size();
+        d.waves = waves.data();
+        int64_t out_elems = P.kind == 0 ? P.out_tensor.total : P.out_boundary.total;
+        d.elems[QCM_BUF_KET_LP] = P.ket_lp_elems; d.elems[QCM_BUF_KET_RP] = P.ket_rp_elems;
+        d.elems[QCM_BUF_LEFT] = left_elems; d.elems[QCM_BUF_RIGHT] = right_elems;
+        d.elems[QCM_BUF_T] = P.t_elems_max; d.elems[QCM_BUF_TP] = P.tp_elems; d.elems[QCM_BUF_Y] = P.y_elems_max;
+        d.elems[QCM_BUF_OUT] = out_elems; d.elems[QCM_BUF_BRA_LP] = P.bra_lp_elems; d.elems[QCM_BUF_BRA_RP] = P.bra_rp_elems;
+        d.flops = P.flops(); d.bytes = P.bytes_algorithmic;
+        std::shared_ptr<CompiledPlan> cp(new CompiledPlan());
+        qcm_check(qcm_plan_create(&d, &cp->handle), "qcm_plan_create");
+        cp->out_tensor = P.out_tensor; cp->out_boundary = P.out_boundary;
+        cp->ket_elems = P.ket_lp_elems; cp->bra_elems = P.bra_lp_elems; cp->out_elems = out_elems;
+        cp->flops = P.flops(); cp->flops_t = P.flops_t; cp->flops_w = P.flops_w; cp->flops_close = P.flops_close; cp->bytes = P.bytes_algorithmic;
+        cp->n_gemm_tasks = P.n_gemm_tasks; cp->n_axpy_tasks = P.n_axpy_tasks; cp->n_waves = P.waves.size();
+        cp->workspace_elems = P.ket_rp_elems + P.t_elems_max + P.tp_elems + P.y_elems_max + P.bra_rp_elems;
+        last = cp;
+        return cp;
+    }
+
+    static uint64_t structure_hash(MPSTensor const& t)
+    {
+        uint64_t h = 1469598103934665603ull;
+        auto mix = [&](uint64_t x) { h ^= x; h *= 1099511628211ull; };
+        auto mix_index = [&](Index const& ix) { for (auto const& e : ix) { mix((uint32_t)e.first[0]); mix((uint32_t)e.first[1]); mix((uint32_t)e.first[2]); mix(e.second); } mix(0xABCDu); };
+        mix_index(t.site_dim()); mix_index(t.row_dim()); mix_index(t.col_dim());
+        for (auto const& b : t.data().basis()) { mix((uint32_t)b.lc[0]); mix((uint32_t)b.lc[1]); mix((uint32_t)b.lc[2]); mix((uint32_t)b.rc[0]); mix((uint32_t)b.rc[1]); mix((uint32_t)b.rc[2]); mix(b.ls); mix(b.rs); }
+        return h;
+    }
+    void remember(PlanKey const& k, std::shared_ptr<CompiledPlan> const& cp)
+    {
+        cache.push_front(std::make_pair(k, cp));
+        if (cache.size() > 4) cache.pop_back();
+    }
+
+    SymmKind symm;
+    int rank, world;
+    int64_t budget;
+    std::list<std::pair<PlanKey, std::shared_ptr<CompiledPlan>>> cache;
+    std::shared_ptr<CompiledPlan> last;
+};
+
+} // namespace qcm

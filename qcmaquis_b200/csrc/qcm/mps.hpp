@@ -7,6 +7,7 @@
 //   left/right_boundary  dmrg/mp_tensors/mps.hpp:244-268
 #pragma once
 #include "block_matrix.hpp"
+#include <memory>
 #include <random>
 
 namespace qcm {
@@ -176,17 +177,25 @@ private:
     mutable MPSStorageLayout cur_storage = LeftPaired;
 };
 
+// A Boundary may live in HBM: `device_mirror` is an opaque handle owned by the GPU engine (qcm::GpuEngine),
+// `host_valid` tells whether the dense blocks on the host hold the data (false: structure-only shells whose
+// contents are fetched with GpuEngine::download).  Mutable access drops the mirror, as the reference's
+// storage layer invalidates a boundary that is assigned to or dropped (utils/storage.h:176-181,363-365).
 class Boundary
 {
 public:
     Boundary() {}
     Boundary(Index const& ud, Index const& ld, size_t ad = 1) : data_(ad, block_matrix(ud, ld)) {}
     size_t aux_dim() const { return data_.size(); }
-    void resize(size_t n) { data_.resize(n); }
-    block_matrix& operator[](size_t k) { return data_[k]; }
+    void resize(size_t n) { data_.resize(n); device_mirror.reset(); }
+    block_matrix& operator[](size_t k) { device_mirror.reset(); return data_[k]; }
     block_matrix const& operator[](size_t k) const { return data_[k]; }
+    block_matrix& raw(size_t k) { return data_[k]; }   // engine-internal: does not invalidate the mirror
     std::vector<double> traces() const { std::vector<double> r; for (auto const& b : data_) r.push_back(b.trace()); return r; }
     size_t num_elements() const { size_t r = 0; for (auto const& b : data_) r += b.num_elements(); return r; }
+
+    mutable std::shared_ptr<void> device_mirror;
+    bool host_valid = true;
 
 private:
     std::vector<block_matrix> data_;

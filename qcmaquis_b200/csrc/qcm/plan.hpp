@@ -1,0 +1,940 @@
+// Flattened contraction schedule ("plan") for the B200 kernels.
+//
+// The reference rebuilds its task structure inside every site_hamil2 call (per-b OpenMP loop bodies,
+// SU2::task_capsule / micro_task lists: contractions/non-abelian/apply_op.hpp:103-209, site_hamil.hpp:181).
+// Here the same loops are walked ONCE per (site, direction) on the host and emitted as three flat task
+// families that the device executes for every Davidson iteration:
+//   * panel copies      (left<->right pairing reshapes, reshapes.h:177-223,289-335)
+//   * grouped GEMMs     (one output block = a list of K-segments; block_matrix_algorithms.h:48-162,
+//                        non-abelian/gemm.hpp:48-204, charge_gemm apply_op.hpp:255-266)
+//   * gather-axpy panels (the W application: alps_detail.hpp:189-224, micro_kernels.hpp:19-198), with the
+//                        SU2 couplings (gsl_coupling.h:177-204) and Hermitian phases folded into scalars.
+// Block structure rules (which output blocks exist, their sizes, the descending charge order) follow the
+// reference loops literally so that the result has the same DualIndex as the CPU implementation.
+#pragma once
+#include "mpo.hpp"
+#include "mps.hpp"
+#include <cstdint>
+#include <map>
+#include <numeric>
+
+namespace qcm { namespace plan {
+
+enum Buf : int { BUF_KET_LP = 0, BUF_KET_RP, BUF_LEFT, BUF_RIGHT, BUF_T, BUF_TP, BUF_Y, BUF_OUT, BUF_BRA_LP, BUF_BRA_RP, BUF_COUNT };
+
+struct Ref { int32_t buf; int64_t off; };
+struct CopyTask { Ref src, dst; int32_t rows, cols, lds, ldd; };
+struct Seg { Ref A, B; int32_t lda, ldb, m, n, k, ta, tb; double alpha; };   // op(A) is m x k, op(B) is k x n
+struct Out { Ref C; int32_t ldc, m, n, seg_begin, seg_end; };
+struct AxpySrc { Ref src; int32_t lds; double coef; };
+struct AxpyDst { Ref dst; int32_t ldd, rows, cols, src_begin, src_end; };
+
+struct GemmList { std::vector<Out> outs; std::vector<Seg> segs; };
+struct AxpyList { std::vector<AxpyDst> dsts; std::vector<AxpySrc> srcs; };
+
+struct Wave
+{
+    GemmList t_gemm;      // step 1 products needed by this wave (single-use bonds) -> BUF_T
+    AxpyList w_apply;     // step 2 -> BUF_Y
+    GemmList close_gemm;  // step 3 -> BUF_OUT (accumulating for sigma, plain for boundary steps)
+    int64_t y_elems = 0;  // BUF_Y region that must be zeroed before the axpy pass
+    int64_t t_elems = 0;
+};
+
+struct Layout   // block offsets of one block matrix inside a flat buffer
+{
+    DualIndex basis;
+    std::vector<int64_t> off;
+    int64_t total = 0;
+    void assign(DualIndex const& b, int64_t base = 0)
+    {
+        basis = b; off.resize(b.size()); total = 0;
+        for (size_t k = 0; k < b.size(); ++k) { off[k] = base + total; total += (int64_t)b[k].ls * (int64_t)b[k].rs; }
+    }
+};
+
+struct BoundaryLayout
+{
+    std::vector<Layout> b;
+    int64_t total = 0;
+    void assign(std::vector<DualIndex> const& bases)
+    {
+        b.resize(bases.size()); total = 0;
+        for (size_t i = 0; i < bases.size(); ++i) { b[i].assign(bases[i], total); total += b[i].total; }
+    }
+    size_t aux_dim() const { return b.size(); }
+};
+
+struct Plan
+{
+    int kind = 0;                          // 0 sigma, 1 left step, 2 right step
+    std::vector<CopyTask> pre_copies;      // pairing reshapes of ket / bra
+    GemmList persistent_t;                 // step 1 products of multi-use bonds -> BUF_TP
+    std::vector<Wave> waves;
+    Layout out_tensor;                     // sigma (left paired)
+    BoundaryLayout out_boundary;           // boundary steps
+    bool accumulate_out = false;
+    int64_t ket_lp_elems = 0, ket_rp_elems = 0, bra_lp_elems = 0, bra_rp_elems = 0;
+    int64_t tp_elems = 0, t_elems_max = 0, y_elems_max = 0;
+    double flops_t = 0, flops_w = 0, flops_close = 0;
+    int64_t bytes_algorithmic = 0;         // 8*(sum|L_b| + sum|R_b| + 2|psi|) resp. boundary-step analogue
+    size_t n_gemm_tasks = 0, n_axpy_tasks = 0;
+    double flops() const { return flops_t + flops_w + flops_close; }
+};
+
+// a (possibly transposed / scaled) view of one stored boundary entry
+struct VBlock { Charge lc, rc; int32_t ls, rs; int64_t off; int32_t ld; int32_t trans; double scale; };
+struct VView
+{
+    std::vector<VBlock> blocks;   // sorted descending by (lc, rc)
+    DualIndex basis;
+    void build(Layout const& L, bool transposed, std::vector<double> const& scales)
+    {
+        blocks.clear(); basis = DualIndex();
+        for (size_t k = 0; k < L.basis.size(); ++k) {
+            QnBlock const& q = L.basis[k];
+            VBlock v;
+            double sc = scales.empty() ? 1. : scales[k];
+            if (!transposed) v = VBlock{q.lc, q.rc, (int32_t)q.ls, (int32_t)q.rs, L.off[k], (int32_t)q.ls, 0, sc};
+            else v = VBlock{q.rc, q.lc, (int32_t)q.rs, (int32_t)q.ls, L.off[k], (int32_t)q.ls, 1, sc};
+            size_t i = basis.insert(QnBlock(v.lc, v.rc, v.ls, v.rs));
+            blocks.insert(blocks.begin() + i, v);
+        }
+    }
+};
+
+struct TensorDesc   // what the planner needs to know about an MPS tensor (no data)
+{
+    Index phys_i, left_i, right_i;
+    DualIndex lp_basis;   // left-paired block structure of the data the caller will pass
+};
+
+class Planner
+{
+public:
+    Planner(SymmKind s, MPOTensor const& mpo_, bool isHermitian_, int rank_ = 0, int world_ = 1, int64_t ws_budget_elems = (int64_t)1 << 30)
+        : symm(s), su2_(is_su2(s)), mpo(mpo_), isHermitian(isHermitian_), rank(rank_), world(world_), budget(ws_budget_elems) {}
+
+    // -----------------------------------------------------------------------------------------------------
+    // sigma = H_eff psi    (abelian/site_hamil.hpp:23-90, non-abelian/site_hamil.hpp:57-147)
+    Plan plan_sigma(TensorDesc const& ket, BoundaryLayout const& left, BoundaryLayout const& right)
+    {
+        Plan P; P.kind = 0; P.accumulate_out = true;
+        TensorDesc const& bra = ket;
+        Layout ket_lp; ket_lp.assign(ket.lp_basis);
+        Layout ket_rp = plan_left_to_right(ket, ket_lp, BUF_KET_LP, BUF_KET_RP, P.pre_copies);
+        P.ket_lp_elems = ket_lp.total; P.ket_rp_elems = ket_rp.total;
+
+        Index const& physical_i = ket.phys_i;
+        Index const& left_i = bra.left_i;
+        Index right_i = ket.right_i;
+        Index out_left_i = physical_i * left_i;
+        if (su2_) { Index right_i_bra = bra.right_i; common_subset(out_left_i, right_i_bra); }
+        else common_subset(out_left_i, right_i);                       // abelian trims BOTH (site_hamil.hpp:42)
+        ProductBasis out_left_pb(physical_i, left_i);
+        ProductBasis in_right_pb(physical_i, right_i, true);
+        Index indexForTrim = ket_rp.basis.left_basis();                // bra == ket, right paired
+
+        setup_t_left(P, left, ket_rp, indexForTrim);
+
+        // output structure: emulate the per-b2 products and their match_and_add_block reduction
+        block_struct sigma_struct;
+        struct Pending { size_t b2; Layout y; std::vector<YTask> ytasks; std::vector<size_t> t_rows; };
+        std::vector<Pending> pend;
+        for (size_t b2 = 0; b2 < mpo.col_dim(); ++b2) {
+            Pending pd; pd.b2 = b2;
+            DualIndex ybasis;
+            if (su2_) y_struct_su2_lbtm(b2, ket_rp, right_i, out_left_i, in_right_pb, out_left_pb, ybasis, pd.ytasks, pd.t_rows);
+            else y_struct_abelian_lbtm(b2, ket_rp.basis, ket_rp.basis, right_i, out_left_i, in_right_pb, out_left_pb, ybasis, pd.ytasks, pd.t_rows);
+            pd.y.assign(ybasis);
+            // closing product structure (decides which sigma blocks exist, on every rank identically)
+            VView rv = right_view(right, b2);
+            for (size_t k = 0; k < ybasis.size(); ++k) {
+                if (su2_) {
+                    Charge al = ybasis[k].lc, ar = ybasis[k].rc;
+                    size_t mb = rv.basis.position(ar, al);
+                    if (mb == rv.basis.size()) continue;
+                    if (!out_left_i.has(al)) continue;   // the num_ops>3 post filter is implied for the plain kernel too
+                    sigma_struct.add(al, al, ybasis[k].ls, rv.blocks[mb].rs);
+                } else {
+                    Charge ar = ybasis[k].rc;
+                    for (auto it = rv.basis.left_lower_bound(ar); it != rv.basis.end() && it->lc == ar; ++it)
+                        sigma_struct.add(ybasis[k].lc, it->rc, ybasis[k].ls, it->rs);
+                }
+            }
+            pend.push_back(std::move(pd));
+        }
+        P.out_tensor.assign(sigma_struct.basis);
+
+        // emit waves over this rank's share of b2
+        std::vector<char> mine = share_mask(pend.size(), [&](size_t i) { return estimate_cost(pend[i].y, right, pend[i].b2); });
+        Wave cur; int64_t cur_y = 0, cur_t = 0;
+        auto flush = [&]() {
+            if (cur.w_apply.dsts.empty() && cur.close_gemm.outs.empty() && cur.t_gemm.outs.empty()) return;
+            cur.y_elems = cur_y; cur.t_elems = cur_t;
+            P.y_elems_max = std::max(P.y_elems_max, cur_y); P.t_elems_max = std::max(P.t_elems_max, cur_t);
+            merge_outputs(cur.close_gemm); merge_outputs(cur.t_gemm);
+            P.waves.push_back(std::move(cur));
+            cur = Wave(); cur_y = 0; cur_t = 0;
+        };
+        for (size_t i = 0; i < pend.size(); ++i) {
+            if (!mine[i]) continue;
+            Pending& pd = pend[i];
+            int64_t need_t = 0;
+            for (size_t b1 : pd.t_rows) if (!t_persistent[b1]) need_t += t_layout_size(b1);
+            if ((cur_y + cur_t) > 0 && cur_y + cur_t + pd.y.total + need_t > budget) flush();
+            // step 1 for single-use rows consumed here
+            std::map<size_t, Layout> tl;
+            for (size_t b1 : pd.t_rows) {
+                if (t_persistent[b1]) { tl[b1] = tp_layout[b1]; continue; }
+                Layout L; L.assign(t_basis[b1], cur_t);
+                emit_t_gemm(P, cur.t_gemm, b1, L, BUF_T, ket_rp);
+                cur_t += L.total; tl[b1] = L;
+            }
+            // step 2
+            Layout yl; yl.assign(pd.y.basis, cur_y);
+            emit_axpy(P, cur.w_apply, pd.ytasks, tl, yl);
+            cur_y += yl.total;
+            // step 3
+            VView rv = right_view(right, pd.b2);
+            for (size_t k = 0; k < yl.basis.size(); ++k) {
+                QnBlock const& yb = yl.basis[k];
+                if (su2_) {
+                    size_t mb = rv.basis.position(yb.rc, yb.lc);
+                    if (mb == rv.basis.size()) continue;
+                    if (!out_left_i.has(yb.lc)) continue;
+                    emit_close(P, cur.close_gemm, P.out_tensor, yb.lc, yb.lc, Ref{BUF_Y, yl.off[k]}, (int32_t)yb.ls, 0, (int32_t)yb.ls, (int32_t)yb.rs, rv.blocks[mb], BUF_RIGHT);
+                } else {
+                    for (auto it = rv.basis.left_lower_bound(yb.rc); it != rv.basis.end() && it->lc == yb.rc; ++it) {
+                        size_t mb = it - rv.basis.begin();
+                        emit_close(P, cur.close_gemm, P.out_tensor, yb.lc, it->rc, Ref{BUF_Y, yl.off[k]}, (int32_t)yb.ls, 0, (int32_t)yb.ls, (int32_t)yb.rs, rv.blocks[mb], BUF_RIGHT);
+                    }
+                }
+            }
+        }
+        flush();
+        merge_outputs(P.persistent_t);
+        P.bytes_algorithmic = 8 * (left.total + right.total + 2 * ket_lp.total);
+        return P;
+    }
+
+    // -----------------------------------------------------------------------------------------------------
+    // L'[b2] = Y[b2]^T conj(bra)      (common/move_boundary.hpp:128-187)
+    Plan plan_left_step(TensorDesc const& bra, TensorDesc const& ket, BoundaryLayout const& left)
+    {
+        Plan P; P.kind = 1; P.accumulate_out = false;
+        Layout ket_lp; ket_lp.assign(ket.lp_basis);
+        Layout ket_rp = plan_left_to_right(ket, ket_lp, BUF_KET_LP, BUF_KET_RP, P.pre_copies);
+        Layout bra_lp; bra_lp.assign(bra.lp_basis);
+        std::vector<CopyTask> dummy;
+        Layout bra_rp = plan_left_to_right(bra, bra_lp, BUF_BRA_LP, BUF_BRA_RP, dummy);   // structure only
+        P.ket_lp_elems = ket_lp.total; P.ket_rp_elems = ket_rp.total; P.bra_lp_elems = bra_lp.total;
+
+        Index braBasis = bra_rp.basis.left_basis();
+        Index const& left_i = bra.left_i;
+        Index right_i = ket.right_i;
+        Index bra_right_i = bra.right_i;
+        Index out_left_i = bra.phys_i * left_i;
+        common_subset(out_left_i, bra_right_i);
+        ProductBasis out_left_pb(bra.phys_i, left_i);
+        ProductBasis in_right_pb(ket.phys_i, right_i, true);
+
+        setup_t_left(P, left, ket_rp, braBasis);
+
+        size_t loop_max = mpo.col_dim();
+        struct Pending { size_t b2; DualIndex y; std::vector<YTask> ytasks; std::vector<size_t> t_rows; DualIndex out; };
+        std::vector<Pending> pend(loop_max);
+        std::vector<DualIndex> out_bases(loop_max);
+        for (size_t b2 = 0; b2 < loop_max; ++b2) {
+            Pending& pd = pend[b2]; pd.b2 = b2;
+            if (mpo.herm_info.right_skip(b2) && isHermitian) continue;
+            if (su2_) y_struct_su2_lbtm(b2, ket_rp, right_i, out_left_i, in_right_pb, out_left_pb, pd.y, pd.ytasks, pd.t_rows);
+            else y_struct_abelian_lbtm(b2, ket_rp.basis, bra_rp.basis, right_i, out_left_i, in_right_pb, out_left_pb, pd.y, pd.ytasks, pd.t_rows);
+            // gemm(transpose(Y), bra_lp, ret[b2], spin)
+            block_struct os;
+            int spin_f = su2_ ? mpo.right_spin(b2).get() : -1;
+            DualIndex yt = pd.y.transposed();
+            for (size_t k = 0; k < yt.size(); ++k)
+                for (auto it = bra_lp.basis.left_lower_bound(yt[k].rc); it != bra_lp.basis.end() && it->lc == yt[k].rc; ++it) {
+                    if (spin_f != -1 && !su2::triangle(spin(yt[k].lc), spin_f, spin(it->rc))) continue;
+                    os.add(yt[k].lc, it->rc, yt[k].ls, it->rs);
+                }
+            out_bases[b2] = os.basis;
+        }
+        P.out_boundary.assign(out_bases);
+
+        std::vector<char> mine = share_mask(loop_max, [&](size_t b2) { double c = 0; for (size_t k = 0; k < pend[b2].y.size(); ++k) c += (double)pend[b2].y[k].ls * pend[b2].y[k].rs; return c; });
+        Wave cur; int64_t cur_y = 0, cur_t = 0;
+        auto flush = [&]() {
+            if (cur.w_apply.dsts.empty() && cur.close_gemm.outs.empty() && cur.t_gemm.outs.empty()) return;
+            cur.y_elems = cur_y; cur.t_elems = cur_t;
+            P.y_elems_max = std::max(P.y_elems_max, cur_y); P.t_elems_max = std::max(P.t_elems_max, cur_t);
+            merge_outputs(cur.close_gemm); merge_outputs(cur.t_gemm);
+            P.waves.push_back(std::move(cur));
+            cur = Wave(); cur_y = 0; cur_t = 0;
+        };
+        for (size_t b2 = 0; b2 < loop_max; ++b2) {
+            Pending& pd = pend[b2];
+            if (!mine[b2] || (mpo.herm_info.right_skip(b2) && isHermitian)) continue;
+            Layout ytmp; ytmp.assign(pd.y);
+            int64_t need_t = 0;
+            for (size_t b1 : pd.t_rows) if (!t_persistent[b1]) need_t += t_layout_size(b1);
+            if ((cur_y + cur_t) > 0 && cur_y + cur_t + ytmp.total + need_t > budget) flush();
+            std::map<size_t, Layout> tl;
+            for (size_t b1 : pd.t_rows) {
+                if (t_persistent[b1]) { tl[b1] = tp_layout[b1]; continue; }
+                Layout L; L.assign(t_basis[b1], cur_t);
+                emit_t_gemm(P, cur.t_gemm, b1, L, BUF_T, ket_rp);
+                cur_t += L.total; tl[b1] = L;
+            }
+            Layout yl; yl.assign(pd.y, cur_y);
+            emit_axpy(P, cur.w_apply, pd.ytasks, tl, yl);
+            cur_y += yl.total;
+            int spin_f = su2_ ? mpo.right_spin(b2).get() : -1;
+            Layout const& ol = P.out_boundary.b[b2];
+            for (size_t k = 0; k < yl.basis.size(); ++k) {
+                QnBlock const& yb = yl.basis[k];   // transposed: (rc, lc), rows rs, cols ls
+                for (auto it = bra_lp.basis.left_lower_bound(yb.lc); it != bra_lp.basis.end() && it->lc == yb.lc; ++it) {
+                    if (spin_f != -1 && !su2::triangle(spin(yb.rc), spin_f, spin(it->rc))) continue;
+                    size_t mb = it - bra_lp.basis.begin();
+                    VBlock bv{it->lc, it->rc, (int32_t)it->ls, (int32_t)it->rs, bra_lp.off[mb], (int32_t)it->ls, 0, 1.};
+                    // A = Y block transposed: m = yb.rs, k = yb.ls
+                    emit_close(P, cur.close_gemm, ol, yb.rc, it->rc, Ref{BUF_Y, yl.off[k]}, (int32_t)yb.ls, 1, (int32_t)yb.rs, (int32_t)yb.ls, bv, BUF_BRA_LP);
+                }
+            }
+        }
+        flush();
+        merge_outputs(P.persistent_t);
+        P.bytes_algorithmic = 8 * (left.total + ket_lp.total + bra_lp.total + P.out_boundary.total);
+        return P;
+    }
+
+    // -----------------------------------------------------------------------------------------------------
+    // R'[b1] = Y'[b1] conj(bra)^T     (common/move_boundary.hpp:189-229)
+    Plan plan_right_step(TensorDesc const& bra, TensorDesc const& ket, BoundaryLayout const& right)
+    {
+        Plan P; P.kind = 2; P.accumulate_out = false;
+        Layout ket_lp; ket_lp.assign(ket.lp_basis);
+        Layout bra_lp; bra_lp.assign(bra.lp_basis);
+        Layout bra_rp = plan_left_to_right(bra, bra_lp, BUF_BRA_LP, BUF_BRA_RP, P.pre_copies);
+        P.ket_lp_elems = ket_lp.total; P.bra_lp_elems = bra_lp.total; P.bra_rp_elems = bra_rp.total;
+
+        Index const& physical_i = ket.phys_i;
+        Index right_i = bra.right_i;
+        Index left_i = ket.left_i, out_right_i = adjoin(physical_i) * right_i, bra_left_i = bra.left_i;
+        Index indexForTrim = bra_lp.basis.right_basis();
+        common_subset(out_right_i, bra_left_i);
+        ProductBasis in_left_pb(physical_i, left_i);
+        ProductBasis out_right_pb(physical_i, right_i, true);
+
+        setup_t_right(P, right, ket_lp, indexForTrim);
+
+        size_t loop_max = mpo.row_dim();
+        struct Pending { DualIndex y; std::vector<YTask> ytasks; std::vector<size_t> t_cols; };
+        std::vector<Pending> pend(loop_max);
+        std::vector<DualIndex> out_bases(loop_max);
+        DualIndex bra_rp_t = bra_rp.basis.transposed();
+        for (size_t b1 = 0; b1 < loop_max; ++b1) {
+            Pending& pd = pend[b1];
+            if (mpo.herm_info.left_skip(b1) && isHermitian) continue;
+            if (su2_) y_struct_su2_rbtm(b1, ket_lp.basis, left_i, out_right_i, in_left_pb, out_right_pb, pd.y, pd.ytasks, pd.t_cols);
+            else y_struct_abelian_rbtm(b1, left_i, out_right_i, in_left_pb, out_right_pb, pd.y, pd.ytasks, pd.t_cols);
+            block_struct os;
+            int spin_f = su2_ ? mpo.left_spin(b1).get() : -1;
+            for (size_t k = 0; k < pd.y.size(); ++k)
+                for (auto it = bra_rp_t.left_lower_bound(pd.y[k].rc); it != bra_rp_t.end() && it->lc == pd.y[k].rc; ++it) {
+                    if (spin_f != -1 && !su2::triangle(spin(pd.y[k].lc), spin_f, spin(it->rc))) continue;
+                    os.add(pd.y[k].lc, it->rc, pd.y[k].ls, it->rs);
+                }
+            out_bases[b1] = os.basis;
+        }
+        P.out_boundary.assign(out_bases);
+
+        std::vector<char> mine = share_mask(loop_max, [&](size_t b1) { double c = 0; for (size_t k = 0; k < pend[b1].y.size(); ++k) c += (double)pend[b1].y[k].ls * pend[b1].y[k].rs; return c; });
+        Wave cur; int64_t cur_y = 0, cur_t = 0;
+        auto flush = [&]() {
+            if (cur.w_apply.dsts.empty() && cur.close_gemm.outs.empty() && cur.t_gemm.outs.empty()) return;
+            cur.y_elems = cur_y; cur.t_elems = cur_t;
+            P.y_elems_max = std::max(P.y_elems_max, cur_y); P.t_elems_max = std::max(P.t_elems_max, cur_t);
+            merge_outputs(cur.close_gemm); merge_outputs(cur.t_gemm);
+            P.waves.push_back(std::move(cur));
+            cur = Wave(); cur_y = 0; cur_t = 0;
+        };
+        // bra right paired, transposed view: block (rc, lc) of the stored (lc, rc)
+        VView brt; { Layout l = bra_rp; brt.build(l, true, std::vector<double>()); }
+        for (size_t b1 = 0; b1 < loop_max; ++b1) {
+            Pending& pd = pend[b1];
+            if (!mine[b1] || (mpo.herm_info.left_skip(b1) && isHermitian)) continue;
+            Layout ytmp; ytmp.assign(pd.y);
+            int64_t need_t = 0;
+            for (size_t b2 : pd.t_cols) if (!t_persistent[b2]) need_t += t_layout_size(b2);
+            if ((cur_y + cur_t) > 0 && cur_y + cur_t + ytmp.total + need_t > budget) flush();
+            std::map<size_t, Layout> tl;
+            for (size_t b2 : pd.t_cols) {
+                if (t_persistent[b2]) { tl[b2] = tp_layout[b2]; continue; }
+                Layout L; L.assign(t_basis[b2], cur_t);
+                emit_t_gemm_right(P, cur.t_gemm, b2, L, BUF_T, ket_lp);
+                cur_t += L.total; tl[b2] = L;
+            }
+            Layout yl; yl.assign(pd.y, cur_y);
+            emit_axpy(P, cur.w_apply, pd.ytasks, tl, yl);
+            cur_y += yl.total;
+            int spin_f = su2_ ? mpo.left_spin(b1).get() : -1;
+            Layout const& ol = P.out_boundary.b[b1];
+            for (size_t k = 0; k < yl.basis.size(); ++k) {
+                QnBlock const& yb = yl.basis[k];
+                for (auto it = brt.basis.left_lower_bound(yb.rc); it != brt.basis.end() && it->lc == yb.rc; ++it) {
+                    if (spin_f != -1 && !su2::triangle(spin(yb.lc), spin_f, spin(it->rc))) continue;
+                    size_t mb = it - brt.basis.begin();
+                    emit_close(P, cur.close_gemm, ol, yb.lc, it->rc, Ref{BUF_Y, yl.off[k]}, (int32_t)yb.ls, 0, (int32_t)yb.ls, (int32_t)yb.rs, brt.blocks[mb], BUF_BRA_RP);
+                }
+            }
+        }
+        flush();
+        merge_outputs(P.persistent_t);
+        P.bytes_algorithmic = 8 * (right.total + ket_lp.total + bra_lp.total + P.out_boundary.total);
+        return P;
+    }
+
+private:
+    struct block_struct   // accumulates an output block structure with match_and_add_block growth semantics
+    {
+        DualIndex basis;
+        void add(Charge const& lc, Charge const& rc, size_t ls, size_t rs)
+        {
+            size_t p = basis.position(lc, rc);
+            if (p == basis.size()) basis.insert(QnBlock(lc, rc, ls, rs));
+            else { basis[p].ls = std::max(basis[p].ls, ls); basis[p].rs = std::max(basis[p].rs, rs); }
+        }
+    };
+    // one W-application contribution: dst panel in Y block `o`, source panel in T[bt] block `t_block`
+    struct YTask { size_t o; int32_t dst_row, dst_col, rows, cols; size_t bt, t_block; int32_t src_row, src_col; double coef; };
+
+    // ---- reshape structure [(phys,left),right] -> [left,(-phys,right)] (reshapes.h:177-223) as panel copies
+    Layout plan_left_to_right(TensorDesc const& t, Layout const& lp, int src_buf, int dst_buf, std::vector<CopyTask>& copies)
+    {
+        ProductBasis in_left(t.phys_i, t.left_i);
+        ProductBasis out_right(t.phys_i, t.right_i, true);
+        DualIndex rb;
+        struct C { size_t block; Charge ol, orc; int32_t in_off, out_off, sdim, ldim, rdim; };
+        std::vector<C> cs;
+        for (size_t block = 0; block < lp.basis.size(); ++block) {
+            size_t r = t.right_i.position(lp.basis[block].rc);
+            if (r == t.right_i.size()) continue;
+            Charge in_r = t.right_i[r].first;
+            for (size_t s = 0; s < t.phys_i.size(); ++s) {
+                size_t l = t.left_i.position(fuse(lp.basis[block].lc, -t.phys_i[s].first));
+                if (l == t.left_i.size()) continue;
+                Charge ol = t.left_i[l].first, orc = fuse(-t.phys_i[s].first, in_r);
+                if (!rb.has(ol, orc)) rb.insert(QnBlock(ol, orc, t.left_i[l].second, out_right.size(orc)));
+                cs.push_back(C{block, ol, orc, (int32_t)in_left(t.phys_i[s].first, t.left_i[l].first), (int32_t)out_right(t.phys_i[s].first, in_r),
+                               (int32_t)t.phys_i[s].second, (int32_t)t.left_i[l].second, (int32_t)t.right_i[r].second});
+            }
+        }
+        Layout rp; rp.assign(rb);
+        for (auto const& c : cs) {
+            size_t ob = rp.basis.position(c.ol, c.orc);
+            int32_t ld_in = (int32_t)lp.basis[c.block].ls, ld_out = (int32_t)rp.basis[ob].ls;
+            for (int32_t ss = 0; ss < c.sdim; ++ss)
+                copies.push_back(CopyTask{Ref{src_buf, lp.off[c.block] + c.in_off + ss * c.ldim}, Ref{dst_buf, rp.off[ob] + (int64_t)(c.out_off + ss * c.rdim) * ld_out},
+                                          c.ldim, c.rdim, ld_in, ld_out});
+        }
+        return rp;
+    }
+
+    // ---- Hermitian-aware views of boundary entries (common/boundary_times_mps.hpp:19-43,163-209,266-361)
+    std::vector<double> conj_phases(DualIndex const& b, size_t k, bool left, bool forward) const
+    {
+        if (!su2_) return std::vector<double>();
+        int S = left ? mpo.left_spin(k).get() : mpo.right_spin(k).get();
+        std::vector<double> ret(b.size());
+        for (size_t i = 0; i < b.size(); ++i) {
+            double scale = su2::conjugate_correction(spin(b[i].lc), spin(b[i].rc), S);
+            if (forward) scale *= left ? mpo.herm_info.left_phase(mpo.herm_info.left_conj(k)) : mpo.herm_info.right_phase(mpo.herm_info.right_conj(k));
+            else scale *= left ? mpo.herm_info.left_phase(k) : mpo.herm_info.right_phase(k);
+            ret[i] = scale;
+        }
+        return ret;
+    }
+    // A operand of step 1 (left): transpose(left[b1]) or conjugate(left[conj]) with conjugate phases
+    VView left_view(BoundaryLayout const& left, size_t b1) const
+    {
+        VView v;
+        if (mpo.herm_info.left_skip(b1) && isHermitian) {
+            Layout const& src = left.b[mpo.herm_info.left_conj(b1)];
+            v.build(src, false, conj_phases(src.basis, b1, true, false));
+        } else
+            v.build(left.b[b1], true, std::vector<double>());
+        return v;
+    }
+    // B operand for right-side products: right[b2] or adjoint(right[conj]) with phases computed on the adjoint view
+    VView right_view(BoundaryLayout const& right, size_t b2) const
+    {
+        VView v;
+        if (mpo.herm_info.right_skip(b2) && isHermitian) {
+            Layout const& src = right.b[mpo.herm_info.right_conj(b2)];
+            v.build(src, true, std::vector<double>());
+            std::vector<double> ph = conj_phases(v.basis, b2, false, true);
+            for (size_t i = 0; i < v.blocks.size(); ++i) v.blocks[i].scale = ph.empty() ? 1. : ph[i];
+        } else
+            v.build(right.b[b2], false, std::vector<double>());
+        return v;
+    }
+
+    // ---- step 1 structure, left: T[b1] = op(L[b1]) * psi_rp  (gemm_trim_left)
+    void setup_t_left(Plan& P, BoundaryLayout const& left, Layout const& ket_rp, Index const& ref_left_basis)
+    {
+        size_t B = left.aux_dim();
+        t_basis.assign(B, DualIndex()); t_views.assign(B, VView()); t_persistent.assign(B, 0); tp_layout.assign(B, Layout());
+        Index B_left_basis = ket_rp.basis.left_basis();
+        for (size_t b1 = 0; b1 < B; ++b1) {
+            t_views[b1] = left_view(left, b1);
+            VView const& A = t_views[b1];
+            DualIndex tb;
+            for (size_t k = 0; k < A.blocks.size(); ++k) {
+                if (!su2_) {
+                    size_t mb = B_left_basis.position(A.blocks[k].rc);
+                    if (mb == ket_rp.basis.size()) continue;
+                    if (!ref_left_basis.has(A.blocks[k].lc)) continue;
+                    tb.insert(QnBlock(A.blocks[k].lc, ket_rp.basis[mb].rc, A.blocks[k].ls, ket_rp.basis[mb].rs));
+                } else {
+                    if (!ref_left_basis.has(A.blocks[k].lc)) continue;
+                    for (auto it = ket_rp.basis.left_lower_bound(A.blocks[k].rc); it != ket_rp.basis.end() && it->lc == A.blocks[k].rc; ++it)
+                        if (!tb.has(A.blocks[k].lc, it->rc)) tb.insert(QnBlock(A.blocks[k].lc, it->rc, A.blocks[k].ls, it->rs));
+                }
+            }
+            t_basis[b1] = tb;
+        }
+        // multi-use bonds are computed once up front and stay resident for all waves
+        int64_t off = 0;
+        for (size_t b1 = 0; b1 < B; ++b1) {
+            if (b1 < mpo.row_dim() && mpo.num_row_non_zeros(b1) == 1) continue;
+            if (b1 >= mpo.row_dim() || mpo.num_row_non_zeros(b1) == 0) continue;
+            t_persistent[b1] = 1;
+            tp_layout[b1].assign(t_basis[b1], off);
+            off += tp_layout[b1].total;
+            emit_t_gemm(P, P.persistent_t, b1, tp_layout[b1], BUF_TP, ket_rp);
+        }
+        P.tp_elems = off;
+    }
+    void emit_t_gemm(Plan& P, GemmList& gl, size_t b1, Layout const& tl, int buf, Layout const& ket_rp)
+    {
+        VView const& A = t_views[b1];
+        Index B_left_basis = ket_rp.basis.left_basis();
+        for (size_t k = 0; k < A.blocks.size(); ++k) {
+            VBlock const& a = A.blocks[k];
+            auto one = [&](size_t mb) {
+                size_t cb = tl.basis.position(a.lc, ket_rp.basis[mb].rc);
+                if (cb == tl.basis.size()) return;
+                Out o; o.C = Ref{buf, tl.off[cb]}; o.ldc = (int32_t)tl.basis[cb].ls; o.m = a.ls; o.n = (int32_t)ket_rp.basis[mb].rs;
+                o.seg_begin = (int32_t)gl.segs.size();
+                gl.segs.push_back(Seg{Ref{BUF_LEFT, a.off}, Ref{BUF_KET_RP, ket_rp.off[mb]}, a.ld, (int32_t)ket_rp.basis[mb].ls, o.m, o.n, a.rs, a.trans, 0, a.scale});
+                o.seg_end = (int32_t)gl.segs.size();
+                gl.outs.push_back(o);
+                P.flops_t += 2.0 * o.m * o.n * a.rs; P.n_gemm_tasks++;
+            };
+            if (!tl.basis.left_has(a.lc)) continue;
+            if (!su2_) { size_t mb = B_left_basis.position(a.rc); if (mb != ket_rp.basis.size()) one(mb); }
+            else for (auto it = ket_rp.basis.left_lower_bound(a.rc); it != ket_rp.basis.end() && it->lc == a.rc; ++it) one(it - ket_rp.basis.begin());
+        }
+    }
+
+    // ---- step 1 structure, right: T[b2] = psi_lp * op(R[b2])  (gemm_trim_right)
+    void setup_t_right(Plan& P, BoundaryLayout const& right, Layout const& ket_lp, Index const& ref_right_basis)
+    {
+        size_t B = right.aux_dim();
+        t_basis.assign(B, DualIndex()); t_views.assign(B, VView()); t_persistent.assign(B, 0); tp_layout.assign(B, Layout());
+        Index A_right_basis = ket_lp.basis.right_basis();
+        for (size_t b2 = 0; b2 < B; ++b2) {
+            t_views[b2] = right_view(right, b2);
+            VView const& Bv = t_views[b2];
+            DualIndex tb;
+            if (!su2_) {
+                for (size_t k = 0; k < Bv.blocks.size(); ++k) {
+                    size_t mb = A_right_basis.position(Bv.blocks[k].lc);
+                    if (mb == ket_lp.basis.size()) continue;
+                    if (!ref_right_basis.has(Bv.blocks[k].rc)) continue;
+                    tb.insert(QnBlock(ket_lp.basis[mb].lc, Bv.blocks[k].rc, ket_lp.basis[mb].ls, Bv.blocks[k].rs));
+                }
+            } else {
+                for (size_t a = 0; a < ket_lp.basis.size(); ++a)
+                    for (auto it = Bv.basis.left_lower_bound(ket_lp.basis[a].rc); it != Bv.basis.end() && it->lc == ket_lp.basis[a].rc; ++it) {
+                        if (!ref_right_basis.has(it->rc)) continue;
+                        if (!tb.has(ket_lp.basis[a].lc, it->rc)) tb.insert(QnBlock(ket_lp.basis[a].lc, it->rc, ket_lp.basis[a].ls, it->rs));
+                    }
+            }
+            t_basis[b2] = tb;
+        }
+        int64_t off = 0;
+        for (size_t b2 = 0; b2 < B; ++b2) {
+            if (b2 >= mpo.col_dim() || mpo.num_col_non_zeros(b2) <= 1) continue;
+            t_persistent[b2] = 1;
+            tp_layout[b2].assign(t_basis[b2], off);
+            off += tp_layout[b2].total;
+            emit_t_gemm_right(P, P.persistent_t, b2, tp_layout[b2], BUF_TP, ket_lp);
+        }
+        P.tp_elems = off;
+        ket_lp_for_right = ket_lp;
+    }
+    void emit_t_gemm_right(Plan& P, GemmList& gl, size_t b2, Layout const& tl, int buf, Layout const& ket_lp)
+    {
+        VView const& Bv = t_views[b2];
+        Index A_right_basis = ket_lp.basis.right_basis();
+        auto one = [&](size_t a, size_t k) {
+            VBlock const& b = Bv.blocks[k];
+            size_t cb = tl.basis.position(ket_lp.basis[a].lc, b.rc);
+            if (cb == tl.basis.size()) return;
+            Out o; o.C = Ref{buf, tl.off[cb]}; o.ldc = (int32_t)tl.basis[cb].ls; o.m = (int32_t)ket_lp.basis[a].ls; o.n = b.rs;
+            o.seg_begin = (int32_t)gl.segs.size();
+            gl.segs.push_back(Seg{Ref{BUF_KET_LP, ket_lp.off[a]}, Ref{BUF_RIGHT, b.off}, (int32_t)ket_lp.basis[a].ls, b.ld, o.m, o.n, (int32_t)ket_lp.basis[a].rs, 0, b.trans, b.scale});
+            o.seg_end = (int32_t)gl.segs.size();
+            gl.outs.push_back(o);
+            P.flops_t += 2.0 * o.m * o.n * ket_lp.basis[a].rs; P.n_gemm_tasks++;
+        };
+        if (!su2_) {
+            for (size_t k = 0; k < Bv.blocks.size(); ++k) {
+                size_t mb = A_right_basis.position(Bv.blocks[k].lc);
+                if (mb == ket_lp.basis.size()) continue;
+                one(mb, k);
+            }
+        } else
+            for (size_t a = 0; a < ket_lp.basis.size(); ++a)
+                for (auto it = Bv.basis.left_lower_bound(ket_lp.basis[a].rc); it != Bv.basis.end() && it->lc == ket_lp.basis[a].rc; ++it)
+                    one(a, it - Bv.basis.begin());
+    }
+    int64_t t_layout_size(size_t b) const
+    {
+        int64_t s = 0;
+        for (size_t k = 0; k < t_basis[b].size(); ++k) s += (int64_t)t_basis[b][k].ls * (int64_t)t_basis[b][k].rs;
+        return s;
+    }
+
+    static Charge delta_of(DualIndex const& b) { return fuse(b.right_charge(0), -b.left_charge(0)); }
+
+    // ---- step 2 structure, abelian lbtm (abelian/apply_op.hpp:23-139)
+    void y_struct_abelian_lbtm(size_t b2, DualIndex const& /*ket_basis*/, DualIndex const& /*bra_basis*/, Index const& right_i, Index const& out_left_i,
+                               ProductBasis const& in_right_pb, ProductBasis const& out_left_pb,
+                               DualIndex& ret, std::vector<YTask>& tasks, std::vector<size_t>& t_rows)
+    {
+        for (size_t e = mpo.col_begin(b2); e < mpo.col_end(b2); ++e) {   // allocate
+            size_t b1 = mpo.row_of(e);
+            DualIndex const& T = t_basis[b1];
+            if (T.size() == 0) continue;
+            for (auto const& term : mpo.at_entry(e)) {
+                SiteOperator const& W = mpo.op(term.first);
+                if (W.n_blocks() == 0) continue;
+                Charge total_delta = fuse(delta_of(W.basis()), -delta_of(T));
+                for (size_t r = 0; r < right_i.size(); ++r) {
+                    Charge out_r = right_i[r].first, out_l = fuse(out_r, total_delta);
+                    if (!out_left_i.has(out_l)) continue;
+                    if (!ret.has(out_l, out_r)) ret.insert(QnBlock(out_l, out_r, out_left_i.size_of_block(out_l), right_i[r].second));
+                }
+            }
+        }
+        for (size_t e = mpo.col_begin(b2); e < mpo.col_end(b2); ++e) {   // execute
+            size_t b1 = mpo.row_of(e);
+            DualIndex const& T = t_basis[b1];
+            if (T.size() == 0) continue;
+            bool used = false;
+            for (auto const& term : mpo.at_entry(e)) {
+                SiteOperator const& W = mpo.op(term.first);
+                if (W.n_blocks() == 0) continue;
+                Charge T_delta = delta_of(T);
+                Charge total_delta = fuse(delta_of(W.basis()), -T_delta);
+                for (size_t r = 0; r < right_i.size(); ++r) {
+                    Charge out_r = right_i[r].first, out_l = fuse(out_r, total_delta);
+                    if (!out_left_i.has(out_l)) continue;
+                    int32_t r_size = (int32_t)right_i[r].second;
+                    size_t o = ret.position(out_l, out_r);
+                    for (size_t w = 0; w < W.n_blocks(); ++w) {
+                        Charge c1 = W.basis().left_charge(w), c2 = W.basis().right_charge(w);
+                        Charge in_r = fuse(out_r, -c1), in_l = fuse(in_r, -T_delta);
+                        size_t tb = T.position(in_l, in_r);
+                        if (tb == T.size()) continue;
+                        int32_t in_off = (int32_t)in_right_pb(c1, out_r), out_off = (int32_t)out_left_pb(c2, in_l);
+                        int32_t ldim = (int32_t)T[tb].ls;
+                        for (size_t s1 = 0; s1 < W[w].rows; ++s1)
+                            for (size_t s2 = 0; s2 < W[w].cols; ++s2) {
+                                double alfa = W[w](s1, s2) * term.second;
+                                if (alfa == 0.0) continue;   // the reference adds 0*x here
+                                tasks.push_back(YTask{o, out_off + (int32_t)s2 * ldim, 0, ldim, r_size, b1, tb, 0, in_off + (int32_t)s1 * r_size, alfa});
+                                used = true;
+                            }
+                    }
+                }
+            }
+            if (used) t_rows.push_back(b1);
+        }
+    }
+
+    // ---- step 2 structure, SU2 lbtm (non-abelian/apply_op.hpp:23-101)
+    void y_struct_su2_lbtm(size_t b2, Layout const& ket_rp, Index const& right_i, Index const& out_left_i,
+                           ProductBasis const& in_right_pb, ProductBasis const& out_left_pb,
+                           DualIndex& ret, std::vector<YTask>& tasks, std::vector<size_t>& t_rows)
+    {
+        // first pass: block structure (blocks are created lazily, in loop order, but sorted on insertion)
+        struct Raw { Charge ol, orc; int32_t dst_row, rows, cols; size_t b1, tb; int32_t src_col; double coef; };
+        std::vector<Raw> raws;
+        for (size_t e = mpo.col_begin(b2); e < mpo.col_end(b2); ++e) {
+            size_t b1 = mpo.row_of(e);
+            DualIndex const& T = t_basis[b1];
+            bool used = false;
+            for (auto const& term : mpo.at_entry(e)) {
+                SiteOperator const& W = mpo.op(term.first);
+                int a = mpo.left_spin(b1).get(), k = W.spin().get(), ap = mpo.right_spin(b2).get();
+                for (size_t tb = 0; tb < T.size(); ++tb) {
+                    Charge lc = T[tb].lc, rc = T[tb].rc;
+                    Charge mc = rc;   // ket right-paired blocks are charge-diagonal: mc == rc (site_hamil.hpp:85-89, apply_op.hpp:62-63)
+                    { auto it = ket_rp.basis.left_lower_bound(rc); if (it != ket_rp.basis.end()) mc = it->lc; }
+                    for (size_t w = 0; w < W.basis().size(); ++w) {
+                        Charge phys_in = W.basis().left_charge(w), phys_out = W.basis().right_charge(w);
+                        Charge out_r = fuse(rc, phys_in);
+                        size_t rb = right_i.position(out_r);
+                        if (rb == right_i.size()) continue;
+                        Charge out_l = fuse(lc, phys_out);
+                        if (!su2::triangle(spin(out_r), ap, spin(out_l))) continue;
+                        if (!out_left_i.has(out_l)) continue;
+                        int32_t r_size = (int32_t)right_i[rb].second;
+                        if (!ret.has(out_l, out_r)) ret.insert(QnBlock(out_l, out_r, out_left_i.size_of_block(out_l), r_size));
+                        int i = spin(lc), ip = spin(out_l), j = spin(mc), jp = spin(out_r);
+                        int two_sp = std::abs(i - ip), two_s = std::abs(j - jp);
+                        double couplings[4];
+                        su2::set_coupling(j, two_s, jp, a, k, ap, i, two_sp, ip, term.second, couplings);
+                        int32_t in_off = (int32_t)in_right_pb(phys_in, out_r), out_off = (int32_t)out_left_pb(phys_out, lc);
+                        int32_t l_size = (int32_t)T[tb].ls;
+                        for (int s = W.sparse_ptr[w]; s < W.sparse_ptr[w + 1]; ++s) {
+                            SparseEntry const& en = W.sparse[s];
+                            int cn = 0;
+                            if (en.row_spin == 2 && en.col_spin == 2) cn = 3; else if (en.row_spin == 2) cn = 1; else if (en.col_spin == 2) cn = 2;
+                            double alfa = en.coefficient * couplings[cn];
+                            if (alfa == 0.0) continue;
+                            raws.push_back(Raw{out_l, out_r, out_off + (int32_t)en.col * l_size, l_size, r_size, b1, tb, in_off + (int32_t)en.row * r_size, alfa});
+                            used = true;
+                        }
+                    }
+                }
+            }
+            if (used) t_rows.push_back(b1);
+        }
+        for (auto const& r : raws)
+            tasks.push_back(YTask{ret.position(r.ol, r.orc), r.dst_row, 0, r.rows, r.cols, r.b1, r.tb, 0, r.src_col, r.coef});
+    }
+
+    // ---- step 2 structure, abelian rbtm (abelian/apply_op.hpp:141-250)
+    void y_struct_abelian_rbtm(size_t b1, Index const& left_i, Index const& out_right_i, ProductBasis const& in_left_pb, ProductBasis const& out_right_pb,
+                               DualIndex& ret, std::vector<YTask>& tasks, std::vector<size_t>& t_cols)
+    {
+        for (size_t b2 : mpo.row(b1)) {
+            DualIndex const& T = t_basis[b2];
+            if (T.size() == 0) continue;
+            for (auto const& term : mpo.at(b1, b2)) {
+                SiteOperator const& W = mpo.op(term.first);
+                if (W.n_blocks() == 0) continue;
+                Charge total_delta = fuse(delta_of(W.basis()), -delta_of(T));
+                for (size_t l = 0; l < left_i.size(); ++l) {
+                    Charge out_l = left_i[l].first, out_r = fuse(out_l, -total_delta);
+                    if (!out_right_i.has(out_r)) continue;
+                    if (!ret.has(out_l, out_r)) ret.insert(QnBlock(out_l, out_r, left_i[l].second, out_right_i.size_of_block(out_r)));
+                }
+            }
+        }
+        for (size_t b2 : mpo.row(b1)) {
+            DualIndex const& T = t_basis[b2];
+            if (T.size() == 0) continue;
+            bool used = false;
+            for (auto const& term : mpo.at(b1, b2)) {
+                SiteOperator const& W = mpo.op(term.first);
+                if (W.n_blocks() == 0) continue;
+                Charge T_delta = delta_of(T);
+                Charge total_delta = fuse(delta_of(W.basis()), -T_delta);
+                for (size_t l = 0; l < left_i.size(); ++l) {
+                    Charge out_l = left_i[l].first, out_r = fuse(out_l, -total_delta);
+                    if (!out_right_i.has(out_r)) continue;
+                    int32_t l_size = (int32_t)left_i[l].second;
+                    size_t o = ret.position(out_l, out_r);
+                    for (size_t w = 0; w < W.n_blocks(); ++w) {
+                        Charge c1 = W.basis().left_charge(w), c2 = W.basis().right_charge(w);
+                        Charge in_l = fuse(out_l, c1), in_r = fuse(in_l, T_delta);
+                        size_t tb = T.position(in_l, in_r);
+                        if (tb == T.size()) continue;
+                        int32_t in_off = (int32_t)in_left_pb(c1, out_l), out_off = (int32_t)out_right_pb(c2, in_r);
+                        int32_t rdim = (int32_t)T[tb].rs;
+                        for (size_t s1 = 0; s1 < W[w].rows; ++s1)
+                            for (size_t s2 = 0; s2 < W[w].cols; ++s2) {
+                                double alfa = W[w](s1, s2) * term.second;
+                                if (alfa == 0.0) continue;
+                                tasks.push_back(YTask{o, 0, out_off + (int32_t)s2 * rdim, l_size, rdim, b2, tb, in_off + (int32_t)s1 * l_size, 0, alfa});
+                                used = true;
+                            }
+                    }
+                }
+            }
+            if (used) t_cols.push_back(b2);
+        }
+    }
+
+    // ---- step 2 structure, SU2 rbtm (non-abelian/apply_op.hpp:114-232)
+    void y_struct_su2_rbtm(size_t b1, DualIndex const& ket_basis, Index const& left_i, Index const& out_right_i,
+                           ProductBasis const& in_left_pb, ProductBasis const& out_right_pb,
+                           DualIndex& ret, std::vector<YTask>& tasks, std::vector<size_t>& t_cols)
+    {
+        struct Raw { Charge ol, orc; int32_t dst_col, rows, cols; size_t b2, tb; int32_t src_row; double coef; };
+        std::vector<Raw> raws;
+        std::map<std::pair<Charge, Charge>, int32_t> first_l_size;   // task_capsule map order decides block creation
+        for (size_t b2 : mpo.row(b1)) {
+            DualIndex const& T = t_basis[b2];
+            bool used = false;
+            for (auto const& term : mpo.at(b1, b2)) {
+                SiteOperator const& W = mpo.op(term.first);
+                int a = mpo.left_spin(b1).get(), k = W.spin().get(), ap = mpo.right_spin(b2).get();
+                for (size_t tb = 0; tb < T.size(); ++tb) {
+                    Charge lc = T[tb].lc, rc = T[tb].rc;
+                    Charge mc = lc;
+                    { auto it = ket_basis.left_lower_bound(lc); if (it != ket_basis.end()) mc = it->rc; }
+                    for (size_t w = 0; w < W.basis().size(); ++w) {
+                        Charge phys_in = W.basis().left_charge(w), phys_out = W.basis().right_charge(w);
+                        Charge out_l = fuse(lc, -phys_in);
+                        size_t lb = left_i.position(out_l);
+                        if (lb == left_i.size()) continue;
+                        Charge out_r = fuse(rc, -phys_out);
+                        if (!su2::triangle(spin(out_l), a, spin(out_r))) continue;
+                        if (!out_right_i.has(out_r)) continue;
+                        int32_t l_size = (int32_t)left_i[lb].second;
+                        int i = spin(out_r), ip = spin(rc), j = spin(out_l), jp = spin(mc);
+                        int two_sp = std::abs(i - ip), two_s = std::abs(j - jp);
+                        double couplings[4];
+                        su2::set_coupling(j, two_s, jp, a, k, ap, i, two_sp, ip, term.second, couplings);
+                        int32_t in_off = (int32_t)in_left_pb(phys_in, out_l), out_off = (int32_t)out_right_pb(phys_out, rc);
+                        int32_t r_size = (int32_t)T[tb].rs;
+                        // the reference creates the map entry before looking at the operator entries (apply_op.hpp:170)
+                        if (!first_l_size.count(std::make_pair(out_l, out_r))) first_l_size[std::make_pair(out_l, out_r)] = -1;
+                        for (int s = W.sparse_ptr[w]; s < W.sparse_ptr[w + 1]; ++s) {
+                            SparseEntry const& en = W.sparse[s];
+                            int cn = 0;
+                            if (en.row_spin == 2 && en.col_spin == 2) cn = 3; else if (en.row_spin == 2) cn = 1; else if (en.col_spin == 2) cn = 2;
+                            double alfa = en.coefficient * couplings[cn];
+                            if (first_l_size[std::make_pair(out_l, out_r)] < 0) first_l_size[std::make_pair(out_l, out_r)] = l_size;
+                            raws.push_back(Raw{out_l, out_r, out_off + (int32_t)en.col * r_size, l_size, r_size, b2, tb, in_off + (int32_t)en.row * l_size, alfa});
+                            used = true;
+                        }
+                    }
+                }
+            }
+            if (used) t_cols.push_back(b2);
+        }
+        for (auto const& kv : first_l_size) {
+            if (kv.second < 0) continue;   // "if (otasks.size() == 0) continue"
+            ret.insert(QnBlock(kv.first.first, kv.first.second, (size_t)kv.second, out_right_i.size_of_block(kv.first.second)));
+        }
+        for (auto const& r : raws) {
+            if (r.coef == 0.0) continue;
+            tasks.push_back(YTask{ret.position(r.ol, r.orc), 0, r.dst_col, r.rows, r.cols, r.b2, r.tb, r.src_row, 0, r.coef});
+        }
+    }
+
+    // group W-application contributions by destination panel -> one gather-axpy per panel
+    void emit_axpy(Plan& P, AxpyList& al, std::vector<YTask> const& tasks, std::map<size_t, Layout> const& tl, Layout const& yl)
+    {
+        std::vector<size_t> order(tasks.size());
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) {
+            YTask const& x = tasks[a]; YTask const& y = tasks[b];
+            return std::tie(x.o, x.dst_col, x.dst_row, x.rows, x.cols) < std::tie(y.o, y.dst_col, y.dst_row, y.rows, y.cols);
+        });
+        for (size_t q = 0; q < order.size();) {
+            YTask const& h = tasks[order[q]];
+            AxpyDst d; d.ldd = (int32_t)yl.basis[h.o].ls;
+            d.dst = Ref{BUF_Y, yl.off[h.o] + h.dst_row + (int64_t)h.dst_col * d.ldd};
+            d.rows = h.rows; d.cols = h.cols; d.src_begin = (int32_t)al.srcs.size();
+            size_t q2 = q;
+            for (; q2 < order.size(); ++q2) {
+                YTask const& t = tasks[order[q2]];
+                if (t.o != h.o || t.dst_col != h.dst_col || t.dst_row != h.dst_row || t.rows != h.rows || t.cols != h.cols) break;
+                Layout const& L = tl.at(t.bt);
+                int32_t lds = (int32_t)L.basis[t.t_block].ls;
+                int srcbuf = t_persistent[t.bt] ? BUF_TP : BUF_T;
+                al.srcs.push_back(AxpySrc{Ref{srcbuf, L.off[t.t_block] + t.src_row + (int64_t)t.src_col * lds}, lds, t.coef});
+                P.flops_w += 2.0 * t.rows * t.cols; P.n_axpy_tasks++;
+            }
+            d.src_end = (int32_t)al.srcs.size();
+            al.dsts.push_back(d);
+            q = q2;
+        }
+    }
+
+    // step 3: one K-segment A(m x k) * op(B)(k x n) into output block (lc, rc)
+    void emit_close(Plan& P, GemmList& gl, Layout const& ol, Charge const& lc, Charge const& rc, Ref A, int32_t lda, int32_t ta, int32_t m, int32_t k,
+                    VBlock const& b, int bbuf)
+    {
+        size_t cb = ol.basis.position(lc, rc);
+        if (cb == ol.basis.size()) return;
+        Out o; o.C = Ref{BUF_OUT, ol.off[cb]}; o.ldc = (int32_t)ol.basis[cb].ls; o.m = m; o.n = b.rs;
+        o.seg_begin = (int32_t)gl.segs.size();
+        gl.segs.push_back(Seg{A, Ref{bbuf, b.off}, lda, b.ld, m, o.n, k, ta, b.trans, b.scale});
+        o.seg_end = (int32_t)gl.segs.size();
+        gl.outs.push_back(o);
+        P.flops_close += 2.0 * m * o.n * k; P.n_gemm_tasks++;
+    }
+    // outputs that target the same block become ONE output with a longer segment list (segments keep their own m, n)
+    static void merge_outputs(GemmList& gl)
+    {
+        std::vector<size_t> order(gl.outs.size());
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) {
+            Out const& x = gl.outs[a]; Out const& y = gl.outs[b];
+            return x.C.off < y.C.off;
+        });
+        GemmList r;
+        for (size_t q = 0; q < order.size();) {
+            Out o = gl.outs[order[q]];
+            int32_t sb = (int32_t)r.segs.size();
+            size_t q2 = q;
+            for (; q2 < order.size(); ++q2) {
+                Out const& x = gl.outs[order[q2]];
+                if (x.C.off != o.C.off) break;
+                o.m = std::max(o.m, x.m); o.n = std::max(o.n, x.n);
+                for (int32_t s = x.seg_begin; s < x.seg_end; ++s) r.segs.push_back(gl.segs[s]);
+            }
+            o.seg_begin = sb; o.seg_end = (int32_t)r.segs.size();
+            r.outs.push_back(o);
+            q = q2;
+        }
+        gl = std::move(r);
+    }
+
+    // ---- sharding of the output bond index across ranks (owner computes), balanced greedily by cost
+    template <class F> std::vector<char> share_mask(size_t n, F cost)
+    {
+        std::vector<char> mine(n, 1);
+        if (world <= 1) return mine;
+        std::vector<std::pair<double, size_t>> c(n);
+        for (size_t i = 0; i < n; ++i) c[i] = std::make_pair(cost(i), i);
+        std::stable_sort(c.begin(), c.end(), [](auto const& a, auto const& b) { return a.first > b.first; });
+        std::vector<double> load(world, 0.);
+        for (auto const& e : c) {
+            int r = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+            load[r] += e.first;
+            mine[e.second] = (r == rank);
+        }
+        return mine;
+    }
+    double estimate_cost(Layout const& y, BoundaryLayout const&, size_t) const
+    {
+        double c = 0;
+        for (size_t k = 0; k < y.basis.size(); ++k) c += (double)y.basis[k].ls * (double)y.basis[k].rs * (double)y.basis[k].rs;
+        return c;
+    }
+
+    SymmKind symm; bool su2_;
+    MPOTensor const& mpo;
+    bool isHermitian;
+    int rank, world;
+    int64_t budget;
+    std::vector<DualIndex> t_basis;
+    std::vector<VView> t_views;
+    std::vector<char> t_persistent;
+    std::vector<Layout> tp_layout;
+    Layout ket_lp_for_right;
+};
+
+}} // namespace qcm::plan

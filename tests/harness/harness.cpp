@@ -1,0 +1,164 @@
+// TEST INFRASTRUCTURE -- C entry points (ctypes) that run the same scenario through the CPU oracle and through
+// an engine under test and report structure equality and relative differences.
+//   engine 0: plan interpreter (CPU; checks the schedule builder, runs without a GPU)
+//   engine 1: qcm::GpuEngine (B200; goes through the C ABI of include/qcm_b200.h)
+// Scenarios mirror the reference's own hot-path tests: boundary chains and the sigma-energy identity of
+// dmrg/tests/test_mps_mpo_ops/test_siteproblem.cpp:38-95, BoundaryPropagatorElectronic.cpp:39-66.
+#include "oracle_engine.hpp"
+#include "qcm/scenarios.hpp"
+#include "plan_interp.hpp"
+#ifdef QCMT_WITH_GPU
+#include "qcm/engine_gpu.hpp"
+#endif
+#include <cstdio>
+#include <cstring>
+
+using namespace qcm;
+
+static void set_err(char* err, int errlen, std::string const& s) { if (err && errlen > 0) { snprintf(err, errlen, "%s", s.c_str()); } }
+
+static double rel_diff(DiffReport const& r) { return r.ref_norm > 0 ? std::sqrt(r.diff_norm / r.ref_norm) : std::sqrt(r.diff_norm); }
+
+static Problem make_problem(const char* fcidump, const char* symm, int L, int nelec)
+{
+    Problem P;
+    P.params.symm = symm_from_string(symm);
+    P.params.integrals = read_fcidump(fcidump);
+    P.params.L = L; P.params.site_types.assign(L, 0);
+    P.params.nelec = nelec; P.params.spin = 0; P.params.nup = nelec / 2; P.params.ndown = nelec - nelec / 2;
+    P.build_model();
+    P.build_mpo();
+    return P;
+}
+
+extern "C" int qcmt_gpu_available()
+{
+#ifdef QCMT_WITH_GPU
+    int n = 0;
+    if (qcm_device_count(&n) != 0) return 0;
+    return n;
+#else
+    return 0;
+#endif
+}
+
+// out[0] n boundaries compared   out[1] all boundary structures equal   out[2] max rel diff over boundaries
+// out[3] n single-site sigma     out[4] structures equal                out[5] max rel diff
+// out[6] n two-site sigma        out[7] structures equal                out[8] max rel diff
+// out[9] max |<psi|sigma> - chain energy| (engine)   out[10] chain energy engine   out[11] chain energy oracle
+// out[12] total flops of the last sigma plan (two-site)  out[13] max rel diff oracle lbtm vs rbtm (SU2 only)
+extern "C" int qcmt_chain_parity(const char* fcidump, const char* symm, int L, int nelec, int Mmax, unsigned seed, int engine_kind, int world,
+                                 long long budget, double* out, int nout, char* err, int errlen)
+{
+    try {
+        for (int i = 0; i < nout; ++i) out[i] = 0;
+        Problem P = make_problem(fcidump, symm, L, nelec);
+        P.init_mps((size_t)Mmax, true, 0., seed);
+        oracle::OracleEngine orc(P.params.symm);
+        std::unique_ptr<EngineIface> eng;
+        qcmtest::InterpEngine* interp = nullptr;
+        if (engine_kind == 0) { interp = new qcmtest::InterpEngine(P.params.symm, world, budget); eng.reset(interp); }
+        else {
+#ifdef QCMT_WITH_GPU
+            eng.reset(new GpuEngine(P.params.symm, 0, 0, 1, budget));
+#else
+            throw std::runtime_error("harness built without GPU support");
+#endif
+        }
+        // boundaries through both engines
+        Problem Po = P;
+        Po.build_boundaries(orc);
+        P.build_boundaries(*eng);
+#ifdef QCMT_WITH_GPU
+        if (engine_kind == 1) {
+            GpuEngine* g = static_cast<GpuEngine*>(eng.get());
+            for (auto& b : P.left) g->download(b);
+            for (auto& b : P.right) g->download(b);
+        }
+#endif
+        double bmax = 0; int bstruct = 1, nb = 0;
+        for (int p = 0; p <= L; ++p) {
+            DiffReport a = compare(P.left[p], Po.left[p]), b = compare(P.right[p], Po.right[p]);
+            bmax = std::max(bmax, std::max(rel_diff(a), rel_diff(b)));
+            bstruct &= a.structure_equal & b.structure_equal;
+            nb += 2;
+        }
+        out[0] = nb; out[1] = bstruct; out[2] = bmax;
+        out[10] = P.left[L][0].trace(); out[11] = Po.left[L][0].trace();
+        // single-site sigma (engine uses its own boundaries)
+        double smax = 0, emax = 0; int sstruct = 1, ns = 0;
+        for (int p = 0; p < L; ++p) {
+            MPSTensor so = orc.site_hamil2(Po.mps[p], Po.left[p], Po.right[p + 1], Po.mpo[p]);
+            MPSTensor se = eng->site_hamil2(P.mps[p], P.left[p], P.right[p + 1], P.mpo[p]);
+            DiffReport d = compare(se.data(), so.data());
+            smax = std::max(smax, rel_diff(d)); sstruct &= d.structure_equal; ns++;
+            emax = std::max(emax, std::abs(se.scalar_overlap(P.mps[p]) - out[10]));
+        }
+        out[3] = ns; out[4] = sstruct; out[5] = smax; out[9] = emax;
+        // two-site sigma on every bond with a random two-site tensor
+        double tmax = 0, lrmax = 0; int tstruct = 1, nt = 0;
+        UniformGen gen(seed + 7);
+        for (int p = 0; p + 1 < L; ++p) {
+            MPOTensor const& ts = P.twosite_mpo(p);
+            MPSTensor x = make_twosite_tensor(P.phys(p), P.phys(p + 1), P.mps[p].row_dim(), P.mps[p + 1].col_dim(), [&]() { return gen() - 0.5; });
+            MPSTensor so = orc.site_hamil2(x, Po.left[p], Po.right[p + 2], ts);
+            MPSTensor se = eng->site_hamil2(x, P.left[p], P.right[p + 2], ts);
+            DiffReport d = compare(se.data(), so.data());
+            tmax = std::max(tmax, rel_diff(d)); tstruct &= d.structure_equal; nt++;
+            if (is_su2(P.params.symm)) {
+                MPSTensor a = orc.site_hamil_lbtm(x, x, Po.left[p], Po.right[p + 2], ts, true);
+                MPSTensor b = orc.site_hamil_rbtm(x, x, Po.left[p], Po.right[p + 2], ts, true);
+                lrmax = std::max(lrmax, rel_diff(compare(a.data(), b.data())));
+            }
+            if (interp) out[12] = interp->last_flops;
+#ifdef QCMT_WITH_GPU
+            if (engine_kind == 1) out[12] = static_cast<GpuEngine*>(eng.get())->last_plan()->flops;
+#endif
+        }
+        out[6] = nt; out[7] = tstruct; out[8] = tmax; out[13] = lrmax;
+        return 0;
+    } catch (std::exception const& e) {
+        set_err(err, errlen, e.what());
+        return 1;
+    }
+}
+
+// MPO bond dimensions / Hermitian pairs ("MPO Bond p: dim/pairs" lines of the reference's stdout) and the
+// exact two-site ground-state energy of tiny systems (dense effective Hamiltonian on complete bases).
+extern "C" int qcmt_mpo_dims(const char* fcidump, const char* symm, int L, int nelec, int* dims, int* pairs, double* core, char* err, int errlen)
+{
+    try {
+        Problem P = make_problem(fcidump, symm, L, nelec);
+        for (int p = 0; p < L; ++p) { dims[p] = (int)P.mpo[p].col_dim(); pairs[p] = (int)P.mpo.herm_pairs[p]; }
+        *core = P.mpo.core_energy;
+        return 0;
+    } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
+}
+
+extern "C" int qcmt_exact_energy(const char* fcidump, const char* symm, int L, int nelec, int engine_kind, double* energy, double* asym, char* err, int errlen)
+{
+    try {
+        Problem P = make_problem(fcidump, symm, L, nelec);
+        std::unique_ptr<EngineIface> eng;
+        if (engine_kind == 0) eng.reset(new qcmtest::InterpEngine(P.params.symm));
+        else if (engine_kind == 2) eng.reset(new oracle::OracleEngine(P.params.symm));
+        else {
+#ifdef QCMT_WITH_GPU
+            eng.reset(new GpuEngine(P.params.symm));
+#else
+            throw std::runtime_error("harness built without GPU support");
+#endif
+        }
+        std::vector<Index> allowed = allowed_sectors(P.params.symm, P.site_types(), P.model->phys_indices, P.model->total_charge, 1000);
+        MPS ex;
+        for (int p = 0; p < L; ++p) ex.push_back(MPSTensor(P.phys(p), allowed[p], allowed[p + 1], []() { return 1.0; }));
+        P.mps = ex;
+        int c = L / 2 - 1;
+        P.build_boundaries(*eng, c, c + 2);
+        MPOTensor const& ts = P.twosite_mpo(c);
+        MPSTensor templ = make_twosite_tensor(P.phys(c), P.phys(c + 1), allowed[c], allowed[c + 2], []() { return 1.0; });
+        std::vector<double> w = dense_heff_spectrum(*eng, templ, P.left[c], P.right[c + 2], ts, asym);
+        *energy = w[0] + P.mpo.core_energy;
+        return 0;
+    } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
+}
