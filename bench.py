@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- sigma-vector (site_hamil2) FP64 throughput on B200.
+
+Step = one application of the effective Hamiltonian to the two-site tensor of a fabricated mid-chain site
+problem (true MPO of a synthetic FCIDUMP, synthetic sector lists truncated to total bond dimension M, random
+boundaries; see qcmaquis_b200/csrc/qcm/scenarios.hpp).  Default workload = BASELINE.json configs[1]:
+10e/26o SU2U1 M=1000 two-site.
+
+  value     whole-job TFLOP/s = schedule-derived algorithmic FLOPs of one sigma / device time (CUDA events on
+            the library stream, max over ranks), psi/sigma and boundaries resident in HBM
+  e2e       same metric through the C ABI call qcm_site_hamil2 with pinned HOST buffers for psi and sigma
+            (H2D + kernels + allreduce + D2H inside the timed region); boundaries and MPO stay resident, as
+            they do for the whole Davidson solve at a site
+  --impl reference   the CPU oracle (restatement of the reference algorithm, OpenMP over the MPO bond index,
+            OpenBLAS dgemm) on the host cores, same instance, same metric
+
+N>1: one process per GPU (torchrun); the MPO bond index is sharded across ranks and the partial sigma vectors
+are summed with one NCCL allreduce per step inside the library (strong scaling: the problem is fixed).
+"""
+import argparse, ctypes, json, os, subprocess, sys, tempfile, threading, time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (norb, nelec, symm, M)
+    "cfg1_8e8o_su2u1_M256": (8, 8, "su2u1", 256),
+    "cfg2_10e26o_su2u1_M1000": (26, 10, "su2u1", 1000),
+    "cfg3_24e30o_su2u1_M2000": (30, 24, "su2u1", 2000),
+    "cfg4_24e30o_2u1_M4000": (30, 24, "2u1", 4000),
+    "cfg5_54e54o_su2u1_M3000": (54, 54, "su2u1", 3000),
+}
+
+
+def errbuf():
+    return ctypes.create_string_buffer(1024)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.samples.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx = max(mx, float(s[1]))
+                for i, n in enumerate(names):
+                    if s[3 + i].lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_fcidump(norb, nelec):
+    from qcmaquis_b200.fcidump import make_fcidump as mk
+    d = tempfile.mkdtemp(prefix="qcm_bench_")
+    path = os.path.join(d, "synthetic_%do%de.fcidump" % (norb, nelec))
+    mk(path, norb, nelec)
+    return path
+
+
+def run_reference(args, cfg_name, norb, nelec, symm, M, site):
+    """CPU arm: the oracle on the host cores (the upstream tree needs Boost/GSL/HDF5 and cannot be built here)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from qcmaquis_b200 import build
+    lib = ctypes.CDLL(build.build_oracle())
+    lib.orc_create.restype = ctypes.c_void_p
+    e = errbuf()
+    path = make_fcidump(norb, nelec)
+    h = lib.orc_create(path.encode(), symm.encode(), norb, nelec, e, 1024)
+    if not h:
+        raise RuntimeError(e.value.decode())
+    h = ctypes.c_void_p(h)
+    pe = ctypes.c_double()
+    if lib.orc_setup_site(h, site, 1, M, args.seed, ctypes.byref(pe), e, 1024):
+        raise RuntimeError(e.value.decode())
+    flops = reference_flops(path, symm, norb, nelec, site, M, args.seed)
+    sec, ov, se = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+    budget_s = 150.0
+    t_begin = time.time()
+    warm = min(args.warmup, 1)
+    for _ in range(warm):
+        lib.orc_sigma(h, 1, ctypes.byref(sec), ctypes.byref(ov), ctypes.byref(se), e, 1024)
+    per = sec.value if warm else None
+    steps = args.steps
+    if per:
+        steps = max(1, min(args.steps, int((budget_s - (time.time() - t_begin)) / per)))
+    total = 0.0
+    done = 0
+    for _ in range(steps):
+        if lib.orc_sigma(h, 1, ctypes.byref(sec), ctypes.byref(ov), ctypes.byref(se), e, 1024):
+            raise RuntimeError(e.value.decode())
+        total += sec.value
+        done += 1
+        if time.time() - t_begin > budget_s:
+            break
+    ms = total / done * 1e3
+    val = flops / (ms * 1e-3) / 1e12
+    cores = lib.orc_threads()
+    sample = "%d full sigma evaluation(s) of the same instance (requested %d; capped to keep the run within minutes)" % (done, args.steps)
+    line = {"impl": "reference", "metric": "sigma_vector_fp64_tflops", "value": val, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": done,
+            "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": cfg_name, "site": site, "twosite": True, "M": M, "symmetry": symm},
+            "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def reference_flops(path, symm, norb, nelec, site, M, seed):
+    """Algorithmic FLOPs of one sigma from the schedule builder (host only, no GPU needed)."""
+    from qcmaquis_b200 import build
+    lib = ctypes.CDLL(build.build_host())
+    lib.qcmd_create.restype = ctypes.c_void_p
+    lib.qcmd_plan_flops.restype = ctypes.c_double
+    e = errbuf()
+    h = lib.qcmd_create(path.encode(), symm.encode(), norb, nelec, e, 1024)
+    if not h:
+        raise RuntimeError(e.value.decode())
+    f = lib.qcmd_plan_flops(ctypes.c_void_p(h), site, 1, M, seed, e, 1024)
+    if f < 0:
+        raise RuntimeError(e.value.decode())
+    lib.qcmd_destroy(ctypes.c_void_p(h))
+    return f
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--config", default="cfg2_10e26o_su2u1_M1000", choices=sorted(CONFIGS))
+    ap.add_argument("--M", type=int, default=0)
+    ap.add_argument("--site", type=int, default=-1)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "native":
+        args.warmup = 3
+    norb, nelec, symm, M = CONFIGS[args.config]
+    if args.M:
+        M = args.M
+    site = args.site if args.site >= 0 else norb // 2 - 1
+    if args.impl == "reference":
+        run_reference(args, args.config, norb, nelec, symm, M, site)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from qcmaquis_b200 import build
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback for the native arm")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cu = ctypes.CDLL(build.build_cuda(), mode=ctypes.RTLD_GLOBAL)
+    host = ctypes.CDLL(build.build_host())
+    cu.qcm_last_error.restype = ctypes.c_char_p
+    cu.qcm_stream.restype = ctypes.c_void_p
+    cu.qcm_launch_count.restype = ctypes.c_int64
+    host.qcmd_create.restype = ctypes.c_void_p
+    if cu.qcm_init(local):
+        raise RuntimeError(cu.qcm_last_error().decode())
+    if world > 1:
+        idbuf = ctypes.create_string_buffer(128)
+        if rank == 0 and cu.qcm_comm_unique_id(idbuf):
+            raise RuntimeError(cu.qcm_last_error().decode())
+        t = torch.tensor(list(idbuf.raw), dtype=torch.uint8, device="cuda")
+        dist.broadcast(t, 0)
+        idbuf = ctypes.create_string_buffer(bytes(t.cpu().tolist()), 128)
+        if cu.qcm_comm_init(rank, world, idbuf):
+            raise RuntimeError(cu.qcm_last_error().decode())
+
+    e = errbuf()
+    path = make_fcidump(norb, nelec)
+    h = host.qcmd_create(path.encode(), symm.encode(), norb, nelec, e, 1024)
+    if not h:
+        raise RuntimeError(e.value.decode())
+    h = ctypes.c_void_p(h)
+    info = (ctypes.c_double * 32)()
+    if host.qcmd_setup_site(h, site, 1, M, args.seed, local, rank, world, info, e, 1024):
+        raise RuntimeError(e.value.decode())
+    flops, bytes_alg = info[0], info[4]
+    psi_n, sig_n = int(info[5]), int(info[6])
+    stream = torch.cuda.ExternalStream(cu.qcm_stream())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        cu.qcm_sync()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing (value) ------------------------------------------------------------------
+    if host.qcmd_sigma_dev(h, args.warmup, e, 1024):
+        raise RuntimeError(e.value.decode())
+    barrier()
+    sampler = ClockSampler(local); sampler.start()
+    l0 = cu.qcm_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    if host.qcmd_sigma_dev(h, args.steps, e, 1024):
+        raise RuntimeError(e.value.decode())
+    ev1.record(stream)
+    barrier()
+    launches = cu.qcm_launch_count() - l0
+    ms_dev = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+    clocks = sampler.finish()
+
+    # ---- per-phase kernel times (same steps, CUDA events between phases) ---------------------------------
+    cu.qcm_set_timing(1)
+    phases = [0.0] * 6
+    nph = 3
+    for _ in range(nph):
+        host.qcmd_sigma_dev(h, 1, e, 1024)
+        cu.qcm_sync()
+        ms = (ctypes.c_double * 6)(); cu.qcm_last_timing(ms)
+        phases = [a + b / nph for a, b in zip(phases, ms)]
+    cu.qcm_set_timing(0)
+
+    # ---- end to end through the C ABI with pinned host buffers -------------------------------------------
+    psi = torch.empty(psi_n, dtype=torch.float64).pin_memory()
+    sig = torch.empty(sig_n, dtype=torch.float64).pin_memory()
+    host.qcmd_get_psi(h, ctypes.c_void_p(psi.data_ptr()))
+    for _ in range(args.warmup):
+        if host.qcmd_sigma_host(h, ctypes.c_void_p(psi.data_ptr()), ctypes.c_void_p(sig.data_ptr()), e, 1024):
+            raise RuntimeError(e.value.decode())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        host.qcmd_sigma_host(h, ctypes.c_void_p(psi.data_ptr()), ctypes.c_void_p(sig.data_ptr()), e, 1024)
+    barrier()
+    ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+
+    peak = ctypes.c_double()
+    cu.qcm_measure_fp64_dmma_peak(ctypes.byref(peak))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+
+    # dominant kernel family by device time
+    fl = {1: info[1], 2: info[2], 3: info[3]}
+    names = {1: "k_gemm_dmma (step 1: T = L^T psi)", 2: "k_axpy_gather (W application)", 3: "k_gemm_dmma (step 3: sigma += Y R)"}
+    dom = max((1, 2, 3), key=lambda i: phases[i])
+    if dom == 2:
+        b = 8.0 * (info[2] / 2.0)   # every W task element is one 8-byte read; writes are the smaller part
+        roof = {"bound": "hbm", "kernel": names[dom], "achieved": b / (phases[dom] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback"}
+    else:
+        roof = {"bound": "tensor", "kernel": names[dom], "achieved": fl[dom] / (phases[dom] * 1e-3) / 1e12 / max(world, 1), "peak": peak.value,
+                "unit": "TFLOP/s", "traffic": None, "peak_source": "FP64 DMMA chain probe measured live (qcm_measure_fp64_dmma_peak); MEASURED_PEAKS.json has no FP64 entry"}
+    roof["frac"] = roof["achieved"] / roof["peak"] if roof["peak"] else None
+    roof["phase_ms"] = {"reshape": phases[0], "step1_gemm": phases[1], "w_apply": phases[2], "step3_gemm": phases[3], "allreduce": phases[4]}
+
+    line = {"metric": "sigma_vector_fp64_tflops", "value": flops / (ms_dev * 1e-3) / 1e12, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": args.config, "site": site, "twosite": True, "M": M, "symmetry": symm, "parallelism": "mpo-bond-sharded x%d" % world,
+                       "l2": "inputs (boundaries %.2f GB + workspaces %.2f GB) exceed L2" % ((info[7] + info[8]) * 8 / 1e9, info[12] / 1e9),
+                       "mpo": "%dx%d nnz %d" % (info[16], info[17], info[18]), "sectors": int(info[14]), "largest_sector": int(info[15]),
+                       "flops_per_step": flops, "flops_split": {"step1": info[1], "w_apply": info[2], "step3": info[3]},
+                       "algorithmic_bytes": bytes_alg, "plan_seconds": info[13]},
+            "fp64_peak_tflops": peak.value, "frac_of_fp64_peak": flops / (ms_dev * 1e-3) / 1e12 / (peak.value * world) if peak.value else None,
+            "roofline": roof, "clocks": clocks,
+            "e2e": {"value": flops / (ms_e2e * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": psi_n * 8, "d2h_bytes_per_step": sig_n * 8},
+            "gpu_launches": int(launches)}
+
+    # ---- CPU baseline + full-size parity on the same instance (rank 0, N=1 only) -------------------------
+    if world == 1 and not args.no_cpu_baseline:
+        olib = ctypes.CDLL(build.build_oracle())
+        olib.orc_create.restype = ctypes.c_void_p
+        oh = olib.orc_create(path.encode(), symm.encode(), norb, nelec, e, 1024)
+        if not oh:
+            raise RuntimeError(e.value.decode())
+        oh = ctypes.c_void_p(oh)
+        pe = ctypes.c_double()
+        if olib.orc_setup_site(oh, site, 1, M, args.seed, ctypes.byref(pe), e, 1024):
+            raise RuntimeError(e.value.decode())
+        sec, ov, se = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+        if olib.orc_sigma(oh, 1, ctypes.byref(sec), ctypes.byref(ov), ctypes.byref(se), e, 1024):
+            raise RuntimeError(e.value.decode())
+        line["cpu_baseline"] = {"value": flops / sec.value / 1e12, "unit": "TFLOP/s", "cores": olib.orc_threads(), "kind": "port",
+                                "sample": "1 full sigma evaluation of the same instance (%.1f s)" % sec.value}
+        if int(se.value) == sig_n:
+            ref = torch.empty(sig_n, dtype=torch.float64)
+            olib.orc_get_sigma(oh, ctypes.c_void_p(ref.data_ptr()))
+            line["parity_rel_err_vs_oracle"] = float((sig - ref).norm() / ref.norm())
+        else:
+            line["parity_rel_err_vs_oracle"] = "structure mismatch: %d vs %d elements" % (int(se.value), sig_n)
+        olib.orc_destroy(oh)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    host.qcmd_destroy(h)
+    if world > 1:
+        cu.qcm_comm_destroy()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

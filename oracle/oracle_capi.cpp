@@ -1,0 +1,71 @@
+// TEST / MEASUREMENT INFRASTRUCTURE -- C entry points of the CPU oracle (ctypes).
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg load this library.
+// It rebuilds the same synthetic site problem as the GPU driver (same generator, same seeds) and times the
+// oracle's site_hamil2 on the host cores: OpenMP over the MPO bond index with one BLAS thread per task, the
+// reference's own threading model (utils/parallel/loops.hpp:11-26).
+#include "oracle_engine.hpp"
+#include "qcm/scenarios.hpp"
+#include <cstdio>
+#include <cstring>
+#include <omp.h>
+
+using namespace qcm;
+extern "C" void scipy_openblas_set_num_threads(int);
+
+namespace {
+struct Orc { Problem P; SyntheticSite S; MPSTensor sigma; };
+void set_err(char* err, int errlen, std::string const& s) { if (err && errlen > 0) snprintf(err, errlen, "%s", s.c_str()); }
+}
+
+extern "C" void* orc_create(const char* fcidump, const char* symm, int L, int nelec, char* err, int errlen)
+{
+    try {
+        std::unique_ptr<Orc> D(new Orc());
+        Problem& P = D->P;
+        P.params.symm = symm_from_string(symm);
+        P.params.integrals = read_fcidump(fcidump);
+        P.params.L = L; P.params.site_types.assign(L, 0);
+        P.params.nelec = nelec; P.params.spin = 0; P.params.nup = nelec / 2; P.params.ndown = nelec - nelec / 2;
+        P.build_model();
+        P.build_mpo();
+        return D.release();
+    } catch (std::exception const& e) { set_err(err, errlen, e.what()); return nullptr; }
+}
+extern "C" void orc_destroy(void* h) { delete static_cast<Orc*>(h); }
+extern "C" int orc_threads() { return omp_get_max_threads(); }
+
+extern "C" int orc_setup_site(void* h, int site, int twosite, int M, unsigned seed, double* psi_elems, char* err, int errlen)
+{
+    try {
+        Orc* D = static_cast<Orc*>(h);
+        D->S = make_synthetic_site(D->P, site, twosite != 0, (size_t)M, seed);
+        D->S.psi.make_left_paired();
+        *psi_elems = (double)D->S.psi.data().num_elements();
+        return 0;
+    } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
+}
+
+// n sigma evaluations; seconds = wall time of all of them; overlap = <psi|sigma>
+extern "C" int orc_sigma(void* h, int n, double* seconds, double* overlap, double* sigma_elems, char* err, int errlen)
+{
+    try {
+        Orc* D = static_cast<Orc*>(h);
+        scipy_openblas_set_num_threads(1);
+        oracle::OracleEngine eng(D->P.symm());
+        auto t0 = std::chrono::steady_clock::now();
+        for (int i = 0; i < n; ++i) D->sigma = eng.site_hamil2(D->S.psi, D->S.left, D->S.right, *D->S.mpo);
+        *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        D->sigma.make_left_paired();
+        *overlap = D->sigma.scalar_overlap(D->S.psi);
+        *sigma_elems = (double)D->sigma.data().num_elements();
+        return 0;
+    } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
+}
+// left-paired blocks of the last sigma, back to back in DualIndex order
+extern "C" int orc_get_sigma(void* h, double* out)
+{
+    Orc* D = static_cast<Orc*>(h);
+    size_t o = 0;
+    for (size_t k = 0; k < D->sigma.data().n_blocks(); ++k) { auto const& v = D->sigma.data()[k].v; std::memcpy(out + o, v.data(), v.size() * 8); o += v.size(); }
+    return 0;
+}

@@ -1,0 +1,161 @@
+// Host driver (C++ above the C ABI) exposed to the measurement harness (bench.py, smoke) through ctypes.
+// It builds the Hamiltonian MPO from a FCIDUMP, fabricates a mid-chain site problem (qcm/scenarios.hpp),
+// keeps its boundaries resident in HBM through qcm::GpuEngine and runs the hot path exactly the way a sweep
+// driver does: plan once per site, then one qcm_site_hamil2 per eigensolver iteration
+// (SweepBasedEnergyMinimization.h:85-100 -> jacobi.h:397 -> ietl::mult -> Engine::site_hamil2).
+// Nothing here touches oracle/.
+#include "qcm/engine_gpu.hpp"
+#include "qcm/scenarios.hpp"
+#include <cstdio>
+#include <cstring>
+
+using namespace qcm;
+
+namespace {
+struct Driver
+{
+    Problem P;
+    SyntheticSite S;
+    std::unique_ptr<GpuEngine> eng;
+    std::shared_ptr<DeviceBoundary> dl, dr;
+    std::shared_ptr<CompiledPlan> plan;
+    qcm_array_t d_psi = nullptr, d_sigma = nullptr;
+    std::vector<double> psi_flat;
+    double plan_seconds = 0;
+    ~Driver() { if (d_psi) qcm_array_free(d_psi); if (d_sigma) qcm_array_free(d_sigma); }
+};
+void set_err(char* err, int errlen, std::string const& s) { if (err && errlen > 0) snprintf(err, errlen, "%s", s.c_str()); }
+}
+
+extern "C" void* qcmd_create(const char* fcidump, const char* symm, int L, int nelec, char* err, int errlen)
+{
+    try {
+        std::unique_ptr<Driver> D(new Driver());
+        Problem& P = D->P;
+        P.params.symm = symm_from_string(symm);
+        P.params.integrals = read_fcidump(fcidump);
+        P.params.L = L; P.params.site_types.assign(L, 0);
+        P.params.nelec = nelec; P.params.spin = 0; P.params.nup = nelec / 2; P.params.ndown = nelec - nelec / 2;
+        P.build_model();
+        P.build_mpo();
+        return D.release();
+    } catch (std::exception const& e) { set_err(err, errlen, e.what()); return nullptr; }
+}
+extern "C" void qcmd_destroy(void* h) { delete static_cast<Driver*>(h); }
+
+extern "C" int qcmd_mpo_dims(void* h, int* dims, int* pairs)
+{
+    Driver* D = static_cast<Driver*>(h);
+    for (size_t p = 0; p < D->P.mpo.size(); ++p) { dims[p] = (int)D->P.mpo[p].col_dim(); pairs[p] = (int)D->P.mpo.herm_pairs[p]; }
+    return 0;
+}
+
+// info: [0] flops [1] flops_t [2] flops_w [3] flops_close [4] algorithmic bytes [5] psi elems [6] sigma elems
+//       [7] left elems [8] right elems [9] gemm tasks [10] axpy tasks [11] waves [12] workspace bytes
+//       [13] plan seconds [14] sectors on the left bond [15] largest sector [16] mpo rows [17] mpo cols [18] mpo nnz
+//       [19] setup seconds [20] kernel launches per sigma
+extern "C" int qcmd_setup_site(void* h, int site, int twosite, int M, unsigned seed, int device, int rank, int world, double* info, char* err, int errlen)
+{
+    try {
+        Driver* D = static_cast<Driver*>(h);
+        D->S = make_synthetic_site(D->P, site, twosite != 0, (size_t)M, seed);
+        D->eng.reset(new GpuEngine(D->P.symm(), device, rank, world));
+        D->dl = D->eng->mirror(D->S.left);
+        D->dr = D->eng->mirror(D->S.right);
+        auto t0 = std::chrono::steady_clock::now();
+        D->plan = D->eng->sigma_plan(D->S.psi, D->dl, D->dr, *D->S.mpo, true);
+        D->plan_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        D->S.psi.make_left_paired();
+        D->psi_flat = GpuEngine::flatten(D->S.psi.data(), D->plan->ket_elems);
+        if (D->d_psi) { qcm_array_free(D->d_psi); D->d_psi = nullptr; }
+        if (D->d_sigma) { qcm_array_free(D->d_sigma); D->d_sigma = nullptr; }
+        qcm_check(qcm_array_alloc(D->plan->ket_elems, &D->d_psi), "alloc psi");
+        qcm_check(qcm_array_alloc(D->plan->out_elems, &D->d_sigma), "alloc sigma");
+        qcm_check(qcm_array_upload(D->d_psi, 0, D->psi_flat.data(), D->plan->ket_elems), "upload psi");
+        int64_t nl = 0, wsb = 0;
+        qcm_plan_stats(D->plan->handle, nullptr, nullptr, &nl, &wsb);
+        CompiledPlan const& cp = *D->plan;
+        size_t mx = 0;
+        for (auto const& e : D->S.psi.row_dim()) mx = std::max(mx, e.second);
+        double v[21] = {cp.flops, cp.flops_t, cp.flops_w, cp.flops_close, (double)cp.bytes, (double)cp.ket_elems, (double)cp.out_elems,
+                        (double)D->dl->layout.total, (double)D->dr->layout.total, (double)cp.n_gemm_tasks, (double)cp.n_axpy_tasks, (double)cp.n_waves,
+                        (double)wsb, D->plan_seconds, (double)D->S.psi.row_dim().size(), (double)mx, (double)D->S.mpo->row_dim(),
+                        (double)D->S.mpo->col_dim(), (double)D->S.mpo->nnz(), D->S.setup_seconds, (double)nl};
+        for (int i = 0; i < 21; ++i) info[i] = v[i];
+        return 0;
+    } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
+}
+
+// copy of the site tensor (left-paired blocks back to back) for callers that own the host buffers
+extern "C" int qcmd_get_psi(void* h, double* psi)
+{
+    Driver* D = static_cast<Driver*>(h);
+    std::memcpy(psi, D->psi_flat.data(), D->psi_flat.size() * sizeof(double));
+    return 0;
+}
+
+// one sigma through the C ABI with HOST buffers (H2D of psi and D2H of sigma inside the call)
+extern "C" int qcmd_sigma_host(void* h, const double* psi, double* sigma, char* err, int errlen)
+{
+    Driver* D = static_cast<Driver*>(h);
+    if (qcm_site_hamil2(D->plan->handle, D->dl->arr, D->dr->arr, psi, sigma) != 0) { set_err(err, errlen, qcm_last_error()); return 1; }
+    return 0;
+}
+
+// n sigma evaluations on device-resident vectors; the caller brackets the call with its own timing
+extern "C" int qcmd_sigma_dev(void* h, int n, char* err, int errlen)
+{
+    Driver* D = static_cast<Driver*>(h);
+    for (int i = 0; i < n; ++i)
+        if (qcm_site_hamil2_dev(D->plan->handle, D->dl->arr, D->dr->arr, D->d_psi, D->d_sigma) != 0) { set_err(err, errlen, qcm_last_error()); return 1; }
+    return 0;
+}
+extern "C" int qcmd_get_sigma_dev(void* h, double* sigma)
+{
+    Driver* D = static_cast<Driver*>(h);
+    return qcm_array_download(D->d_sigma, 0, sigma, D->plan->out_elems);
+}
+
+// the drop-in call itself: Engine::site_hamil2 on host MPSTensor objects (includes block flatten/unflatten)
+extern "C" int qcmd_sigma_engine(void* h, double* overlap, char* err, int errlen)
+{
+    try {
+        Driver* D = static_cast<Driver*>(h);
+        MPSTensor s = D->eng->site_hamil2(D->S.psi, D->S.left, D->S.right, *D->S.mpo);
+        if (overlap) *overlap = s.scalar_overlap(D->S.psi);
+        return 0;
+    } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
+}
+
+// one boundary propagation with the site tensor as bra and ket (single-site problems only): returns device ms via wall clock
+extern "C" int qcmd_boundary_step(void* h, int direction, double* seconds, double* out_elems, char* err, int errlen)
+{
+    try {
+        Driver* D = static_cast<Driver*>(h);
+        if (D->S.twosite) throw std::runtime_error("boundary step needs a single-site problem");
+        auto t0 = std::chrono::steady_clock::now();
+        Boundary b = direction == 0 ? D->eng->overlap_mpo_left_step(D->S.psi, D->S.psi, D->S.left, *D->S.mpo)
+                                    : D->eng->overlap_mpo_right_step(D->S.psi, D->S.psi, D->S.right, *D->S.mpo);
+        qcm_sync();
+        *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        *out_elems = (double)D->eng->last_plan()->out_elems;
+        return 0;
+    } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
+}
+
+// schedule-derived algorithmic FLOPs of one sigma for a synthetic site (host only; used by the CPU arm of bench.py)
+extern "C" double qcmd_plan_flops(void* h, int site, int twosite, int M, unsigned seed, char* err, int errlen)
+{
+    try {
+        Driver* D = static_cast<Driver*>(h);
+        SyntheticSite S = make_synthetic_site(D->P, site, twosite != 0, (size_t)M, seed);
+        S.psi.make_left_paired();
+        std::vector<DualIndex> lb(S.left.aux_dim()), rb(S.right.aux_dim());
+        for (size_t k = 0; k < lb.size(); ++k) lb[k] = S.left[k].basis();
+        for (size_t k = 0; k < rb.size(); ++k) rb[k] = S.right[k].basis();
+        plan::BoundaryLayout ll, rl; ll.assign(lb); rl.assign(rb);
+        plan::Planner pl(D->P.symm(), *S.mpo, true);
+        plan::Plan pp = pl.plan_sigma(GpuEngine::desc_of(S.psi), ll, rl);
+        return pp.flops();
+    } catch (std::exception const& e) { set_err(err, errlen, e.what()); return -1.; }
+}

@@ -114,6 +114,8 @@ class Planner
 public:
     Planner(SymmKind s, MPOTensor const& mpo_, bool isHermitian_, int rank_ = 0, int world_ = 1, int64_t ws_budget_elems = (int64_t)1 << 30)
         : symm(s), su2_(is_su2(s)), mpo(mpo_), isHermitian(isHermitian_), rank(rank_), world(world_), budget(ws_budget_elems) {}
+    // only the output block structure is wanted (Plan::out_tensor / out_boundary); no tasks are emitted
+    bool structure_only = false;
 
     // -----------------------------------------------------------------------------------------------------
     // sigma = H_eff psi    (abelian/site_hamil.hpp:23-90, non-abelian/site_hamil.hpp:57-147)
@@ -140,13 +142,18 @@ public:
         // output structure: emulate the per-b2 products and their match_and_add_block reduction
         block_struct sigma_struct;
         struct Pending { size_t b2; Layout y; std::vector<YTask> ytasks; std::vector<size_t> t_rows; };
-        std::vector<Pending> pend;
-        for (size_t b2 = 0; b2 < mpo.col_dim(); ++b2) {
-            Pending pd; pd.b2 = b2;
+        std::vector<Pending> pend(mpo.col_dim());
+        int n_b2 = (int)mpo.col_dim();
+#pragma omp parallel for schedule(dynamic, 4)
+        for (int b2 = 0; b2 < n_b2; ++b2) {
+            Pending& pd = pend[b2]; pd.b2 = (size_t)b2;
             DualIndex ybasis;
             if (su2_) y_struct_su2_lbtm(b2, ket_rp, right_i, out_left_i, in_right_pb, out_left_pb, ybasis, pd.ytasks, pd.t_rows);
             else y_struct_abelian_lbtm(b2, ket_rp.basis, ket_rp.basis, right_i, out_left_i, in_right_pb, out_left_pb, ybasis, pd.ytasks, pd.t_rows);
             pd.y.assign(ybasis);
+        }
+        for (size_t b2 = 0; b2 < mpo.col_dim(); ++b2) {
+            DualIndex const& ybasis = pend[b2].y.basis;
             // closing product structure (decides which sigma blocks exist, on every rank identically)
             VView rv = right_view(right, b2);
             for (size_t k = 0; k < ybasis.size(); ++k) {
@@ -162,9 +169,9 @@ public:
                         sigma_struct.add(ybasis[k].lc, it->rc, ybasis[k].ls, it->rs);
                 }
             }
-            pend.push_back(std::move(pd));
         }
         P.out_tensor.assign(sigma_struct.basis);
+        if (structure_only) return P;
 
         // emit waves over this rank's share of b2
         std::vector<char> mine = share_mask(pend.size(), [&](size_t i) { return estimate_cost(pend[i].y, right, pend[i].b2); });
@@ -245,7 +252,9 @@ public:
         struct Pending { size_t b2; DualIndex y; std::vector<YTask> ytasks; std::vector<size_t> t_rows; DualIndex out; };
         std::vector<Pending> pend(loop_max);
         std::vector<DualIndex> out_bases(loop_max);
-        for (size_t b2 = 0; b2 < loop_max; ++b2) {
+#pragma omp parallel for schedule(dynamic, 4)
+        for (long b2l = 0; b2l < (long)loop_max; ++b2l) {
+            size_t b2 = (size_t)b2l;
             Pending& pd = pend[b2]; pd.b2 = b2;
             if (mpo.herm_info.right_skip(b2) && isHermitian) continue;
             if (su2_) y_struct_su2_lbtm(b2, ket_rp, right_i, out_left_i, in_right_pb, out_left_pb, pd.y, pd.ytasks, pd.t_rows);
@@ -262,6 +271,7 @@ public:
             out_bases[b2] = os.basis;
         }
         P.out_boundary.assign(out_bases);
+        if (structure_only) return P;
 
         std::vector<char> mine = share_mask(loop_max, [&](size_t b2) { double c = 0; for (size_t k = 0; k < pend[b2].y.size(); ++k) c += (double)pend[b2].y[k].ls * pend[b2].y[k].rs; return c; });
         Wave cur; int64_t cur_y = 0, cur_t = 0;
@@ -334,7 +344,9 @@ public:
         std::vector<Pending> pend(loop_max);
         std::vector<DualIndex> out_bases(loop_max);
         DualIndex bra_rp_t = bra_rp.basis.transposed();
-        for (size_t b1 = 0; b1 < loop_max; ++b1) {
+#pragma omp parallel for schedule(dynamic, 4)
+        for (long b1l = 0; b1l < (long)loop_max; ++b1l) {
+            size_t b1 = (size_t)b1l;
             Pending& pd = pend[b1];
             if (mpo.herm_info.left_skip(b1) && isHermitian) continue;
             if (su2_) y_struct_su2_rbtm(b1, ket_lp.basis, left_i, out_right_i, in_left_pb, out_right_pb, pd.y, pd.ytasks, pd.t_cols);
@@ -349,6 +361,7 @@ public:
             out_bases[b1] = os.basis;
         }
         P.out_boundary.assign(out_bases);
+        if (structure_only) return P;
 
         std::vector<char> mine = share_mask(loop_max, [&](size_t b1) { double c = 0; for (size_t k = 0; k < pend[b1].y.size(); ++k) c += (double)pend[b1].y[k].ls * pend[b1].y[k].rs; return c; });
         Wave cur; int64_t cur_y = 0, cur_t = 0;
@@ -631,6 +644,7 @@ private:
                 }
             }
         }
+        if (structure_only) return;
         for (size_t e = mpo.col_begin(b2); e < mpo.col_end(b2); ++e) {   // execute
             size_t b1 = mpo.row_of(e);
             DualIndex const& T = t_basis[b1];
@@ -696,6 +710,7 @@ private:
                         if (!out_left_i.has(out_l)) continue;
                         int32_t r_size = (int32_t)right_i[rb].second;
                         if (!ret.has(out_l, out_r)) ret.insert(QnBlock(out_l, out_r, out_left_i.size_of_block(out_l), r_size));
+                        if (structure_only) continue;
                         int i = spin(lc), ip = spin(out_l), j = spin(mc), jp = spin(out_r);
                         int two_sp = std::abs(i - ip), two_s = std::abs(j - jp);
                         double couplings[4];
@@ -738,6 +753,7 @@ private:
                 }
             }
         }
+        if (structure_only) return;
         for (size_t b2 : mpo.row(b1)) {
             DualIndex const& T = t_basis[b2];
             if (T.size() == 0) continue;
@@ -800,6 +816,12 @@ private:
                         if (!su2::triangle(spin(out_l), a, spin(out_r))) continue;
                         if (!out_right_i.has(out_r)) continue;
                         int32_t l_size = (int32_t)left_i[lb].second;
+                        if (structure_only) {
+                            auto key = std::make_pair(out_l, out_r);
+                            if (!first_l_size.count(key)) first_l_size[key] = -1;
+                            if (W.sparse_ptr[w + 1] > W.sparse_ptr[w] && first_l_size[key] < 0) first_l_size[key] = l_size;
+                            continue;
+                        }
                         int i = spin(out_r), ip = spin(rc), j = spin(out_l), jp = spin(mc);
                         int two_sp = std::abs(i - ip), two_s = std::abs(j - jp);
                         double couplings[4];

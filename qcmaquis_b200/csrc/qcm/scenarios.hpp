@@ -5,6 +5,8 @@
 #pragma once
 #include "engine_iface.hpp"
 #include "models.hpp"
+#include "plan.hpp"
+#include <chrono>
 
 extern "C" void scipy_dsyev_(const char* jobz, const char* uplo, const int* n, double* a, const int* lda, double* w,
                              double* work, const int* lwork, int* info);
@@ -54,6 +56,150 @@ struct Problem
 inline MPSTensor make_twosite_tensor(Index const& phys1, Index const& phys2, Index const& left_i, Index const& right_i, std::function<double()> gen)
 {
     return MPSTensor(phys1 * phys2, left_i, right_i, gen);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Synthetic mid-chain site problems for the large BASELINE configurations.  The MPO is the true
+// one (built from the FCIDUMP by the term maker + TaggedMPOMaker restatement, so bond indexing, Hermitian
+// pairs and bond spins are those the reference would produce); what is fabricated is the STATE: sector lists
+// per bond from a smooth weight around the mean filling, truncated to a total bond dimension M, the boundary
+// block structures obtained by propagating structure (no data) from both chain ends through the schedule
+// builder, and N(0,1) contents.  Hermitian-skipped boundary entries stay empty, as in a real sweep.
+inline std::vector<Index> synthetic_sectors(Problem const& P, size_t M)
+{
+    SymmKind symm = P.params.symm;
+    int L = P.params.L;
+    std::vector<Index> full = allowed_sectors(symm, P.model->lat.irreps, P.model->phys_indices, P.model->total_charge, (size_t)1 << 40);
+    int nelec = is_su2(symm) ? P.params.nelec : P.params.nup + P.params.ndown;
+    std::vector<Index> ret(L + 1);
+    for (int i = 0; i <= L; ++i) {
+        double nbar = (double)nelec * i / L;
+        std::vector<double> w(full[i].size());
+        double wsum = 0;
+        for (size_t k = 0; k < full[i].size(); ++k) {
+            Charge c = full[i][k].first;
+            if (is_su2(symm)) {
+                double dn = c[0] - nbar, s2 = c[1];
+                w[k] = std::exp(-dn * dn / (2 * 1.3 * 1.3)) * (s2 + 1) * std::exp(-s2 * s2 / (2 * 2.0 * 2.0));
+            } else {
+                double du = c[0] - nbar / 2, dd = c[1] - nbar / 2;
+                w[k] = std::exp(-(du * du + dd * dd) / (2 * 1.0 * 1.0));
+            }
+            wsum += w[k];
+        }
+        // proportional shares, capped by the sector's full dimension; leftover redistributed over uncapped sectors
+        std::vector<double> share(w.size(), 0.);
+        std::vector<char> capped(w.size(), 0);
+        double remaining = (double)M;
+        for (int pass = 0; pass < 8; ++pass) {
+            double ws = 0;
+            for (size_t k = 0; k < w.size(); ++k) if (!capped[k]) ws += w[k];
+            if (ws <= 0) break;
+            bool changed = false;
+            for (size_t k = 0; k < w.size(); ++k) {
+                if (capped[k]) continue;
+                double want = remaining * w[k] / ws;
+                if (want >= (double)full[i][k].second) { share[k] = (double)full[i][k].second; capped[k] = 1; changed = true; }
+                else share[k] = want;
+            }
+            remaining = (double)M;
+            for (size_t k = 0; k < w.size(); ++k) if (capped[k]) remaining -= share[k];
+            if (!changed || remaining <= 0) break;
+        }
+        for (size_t k = 0; k < w.size(); ++k) {
+            if (share[k] < 0.05) continue;                       // negligible weight: sector absent
+            size_t sz = std::max<size_t>(1, (size_t)std::llround(share[k]));
+            sz = std::min(sz, full[i][k].second);
+            ret[i].insert(std::make_pair(full[i][k].first, sz));
+        }
+    }
+    return ret;
+}
+
+struct SyntheticSite
+{
+    int site = 0; bool twosite = true;
+    MPSTensor psi;
+    Boundary left, right;
+    MPOTensor const* mpo = nullptr;
+    std::vector<Index> sectors;
+    double setup_seconds = 0;
+};
+
+inline void fill_normal(block_matrix& m, uint64_t seed)
+{
+    std::mt19937_64 eng(seed);
+    std::normal_distribution<double> nd(0., 1.);
+    for (size_t k = 0; k < m.n_blocks(); ++k) for (auto& x : m[k].v) x = nd(eng);
+}
+
+inline Boundary boundary_from_layout(plan::BoundaryLayout const& L, uint64_t seed)
+{
+    Boundary b; b.resize(L.aux_dim());
+    for (size_t k = 0; k < L.aux_dim(); ++k) {
+        for (size_t j = 0; j < L.b[k].basis.size(); ++j) {
+            QnBlock const& q = L.b[k].basis[j];
+            b.raw(k).insert_block(Matrix(q.ls, q.rs), q.lc, q.rc);
+        }
+        fill_normal(b.raw(k), seed * 1000003ull + k);
+    }
+    return b;
+}
+
+inline SyntheticSite make_synthetic_site(Problem& P, int site, bool twosite, size_t M, unsigned seed)
+{
+    auto t0 = std::chrono::steady_clock::now();
+    SyntheticSite S; S.site = site; S.twosite = twosite;
+    SymmKind symm = P.symm();
+    int L = P.params.L, last = twosite ? site + 1 : site;
+    if (site < 0 || last >= L) throw std::runtime_error("make_synthetic_site: site outside the lattice");
+    S.sectors = synthetic_sectors(P, M);
+    auto zero = []() { return 0.0; };
+    auto desc = [&](MPSTensor const& t) { t.make_left_paired(); return plan::TensorDesc{t.site_dim(), t.row_dim(), t.col_dim(), t.data().basis()}; };
+    // structure chain from the left end
+    std::vector<MPSTensor> tens(L);
+    for (int i = 0; i < L; ++i) if (i < site || i > last) tens[i] = MPSTensor(P.phys(i), S.sectors[i], S.sectors[i + 1], zero);
+    plan::BoundaryLayout ll, rl;
+    {
+        Index i0 = tens[0].left_i.size() ? tens[0].row_dim() : S.sectors[0];
+        if (site == 0) i0 = S.sectors[0];
+        std::vector<DualIndex> b0(1);
+        for (auto const& e : i0) b0[0].insert(QnBlock(e.first, e.first, e.second, e.second));
+        ll.assign(b0);
+        for (int i = 0; i < site; ++i) {
+            plan::Planner pl(symm, P.mpo[i], true);
+            pl.structure_only = true;
+            plan::TensorDesc d = desc(tens[i]);
+            plan::Plan pp = pl.plan_left_step(d, d, ll);
+            ll = pp.out_boundary;
+        }
+    }
+    {
+        Index iL = S.sectors[L];
+        std::vector<DualIndex> bL(1);
+        for (auto const& e : iL) bL[0].insert(QnBlock(e.first, e.first, e.second, e.second));
+        rl.assign(bL);
+        for (int i = L - 1; i > last; --i) {
+            plan::Planner pl(symm, P.mpo[i], true);
+            pl.structure_only = true;
+            plan::TensorDesc d = desc(tens[i]);
+            plan::Plan pp = pl.plan_right_step(d, d, rl);
+            rl = pp.out_boundary;
+        }
+    }
+    S.left = boundary_from_layout(ll, 7919ull * seed + 1);
+    S.right = boundary_from_layout(rl, 7919ull * seed + 2);
+    // the site tensor lives between the sector lists the neighbouring tensors actually kept
+    Index li = site > 0 ? tens[site - 1].col_dim() : S.sectors[0];
+    Index ri = last + 1 < L ? tens[last + 1].row_dim() : S.sectors[L];
+    Index phys = twosite ? P.phys(site) * P.phys(site + 1) : P.phys(site);
+    S.psi = MPSTensor(phys, li, ri, zero);
+    fill_normal(S.psi.data(), 7919ull * seed + 3);
+    S.psi.divide_by_scalar(S.psi.scalar_norm());
+    S.mpo = twosite ? &P.twosite_mpo(site) : &P.mpo[site];
+    S.setup_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return S;
 }
 
 struct DiffReport { double max_abs = 0, ref_norm = 0, diff_norm = 0; int structure_equal = 1; };

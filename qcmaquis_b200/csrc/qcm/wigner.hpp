@@ -10,7 +10,10 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <cstdint>
 #include <cstdlib>
+#include <stdexcept>
+#include <unordered_map>
 
 namespace qcm { namespace su2 {
 
@@ -70,7 +73,7 @@ inline double mod_coupling(int a, int b, int c, int d, int e, int f, int g, int 
 }
 
 // gsl_coupling.h:177-204: the four couplings selected per W entry by (row_spin==2, col_spin==2)
-inline void set_coupling(int a, int b, int c, int d, int e, int f, int g, int h, int i, double init, double couplings[4])
+inline void set_coupling_uncached(int a, int b, int c, int d, int e, int f, int g, int h, int i, double init, double couplings[4])
 {
     double prefactor = std::sqrt((i + 1.) * (a + 1.) / ((g + 1.) * (c + 1.))) * init;
     if (triangle(a, b, c)) {
@@ -81,6 +84,27 @@ inline void set_coupling(int a, int b, int c, int d, int e, int f, int g, int h,
         couplings[1] = prefactor * mod_coupling(a, 2, c, d, e, f, g, h, i);
         couplings[3] = prefactor * mod_coupling(a, 2, c, d, e, f, g, 2, i);
     } else { couplings[1] = 0.0; couplings[3] = 0.0; }
+}
+
+// The reference never evaluates a 9j twice: WignerWrapper keeps every value in a hash table filled at start-up
+// (gsl_coupling.h:113-144, su2_wrapper.cpp:14-36).  Same idea here, per thread (no locking), keyed by the nine
+// doubled spins; the table holds the couplings for init == 1.
+inline void set_coupling(int a, int b, int c, int d, int e, int f, int g, int h, int i, double init, double couplings[4])
+{
+    struct Entry { double v[4]; };
+    static thread_local std::unordered_map<uint64_t, Entry> cache;
+    const int args[9] = {a, b, c, d, e, f, g, h, i};
+    uint64_t key = 0;
+    bool cacheable = true;
+    for (int q = 0; q < 9; ++q) { if (args[q] < 0 || args[q] > 126) cacheable = false; key = (key << 7) | (uint64_t)(args[q] & 127); }
+    if (!cacheable) { set_coupling_uncached(a, b, c, d, e, f, g, h, i, init, couplings); return; }
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        Entry en;
+        set_coupling_uncached(a, b, c, d, e, f, g, h, i, 1.0, en.v);
+        it = cache.emplace(key, en).first;
+    }
+    for (int q = 0; q < 4; ++q) couplings[q] = it->second.v[q] * init;
 }
 
 // non-abelian/gemm.hpp:17-46; lspin/rspin = SU2 spin components of the block's left/right charge
