@@ -280,10 +280,10 @@ def main():
 
     # dominant kernel family by device time
     fl = {1: info[1], 2: info[2], 3: info[3]}
-    names = {1: "k_gemm_dmma (step 1: T = L^T psi)", 2: "k_axpy_gather (W application)", 3: "k_gemm_dmma (step 3: sigma += Y R)"}
+    names = {1: "k_gemm_dmma (step 1: T = L^T psi)", 2: "k_wapply_dmma (W application)", 3: "k_gemm_dmma (step 3: sigma += Y R)"}
     dom = max((1, 2, 3), key=lambda i: phases[i])
     if dom == 2:
-        b = 8.0 * (info[2] / 2.0)   # every W task element is one 8-byte read; writes are the smaller part
+        b = 8.0 * (info[21] + info[22])   # panel elements the grouped W application reads and writes (plan-derived)
         roof = {"bound": "hbm", "kernel": names[dom], "achieved": b / (phases[dom] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback"}
     else:
@@ -299,7 +299,8 @@ def main():
                        "l2": "inputs (boundaries %.2f GB + workspaces %.2f GB) exceed L2" % ((info[7] + info[8]) * 8 / 1e9, info[12] / 1e9),
                        "mpo": "%dx%d nnz %d" % (info[16], info[17], info[18]), "sectors": int(info[14]), "largest_sector": int(info[15]),
                        "flops_per_step": flops, "flops_split": {"step1": info[1], "w_apply": info[2], "step3": info[3]},
-                       "algorithmic_bytes": bytes_alg, "plan_seconds": info[13]},
+                       "algorithmic_bytes": bytes_alg, "plan_seconds": info[13],
+                       "w_apply_bytes": 8.0 * (info[21] + info[22]), "w_groups": int(info[23])},
             "fp64_peak_tflops": peak.value, "frac_of_fp64_peak": flops / (ms_dev * 1e-3) / 1e12 / (peak.value * world) if peak.value else None,
             "roofline": roof, "clocks": clocks,
             "e2e": {"value": flops / (ms_e2e * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": psi_n * 8, "d2h_bytes_per_step": sig_n * 8},

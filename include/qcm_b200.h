@@ -49,17 +49,22 @@ typedef struct { qcm_ref A, B; int32_t lda, ldb, m, n, k, ta, tb, pad; double al
 /* one output block = a list of K-segments (the sum over MPO bond terms b that hit the same sector) */
 typedef struct { qcm_ref C; int32_t ldc, m, n, seg_begin, seg_end, pad; } qcm_gemm_out;
 
-/* W application as gather-axpy: dst panel = sum_i coef_i * src panel_i
- * (lb_tensor_mpo/rb_tensor_mpo alps_detail.hpp:189-224; SU2 detail::lbtm/rbtm/task_axpy micro_kernels.hpp:19-198;
- *  coef = W entry * scale * Wigner-9j coupling (gsl_coupling.h:177-204) * Hermitian phase) */
-typedef struct { qcm_ref src; int32_t lds, pad; double coef; } qcm_axpy_src;
-typedef struct { qcm_ref dst; int32_t ldd, rows, cols, src_begin, src_end, pad; } qcm_axpy_dst;
+/* W application (lb_tensor_mpo/rb_tensor_mpo alps_detail.hpp:189-224; SU2 detail::lbtm/rbtm/task_axpy
+ * micro_kernels.hpp:19-198) as grouped small dense products: a group holds up to 16 destination panels that are
+ * fed by (nearly) the same source panels; dst_d[e] = sum_u coef[u*ng + d] * src_u[e] over the panel elements e.
+ * coef = W entry * scale * Wigner-9j coupling (gsl_coupling.h:177-204) * Hermitian phase, zero where a
+ * destination does not use a source.  All panels of a group are rows x cols (column-major, own leading dims). */
+typedef struct { qcm_ref src; int32_t lds, pad; } qcm_w_src;
+typedef struct { qcm_ref dst; int32_t ldd, pad; } qcm_w_dst;
+typedef struct { int32_t rows, cols, n_src, n_dst, ng /* 8 or 16 */, src_begin, dst_begin, pad; int64_t coef_begin; } qcm_w_group;
 
 typedef struct {
     const qcm_gemm_out* t_outs;     int64_t n_t_outs;      /* step 1 for this wave -> QCM_BUF_T   */
     const qcm_gemm_seg* t_segs;     int64_t n_t_segs;
-    const qcm_axpy_dst* w_dsts;     int64_t n_w_dsts;      /* step 2 -> QCM_BUF_Y                 */
-    const qcm_axpy_src* w_srcs;     int64_t n_w_srcs;
+    const qcm_w_group* w_groups;    int64_t n_w_groups;    /* step 2 -> QCM_BUF_Y                 */
+    const qcm_w_src* w_srcs;        int64_t n_w_srcs;
+    const qcm_w_dst* w_dsts;        int64_t n_w_dsts;
+    const double* w_coefs;          int64_t n_w_coefs;
     const qcm_gemm_out* c_outs;     int64_t n_c_outs;      /* step 3 -> QCM_BUF_OUT (accumulating) */
     const qcm_gemm_seg* c_segs;     int64_t n_c_segs;
     int64_t y_elems, t_elems;

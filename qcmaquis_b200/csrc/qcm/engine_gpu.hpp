@@ -40,6 +40,7 @@ struct CompiledPlan
     double flops = 0, flops_t = 0, flops_w = 0, flops_close = 0;
     int64_t bytes = 0;
     size_t n_gemm_tasks = 0, n_axpy_tasks = 0, n_waves = 0;
+    int64_t w_elems_read = 0, w_elems_written = 0, w_groups = 0;
     int64_t workspace_elems = 0;
     ~CompiledPlan() { if (handle) qcm_plan_destroy(handle); }
 };
@@ -197,7 +198,7 @@ private:
 
     std::shared_ptr<CompiledPlan> compile(plan::Plan const& P, int64_t left_elems, int64_t right_elems)
     {
-        struct WaveStore { std::vector<qcm_gemm_out> to, co; std::vector<qcm_gemm_seg> ts, cs; std::vector<qcm_axpy_dst> wd; std::vector<qcm_axpy_src> wsrc; };
+        struct WaveStore { std::vector<qcm_gemm_out> to, co; std::vector<qcm_gemm_seg> ts, cs; std::vector<qcm_w_group> wg; std::vector<qcm_w_dst> wd; std::vector<qcm_w_src> wsrc; };
         std::vector<WaveStore> store(P.waves.size());
         std::vector<qcm_wave_desc> waves(P.waves.size());
         for (size_t w = 0; w < P.waves.size(); ++w) {
@@ -205,17 +206,17 @@ private:
             WaveStore& S = store[w];
             cvt(W.t_gemm, S.to, S.ts);
             cvt(W.close_gemm, S.co, S.cs);
-            S.wd.resize(W.w_apply.dsts.size()); S.wsrc.resize(W.w_apply.srcs.size());
-            for (size_t i = 0; i < S.wd.size(); ++i) {
-                plan::AxpyDst const& d = W.w_apply.dsts[i];
-                S.wd[i] = qcm_axpy_dst{qcm_ref{d.dst.buf, 0, d.dst.off}, d.ldd, d.rows, d.cols, d.src_begin, d.src_end, 0};
+            plan::WList const& wl = W.w_groups;
+            S.wg.resize(wl.groups.size()); S.wd.resize(wl.dsts.size()); S.wsrc.resize(wl.srcs.size());
+            for (size_t i = 0; i < S.wg.size(); ++i) {
+                plan::WGroup const& g = wl.groups[i];
+                S.wg[i] = qcm_w_group{g.rows, g.cols, g.n_src, g.n_dst, g.ng, g.src_begin, g.dst_begin, 0, g.coef_begin};
             }
-            for (size_t i = 0; i < S.wsrc.size(); ++i) {
-                plan::AxpySrc const& s = W.w_apply.srcs[i];
-                S.wsrc[i] = qcm_axpy_src{qcm_ref{s.src.buf, 0, s.src.off}, s.lds, 0, s.coef};
-            }
+            for (size_t i = 0; i < S.wd.size(); ++i) S.wd[i] = qcm_w_dst{qcm_ref{wl.dsts[i].dst.buf, 0, wl.dsts[i].dst.off}, wl.dsts[i].ldd, 0};
+            for (size_t i = 0; i < S.wsrc.size(); ++i) S.wsrc[i] = qcm_w_src{qcm_ref{wl.srcs[i].src.buf, 0, wl.srcs[i].src.off}, wl.srcs[i].lds, 0};
             waves[w] = qcm_wave_desc{S.to.data(), (int64_t)S.to.size(), S.ts.data(), (int64_t)S.ts.size(),
-                                     S.wd.data(), (int64_t)S.wd.size(), S.wsrc.data(), (int64_t)S.wsrc.size(),
+                                     S.wg.data(), (int64_t)S.wg.size(), S.wsrc.data(), (int64_t)S.wsrc.size(), S.wd.data(), (int64_t)S.wd.size(),
+                                     wl.coefs.data(), (int64_t)wl.coefs.size(),
                                      S.co.data(), (int64_t)S.co.size(), S.cs.data(), (int64_t)S.cs.size(), W.y_elems, W.t_elems};
         }
         std::vector<qcm_gemm_out> po; std::vector<qcm_gemm_seg> ps;
@@ -242,6 +243,7 @@ private:
         cp->out_tensor = P.out_tensor; cp->out_boundary = P.out_boundary;
         cp->ket_elems = P.ket_lp_elems; cp->bra_elems = P.bra_lp_elems; cp->out_elems = out_elems;
         cp->flops = P.flops(); cp->flops_t = P.flops_t; cp->flops_w = P.flops_w; cp->flops_close = P.flops_close; cp->bytes = P.bytes_algorithmic;
+        cp->w_elems_read = P.w_elems_read; cp->w_elems_written = P.w_elems_written; cp->w_groups = P.w_groups;
         cp->n_gemm_tasks = P.n_gemm_tasks; cp->n_axpy_tasks = P.n_axpy_tasks; cp->n_waves = P.waves.size();
         cp->workspace_elems = P.ket_rp_elems + P.t_elems_max + P.tp_elems + P.y_elems_max + P.bra_rp_elems;
         last = cp;

@@ -17,6 +17,7 @@
 #include <cstdint>
 #include <map>
 #include <numeric>
+#include <unordered_map>
 
 namespace qcm { namespace plan {
 
@@ -32,10 +33,24 @@ struct AxpyDst { Ref dst; int32_t ldd, rows, cols, src_begin, src_end; };
 struct GemmList { std::vector<Out> outs; std::vector<Seg> segs; };
 struct AxpyList { std::vector<AxpyDst> dsts; std::vector<AxpySrc> srcs; };
 
+// The W application in the form the device executes: destination panels that are fed by the SAME set of source
+// panels (typical for quantum-chemistry MPOs: all bond terms that differ only by an integral value) are grouped,
+// and a group is evaluated as one small dense product  dst[e, d] = sum_u src_u[e] * coef[u][d]  over the panel
+// elements e.  Every source panel is then read once per group instead of once per (source, destination) pair.
+struct WSrc { Ref src; int32_t lds; };
+struct WDst { Ref dst; int32_t ldd; };
+struct WGroup { int32_t rows, cols, n_src, n_dst, ng, src_begin, dst_begin; int64_t coef_begin; };   // coef[(coef_begin + u*ng + d)], u < pad4(n_src)
+struct WList
+{
+    std::vector<WGroup> groups; std::vector<WSrc> srcs; std::vector<WDst> dsts; std::vector<double> coefs;
+    int64_t elems_read = 0, elems_written = 0;   // panel elements moved by the grouped form
+};
+
 struct Wave
 {
     GemmList t_gemm;      // step 1 products needed by this wave (single-use bonds) -> BUF_T
-    AxpyList w_apply;     // step 2 -> BUF_Y
+    AxpyList w_apply;     // step 2 -> BUF_Y (planner-internal list, cleared once grouped)
+    WList w_groups;       // step 2 as executed
     GemmList close_gemm;  // step 3 -> BUF_OUT (accumulating for sigma, plain for boundary steps)
     int64_t y_elems = 0;  // BUF_Y region that must be zeroed before the axpy pass
     int64_t t_elems = 0;
@@ -77,6 +92,7 @@ struct Plan
     int64_t ket_lp_elems = 0, ket_rp_elems = 0, bra_lp_elems = 0, bra_rp_elems = 0;
     int64_t tp_elems = 0, t_elems_max = 0, y_elems_max = 0;
     double flops_t = 0, flops_w = 0, flops_close = 0;
+    int64_t w_elems_read = 0, w_elems_written = 0, w_groups = 0;   // traffic of the grouped W application (panel elements)
     int64_t bytes_algorithmic = 0;         // 8*(sum|L_b| + sum|R_b| + 2|psi|) resp. boundary-step analogue
     size_t n_gemm_tasks = 0, n_axpy_tasks = 0;
     double flops() const { return flops_t + flops_w + flops_close; }
@@ -181,6 +197,7 @@ public:
             cur.y_elems = cur_y; cur.t_elems = cur_t;
             P.y_elems_max = std::max(P.y_elems_max, cur_y); P.t_elems_max = std::max(P.t_elems_max, cur_t);
             merge_outputs(cur.close_gemm); merge_outputs(cur.t_gemm);
+            group_axpy(P, cur.w_apply, cur.w_groups);
             P.waves.push_back(std::move(cur));
             cur = Wave(); cur_y = 0; cur_t = 0;
         };
@@ -280,6 +297,7 @@ public:
             cur.y_elems = cur_y; cur.t_elems = cur_t;
             P.y_elems_max = std::max(P.y_elems_max, cur_y); P.t_elems_max = std::max(P.t_elems_max, cur_t);
             merge_outputs(cur.close_gemm); merge_outputs(cur.t_gemm);
+            group_axpy(P, cur.w_apply, cur.w_groups);
             P.waves.push_back(std::move(cur));
             cur = Wave(); cur_y = 0; cur_t = 0;
         };
@@ -370,6 +388,7 @@ public:
             cur.y_elems = cur_y; cur.t_elems = cur_t;
             P.y_elems_max = std::max(P.y_elems_max, cur_y); P.t_elems_max = std::max(P.t_elems_max, cur_t);
             merge_outputs(cur.close_gemm); merge_outputs(cur.t_gemm);
+            group_axpy(P, cur.w_apply, cur.w_groups);
             P.waves.push_back(std::move(cur));
             cur = Wave(); cur_y = 0; cur_t = 0;
         };
@@ -882,6 +901,103 @@ private:
             al.dsts.push_back(d);
             q = q2;
         }
+    }
+
+
+    // Destinations fed by (nearly) the same set of source panels -> one group of at most 16 destinations.
+    // Candidates are bucketed by two min-hashes of their source sets and accepted when they share >= 50 % of the
+    // sources with the group leader; the group works on the union of the members' sources (absent pairs get a zero
+    // coefficient), so grouping never adds memory traffic, it only removes repeated reads of shared panels.
+    static void group_axpy(Plan& P, AxpyList& al, WList& wl)
+    {
+        size_t nd = al.dsts.size();
+        struct Key { uint64_t h1, h2; int32_t rows, cols, n; size_t idx; };
+        std::vector<Key> keys(nd);
+        typedef std::vector<std::pair<int64_t, double>> SrcVec;   // (packed src ref, coef), sorted by ref
+        std::vector<SrcVec> sorted(nd);
+        auto mixh = [](uint64_t x, uint64_t seed) { x ^= seed; x *= 0x9E3779B97F4A7C15ull; x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull; x ^= x >> 29; return x; };
+#pragma omp parallel for schedule(dynamic, 256)
+        for (long il = 0; il < (long)nd; ++il) {
+            size_t i = (size_t)il;
+            AxpyDst const& d = al.dsts[i];
+            SrcVec& v = sorted[i];
+            v.reserve(d.src_end - d.src_begin);
+            for (int32_t q = d.src_begin; q < d.src_end; ++q) {
+                AxpySrc const& a = al.srcs[q];
+                v.push_back(std::make_pair(((int64_t)a.src.buf << 56) | a.src.off, a.coef));
+            }
+            std::sort(v.begin(), v.end(), [](auto const& x, auto const& y) { return x.first < y.first; });
+            size_t o = 0;   // the same panel reached through several MPO terms: coefficients add up
+            for (size_t q = 0; q < v.size(); ++q) { if (o && v[o - 1].first == v[q].first) v[o - 1].second += v[q].second; else v[o++] = v[q]; }
+            v.resize(o);
+            uint64_t h1 = ~0ull, h2 = ~0ull;
+            for (auto const& e : v) { h1 = std::min(h1, mixh((uint64_t)e.first, 0x1234567ull)); h2 = std::min(h2, mixh((uint64_t)e.first, 0xABCDEF01ull)); }
+            keys[i] = Key{h1, h2, d.rows, d.cols, (int32_t)v.size(), i};
+        }
+        std::sort(keys.begin(), keys.end(), [](Key const& a, Key const& b) {
+            return std::tie(a.rows, a.cols, a.h1, a.h2, a.n, a.idx) < std::tie(b.rows, b.cols, b.h1, b.h2, b.n, b.idx);
+        });
+        auto overlap = [&](SrcVec const& a, SrcVec const& b) {
+            size_t i = 0, j = 0, c = 0;
+            while (i < a.size() && j < b.size()) { if (a[i].first == b[j].first) { ++c; ++i; ++j; } else if (a[i].first < b[j].first) ++i; else ++j; }
+            return c;
+        };
+        std::unordered_map<int64_t, int32_t> lds_map;
+        lds_map.reserve(al.srcs.size());
+        for (auto const& a : al.srcs) lds_map[((int64_t)a.src.buf << 56) | a.src.off] = a.lds;
+        std::vector<int64_t> uni, tmp;
+        for (size_t q = 0; q < nd;) {
+            size_t lead = keys[q].idx;
+            size_t q2 = q + 1;
+            if (!sorted[lead].empty())
+                while (q2 < nd && q2 - q < 16 && keys[q2].rows == keys[q].rows && keys[q2].cols == keys[q].cols && keys[q2].h1 == keys[q].h1) {
+                    SrcVec const& cand = sorted[keys[q2].idx];
+                    size_t c = overlap(sorted[lead], cand);
+                    if (2 * c < std::max(sorted[lead].size(), cand.size())) break;
+                    ++q2;
+                }
+            int32_t g = (int32_t)(q2 - q);
+            if (getenv("QCM_DEBUG_GROUPS") && g == 1 && sorted[lead].size() > 1000 && q2 < nd) {
+                SrcVec const& cand = sorted[keys[q2].idx];
+                fprintf(stderr, "single: rows %d cols %d n %zu h1 %llx | next rows %d cols %d n %zu h1 %llx overlap %zu | prev n %zu h1 %llx overlap %zu\n", keys[q].rows, keys[q].cols, sorted[lead].size(), (unsigned long long)keys[q].h1,
+                        keys[q2].rows, keys[q2].cols, cand.size(), (unsigned long long)keys[q2].h1, overlap(sorted[lead], cand), q ? sorted[keys[q-1].idx].size() : 0, q ? (unsigned long long)keys[q-1].h1 : 0ull, q ? overlap(sorted[lead], sorted[keys[q-1].idx]) : 0);
+            }
+            uni.clear();
+            for (auto const& e : sorted[lead]) uni.push_back(e.first);
+            for (int32_t d = 1; d < g; ++d) {
+                tmp.clear();
+                SrcVec const& m = sorted[keys[q + d].idx];
+                size_t i = 0, j = 0;
+                while (i < uni.size() || j < m.size()) {
+                    if (j == m.size() || (i < uni.size() && uni[i] < m[j].first)) tmp.push_back(uni[i++]);
+                    else if (i == uni.size() || m[j].first < uni[i]) tmp.push_back(m[j++].first);
+                    else { tmp.push_back(uni[i]); ++i; ++j; }
+                }
+                uni.swap(tmp);
+            }
+            int32_t ns = (int32_t)uni.size();
+            WGroup G; G.rows = keys[q].rows; G.cols = keys[q].cols; G.n_src = ns; G.n_dst = g; G.ng = g <= 8 ? 8 : 16;
+            G.src_begin = (int32_t)wl.srcs.size(); G.dst_begin = (int32_t)wl.dsts.size(); G.coef_begin = (int64_t)wl.coefs.size();
+            for (int64_t ref : uni) wl.srcs.push_back(WSrc{Ref{(int32_t)(ref >> 56), ref & (((int64_t)1 << 56) - 1)}, lds_map[ref]});
+            int32_t ns_pad = (ns + 3) / 4 * 4;
+            wl.coefs.resize(wl.coefs.size() + (size_t)ns_pad * G.ng, 0.);
+            for (int32_t d = 0; d < g; ++d) {
+                size_t di = keys[q + d].idx;
+                wl.dsts.push_back(WDst{al.dsts[di].dst, al.dsts[di].ldd});
+                SrcVec const& m = sorted[di];
+                size_t u = 0;
+                for (auto const& e : m) {
+                    while (uni[u] != e.first) ++u;
+                    wl.coefs[(size_t)G.coef_begin + u * G.ng + d] = e.second;
+                }
+            }
+            wl.groups.push_back(G);
+            wl.elems_read += (int64_t)ns * G.rows * G.cols;
+            wl.elems_written += (int64_t)g * G.rows * G.cols;
+            q = q2;
+        }
+        P.w_elems_read += wl.elems_read; P.w_elems_written += wl.elems_written; P.w_groups += (int64_t)wl.groups.size();
+        AxpyList().dsts.swap(al.dsts); AxpyList().srcs.swap(al.srcs);
     }
 
     // step 3: one K-segment A(m x k) * op(B)(k x n) into output block (lc, rc)

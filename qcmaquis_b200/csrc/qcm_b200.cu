@@ -12,8 +12,9 @@
 //                   K-segments (the sum over MPO bond terms that hit the same symmetry sector), stages
 //                   operand tiles in shared memory and issues mma.sync.m8n8k4.f64 (DMMA).  tcgen05 has no
 //                   FP64 kind, so DMMA is the FP64 tensor path of sm_100a.
-//   k_axpy_gather   the W application: every destination panel is written once as sum_i coef_i * src_i
-//                   (SU2 Wigner-9j couplings and Hermitian phases are folded into coef_i on the host)
+//   k_wapply_dmma   the W application as grouped small dense products on DMMA: destination panels fed by the
+//                   same source panels share one pass over those sources (SU2 Wigner-9j couplings and
+//                   Hermitian phases are folded into the coefficients on the host)
 //   k_vec_*         solver-side BLAS-1 on device-resident vectors
 //
 // There is no CPU fallback: every entry point fails with a status when the device is not usable.
@@ -42,13 +43,15 @@ struct BufTable { double* p[QCM_BUF_COUNT]; };
 // device-side task records ---------------------------------------------------------------------------------
 struct DSeg { long long a_off, b_off; int a_buf, b_buf, lda, ldb, m, n, k, ta, tb, pad; double alpha; };
 struct DWork { long long c_off; int c_buf, ldc, m0, n0, m, n, seg_begin, seg_end, mode, pad; };   // mode 0 store, 1 add, 2 atomic
-struct DAxSrc { long long off; int buf, lds; double coef; };
-struct DAxWork { long long dst_off; int dst_buf, ldd, rows, cols, src_begin, src_end, e0, e1; };
+struct DWSrc { long long off; int buf, lds; };
+struct DWDst { long long off; int buf, ldd; };
+struct DWGroup { int rows, cols, n_src, n_dst, ng, src_begin, dst_begin, tpc; long long coef_begin; };   // tpc = 8-row tiles per column
+struct DWWork { int group, tile0; };
 struct DCopy { long long src_off, dst_off; int src_buf, dst_buf, rows, cols, lds, ldd; };
 
 // --------------------------------------------------------------------------------------------------------
 // kernels
-__global__ void k_copy_panels(const DCopy* __restrict__ tasks, BufTable bufs)
+__global__ void k_copy_panels(const DCopy* __restrict__ tasks, const __grid_constant__ BufTable bufs)
 {
     DCopy t = tasks[blockIdx.x];
     const double* __restrict__ s = bufs.p[t.src_buf] + t.src_off;
@@ -60,39 +63,106 @@ __global__ void k_copy_panels(const DCopy* __restrict__ tasks, BufTable bufs)
     }
 }
 
-__global__ void k_axpy_gather(const DAxWork* __restrict__ works, const DAxSrc* __restrict__ srcs, BufTable bufs)
-{
-    DAxWork w = works[blockIdx.x];
-    double* __restrict__ d = bufs.p[w.dst_buf] + w.dst_off;
-    for (int i = w.e0 + threadIdx.x; i < w.e1; i += blockDim.x) {
-        int r = i % w.rows, c = i / w.rows;
-        double acc = 0.;
-        for (int s = w.src_begin; s < w.src_end; ++s) {
-            DAxSrc q = srcs[s];
-            acc = fma(q.coef, bufs.p[q.buf][q.off + r + (long long)c * q.lds], acc);
-        }
-        d[r + (long long)c * w.ldd] = acc;
-    }
-}
-
 __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b)
 {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-constexpr int KC = 16;         // K chunk staged per iteration
-constexpr int SPAD = 4;        // row padding: (TM + 4) % 16 == 4 makes the fragment reads conflict free
+// W application: one warp owns WT element tiles (8 consecutive rows of one panel column each) of a group and
+// streams over the group's source panels four at a time.  DMMA shape: M = 8 panel elements, K = 4 sources,
+// N = 8 destinations (two N tiles when the group has more than 8 destinations).  A fragments come straight from
+// global memory (every source element is needed exactly once per group), B fragments are the coefficients.
+constexpr int W_WT = 8;          // element tiles per warp
+constexpr int W_WARPS = 4;
+__global__ void __launch_bounds__(W_WARPS * 32)
+k_wapply_dmma(const DWWork* __restrict__ works, const DWGroup* __restrict__ groups, const DWSrc* __restrict__ srcs,
+              const DWDst* __restrict__ dsts, const double* __restrict__ coefs, const __grid_constant__ BufTable bufs)
+{
+    const DWWork w = works[blockIdx.x];
+    const DWGroup g = groups[w.group];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int fr = lane >> 2, fk = lane & 3;
+    const int ntiles = g.tpc * g.cols;
+    int eoff[W_WT];     // row + 32-bit column index packed: row in the low 12 bits would limit sizes, keep two arrays
+    int ecol[W_WT];
+    bool ok[W_WT];
+#pragma unroll
+    for (int i = 0; i < W_WT; ++i) {
+        int t = w.tile0 + warp * W_WT + i;
+        int c = t / g.tpc, r = (t - c * g.tpc) * 8 + fr;
+        ok[i] = (t < ntiles) && (r < g.rows);
+        eoff[i] = r; ecol[i] = c;
+    }
+    double acc[W_WT][2][2];
+#pragma unroll
+    for (int i = 0; i < W_WT; ++i) acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.;
+    const bool wide = g.ng == 16;
+    const DWSrc* __restrict__ sp = srcs + g.src_begin;
+    const double* __restrict__ cp = coefs + g.coef_begin;
+    for (int u0 = 0; u0 < g.n_src; u0 += 4) {
+        const int u = u0 + fk;
+        const bool uv = u < g.n_src;
+        const double* __restrict__ p = nullptr;
+        int lds = 0;
+        if (uv) { DWSrc q = sp[u]; p = bufs.p[q.buf] + q.off; lds = q.lds; }
+        const double b0 = cp[(long long)u * g.ng + fr];          // coefficient rows are padded to a multiple of 4 sources
+        const double b1 = wide ? cp[(long long)u * g.ng + 8 + fr] : 0.;
+        double a[W_WT];
+#pragma unroll
+        for (int i = 0; i < W_WT; ++i) a[i] = (uv && ok[i]) ? p[eoff[i] + (long long)ecol[i] * lds] : 0.;
+#pragma unroll
+        for (int i = 0; i < W_WT; ++i) {
+            dmma8x8x4(acc[i][0][0], acc[i][0][1], a[i], b0);
+            if (wide) dmma8x8x4(acc[i][1][0], acc[i][1][1], a[i], b1);
+        }
+    }
+    // C fragment: row = panel element (lane/4), cols = destinations 2*(lane%4) + {0,1} (+8 for the second N tile)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        if (j == 1 && !wide) break;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            int d = j * 8 + 2 * fk + e;
+            if (d >= g.n_dst) continue;
+            DWDst q = dsts[g.dst_begin + d];
+            double* __restrict__ o = bufs.p[q.buf] + q.off;
+#pragma unroll
+            for (int i = 0; i < W_WT; ++i)
+                if (ok[i]) o[eoff[i] + (long long)ecol[i] * q.ldd] = acc[i][j][e];
+        }
+    }
+}
 
-// CTA = WARPS_M x WARPS_N warps, each warp owns WMT x WNT DMMA tiles of 8x8.
+constexpr int KC = 16;         // K chunk staged per pipeline stage
+constexpr int SPAD = 4;        // row padding: (TM + 4) % 16 == 4 makes the fragment reads conflict free
+constexpr int STAGES = 3;
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool valid)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    int bytes = valid ? 8 : 0;    // src-size 0: nothing is read, the 8 destination bytes are zero-filled
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// Grouped, variable-size FP64 GEMM.  CTA = WARPS_M x WARPS_N warps, each warp owns WMT x WNT DMMA tiles (8x8).
+// One CTA computes one output tile and walks the K-segments of its work item (the terms of the sum over the MPO
+// bond index that land in this symmetry sector).  Operand tiles are staged in shared memory by a STAGES-deep
+// cp.async pipeline that runs across segment borders; alpha (Hermitian phase / conjugate correction) is applied
+// to the A fragments.
 template <int WARPS_M, int WARPS_N, int WMT, int WNT>
 __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32)
-k_gemm_dmma(const DWork* __restrict__ works, const DSeg* __restrict__ segs, BufTable bufs)
+k_gemm_dmma(const DWork* __restrict__ works, const DSeg* __restrict__ segs, const __grid_constant__ BufTable bufs)
 {
     constexpr int TM = WARPS_M * WMT * 8, TN = WARPS_N * WNT * 8, NT = WARPS_M * WARPS_N * 32;
     constexpr int LDA_S = TM + SPAD, LDB_S = TN + SPAD;
-    __shared__ double As[KC * LDA_S];
-    __shared__ double Bs[KC * LDB_S];
+    constexpr int A_STAGE = KC * LDA_S, B_STAGE = KC * LDB_S;
+    extern __shared__ double smem[];
+    double* As = smem;                          // [STAGES][KC][LDA_S]
+    double* Bs = smem + STAGES * A_STAGE;       // [STAGES][KC][LDB_S]
+    __shared__ double alpha_s[STAGES];
 
     const DWork w = works[blockIdx.x];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -105,61 +175,95 @@ k_gemm_dmma(const DWork* __restrict__ works, const DSeg* __restrict__ segs, BufT
 #pragma unroll
         for (int j = 0; j < WNT; ++j) acc[i][j][0] = acc[i][j][1] = 0.;
 
-    for (int s = w.seg_begin; s < w.seg_end; ++s) {
-        const DSeg sg = segs[s];
-        const int mrem = sg.m - w.m0, nrem = sg.n - w.n0;      // segments may be smaller than the output block
-        if (mrem <= 0 || nrem <= 0) continue;
-        const double* __restrict__ A = bufs.p[sg.a_buf] + sg.a_off;
-        const double* __restrict__ B = bufs.p[sg.b_buf] + sg.b_off;
-        for (int k0 = 0; k0 < sg.k; k0 += KC) {
-            const int krem = sg.k - k0;
-            // ---- stage op(A) tile as As[kk][mm] (alpha folded in) and op(B) tile as Bs[kk][nn]
-            if (!sg.ta) {
+    // producer cursor over the flattened (segment, k-chunk) sequence
+    int ps = w.seg_begin, pk0 = 0;
+    DSeg psg;
+    const double* __restrict__ pA = nullptr;
+    const double* __restrict__ pB = nullptr;
+    int pmrem = 0, pnrem = 0;
+    auto load_seg = [&]() {
+        while (ps < w.seg_end) {
+            psg = segs[ps];
+            pmrem = psg.m - w.m0; pnrem = psg.n - w.n0;
+            if (pmrem > 0 && pnrem > 0 && psg.k > 0) break;      // segments may be smaller than the output block
+            ++ps;
+        }
+        if (ps < w.seg_end) { pA = bufs.p[psg.a_buf] + psg.a_off; pB = bufs.p[psg.b_buf] + psg.b_off; pk0 = 0; }
+    };
+    load_seg();
+    auto issue = [&](int stage) {
+        if (ps < w.seg_end) {
+            double* as = As + stage * A_STAGE;
+            double* bs = Bs + stage * B_STAGE;
+            const int krem = psg.k - pk0;
+            if (!psg.ta) {
+#pragma unroll
                 for (int idx = tid; idx < TM * KC; idx += NT) {
                     int mm = idx % TM, kk = idx / TM;
-                    double v = 0.;
-                    if (mm < mrem && kk < krem) v = sg.alpha * A[(long long)(w.m0 + mm) + (long long)(k0 + kk) * sg.lda];
-                    As[kk * LDA_S + mm] = v;
+                    bool v = mm < pmrem && kk < krem;
+                    cp_async8(as + kk * LDA_S + mm, v ? pA + (long long)(w.m0 + mm) + (long long)(pk0 + kk) * psg.lda : pA, v);
                 }
             } else {
+#pragma unroll
                 for (int idx = tid; idx < TM * KC; idx += NT) {
                     int kk = idx % KC, mm = idx / KC;
-                    double v = 0.;
-                    if (mm < mrem && kk < krem) v = sg.alpha * A[(long long)(k0 + kk) + (long long)(w.m0 + mm) * sg.lda];
-                    As[kk * LDA_S + mm] = v;
+                    bool v = mm < pmrem && kk < krem;
+                    cp_async8(as + kk * LDA_S + mm, v ? pA + (long long)(pk0 + kk) + (long long)(w.m0 + mm) * psg.lda : pA, v);
                 }
             }
-            if (!sg.tb) {
+            if (!psg.tb) {
+#pragma unroll
                 for (int idx = tid; idx < TN * KC; idx += NT) {
                     int kk = idx % KC, nn = idx / KC;
-                    double v = 0.;
-                    if (nn < nrem && kk < krem) v = B[(long long)(k0 + kk) + (long long)(w.n0 + nn) * sg.ldb];
-                    Bs[kk * LDB_S + nn] = v;
+                    bool v = nn < pnrem && kk < krem;
+                    cp_async8(bs + kk * LDB_S + nn, v ? pB + (long long)(pk0 + kk) + (long long)(w.n0 + nn) * psg.ldb : pB, v);
                 }
             } else {
+#pragma unroll
                 for (int idx = tid; idx < TN * KC; idx += NT) {
                     int nn = idx % TN, kk = idx / TN;
-                    double v = 0.;
-                    if (nn < nrem && kk < krem) v = B[(long long)(w.n0 + nn) + (long long)(k0 + kk) * sg.ldb];
-                    Bs[kk * LDB_S + nn] = v;
+                    bool v = nn < pnrem && kk < krem;
+                    cp_async8(bs + kk * LDB_S + nn, v ? pB + (long long)(w.n0 + nn) + (long long)(pk0 + kk) * psg.ldb : pB, v);
                 }
             }
-            __syncthreads();
+            if (tid == 0) alpha_s[stage] = psg.alpha;
+            pk0 += KC;
+            if (pk0 >= psg.k) { ++ps; load_seg(); }
+        }
+        cp_async_commit();
+    };
+
+    // total number of chunks this work item will consume (same walk as the producer, without loading)
+    int nchunks = 0;
+    for (int s = w.seg_begin; s < w.seg_end; ++s) {
+        int m = segs[s].m, n = segs[s].n, k = segs[s].k;
+        if (m - w.m0 > 0 && n - w.n0 > 0 && k > 0) nchunks += (k + KC - 1) / KC;
+    }
+
 #pragma unroll
-            for (int k4 = 0; k4 < KC / 4; ++k4) {
-                double a[WMT], b[WNT];
+    for (int st = 0; st < STAGES - 1; ++st) issue(st);
+    for (int it = 0; it < nchunks; ++it) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        issue((it + STAGES - 1) % STAGES);      // refills the stage consumed in the previous iteration
+        const int stage = it % STAGES;
+        const double* as = As + stage * A_STAGE;
+        const double* bs = Bs + stage * B_STAGE;
+        const double alpha = alpha_s[stage];
 #pragma unroll
-                for (int i = 0; i < WMT; ++i) a[i] = As[(k4 * 4 + fk) * LDA_S + (wm * WMT + i) * 8 + fr];
+        for (int k4 = 0; k4 < KC / 4; ++k4) {
+            double a[WMT], b[WNT];
 #pragma unroll
-                for (int j = 0; j < WNT; ++j) b[j] = Bs[(k4 * 4 + fk) * LDB_S + (wn * WNT + j) * 8 + fr];
+            for (int i = 0; i < WMT; ++i) a[i] = alpha * as[(k4 * 4 + fk) * LDA_S + (wm * WMT + i) * 8 + fr];
 #pragma unroll
-                for (int i = 0; i < WMT; ++i)
+            for (int j = 0; j < WNT; ++j) b[j] = bs[(k4 * 4 + fk) * LDB_S + (wn * WNT + j) * 8 + fr];
 #pragma unroll
-                    for (int j = 0; j < WNT; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-            }
-            __syncthreads();
+            for (int i = 0; i < WMT; ++i)
+#pragma unroll
+                for (int j = 0; j < WNT; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
     }
+    cp_async_wait<0>();
     // ---- epilogue: C fragment (row = lane/4, cols = 2*(lane%4) + {0,1})
     double* __restrict__ C = bufs.p[w.c_buf] + w.c_off;
 #pragma unroll
@@ -243,7 +347,7 @@ struct GemmGroup
     std::vector<GemmLaunch> launches;
     int64_t n_works = 0;
 };
-struct AxpyGroup { DAxWork* d_works = nullptr; DAxSrc* d_srcs = nullptr; int64_t n_works = 0; };
+struct AxpyGroup { DWWork* d_works = nullptr; DWGroup* d_groups = nullptr; DWSrc* d_srcs = nullptr; DWDst* d_dsts = nullptr; double* d_coefs = nullptr; int64_t n_works = 0; };
 struct WaveDev { GemmGroup t, c; AxpyGroup w; int64_t y_elems = 0, t_elems = 0; };
 
 struct qcm_plan_s
@@ -286,6 +390,7 @@ static struct Global
     nccl_destroy_fn f_destroy = nullptr; nccl_errstr_fn f_err = nullptr;
 } G;
 
+static int gemm_set_attributes();
 static int ensure_ws(int slot, int64_t n)
 {
     if (n <= G.ws_elems[slot]) return 0;
@@ -317,6 +422,7 @@ extern "C" int qcm_init(int device)
     CU(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
     for (auto& ev : G.ev) CU(cudaEventCreate(&ev));
     CU(cudaMalloc((void**)&G.scratch, 4096));
+    if (gemm_set_attributes()) return 1;
     G.device = device;
     G.ready = true;
     return 0;
@@ -403,33 +509,43 @@ extern "C" int qcm_array_zero(qcm_array_t a)
 }
 
 // ---- plan construction ----------------------------------------------------------------------------------
-struct TileVariant { int tm, tn; double eff; };
+struct TileVariant { int tm, tn, threads; double eff; };
 static const TileVariant kVariants[] = {
-    {64, 64, 1.00},   // 0: 2x2 warps, 4x4 tiles
-    {32, 128, 1.00},  // 1: 1x4 warps, 4x4
-    {128, 32, 1.00},  // 2: 4x1 warps, 4x4
-    {16, 128, 0.70},  // 3: 1x4 warps, 2x4
-    {128, 16, 0.70},  // 4: 4x1 warps, 4x2
-    {32, 32, 0.55},   // 5: 2x2 warps, 2x2
-    {16, 16, 0.25},   // 6: 2x2 warps, 1x1
-    {8, 128, 0.40},   // 7: 1x4 warps, 1x4
-    {128, 8, 0.40},   // 8: 4x1 warps, 4x1
+    {64, 128, 256, 1.00},  // 0: 2x4 warps, 4x4 tiles
+    {128, 64, 256, 1.00},  // 1: 4x2 warps, 4x4
+    {64, 64, 128, 0.90},   // 2: 2x2 warps, 4x4
+    {32, 128, 128, 0.85},  // 3: 1x4 warps, 4x4
+    {128, 32, 128, 0.85},  // 4: 4x1 warps, 4x4
+    {16, 128, 128, 0.60},  // 5: 1x4 warps, 2x4
+    {128, 16, 128, 0.60},  // 6: 4x1 warps, 4x2
+    {32, 32, 128, 0.45},   // 7: 2x2 warps, 2x2
+    {16, 16, 128, 0.20},   // 8: 2x2 warps, 1x1
+    {8, 128, 128, 0.35},   // 9: 1x4 warps, 1x4
+    {128, 8, 128, 0.35},   // 10: 4x1 warps, 4x1
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
+static size_t variant_smem(int v) { return (size_t)STAGES * KC * (kVariants[v].tm + SPAD + kVariants[v].tn + SPAD) * sizeof(double); }
+
+#define QCM_FOR_EACH_VARIANT(X) \
+    X(0, 2, 4, 4, 4) X(1, 4, 2, 4, 4) X(2, 2, 2, 4, 4) X(3, 1, 4, 4, 4) X(4, 4, 1, 4, 4) X(5, 1, 4, 2, 4) X(6, 4, 1, 4, 2) \
+    X(7, 2, 2, 2, 2) X(8, 2, 2, 1, 1) X(9, 1, 4, 1, 4) X(10, 4, 1, 4, 1)
+
+static int gemm_set_attributes()
+{
+#define X(v, a, b, c, d) CU(cudaFuncSetAttribute(k_gemm_dmma<a, b, c, d>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)variant_smem(v)));
+    QCM_FOR_EACH_VARIANT(X)
+#undef X
+    return 0;
+}
 
 static void launch_gemm_variant(int v, int64_t n, const DWork* works, const DSeg* segs, BufTable const& bufs, cudaStream_t st)
 {
-    dim3 g((unsigned)n), b(128);
+    dim3 g((unsigned)n), b(kVariants[v].threads);
+    size_t sm = variant_smem(v);
     switch (v) {
-    case 0: k_gemm_dmma<2, 2, 4, 4><<<g, b, 0, st>>>(works, segs, bufs); break;
-    case 1: k_gemm_dmma<1, 4, 4, 4><<<g, b, 0, st>>>(works, segs, bufs); break;
-    case 2: k_gemm_dmma<4, 1, 4, 4><<<g, b, 0, st>>>(works, segs, bufs); break;
-    case 3: k_gemm_dmma<1, 4, 2, 4><<<g, b, 0, st>>>(works, segs, bufs); break;
-    case 4: k_gemm_dmma<4, 1, 4, 2><<<g, b, 0, st>>>(works, segs, bufs); break;
-    case 5: k_gemm_dmma<2, 2, 2, 2><<<g, b, 0, st>>>(works, segs, bufs); break;
-    case 6: k_gemm_dmma<2, 2, 1, 1><<<g, b, 0, st>>>(works, segs, bufs); break;
-    case 7: k_gemm_dmma<1, 4, 1, 4><<<g, b, 0, st>>>(works, segs, bufs); break;
-    case 8: k_gemm_dmma<4, 1, 4, 1><<<g, b, 0, st>>>(works, segs, bufs); break;
+#define X(vv, a, bb, c, d) case vv: k_gemm_dmma<a, bb, c, d><<<g, b, sm, st>>>(works, segs, bufs); break;
+    QCM_FOR_EACH_VARIANT(X)
+#undef X
     }
 }
 
@@ -504,21 +620,28 @@ static int build_gemm_group(qcm_plan_s* P, GemmGroup& g, const qcm_gemm_out* out
     return 0;
 }
 
-static int build_axpy_group(qcm_plan_s* P, AxpyGroup& g, const qcm_axpy_dst* dsts, int64_t n_dsts, const qcm_axpy_src* srcs, int64_t n_srcs)
+static int build_axpy_group(qcm_plan_s* P, AxpyGroup& g, qcm_wave_desc const& wd)
 {
-    std::vector<DAxSrc> hs((size_t)n_srcs);
-    for (int64_t i = 0; i < n_srcs; ++i) hs[i] = DAxSrc{srcs[i].src.off, srcs[i].src.buf, srcs[i].lds, srcs[i].coef};
-    std::vector<DAxWork> hw;
-    const int chunk = 4096;
-    for (int64_t i = 0; i < n_dsts; ++i) {
-        qcm_axpy_dst const& d = dsts[i];
-        int n = d.rows * d.cols;
-        for (int e0 = 0; e0 < n; e0 += chunk)
-            hw.push_back(DAxWork{d.dst.off, d.dst.buf, d.ldd, d.rows, d.cols, d.src_begin, d.src_end, e0, std::min(n, e0 + chunk)});
+    std::vector<DWSrc> hs((size_t)wd.n_w_srcs);
+    for (int64_t i = 0; i < wd.n_w_srcs; ++i) hs[i] = DWSrc{wd.w_srcs[i].src.off, wd.w_srcs[i].src.buf, wd.w_srcs[i].lds};
+    std::vector<DWDst> hd((size_t)wd.n_w_dsts);
+    for (int64_t i = 0; i < wd.n_w_dsts; ++i) hd[i] = DWDst{wd.w_dsts[i].dst.off, wd.w_dsts[i].dst.buf, wd.w_dsts[i].ldd};
+    std::vector<DWGroup> hg((size_t)wd.n_w_groups);
+    std::vector<DWWork> hw;
+    const int tiles_per_cta = W_WT * W_WARPS;
+    for (int64_t i = 0; i < wd.n_w_groups; ++i) {
+        qcm_w_group const& q = wd.w_groups[i];
+        if (q.ng != 8 && q.ng != 16) return fail("qcm_plan_create: W group with ng outside {8,16}");
+        if (q.n_dst > q.ng) return fail("qcm_plan_create: W group with more destinations than ng");
+        int tpc = (q.rows + 7) / 8;
+        hg[i] = DWGroup{q.rows, q.cols, q.n_src, q.n_dst, q.ng, q.src_begin, q.dst_begin, tpc, q.coef_begin};
+        int ntiles = tpc * q.cols;
+        for (int t0 = 0; t0 < ntiles; t0 += tiles_per_cta) hw.push_back(DWWork{(int)i, t0});
     }
+    std::vector<double> hc(wd.w_coefs, wd.w_coefs + wd.n_w_coefs);
     g.n_works = (int64_t)hw.size();
-    if (dev_upload(P, hw, &g.d_works)) return 1;
-    if (dev_upload(P, hs, &g.d_srcs)) return 1;
+    if (dev_upload(P, hw, &g.d_works) || dev_upload(P, hg, &g.d_groups) || dev_upload(P, hs, &g.d_srcs) || dev_upload(P, hd, &g.d_dsts) ||
+        dev_upload(P, hc, &g.d_coefs)) return 1;
     if (g.n_works) P->n_launches += 1;
     return 0;
 }
@@ -548,7 +671,7 @@ extern "C" int qcm_plan_create(const qcm_plan_desc* d, qcm_plan_t* out)
         WaveDev& W = P->waves[w];
         W.y_elems = wd.y_elems; W.t_elems = wd.t_elems;
         if (build_gemm_group(P, W.t, wd.t_outs, wd.n_t_outs, wd.t_segs, wd.n_t_segs, 0)) return bail();
-        if (build_axpy_group(P, W.w, wd.w_dsts, wd.n_w_dsts, wd.w_srcs, wd.n_w_srcs)) return bail();
+        if (build_axpy_group(P, W.w, wd)) return bail();
         if (build_gemm_group(P, W.c, wd.c_outs, wd.n_c_outs, wd.c_segs, wd.n_c_segs, 1)) return bail();
     }
     *out = P;
@@ -617,7 +740,7 @@ static int execute(qcm_plan_s* P, BufTable bufs)
         if (run_gemm_group(W.t, bufs)) return 1;
         mark(4); lap(1, 3, 4);
         if (W.y_elems) CU(cudaMemsetAsync(bufs.p[QCM_BUF_Y], 0, (size_t)W.y_elems * 8, G.stream));
-        if (W.w.n_works) { k_axpy_gather<<<(unsigned)W.w.n_works, 256, 0, G.stream>>>(W.w.d_works, W.w.d_srcs, bufs); G.launches++; }
+        if (W.w.n_works) { k_wapply_dmma<<<(unsigned)W.w.n_works, W_WARPS * 32, 0, G.stream>>>(W.w.d_works, W.w.d_groups, W.w.d_srcs, W.w.d_dsts, W.w.d_coefs, bufs); G.launches++; }
         mark(5); lap(2, 4, 5);
         if (run_gemm_group(W.c, bufs)) return 1;
         mark(6); lap(3, 5, 6);

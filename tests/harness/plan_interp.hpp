@@ -52,18 +52,20 @@ inline void run_plan(plan::Plan const& P, Bufs& B)
         std::fill(B.b[plan::BUF_T].begin(), B.b[plan::BUF_T].end(), std::nan(""));
         run_gemm(W.t_gemm, B, false);
         std::fill(B.b[plan::BUF_Y].begin(), B.b[plan::BUF_Y].begin() + W.y_elems, 0.);
-        for (auto const& d : W.w_apply.dsts) {
-            double* dst = B.p(d.dst);
-            for (int j = 0; j < d.cols; ++j)
-                for (int i = 0; i < d.rows; ++i) {
-                    double acc = 0.;
-                    for (int s = d.src_begin; s < d.src_end; ++s) {
-                        plan::AxpySrc const& q = W.w_apply.srcs[s];
-                        acc += q.coef * B.p(q.src)[i + (size_t)j * q.lds];
+        for (auto const& G : W.w_groups.groups)
+            for (int d = 0; d < G.n_dst; ++d) {
+                plan::WDst const& D = W.w_groups.dsts[G.dst_begin + d];
+                double* dst = B.p(D.dst);
+                for (int j = 0; j < G.cols; ++j)
+                    for (int i = 0; i < G.rows; ++i) {
+                        double acc = 0.;
+                        for (int u = 0; u < G.n_src; ++u) {
+                            plan::WSrc const& q = W.w_groups.srcs[G.src_begin + u];
+                            acc += W.w_groups.coefs[G.coef_begin + (size_t)u * G.ng + d] * B.p(q.src)[i + (size_t)j * q.lds];
+                        }
+                        dst[i + (size_t)j * D.ldd] = acc;
                     }
-                    dst[i + (size_t)j * d.ldd] = acc;
-                }
-        }
+            }
         run_gemm(W.close_gemm, B, true);
     }
 }
