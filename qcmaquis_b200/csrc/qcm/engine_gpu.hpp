@@ -48,7 +48,7 @@ struct CompiledPlan
 class GpuEngine : public EngineIface
 {
 public:
-    explicit GpuEngine(SymmKind s, int device = 0, int rank_ = 0, int world_ = 1, int64_t ws_budget_elems = (int64_t)1 << 29)
+    explicit GpuEngine(SymmKind s, int device = 0, int rank_ = 0, int world_ = 1, int64_t ws_budget_elems = (int64_t)1 << 31)
         : symm(s), rank(rank_), world(world_), budget(ws_budget_elems)
     {
         qcm_check(qcm_init(device), "qcm_init");

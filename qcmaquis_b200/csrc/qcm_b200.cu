@@ -46,7 +46,7 @@ struct DWork { long long c_off; int c_buf, ldc, m0, n0, m, n, seg_begin, seg_end
 struct DWSrc { long long off; int buf, lds; };
 struct DWDst { long long off; int buf, ldd; };
 struct DWGroup { int rows, cols, n_src, n_dst, ng, src_begin, dst_begin, tpc; long long coef_begin; };   // tpc = 8-row tiles per column
-struct DWWork { int group, tile0; };
+struct DWWork { int group, r8, c0, pad; };
 struct DCopy { long long src_off, dst_off; int src_buf, dst_buf, rows, cols, lds, ldd; };
 
 // --------------------------------------------------------------------------------------------------------
@@ -69,69 +69,87 @@ __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, doub
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// W application: one warp owns WT element tiles (8 consecutive rows of one panel column each) of a group and
-// streams over the group's source panels four at a time.  DMMA shape: M = 8 panel elements, K = 4 sources,
-// N = 8 destinations (two N tiles when the group has more than 8 destinations).  A fragments come straight from
-// global memory (every source element is needed exactly once per group), B fragments are the coefficients.
-constexpr int W_WT = 8;          // element tiles per warp
+// W application.  One WARP owns one work item: a strip of WT consecutive panel columns x 8 consecutive rows of a
+// group, and streams over the group's source panels four at a time.  DMMA shape: M = 8 panel rows, K = 4 sources,
+// N = 8 destinations (two N tiles in the WIDE variant for groups of 9..16 destinations).  A fragments come
+// straight from global memory (every source element is needed exactly once per group), B fragments are the
+// coefficients.  The loop is software pipelined: source descriptors are fetched two chunks ahead, source elements
+// one chunk ahead of the DMMAs that consume them.
 constexpr int W_WARPS = 4;
-__global__ void __launch_bounds__(W_WARPS * 32)
-k_wapply_dmma(const DWWork* __restrict__ works, const DWGroup* __restrict__ groups, const DWSrc* __restrict__ srcs,
+template <bool WIDE>
+__global__ void __launch_bounds__(W_WARPS * 32, 5)
+k_wapply_dmma(const DWWork* __restrict__ works, int n_works, const DWGroup* __restrict__ groups, const DWSrc* __restrict__ srcs,
               const DWDst* __restrict__ dsts, const double* __restrict__ coefs, const __grid_constant__ BufTable bufs)
 {
-    const DWWork w = works[blockIdx.x];
-    const DWGroup g = groups[w.group];
+    constexpr int WT = WIDE ? 4 : 8;
+    constexpr int NG = WIDE ? 16 : 8;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wi = blockIdx.x * W_WARPS + warp;
+    if (wi >= n_works) return;
+    const DWWork w = works[wi];
+    const DWGroup g = groups[w.group];
     const int fr = lane >> 2, fk = lane & 3;
-    const int ntiles = g.tpc * g.cols;
-    int eoff[W_WT];     // row + 32-bit column index packed: row in the low 12 bits would limit sizes, keep two arrays
-    int ecol[W_WT];
-    bool ok[W_WT];
-#pragma unroll
-    for (int i = 0; i < W_WT; ++i) {
-        int t = w.tile0 + warp * W_WT + i;
-        int c = t / g.tpc, r = (t - c * g.tpc) * 8 + fr;
-        ok[i] = (t < ntiles) && (r < g.rows);
-        eoff[i] = r; ecol[i] = c;
-    }
-    double acc[W_WT][2][2];
-#pragma unroll
-    for (int i = 0; i < W_WT; ++i) acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.;
-    const bool wide = g.ng == 16;
+    const int r = w.r8 * 8 + fr;
+    const bool rok = r < g.rows;
+    const int ncv = min(WT, g.cols - w.c0);
     const DWSrc* __restrict__ sp = srcs + g.src_begin;
-    const double* __restrict__ cp = coefs + g.coef_begin;
-    for (int u0 = 0; u0 < g.n_src; u0 += 4) {
+    const double* __restrict__ cp = coefs + g.coef_begin + fr;
+
+    double acc[WT][WIDE ? 2 : 1][2];
+#pragma unroll
+    for (int i = 0; i < WT; ++i)
+#pragma unroll
+        for (int j = 0; j < (WIDE ? 2 : 1); ++j) acc[i][j][0] = acc[i][j][1] = 0.;
+
+    // pipeline registers
+    const double* p_nn = nullptr; int lds_nn = 0;      // descriptor of chunk (cur + 2)
+    const double* p_n = nullptr; int lds_n = 0;        // descriptor of chunk (cur + 1)
+    double a_n[WT];                                     // elements of chunk (cur + 1)
+    double b_n[WIDE ? 2 : 1];
+    auto fetch_desc = [&](int u0, const double*& p, int& lds) {
         const int u = u0 + fk;
-        const bool uv = u < g.n_src;
-        const double* __restrict__ p = nullptr;
-        int lds = 0;
-        if (uv) { DWSrc q = sp[u]; p = bufs.p[q.buf] + q.off; lds = q.lds; }
-        const double b0 = cp[(long long)u * g.ng + fr];          // coefficient rows are padded to a multiple of 4 sources
-        const double b1 = wide ? cp[(long long)u * g.ng + 8 + fr] : 0.;
-        double a[W_WT];
+        p = nullptr; lds = 0;
+        if (u < g.n_src && rok) { DWSrc q = sp[u]; p = bufs.p[q.buf] + q.off + r + (long long)w.c0 * q.lds; lds = q.lds; }
+    };
+    auto fetch_elems = [&](int u0, const double* p, int lds, double (&a)[WT], double (&b)[WIDE ? 2 : 1]) {
 #pragma unroll
-        for (int i = 0; i < W_WT; ++i) a[i] = (uv && ok[i]) ? p[eoff[i] + (long long)ecol[i] * lds] : 0.;
+        for (int i = 0; i < WT; ++i) a[i] = (p != nullptr && i < ncv) ? p[(long long)i * lds] : 0.;
+        const int u = u0 + fk;                         // coefficient rows are padded to a multiple of 4 sources
+        b[0] = u0 < g.n_src ? cp[(long long)u * NG] : 0.;
+        if (WIDE) b[WIDE ? 1 : 0] = u0 < g.n_src ? cp[(long long)u * NG + 8] : 0.;
+    };
+    fetch_desc(0, p_n, lds_n);
+    fetch_desc(4, p_nn, lds_nn);
+    fetch_elems(0, p_n, lds_n, a_n, b_n);
+    for (int u0 = 0; u0 < g.n_src; u0 += 4) {
+        double a[WT], b[WIDE ? 2 : 1];
 #pragma unroll
-        for (int i = 0; i < W_WT; ++i) {
-            dmma8x8x4(acc[i][0][0], acc[i][0][1], a[i], b0);
-            if (wide) dmma8x8x4(acc[i][1][0], acc[i][1][1], a[i], b1);
+        for (int i = 0; i < WT; ++i) a[i] = a_n[i];
+        b[0] = b_n[0];
+        if (WIDE) b[WIDE ? 1 : 0] = b_n[WIDE ? 1 : 0];
+        p_n = p_nn; lds_n = lds_nn;
+        fetch_desc(u0 + 8, p_nn, lds_nn);
+        fetch_elems(u0 + 4, p_n, lds_n, a_n, b_n);
+#pragma unroll
+        for (int i = 0; i < WT; ++i) {
+            dmma8x8x4(acc[i][0][0], acc[i][0][1], a[i], b[0]);
+            if (WIDE) dmma8x8x4(acc[i][WIDE ? 1 : 0][0], acc[i][WIDE ? 1 : 0][1], a[i], b[WIDE ? 1 : 0]);
         }
     }
-    // C fragment: row = panel element (lane/4), cols = destinations 2*(lane%4) + {0,1} (+8 for the second N tile)
+    // C fragment: row = panel row (lane/4), cols = destinations 2*(lane%4) + {0,1} (+8 for the second N tile)
+    if (!rok) return;
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        if (j == 1 && !wide) break;
+    for (int j = 0; j < (WIDE ? 2 : 1); ++j)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            int d = j * 8 + 2 * fk + e;
+            const int d = j * 8 + 2 * fk + e;
             if (d >= g.n_dst) continue;
-            DWDst q = dsts[g.dst_begin + d];
-            double* __restrict__ o = bufs.p[q.buf] + q.off;
+            const DWDst q = dsts[g.dst_begin + d];
+            double* __restrict__ o = bufs.p[q.buf] + q.off + r + (long long)w.c0 * q.ldd;
 #pragma unroll
-            for (int i = 0; i < W_WT; ++i)
-                if (ok[i]) o[eoff[i] + (long long)ecol[i] * q.ldd] = acc[i][j][e];
+            for (int i = 0; i < WT; ++i)
+                if (i < ncv) o[(long long)i * q.ldd] = acc[i][j][e];
         }
-    }
 }
 
 constexpr int KC = 16;         // K chunk staged per pipeline stage
@@ -152,17 +170,23 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // bond index that land in this symmetry sector).  Operand tiles are staged in shared memory by a STAGES-deep
 // cp.async pipeline that runs across segment borders; alpha (Hermitian phase / conjugate correction) is applied
 // to the A fragments.
+constexpr int LDK = KC + 4;     // K-major rows: (KC + 4) % 16 == 4, conflict free as well
 template <int WARPS_M, int WARPS_N, int WMT, int WNT>
 __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32)
 k_gemm_dmma(const DWork* __restrict__ works, const DSeg* __restrict__ segs, const __grid_constant__ BufTable bufs)
 {
     constexpr int TM = WARPS_M * WMT * 8, TN = WARPS_N * WNT * 8, NT = WARPS_M * WARPS_N * 32;
     constexpr int LDA_S = TM + SPAD, LDB_S = TN + SPAD;
-    constexpr int A_STAGE = KC * LDA_S, B_STAGE = KC * LDB_S;
+    // a staged operand tile is stored in the orientation in which global memory is contiguous:
+    //   "M-major"  [kk][mm]  when the m (resp. n) index is contiguous in memory (A not transposed, B transposed)
+    //   "K-major"  [mm][kk]  when the k index is contiguous (A transposed, B not transposed)
+    constexpr int A_STAGE = (KC * LDA_S > TM * LDK) ? KC * LDA_S : TM * LDK;
+    constexpr int B_STAGE = (KC * LDB_S > TN * LDK) ? KC * LDB_S : TN * LDK;
     extern __shared__ double smem[];
-    double* As = smem;                          // [STAGES][KC][LDA_S]
-    double* Bs = smem + STAGES * A_STAGE;       // [STAGES][KC][LDB_S]
+    double* As = smem;                          // [STAGES][A_STAGE]
+    double* Bs = smem + STAGES * A_STAGE;       // [STAGES][B_STAGE]
     __shared__ double alpha_s[STAGES];
+    __shared__ int flags_s[STAGES];             // bit 0: A is K-major, bit 1: B is K-major
 
     const DWork w = works[blockIdx.x];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -177,66 +201,76 @@ k_gemm_dmma(const DWork* __restrict__ works, const DSeg* __restrict__ segs, cons
 
     // producer cursor over the flattened (segment, k-chunk) sequence
     int ps = w.seg_begin, pk0 = 0;
-    DSeg psg;
+    int p_lda = 0, p_ldb = 0, p_k = 0, p_ta = 0, p_tb = 0, pmrem = 0, pnrem = 0;
+    double p_alpha = 0.;
     const double* __restrict__ pA = nullptr;
     const double* __restrict__ pB = nullptr;
-    int pmrem = 0, pnrem = 0;
+    int nchunks = 0;
     auto load_seg = [&]() {
         while (ps < w.seg_end) {
-            psg = segs[ps];
-            pmrem = psg.m - w.m0; pnrem = psg.n - w.n0;
-            if (pmrem > 0 && pnrem > 0 && psg.k > 0) break;      // segments may be smaller than the output block
+            const DSeg sg = segs[ps];
+            pmrem = sg.m - w.m0; pnrem = sg.n - w.n0;
+            if (pmrem > 0 && pnrem > 0 && sg.k > 0) {          // segments may be smaller than the output block
+                p_lda = sg.lda; p_ldb = sg.ldb; p_k = sg.k; p_ta = sg.ta; p_tb = sg.tb; p_alpha = sg.alpha;
+                // tile origin folded into the base pointers
+                pA = bufs.p[sg.a_buf] + sg.a_off + (sg.ta ? (long long)w.m0 * sg.lda : (long long)w.m0);
+                pB = bufs.p[sg.b_buf] + sg.b_off + (sg.tb ? (long long)w.n0 : (long long)w.n0 * sg.ldb);
+                pk0 = 0;
+                return;
+            }
             ++ps;
         }
-        if (ps < w.seg_end) { pA = bufs.p[psg.a_buf] + psg.a_off; pB = bufs.p[psg.b_buf] + psg.b_off; pk0 = 0; }
     };
     load_seg();
     auto issue = [&](int stage) {
         if (ps < w.seg_end) {
             double* as = As + stage * A_STAGE;
             double* bs = Bs + stage * B_STAGE;
-            const int krem = psg.k - pk0;
-            if (!psg.ta) {
+            const int krem = p_k - pk0;
+            if (!p_ta) {
+                const double* __restrict__ base = pA + (long long)pk0 * p_lda;
 #pragma unroll
                 for (int idx = tid; idx < TM * KC; idx += NT) {
-                    int mm = idx % TM, kk = idx / TM;
-                    bool v = mm < pmrem && kk < krem;
-                    cp_async8(as + kk * LDA_S + mm, v ? pA + (long long)(w.m0 + mm) + (long long)(pk0 + kk) * psg.lda : pA, v);
+                    const int mm = idx % TM, kk = idx / TM;
+                    const bool v = mm < pmrem && kk < krem;
+                    cp_async8(as + kk * LDA_S + mm, v ? base + (mm + kk * p_lda) : pA, v);
                 }
             } else {
+                const double* __restrict__ base = pA + pk0;
 #pragma unroll
                 for (int idx = tid; idx < TM * KC; idx += NT) {
-                    int kk = idx % KC, mm = idx / KC;
-                    bool v = mm < pmrem && kk < krem;
-                    cp_async8(as + kk * LDA_S + mm, v ? pA + (long long)(pk0 + kk) + (long long)(w.m0 + mm) * psg.lda : pA, v);
+                    const int kk = idx % KC, mm = idx / KC;
+                    const bool v = mm < pmrem && kk < krem;
+                    cp_async8(as + mm * LDK + kk, v ? base + (kk + mm * p_lda) : pA, v);
                 }
             }
-            if (!psg.tb) {
+            if (!p_tb) {
+                const double* __restrict__ base = pB + pk0;
 #pragma unroll
                 for (int idx = tid; idx < TN * KC; idx += NT) {
-                    int kk = idx % KC, nn = idx / KC;
-                    bool v = nn < pnrem && kk < krem;
-                    cp_async8(bs + kk * LDB_S + nn, v ? pB + (long long)(pk0 + kk) + (long long)(w.n0 + nn) * psg.ldb : pB, v);
+                    const int kk = idx % KC, nn = idx / KC;
+                    const bool v = nn < pnrem && kk < krem;
+                    cp_async8(bs + nn * LDK + kk, v ? base + (kk + nn * p_ldb) : pB, v);
                 }
             } else {
+                const double* __restrict__ base = pB + (long long)pk0 * p_ldb;
 #pragma unroll
                 for (int idx = tid; idx < TN * KC; idx += NT) {
-                    int nn = idx % TN, kk = idx / TN;
-                    bool v = nn < pnrem && kk < krem;
-                    cp_async8(bs + kk * LDB_S + nn, v ? pB + (long long)(w.n0 + nn) + (long long)(pk0 + kk) * psg.ldb : pB, v);
+                    const int nn = idx % TN, kk = idx / TN;
+                    const bool v = nn < pnrem && kk < krem;
+                    cp_async8(bs + kk * LDB_S + nn, v ? base + (nn + kk * p_ldb) : pB, v);
                 }
             }
-            if (tid == 0) alpha_s[stage] = psg.alpha;
+            if (tid == 0) { alpha_s[stage] = p_alpha; flags_s[stage] = (p_ta ? 1 : 0) | (p_tb ? 0 : 2); }
             pk0 += KC;
-            if (pk0 >= psg.k) { ++ps; load_seg(); }
+            if (pk0 >= p_k) { ++ps; load_seg(); }
         }
         cp_async_commit();
     };
 
     // total number of chunks this work item will consume (same walk as the producer, without loading)
-    int nchunks = 0;
     for (int s = w.seg_begin; s < w.seg_end; ++s) {
-        int m = segs[s].m, n = segs[s].n, k = segs[s].k;
+        const int m = segs[s].m, n = segs[s].n, k = segs[s].k;
         if (m - w.m0 > 0 && n - w.n0 > 0 && k > 0) nchunks += (k + KC - 1) / KC;
     }
 
@@ -250,13 +284,19 @@ k_gemm_dmma(const DWork* __restrict__ works, const DSeg* __restrict__ segs, cons
         const double* as = As + stage * A_STAGE;
         const double* bs = Bs + stage * B_STAGE;
         const double alpha = alpha_s[stage];
+        const int fl = flags_s[stage];
+        // per-lane fragment base and strides for the two orientations
+        const int a_base = (fl & 1) ? (wm * WMT * 8 + fr) * LDK + fk : fk * LDA_S + wm * WMT * 8 + fr;
+        const int a_ti = (fl & 1) ? 8 * LDK : 8, a_tk = (fl & 1) ? 4 : 4 * LDA_S;
+        const int b_base = (fl & 2) ? (wn * WNT * 8 + fr) * LDK + fk : fk * LDB_S + wn * WNT * 8 + fr;
+        const int b_tj = (fl & 2) ? 8 * LDK : 8, b_tk = (fl & 2) ? 4 : 4 * LDB_S;
 #pragma unroll
         for (int k4 = 0; k4 < KC / 4; ++k4) {
             double a[WMT], b[WNT];
 #pragma unroll
-            for (int i = 0; i < WMT; ++i) a[i] = alpha * as[(k4 * 4 + fk) * LDA_S + (wm * WMT + i) * 8 + fr];
+            for (int i = 0; i < WMT; ++i) a[i] = alpha * as[a_base + i * a_ti + k4 * a_tk];
 #pragma unroll
-            for (int j = 0; j < WNT; ++j) b[j] = bs[(k4 * 4 + fk) * LDB_S + (wn * WNT + j) * 8 + fr];
+            for (int j = 0; j < WNT; ++j) b[j] = bs[b_base + j * b_tj + k4 * b_tk];
 #pragma unroll
             for (int i = 0; i < WMT; ++i)
 #pragma unroll
@@ -347,7 +387,7 @@ struct GemmGroup
     std::vector<GemmLaunch> launches;
     int64_t n_works = 0;
 };
-struct AxpyGroup { DWWork* d_works = nullptr; DWGroup* d_groups = nullptr; DWSrc* d_srcs = nullptr; DWDst* d_dsts = nullptr; double* d_coefs = nullptr; int64_t n_works = 0; };
+struct AxpyGroup { DWWork* d_works = nullptr; DWGroup* d_groups = nullptr; DWSrc* d_srcs = nullptr; DWDst* d_dsts = nullptr; double* d_coefs = nullptr; int64_t n_works = 0, n_narrow = 0; };
 struct WaveDev { GemmGroup t, c; AxpyGroup w; int64_t y_elems = 0, t_elems = 0; };
 
 struct qcm_plan_s
@@ -377,6 +417,9 @@ static struct Global
     int device = -1;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    static constexpr int kAux = 3;
+    cudaStream_t aux[kAux] = {nullptr, nullptr, nullptr};   // tile variants of one GEMM group run side by side
+    cudaEvent_t fork_ev = nullptr, join_ev[kAux] = {nullptr, nullptr, nullptr};
     int64_t launches = 0;
     double* ws[QCM_BUF_COUNT] = {nullptr};
     int64_t ws_elems[QCM_BUF_COUNT] = {0};
@@ -421,6 +464,8 @@ extern "C" int qcm_init(int device)
     G.sm_count = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
     for (auto& ev : G.ev) CU(cudaEventCreate(&ev));
+    for (int i = 0; i < Global::kAux; ++i) { CU(cudaStreamCreateWithFlags(&G.aux[i], cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&G.join_ev[i], cudaEventDisableTiming)); }
+    CU(cudaEventCreateWithFlags(&G.fork_ev, cudaEventDisableTiming));
     CU(cudaMalloc((void**)&G.scratch, 4096));
     if (gemm_set_attributes()) return 1;
     G.device = device;
@@ -436,6 +481,8 @@ extern "C" int qcm_finalize(void)
     if (G.scratch) cudaFree(G.scratch);
     G.scratch = nullptr;
     for (auto& ev : G.ev) cudaEventDestroy(ev);
+    for (int i = 0; i < Global::kAux; ++i) { cudaStreamDestroy(G.aux[i]); cudaEventDestroy(G.join_ev[i]); }
+    cudaEventDestroy(G.fork_ev);
     cudaStreamDestroy(G.stream);
     G.stream = nullptr; G.ready = false; G.device = -1;
     return 0;
@@ -524,7 +571,11 @@ static const TileVariant kVariants[] = {
     {128, 8, 128, 0.35},   // 10: 4x1 warps, 4x1
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
-static size_t variant_smem(int v) { return (size_t)STAGES * KC * (kVariants[v].tm + SPAD + kVariants[v].tn + SPAD) * sizeof(double); }
+static size_t variant_smem(int v)
+{
+    size_t a = std::max(KC * (kVariants[v].tm + SPAD), kVariants[v].tm * LDK), b = std::max(KC * (kVariants[v].tn + SPAD), kVariants[v].tn * LDK);
+    return (size_t)STAGES * (a + b) * sizeof(double);
+}
 
 #define QCM_FOR_EACH_VARIANT(X) \
     X(0, 2, 4, 4, 4) X(1, 4, 2, 4, 4) X(2, 2, 2, 4, 4) X(3, 1, 4, 4, 4) X(4, 4, 1, 4, 4) X(5, 1, 4, 2, 4) X(6, 4, 1, 4, 2) \
@@ -581,7 +632,7 @@ static int build_gemm_group(qcm_plan_s* P, GemmGroup& g, const qcm_gemm_out* out
         hs[i] = DSeg{s.A.off, s.B.off, s.A.buf, s.B.buf, s.lda, s.ldb, s.m, s.n, s.k, s.ta, s.tb, 0, s.alpha};
     }
     std::vector<std::vector<DWork>> per_variant(kNumVariants);
-    const double k_target = 4096.;   // sum of k per work item before a split
+    const int max_chunks = 96;       // K chunks (of KC) per work item before the segment list is split
     for (int64_t o = 0; o < n_outs; ++o) {
         qcm_gemm_out const& out = outs[o];
         if (out.m <= 0 || out.n <= 0) continue;
@@ -589,10 +640,10 @@ static int build_gemm_group(qcm_plan_s* P, GemmGroup& g, const qcm_gemm_out* out
         // chunk the segment list
         std::vector<std::pair<int, int>> chunks;
         {
-            double ksum = 0; int cb = out.seg_begin;
+            int csum = 0, cb = out.seg_begin;
             for (int s = out.seg_begin; s < out.seg_end; ++s) {
-                ksum += segs[s].k;
-                if (ksum >= k_target && s + 1 < out.seg_end) { chunks.push_back(std::make_pair(cb, s + 1)); cb = s + 1; ksum = 0; }
+                csum += (segs[s].k + KC - 1) / KC;
+                if (csum >= max_chunks && s + 1 < out.seg_end) { chunks.push_back(std::make_pair(cb, s + 1)); cb = s + 1; csum = 0; }
             }
             chunks.push_back(std::make_pair(cb, out.seg_end));
         }
@@ -627,22 +678,26 @@ static int build_axpy_group(qcm_plan_s* P, AxpyGroup& g, qcm_wave_desc const& wd
     std::vector<DWDst> hd((size_t)wd.n_w_dsts);
     for (int64_t i = 0; i < wd.n_w_dsts; ++i) hd[i] = DWDst{wd.w_dsts[i].dst.off, wd.w_dsts[i].dst.buf, wd.w_dsts[i].ldd};
     std::vector<DWGroup> hg((size_t)wd.n_w_groups);
-    std::vector<DWWork> hw;
-    const int tiles_per_cta = W_WT * W_WARPS;
+    std::vector<DWWork> hw, hw_wide;      // one work item per warp: 8 rows x WT columns of the group's panels
     for (int64_t i = 0; i < wd.n_w_groups; ++i) {
         qcm_w_group const& q = wd.w_groups[i];
         if (q.ng != 8 && q.ng != 16) return fail("qcm_plan_create: W group with ng outside {8,16}");
         if (q.n_dst > q.ng) return fail("qcm_plan_create: W group with more destinations than ng");
         int tpc = (q.rows + 7) / 8;
         hg[i] = DWGroup{q.rows, q.cols, q.n_src, q.n_dst, q.ng, q.src_begin, q.dst_begin, tpc, q.coef_begin};
-        int ntiles = tpc * q.cols;
-        for (int t0 = 0; t0 < ntiles; t0 += tiles_per_cta) hw.push_back(DWWork{(int)i, t0});
+        const int wt = q.ng == 16 ? 4 : 8;
+        std::vector<DWWork>& dstv = q.ng == 16 ? hw_wide : hw;
+        for (int c0 = 0; c0 < q.cols; c0 += wt)
+            for (int r8 = 0; r8 < tpc; ++r8) dstv.push_back(DWWork{(int)i, r8, c0, 0});
     }
+    g.n_narrow = (int64_t)hw.size();
+    hw.insert(hw.end(), hw_wide.begin(), hw_wide.end());
     std::vector<double> hc(wd.w_coefs, wd.w_coefs + wd.n_w_coefs);
     g.n_works = (int64_t)hw.size();
     if (dev_upload(P, hw, &g.d_works) || dev_upload(P, hg, &g.d_groups) || dev_upload(P, hs, &g.d_srcs) || dev_upload(P, hd, &g.d_dsts) ||
         dev_upload(P, hc, &g.d_coefs)) return 1;
-    if (g.n_works) P->n_launches += 1;
+    if (g.n_narrow) P->n_launches += 1;
+    if (g.n_works > g.n_narrow) P->n_launches += 1;
     return 0;
 }
 
@@ -704,10 +759,25 @@ extern "C" int qcm_plan_stats(qcm_plan_t P, double* flops, int64_t* bytes, int64
 // ---- execution ------------------------------------------------------------------------------------------
 static int run_gemm_group(GemmGroup const& g, BufTable const& bufs)
 {
-    for (auto const& l : g.launches) {
-        launch_gemm_variant(l.variant, l.n_works, g.d_works + l.work_begin, g.d_segs, bufs, G.stream);
-        G.launches++;
+    if (g.launches.empty()) return 0;
+    // the variants of one group write disjoint output tiles (or combine with atomics): they may overlap, which
+    // hides the tails of the small-tile launches behind the large ones
+    const bool fork = g.launches.size() > 1;
+    if (fork) {
+        CU(cudaEventRecord(G.fork_ev, G.stream));
+        for (int i = 0; i < Global::kAux; ++i) CU(cudaStreamWaitEvent(G.aux[i], G.fork_ev, 0));
     }
+    int li = 0;
+    bool used[Global::kAux] = {false, false, false};
+    for (auto const& l : g.launches) {
+        cudaStream_t st = G.stream;
+        if (fork && li > 0) { int a = (li - 1) % Global::kAux; st = G.aux[a]; used[a] = true; }
+        launch_gemm_variant(l.variant, l.n_works, g.d_works + l.work_begin, g.d_segs, bufs, st);
+        G.launches++; ++li;
+    }
+    if (fork)
+        for (int i = 0; i < Global::kAux; ++i)
+            if (used[i]) { CU(cudaEventRecord(G.join_ev[i], G.aux[i])); CU(cudaStreamWaitEvent(G.stream, G.join_ev[i], 0)); }
     CU(cudaGetLastError());
     return 0;
 }
@@ -740,7 +810,15 @@ static int execute(qcm_plan_s* P, BufTable bufs)
         if (run_gemm_group(W.t, bufs)) return 1;
         mark(4); lap(1, 3, 4);
         if (W.y_elems) CU(cudaMemsetAsync(bufs.p[QCM_BUF_Y], 0, (size_t)W.y_elems * 8, G.stream));
-        if (W.w.n_works) { k_wapply_dmma<<<(unsigned)W.w.n_works, W_WARPS * 32, 0, G.stream>>>(W.w.d_works, W.w.d_groups, W.w.d_srcs, W.w.d_dsts, W.w.d_coefs, bufs); G.launches++; }
+        if (W.w.n_narrow) {
+            k_wapply_dmma<false><<<(unsigned)((W.w.n_narrow + W_WARPS - 1) / W_WARPS), W_WARPS * 32, 0, G.stream>>>(W.w.d_works, (int)W.w.n_narrow, W.w.d_groups, W.w.d_srcs, W.w.d_dsts, W.w.d_coefs, bufs);
+            G.launches++;
+        }
+        if (W.w.n_works > W.w.n_narrow) {
+            int64_t nw = W.w.n_works - W.w.n_narrow;
+            k_wapply_dmma<true><<<(unsigned)((nw + W_WARPS - 1) / W_WARPS), W_WARPS * 32, 0, G.stream>>>(W.w.d_works + W.w.n_narrow, (int)nw, W.w.d_groups, W.w.d_srcs, W.w.d_dsts, W.w.d_coefs, bufs);
+            G.launches++;
+        }
         mark(5); lap(2, 4, 5);
         if (run_gemm_group(W.c, bufs)) return 1;
         mark(6); lap(3, 5, 6);
