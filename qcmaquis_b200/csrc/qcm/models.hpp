@@ -19,7 +19,7 @@ struct ModelParams
     int L = 0;
     std::vector<int> site_types;        // irrep per orbital (all 0 without point group)
     std::vector<Integral> integrals;    // 1-based indices, FCIDUMP convention (0 = absent index)
-    double integral_cutoff = 1e-300;
+    double integral_cutoff = 0.;      // DmrgParameters.h:116
     int nelec = 0, spin = 0, irrep = 0; // SU2 groups
     int nup = 0, ndown = 0;             // TwoU1 groups (u1_total_charge1/2)
 };

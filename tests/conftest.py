@@ -1,0 +1,68 @@
+"""Shared fixtures.  CPU tests (`-m "not gpu"`) use the oracle, the host logic and the plan interpreter; GPU tests
+(`-m gpu`) go through the C ABI of include/qcm_b200.h and compare with the oracle on the same seeded inputs."""
+import ctypes, os, sys
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); runs through the C ABI library")
+
+
+def golden(name):
+    return os.path.join(GOLDEN, name).encode()
+
+
+class Harness:
+    """ctypes view of tests/harness/libqcm_harness*.so (oracle + engine under test)."""
+
+    def __init__(self, lib):
+        self.lib = lib
+        lib.qcmt_wigner9j.restype = ctypes.c_double
+        lib.qcmt_wigner6j.restype = ctypes.c_double
+
+    def chain_parity(self, f, symm, L, ne, M, seed=42, engine=0, world=1, budget=1 << 28):
+        out = (ctypes.c_double * 16)(); err = ctypes.create_string_buffer(1024)
+        rc = self.lib.qcmt_chain_parity(golden(f), symm.encode(), L, ne, M, seed, engine, world, ctypes.c_longlong(budget), out, 16, err, 1024)
+        assert rc == 0, err.value.decode()
+        return list(out)
+
+    def synth_parity(self, f, symm, L, ne, site, twosite, M, seed=1, engine=0, world=1, budget=1 << 28):
+        out = (ctypes.c_double * 16)(); err = ctypes.create_string_buffer(1024)
+        rc = self.lib.qcmt_synth_parity(golden(f), symm.encode(), L, ne, site, int(twosite), M, seed, engine, world, ctypes.c_longlong(budget), out, 16, err, 1024)
+        assert rc == 0, err.value.decode()
+        return list(out)
+
+    def exact_energy(self, f, symm, L, ne, engine):
+        e, a = ctypes.c_double(), ctypes.c_double(); err = ctypes.create_string_buffer(1024)
+        rc = self.lib.qcmt_exact_energy(golden(f), symm.encode(), L, ne, engine, ctypes.byref(e), ctypes.byref(a), err, 1024)
+        assert rc == 0, err.value.decode()
+        return e.value, a.value
+
+    def mpo_dims(self, f, symm, L, ne):
+        dims, pairs = (ctypes.c_int * L)(), (ctypes.c_int * L)(); core = ctypes.c_double(); n = ctypes.c_int(); err = ctypes.create_string_buffer(1024)
+        assert self.lib.qcmt_mpo_dims(golden(f), symm.encode(), L, ne, dims, pairs, ctypes.byref(core), err, 1024) == 0, err.value.decode()
+        assert self.lib.qcmt_num_terms(golden(f), symm.encode(), L, ne, ctypes.byref(n), err, 1024) == 0, err.value.decode()
+        return list(dims), list(pairs), n.value, core.value
+
+
+@pytest.fixture(scope="session")
+def built():
+    from qcmaquis_b200 import build
+    return build.build_all()
+
+
+@pytest.fixture(scope="session")
+def harness_cpu(built):
+    return Harness(ctypes.CDLL(built["harness"][0]))
+
+
+@pytest.fixture(scope="session")
+def harness_gpu(built):
+    h = Harness(ctypes.CDLL(built["harness"][1]))
+    if h.lib.qcmt_gpu_available() < 1:
+        pytest.fail("a test marked gpu ran without a CUDA device: the hot path has no CPU fallback")
+    return h

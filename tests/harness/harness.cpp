@@ -162,3 +162,95 @@ extern "C" int qcmt_exact_energy(const char* fcidump, const char* symm, int L, i
         return 0;
     } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
 }
+
+// "The hamiltonian will contain N terms" (models/chem/*/model.hpp) -- a golden of the term makers
+extern "C" int qcmt_num_terms(const char* fcidump, const char* symm, int L, int nelec, int* nterms, char* err, int errlen)
+{
+    try {
+        Problem P = make_problem(fcidump, symm, L, nelec);
+        *nterms = (int)P.model->terms.size();
+        return 0;
+    } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
+}
+
+// Racah-sum restatement of gsl_sf_coupling_9j (arguments are 2*j), pinned by dmrg/tests/test_wigner.cpp:21-46
+extern "C" double qcmt_wigner9j(int a, int b, int c, int d, int e, int f, int g, int h, int i) { return su2::wigner9j(a, b, c, d, e, f, g, h, i); }
+extern "C" double qcmt_wigner6j(int a, int b, int c, int d, int e, int f) { return su2::wigner6j(a, b, c, d, e, f); }
+
+// Synthetic mid-chain site problem (the generator behind bench.py) through the oracle and an engine under test.
+// out[0] sigma structure equal  out[1] sigma rel diff  out[2] n sigma elements  out[3] <psi|sigma> oracle
+// single-site problems additionally: out[4]/out[5] left-step structure/rel diff, out[6]/out[7] right step
+// out[8] plan flops  out[9] waves
+extern "C" int qcmt_synth_parity(const char* fcidump, const char* symm, int L, int nelec, int site, int twosite, int M, unsigned seed, int engine_kind,
+                                 int world, long long budget, double* out, int nout, char* err, int errlen)
+{
+    try {
+        for (int i = 0; i < nout; ++i) out[i] = 0;
+        Problem P = make_problem(fcidump, symm, L, nelec);
+        SyntheticSite S = make_synthetic_site(P, site, twosite != 0, (size_t)M, seed);
+        oracle::OracleEngine orc(P.params.symm);
+        std::unique_ptr<EngineIface> eng;
+        qcmtest::InterpEngine* interp = nullptr;
+        if (engine_kind == 0) { interp = new qcmtest::InterpEngine(P.params.symm, world, budget); eng.reset(interp); }
+        else {
+#ifdef QCMT_WITH_GPU
+            eng.reset(new GpuEngine(P.params.symm, 0, 0, 1, budget));
+#else
+            throw std::runtime_error("harness built without GPU support");
+#endif
+        }
+        MPSTensor so = orc.site_hamil2(S.psi, S.left, S.right, *S.mpo);
+        MPSTensor se = eng->site_hamil2(S.psi, S.left, S.right, *S.mpo);
+        DiffReport d = compare(se.data(), so.data());
+        out[0] = d.structure_equal; out[1] = rel_diff(d); out[2] = (double)so.data().num_elements(); out[3] = so.scalar_overlap(S.psi);
+        if (interp) { out[8] = interp->last_flops; out[9] = (double)interp->last_waves; }
+#ifdef QCMT_WITH_GPU
+        if (engine_kind == 1) { out[8] = static_cast<GpuEngine*>(eng.get())->last_plan()->flops; out[9] = (double)static_cast<GpuEngine*>(eng.get())->last_plan()->n_waves; }
+#endif
+        if (!twosite) {
+            Boundary lo = orc.overlap_mpo_left_step(S.psi, S.psi, S.left, *S.mpo), le = eng->overlap_mpo_left_step(S.psi, S.psi, S.left, *S.mpo);
+            Boundary ro = orc.overlap_mpo_right_step(S.psi, S.psi, S.right, *S.mpo), re = eng->overlap_mpo_right_step(S.psi, S.psi, S.right, *S.mpo);
+#ifdef QCMT_WITH_GPU
+            if (engine_kind == 1) { static_cast<GpuEngine*>(eng.get())->download(le); static_cast<GpuEngine*>(eng.get())->download(re); }
+#endif
+            DiffReport a = compare(le, lo), b = compare(re, ro);
+            out[4] = a.structure_equal; out[5] = rel_diff(a); out[6] = b.structure_equal; out[7] = rel_diff(b);
+        }
+        return 0;
+    } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
+}
+
+// One rank's share of a sharded sigma (plan interpreter; what one GPU computes before the allreduce) and the
+// oracle's full sigma, both as flat left-paired block buffers.  Used by the world_size-2 gloo test.
+// mode 0: number of sigma elements -> *n_out;  mode 1: rank share -> buf;  mode 2: oracle -> buf
+extern "C" int qcmt_rank_sigma(const char* fcidump, const char* symm, int L, int nelec, int site, int twosite, int M, unsigned seed, int rank, int world,
+                               int mode, double* buf, long long* n_out, char* err, int errlen)
+{
+    try {
+        Problem P = make_problem(fcidump, symm, L, nelec);
+        SyntheticSite S = make_synthetic_site(P, site, twosite != 0, (size_t)M, seed);
+        S.psi.make_left_paired();
+        if (mode == 2) {
+            oracle::OracleEngine orc(P.params.symm);
+            MPSTensor so = orc.site_hamil2(S.psi, S.left, S.right, *S.mpo);
+            so.make_left_paired();
+            size_t o = 0;
+            for (size_t k = 0; k < so.data().n_blocks(); ++k) { auto const& v = so.data()[k].v; std::memcpy(buf + o, v.data(), v.size() * 8); o += v.size(); }
+            *n_out = (long long)o;
+            return 0;
+        }
+        plan::BoundaryLayout ll = qcmtest::InterpEngine::layout_of(S.left), rl = qcmtest::InterpEngine::layout_of(S.right);
+        plan::Planner pl(P.params.symm, *S.mpo, true, rank, world, (int64_t)1 << 28);
+        if (mode == 0) pl.structure_only = true;
+        plan::Plan pp = pl.plan_sigma(qcmtest::InterpEngine::desc_of(S.psi), ll, rl);
+        *n_out = pp.out_tensor.total;
+        if (mode == 0) return 0;
+        qcmtest::Bufs B;
+        B.b[plan::BUF_KET_LP] = qcmtest::InterpEngine::flat(S.psi.data()); B.b[plan::BUF_LEFT] = qcmtest::InterpEngine::flat(S.left);
+        B.b[plan::BUF_RIGHT] = qcmtest::InterpEngine::flat(S.right);
+        B.b[plan::BUF_OUT].assign((size_t)pp.out_tensor.total, 0.);
+        qcmtest::run_plan(pp, B);
+        std::memcpy(buf, B.b[plan::BUF_OUT].data(), (size_t)pp.out_tensor.total * 8);
+        return 0;
+    } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
+}

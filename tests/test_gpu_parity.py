@@ -1,0 +1,189 @@
+"""Parity tests proper: the B200 path (qcm::GpuEngine -> C ABI of include/qcm_b200.h -> sm_100a kernels) against the
+CPU oracle on the same seeded inputs.  Bar (BASELINE.json north_star): symmetry block structure and quantum-number
+indexing bit-exact, sigma vectors and boundaries within 1e-10 relative, energies within 1e-8 Eh."""
+import ctypes, json, os, tempfile
+import pytest
+import torch
+from conftest import GOLDEN, ROOT
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10       # north_star: "sigma vectors within 1e-10 relative"
+E_TOL = 1e-8      # north_star: "energies ... within 1e-8 Eh"
+REF = json.load(open(os.path.join(GOLDEN, "reference_values.json")))
+GPU = 1
+
+
+@pytest.fixture(scope="module")
+def fcidump_8o8e():
+    from qcmaquis_b200.fcidump import make_fcidump
+    path = os.path.join(tempfile.mkdtemp(prefix="qcm_test_"), "synth_8o8e.fcidump")
+    make_fcidump(path, 8, 8)
+    return path
+
+
+@pytest.mark.parametrize("f,L,ne", [("synth_4o4e.fcidump", 4, 4), ("synth_6o6e.fcidump", 6, 6), ("lih_4o.fcidump", 4, 2), ("benzene_6o.fcidump", 6, 6)])
+@pytest.mark.parametrize("symm", ["2u1", "su2u1", "2u1pg", "su2u1pg"])
+def test_chain_parity(harness_gpu, f, L, ne, symm):
+    out = harness_gpu.chain_parity(f, symm, L, ne, 20, engine=GPU)
+    assert out[0] == 2 * (L + 1) and out[3] == L and out[6] == L - 1
+    assert out[1] == 1 and out[4] == 1 and out[7] == 1, "block structure differs from the oracle"
+    assert out[2] < TOL and out[5] < TOL and out[8] < TOL, out[:9]
+    assert abs(out[10] - out[11]) < E_TOL
+    assert out[9] < E_TOL            # <psi|sigma> == boundary-chain energy (test_siteproblem.cpp:38-95)
+
+
+@pytest.mark.parametrize("symm", ["2u1", "su2u1"])
+def test_waves_under_a_small_workspace_budget(harness_gpu, symm):
+    out = harness_gpu.chain_parity("synth_6o6e.fcidump", symm, 6, 6, 20, engine=GPU, budget=300)
+    assert out[1] == 1 and out[4] == 1 and out[7] == 1
+    assert out[2] < TOL and out[5] < TOL and out[8] < TOL, out[:9]
+
+
+@pytest.mark.parametrize("M", [1, 3, 7])
+@pytest.mark.parametrize("symm", ["2u1", "su2u1"])
+def test_ragged_and_degenerate_blocks(harness_gpu, symm, M):
+    out = harness_gpu.chain_parity("synth_6o6e.fcidump", symm, 6, 6, M, seed=5, engine=GPU)
+    assert out[1] == 1 and out[4] == 1 and out[7] == 1
+    assert out[2] < TOL and out[5] < TOL and out[8] < TOL, out[:9]
+
+
+@pytest.mark.parametrize("symm", ["su2u1pg", "su2u1", "2u1pg", "2u1"])
+def test_h2_energy(harness_gpu, symm):
+    e, asym = harness_gpu.exact_energy("h2_2o.fcidump", symm, 2, 2, GPU)       # dmrg/tests/test1.cpp:93
+    assert e == pytest.approx(REF["energies"]["h2_2o"]["value"], abs=E_TOL)
+
+
+@pytest.mark.parametrize("symm", ["su2u1", "2u1"])
+def test_lih_energy(harness_gpu, symm):
+    e, asym = harness_gpu.exact_energy("lih_4o.fcidump", symm, 4, 2, GPU)      # LiHFixture.h:112
+    assert e == pytest.approx(REF["energies"]["lih_4o"]["value"], abs=E_TOL)
+    assert asym < 1e-9
+
+
+def test_h2_4o_energy(harness_gpu):
+    e, _ = harness_gpu.exact_energy("h2_4o.fcidump", "su2u1pg", 4, 2, GPU)     # H2_2e4o.TI.SS.out:70
+    assert e == pytest.approx(REF["energies"]["h2_4o"]["value"], abs=E_TOL)
+
+
+@pytest.mark.parametrize("symm", ["su2u1", "2u1"])
+@pytest.mark.parametrize("site,twosite", [(3, True), (0, True), (6, True), (4, False), (1, False)])
+def test_config1_sized_site_problems(harness_gpu, fcidump_8o8e, symm, site, twosite):
+    # BASELINE.json configs[0]: 8e/8o, M = 256 (sigma two-site; single-site problems also run both boundary steps)
+    out = harness_gpu.synth_parity(fcidump_8o8e, symm, 8, 8, site, twosite, 256, engine=GPU)
+    assert out[0] == 1 and out[1] < TOL and out[2] > 0, out[:4]
+    if not twosite:
+        assert out[4] == 1 and out[6] == 1 and out[5] < TOL and out[7] < TOL, out[4:8]
+
+
+@pytest.mark.parametrize("symm,M", [("su2u1", 400), ("2u1", 600)])
+def test_mid_sized_blocks_use_every_tile_variant(harness_gpu, symm, M):
+    # 12 orbitals: sector sizes from 1 to > 128, several K-segments per output block, split-K with atomics
+    from qcmaquis_b200.fcidump import make_fcidump
+    path = os.path.join(tempfile.mkdtemp(prefix="qcm_test_"), "synth_12o12e.fcidump")
+    make_fcidump(path, 12, 12)
+    out = harness_gpu.synth_parity(path, symm, 12, 12, 5, True, M, engine=GPU)
+    assert out[0] == 1 and out[1] < TOL, out[:4]
+    out = harness_gpu.synth_parity(path, symm, 12, 12, 6, False, M, engine=GPU)
+    assert out[0] == 1 and out[1] < TOL and out[4] == 1 and out[6] == 1 and out[5] < TOL and out[7] < TOL, out[:8]
+
+
+class Driver:
+    """qcmaquis_b200/lib/libqcm_host.so: the host driver bench.py uses (plan once, sigma per eigensolver iteration)."""
+
+    def __init__(self, built, norb, nelec, symm, M, site, seed=1):
+        from qcmaquis_b200.fcidump import make_fcidump
+        self.cu = ctypes.CDLL(built["cuda"], mode=ctypes.RTLD_GLOBAL)
+        self.cu.qcm_last_error.restype = ctypes.c_char_p
+        self.host = ctypes.CDLL(built["host"])
+        self.host.qcmd_create.restype = ctypes.c_void_p
+        assert self.cu.qcm_init(0) == 0, self.cu.qcm_last_error()
+        self.path = os.path.join(tempfile.mkdtemp(prefix="qcm_test_"), "s.fcidump")
+        make_fcidump(self.path, norb, nelec)
+        self.err = ctypes.create_string_buffer(1024)
+        h = self.host.qcmd_create(self.path.encode(), symm.encode(), norb, nelec, self.err, 1024)
+        assert h, self.err.value
+        self.h = ctypes.c_void_p(h)
+        self.info = (ctypes.c_double * 32)()
+        assert self.host.qcmd_setup_site(self.h, site, 1, M, seed, 0, 0, 1, self.info, self.err, 1024) == 0, self.err.value
+        self.n_psi, self.n_sigma = int(self.info[5]), int(self.info[6])
+
+    def sigma(self, x):
+        y = torch.empty(self.n_sigma, dtype=torch.float64)
+        assert self.host.qcmd_sigma_host(self.h, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(y.data_ptr()), self.err, 1024) == 0, self.err.value
+        return y
+
+    def sigma_dev(self):
+        assert self.host.qcmd_sigma_dev(self.h, 1, self.err, 1024) == 0, self.err.value
+        y = torch.empty(self.n_sigma, dtype=torch.float64)
+        assert self.host.qcmd_get_sigma_dev(self.h, ctypes.c_void_p(y.data_ptr())) == 0
+        return y
+
+    def psi(self):
+        x = torch.empty(self.n_psi, dtype=torch.float64)
+        self.host.qcmd_get_psi(self.h, ctypes.c_void_p(x.data_ptr()))
+        return x
+
+
+@pytest.fixture(scope="module")
+def driver_cfg2(built):
+    return Driver(built, 26, 10, "su2u1", 1000, 12)      # BASELINE.json configs[1]
+
+
+def test_full_size_linearity(driver_cfg2):
+    # size-independent property at BASELINE's full size: sigma is linear in psi
+    d = driver_cfg2
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(d.n_psi, dtype=torch.float64, generator=g); y = torch.randn(d.n_psi, dtype=torch.float64, generator=g)
+    hx, hy, hz = d.sigma(x), d.sigma(y), d.sigma(0.75 * x - 1.5 * y)
+    ref = 0.75 * hx - 1.5 * hy
+    assert float((hz - ref).norm() / ref.norm()) < 1e-12
+    assert float(d.sigma(torch.zeros(d.n_psi, dtype=torch.float64)).abs().max()) == 0.0
+
+
+def test_full_size_host_and_device_paths_agree(driver_cfg2):
+    d = driver_cfg2
+    a, b = d.sigma(d.psi()), d.sigma_dev()
+    assert float((a - b).norm() / a.norm()) < 1e-13
+
+
+def test_full_size_against_the_oracle(built, driver_cfg2):
+    d = driver_cfg2
+    olib = ctypes.CDLL(built["oracle"])
+    olib.orc_create.restype = ctypes.c_void_p
+    err = ctypes.create_string_buffer(1024)
+    oh = ctypes.c_void_p(olib.orc_create(d.path.encode(), b"su2u1", 26, 10, err, 1024))
+    assert oh.value, err.value
+    pe, sec, ov, se = ctypes.c_double(), ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+    assert olib.orc_setup_site(oh, 12, 1, 1000, 1, ctypes.byref(pe), err, 1024) == 0, err.value
+    assert olib.orc_sigma(oh, 1, ctypes.byref(sec), ctypes.byref(ov), ctypes.byref(se), err, 1024) == 0, err.value
+    assert int(se.value) == d.n_sigma, "sigma block structure differs from the oracle"
+    ref = torch.empty(d.n_sigma, dtype=torch.float64)
+    olib.orc_get_sigma(oh, ctypes.c_void_p(ref.data_ptr()))
+    got = d.sigma(d.psi())
+    assert float((got - ref).norm() / ref.norm()) < TOL
+    olib.orc_destroy(oh)
+
+
+def test_vector_algebra(built):
+    # solver-side BLAS-1 on device arrays (mpstensor.hpp:346-395,458-522)
+    cu = ctypes.CDLL(built["cuda"])
+    cu.qcm_last_error.restype = ctypes.c_char_p
+    assert cu.qcm_init(0) == 0, cu.qcm_last_error()
+    n = 1_000_003
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(n, dtype=torch.float64, generator=g); y = torch.randn(n, dtype=torch.float64, generator=g)
+    ax, ay = ctypes.c_void_p(), ctypes.c_void_p()
+    assert cu.qcm_array_alloc(ctypes.c_int64(n), ctypes.byref(ax)) == 0 and cu.qcm_array_alloc(ctypes.c_int64(n), ctypes.byref(ay)) == 0
+    cu.qcm_array_upload(ax, ctypes.c_int64(0), ctypes.c_void_p(x.data_ptr()), ctypes.c_int64(n))
+    cu.qcm_array_upload(ay, ctypes.c_int64(0), ctypes.c_void_p(y.data_ptr()), ctypes.c_int64(n))
+    r = ctypes.c_double()
+    assert cu.qcm_vec_dot(ax, ay, ctypes.c_int64(n), ctypes.byref(r)) == 0
+    assert r.value == pytest.approx(float(x @ y), rel=1e-12)
+    assert cu.qcm_vec_axpy(ctypes.c_double(-0.5), ax, ay, ctypes.c_int64(n)) == 0
+    assert cu.qcm_vec_scal(ctypes.c_double(3.0), ay, ctypes.c_int64(n)) == 0
+    out = torch.empty(n, dtype=torch.float64)
+    cu.qcm_array_download(ay, ctypes.c_int64(0), ctypes.c_void_p(out.data_ptr()), ctypes.c_int64(n))
+    assert torch.equal(out, 3.0 * torch.addcmul(y, torch.full_like(x, -0.5), x)) or float((out - 3.0 * (y - 0.5 * x)).abs().max()) < 1e-14
+    # range errors are reported, not ignored
+    assert cu.qcm_vec_dot(ax, ay, ctypes.c_int64(n + 1), ctypes.byref(r)) != 0
+    cu.qcm_array_free(ax); cu.qcm_array_free(ay)
