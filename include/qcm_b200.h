@@ -50,13 +50,16 @@ typedef struct { qcm_ref A, B; int32_t lda, ldb, m, n, k, ta, tb, pad; double al
 typedef struct { qcm_ref C; int32_t ldc, m, n, seg_begin, seg_end, pad; } qcm_gemm_out;
 
 /* W application (lb_tensor_mpo/rb_tensor_mpo alps_detail.hpp:189-224; SU2 detail::lbtm/rbtm/task_axpy
- * micro_kernels.hpp:19-198) as grouped small dense products: a group holds up to 16 destination panels that are
- * fed by (nearly) the same source panels; dst_d[e] = sum_u coef[u*ng + d] * src_u[e] over the panel elements e.
- * coef = W entry * scale * Wigner-9j coupling (gsl_coupling.h:177-204) * Hermitian phase, zero where a
- * destination does not use a source.  All panels of a group are rows x cols (column-major, own leading dims). */
+ * micro_kernels.hpp:19-198) for destination panels that are sums over SEVERAL source panels (a destination with a
+ * single source is never materialised: the closing product reads the source panel with the coefficient as alpha).
+ * A group holds destination panels fed by (nearly) the same sources: dst_d[e] = sum_u coef[u*ng + d] * src_u[e] over
+ * the panel elements e.  coef = W entry * scale * Wigner-9j coupling (gsl_coupling.h:177-204) * Hermitian phase,
+ * zero where a destination does not use a source.  All panels of a group are rows x cols, column-major with their own
+ * leading dimensions.  cls 1: n_src <= 4, n_dst <= 4, ng = 4 (FMA streaming kernel); cls 0: n_dst <= ng in
+ * {8,16,32,64}, coefficient rows padded to a multiple of 8 sources (DMMA kernel). */
 typedef struct { qcm_ref src; int32_t lds, pad; } qcm_w_src;
 typedef struct { qcm_ref dst; int32_t ldd, pad; } qcm_w_dst;
-typedef struct { int32_t rows, cols, n_src, n_dst, ng /* 8 or 16 */, src_begin, dst_begin, pad; int64_t coef_begin; } qcm_w_group;
+typedef struct { int32_t rows, cols, n_src, n_dst, ng, src_begin, dst_begin, cls; int64_t coef_begin; } qcm_w_group;
 
 typedef struct {
     const qcm_gemm_out* t_outs;     int64_t n_t_outs;      /* step 1 for this wave -> QCM_BUF_T   */

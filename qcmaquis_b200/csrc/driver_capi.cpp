@@ -54,6 +54,8 @@ extern "C" int qcmd_mpo_dims(void* h, int* dims, int* pairs)
 //       [7] left elems [8] right elems [9] gemm tasks [10] axpy tasks [11] waves [12] workspace bytes
 //       [13] plan seconds [14] sectors on the left bond [15] largest sector [16] mpo rows [17] mpo cols [18] mpo nnz
 //       [19] setup seconds [20] kernel launches per sigma [21] W panel elements read [22] written [23] W groups
+//       [24] executed W flops [25] executed closing flops [26] panel elements consumed directly from T [27] formed by the W kernels
+//       [28] panel elements skipped (no closing product)
 extern "C" int qcmd_setup_site(void* h, int site, int twosite, int M, unsigned seed, int device, int rank, int world, double* info, char* err, int errlen)
 {
     try {
@@ -77,12 +79,13 @@ extern "C" int qcmd_setup_site(void* h, int site, int twosite, int M, unsigned s
         CompiledPlan const& cp = *D->plan;
         size_t mx = 0;
         for (auto const& e : D->S.psi.row_dim()) mx = std::max(mx, e.second);
-        double v[24] = {cp.flops, cp.flops_t, cp.flops_w, cp.flops_close, (double)cp.bytes, (double)cp.ket_elems, (double)cp.out_elems,
+        double v[29] = {cp.flops, cp.flops_t, cp.flops_w, cp.flops_close, (double)cp.bytes, (double)cp.ket_elems, (double)cp.out_elems,
                         (double)D->dl->layout.total, (double)D->dr->layout.total, (double)cp.n_gemm_tasks, (double)cp.n_axpy_tasks, (double)cp.n_waves,
                         (double)wsb, D->plan_seconds, (double)D->S.psi.row_dim().size(), (double)mx, (double)D->S.mpo->row_dim(),
                         (double)D->S.mpo->col_dim(), (double)D->S.mpo->nnz(), D->S.setup_seconds, (double)nl,
-                        (double)cp.w_elems_read, (double)cp.w_elems_written, (double)cp.w_groups};
-        for (int i = 0; i < 24; ++i) info[i] = v[i];
+                        (double)cp.w_elems_read, (double)cp.w_elems_written, (double)cp.w_groups,
+                        cp.exec_w, cp.exec_close, (double)cp.direct_panel_elems, (double)cp.w_panel_elems, (double)cp.skipped_panel_elems};
+        for (int i = 0; i < 29; ++i) info[i] = v[i];
         return 0;
     } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
 }

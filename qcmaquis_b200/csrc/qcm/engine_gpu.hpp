@@ -41,6 +41,8 @@ struct CompiledPlan
     int64_t bytes = 0;
     size_t n_gemm_tasks = 0, n_axpy_tasks = 0, n_waves = 0;
     int64_t w_elems_read = 0, w_elems_written = 0, w_groups = 0;
+    double exec_w = 0, exec_close = 0;
+    int64_t direct_panel_elems = 0, w_panel_elems = 0, skipped_panel_elems = 0;
     int64_t workspace_elems = 0;
     ~CompiledPlan() { if (handle) qcm_plan_destroy(handle); }
 };
@@ -210,7 +212,7 @@ private:
             S.wg.resize(wl.groups.size()); S.wd.resize(wl.dsts.size()); S.wsrc.resize(wl.srcs.size());
             for (size_t i = 0; i < S.wg.size(); ++i) {
                 plan::WGroup const& g = wl.groups[i];
-                S.wg[i] = qcm_w_group{g.rows, g.cols, g.n_src, g.n_dst, g.ng, g.src_begin, g.dst_begin, 0, g.coef_begin};
+                S.wg[i] = qcm_w_group{g.rows, g.cols, g.n_src, g.n_dst, g.ng, g.src_begin, g.dst_begin, g.cls, g.coef_begin};
             }
             for (size_t i = 0; i < S.wd.size(); ++i) S.wd[i] = qcm_w_dst{qcm_ref{wl.dsts[i].dst.buf, 0, wl.dsts[i].dst.off}, wl.dsts[i].ldd, 0};
             for (size_t i = 0; i < S.wsrc.size(); ++i) S.wsrc[i] = qcm_w_src{qcm_ref{wl.srcs[i].src.buf, 0, wl.srcs[i].src.off}, wl.srcs[i].lds, 0};
@@ -244,6 +246,8 @@ private:
         cp->ket_elems = P.ket_lp_elems; cp->bra_elems = P.bra_lp_elems; cp->out_elems = out_elems;
         cp->flops = P.flops(); cp->flops_t = P.flops_t; cp->flops_w = P.flops_w; cp->flops_close = P.flops_close; cp->bytes = P.bytes_algorithmic;
         cp->w_elems_read = P.w_elems_read; cp->w_elems_written = P.w_elems_written; cp->w_groups = P.w_groups;
+        cp->exec_w = P.exec_w; cp->exec_close = P.exec_close;
+        cp->direct_panel_elems = P.direct_panel_elems; cp->w_panel_elems = P.w_panel_elems; cp->skipped_panel_elems = P.skipped_panel_elems;
         cp->n_gemm_tasks = P.n_gemm_tasks; cp->n_axpy_tasks = P.n_axpy_tasks; cp->n_waves = P.waves.size();
         cp->workspace_elems = P.ket_rp_elems + P.t_elems_max + P.tp_elems + P.y_elems_max + P.bra_rp_elems;
         last = cp;

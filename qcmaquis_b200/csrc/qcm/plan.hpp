@@ -39,7 +39,7 @@ struct AxpyList { std::vector<AxpyDst> dsts; std::vector<AxpySrc> srcs; };
 // elements e.  Every source panel is then read once per group instead of once per (source, destination) pair.
 struct WSrc { Ref src; int32_t lds; };
 struct WDst { Ref dst; int32_t ldd; };
-struct WGroup { int32_t rows, cols, n_src, n_dst, ng, src_begin, dst_begin; int64_t coef_begin; };   // coef[(coef_begin + u*ng + d)], u < pad4(n_src)
+struct WGroup { int32_t rows, cols, n_src, n_dst, ng, cls, src_begin, dst_begin; int64_t coef_begin; };   // coef[coef_begin + u*ng + d]; cls 0: DMMA product (u padded to 8), 1: FMA stream
 struct WList
 {
     std::vector<WGroup> groups; std::vector<WSrc> srcs; std::vector<WDst> dsts; std::vector<double> coefs;
@@ -52,7 +52,7 @@ struct Wave
     AxpyList w_apply;     // step 2 -> BUF_Y (planner-internal list, cleared once grouped)
     WList w_groups;       // step 2 as executed
     GemmList close_gemm;  // step 3 -> BUF_OUT (accumulating for sigma, plain for boundary steps)
-    int64_t y_elems = 0;  // BUF_Y region that must be zeroed before the axpy pass
+    int64_t y_elems = 0;  // BUF_Y elements this wave uses (compact multi-source panels; all written by the W pass before they are read)
     int64_t t_elems = 0;
 };
 
@@ -91,7 +91,9 @@ struct Plan
     bool accumulate_out = false;
     int64_t ket_lp_elems = 0, ket_rp_elems = 0, bra_lp_elems = 0, bra_rp_elems = 0;
     int64_t tp_elems = 0, t_elems_max = 0, y_elems_max = 0;
-    double flops_t = 0, flops_w = 0, flops_close = 0;
+    double flops_t = 0, flops_w = 0, flops_close = 0;          // algorithmic (reference schedule)
+    double exec_w = 0, exec_close = 0;                         // what the device executes after panel routing (before tile padding)
+    int64_t direct_panel_elems = 0, w_panel_elems = 0, skipped_panel_elems = 0;
     int64_t w_elems_read = 0, w_elems_written = 0, w_groups = 0;   // traffic of the grouped W application (panel elements)
     int64_t bytes_algorithmic = 0;         // 8*(sum|L_b| + sum|R_b| + 2|psi|) resp. boundary-step analogue
     size_t n_gemm_tasks = 0, n_axpy_tasks = 0;
@@ -215,25 +217,33 @@ public:
                 emit_t_gemm(P, cur.t_gemm, b1, L, BUF_T, ket_rp);
                 cur_t += L.total; tl[b1] = L;
             }
-            // step 2
-            Layout yl; yl.assign(pd.y.basis, cur_y);
-            emit_axpy(P, cur.w_apply, pd.ytasks, tl, yl);
-            cur_y += yl.total;
-            // step 3
+            // steps 2 + 3, panel by panel: a destination panel of Y[b2] (rows (phys_out, lc, col) of one Y block) is
+            // either a single scaled T panel -- then the closing product reads T directly and Y is never materialised --
+            // or a sum over several T panels, formed by the W kernel in a compact Y region.  Each row unit of a sigma
+            // block is its own output with its own K-segment list over (b2, panel).
+            DualIndex const& ybasis = pd.y.basis;
             VView rv = right_view(right, pd.b2);
-            for (size_t k = 0; k < yl.basis.size(); ++k) {
-                QnBlock const& yb = yl.basis[k];
+            std::vector<std::vector<size_t>> match(ybasis.size());
+            for (size_t k = 0; k < ybasis.size(); ++k) {
+                QnBlock const& yb = ybasis[k];
                 if (su2_) {
                     size_t mb = rv.basis.position(yb.rc, yb.lc);
-                    if (mb == rv.basis.size()) continue;
-                    if (!out_left_i.has(yb.lc)) continue;
-                    emit_close(P, cur.close_gemm, P.out_tensor, yb.lc, yb.lc, Ref{BUF_Y, yl.off[k]}, (int32_t)yb.ls, 0, (int32_t)yb.ls, (int32_t)yb.rs, rv.blocks[mb], BUF_RIGHT);
-                } else {
-                    for (auto it = rv.basis.left_lower_bound(yb.rc); it != rv.basis.end() && it->lc == yb.rc; ++it) {
-                        size_t mb = it - rv.basis.begin();
-                        emit_close(P, cur.close_gemm, P.out_tensor, yb.lc, it->rc, Ref{BUF_Y, yl.off[k]}, (int32_t)yb.ls, 0, (int32_t)yb.ls, (int32_t)yb.rs, rv.blocks[mb], BUF_RIGHT);
-                    }
-                }
+                    if (mb == rv.basis.size() || !out_left_i.has(yb.lc)) continue;
+                    match[k].push_back(mb);
+                } else
+                    for (auto it = rv.basis.left_lower_bound(yb.rc); it != rv.basis.end() && it->lc == yb.rc; ++it) match[k].push_back(it - rv.basis.begin());
+                for (size_t mb : match[k])
+                    if (P.out_tensor.basis.has(yb.lc, su2_ ? yb.lc : rv.blocks[mb].rc)) { P.flops_close += 2.0 * yb.ls * rv.blocks[mb].rs * yb.rs; P.n_gemm_tasks++; }
+            }
+            std::vector<Panel> panels = collect_panels(P, pd.ytasks, tl);
+            for (Panel const& pn : panels) {
+                if (match[pn.o].empty()) { P.skipped_panel_elems += (int64_t)pn.rows * pn.cols; continue; }
+                PanelRef pr;
+                if (!place_panel(P, cur.w_apply, pn, cur_y, pr)) continue;
+                QnBlock const& yb = ybasis[pn.o];
+                for (size_t mb : match[pn.o])
+                    emit_close(P, cur.close_gemm, P.out_tensor, yb.lc, su2_ ? yb.lc : rv.blocks[mb].rc, pr.A, pr.lda, 0, pn.rows, pn.cols, pr.alpha, rv.blocks[mb], BUF_RIGHT,
+                               pn.dst_row, 0);
             }
         }
         flush();
@@ -315,19 +325,28 @@ public:
                 emit_t_gemm(P, cur.t_gemm, b1, L, BUF_T, ket_rp);
                 cur_t += L.total; tl[b1] = L;
             }
-            Layout yl; yl.assign(pd.y, cur_y);
-            emit_axpy(P, cur.w_apply, pd.ytasks, tl, yl);
-            cur_y += yl.total;
             int spin_f = su2_ ? mpo.right_spin(b2).get() : -1;
             Layout const& ol = P.out_boundary.b[b2];
-            for (size_t k = 0; k < yl.basis.size(); ++k) {
-                QnBlock const& yb = yl.basis[k];   // transposed: (rc, lc), rows rs, cols ls
+            // gemm(transpose(Y), bra_lp): the panels of a Y block are row ranges = K ranges of the closing product
+            std::vector<std::vector<size_t>> match(pd.y.size());
+            for (size_t k = 0; k < pd.y.size(); ++k) {
+                QnBlock const& yb = pd.y[k];
                 for (auto it = bra_lp.basis.left_lower_bound(yb.lc); it != bra_lp.basis.end() && it->lc == yb.lc; ++it) {
                     if (spin_f != -1 && !su2::triangle(spin(yb.rc), spin_f, spin(it->rc))) continue;
-                    size_t mb = it - bra_lp.basis.begin();
-                    VBlock bv{it->lc, it->rc, (int32_t)it->ls, (int32_t)it->rs, bra_lp.off[mb], (int32_t)it->ls, 0, 1.};
-                    // A = Y block transposed: m = yb.rs, k = yb.ls
-                    emit_close(P, cur.close_gemm, ol, yb.rc, it->rc, Ref{BUF_Y, yl.off[k]}, (int32_t)yb.ls, 1, (int32_t)yb.rs, (int32_t)yb.ls, bv, BUF_BRA_LP);
+                    match[k].push_back(it - bra_lp.basis.begin());
+                    P.flops_close += 2.0 * yb.rs * it->rs * yb.ls; P.n_gemm_tasks++;
+                }
+            }
+            std::vector<Panel> panels = collect_panels(P, pd.ytasks, tl);
+            for (Panel const& pn : panels) {
+                if (match[pn.o].empty()) { P.skipped_panel_elems += (int64_t)pn.rows * pn.cols; continue; }
+                PanelRef pr;
+                if (!place_panel(P, cur.w_apply, pn, cur_y, pr)) continue;
+                QnBlock const& yb = pd.y[pn.o];
+                for (size_t mb : match[pn.o]) {
+                    QnBlock const& q = bra_lp.basis[mb];
+                    VBlock bv{q.lc, q.rc, (int32_t)q.ls, (int32_t)q.rs, bra_lp.off[mb], (int32_t)q.ls, 0, 1.};
+                    emit_close(P, cur.close_gemm, ol, yb.rc, q.rc, pr.A, pr.lda, 1, pn.cols, pn.rows, pr.alpha, bv, BUF_BRA_LP, 0, pn.dst_row);
                 }
             }
         }
@@ -408,18 +427,26 @@ public:
                 emit_t_gemm_right(P, cur.t_gemm, b2, L, BUF_T, ket_lp);
                 cur_t += L.total; tl[b2] = L;
             }
-            Layout yl; yl.assign(pd.y, cur_y);
-            emit_axpy(P, cur.w_apply, pd.ytasks, tl, yl);
-            cur_y += yl.total;
             int spin_f = su2_ ? mpo.left_spin(b1).get() : -1;
             Layout const& ol = P.out_boundary.b[b1];
-            for (size_t k = 0; k < yl.basis.size(); ++k) {
-                QnBlock const& yb = yl.basis[k];
+            // gemm(Y, transpose(bra_rp)): the panels of a Y block are column ranges = K ranges of the closing product
+            std::vector<std::vector<size_t>> match(pd.y.size());
+            for (size_t k = 0; k < pd.y.size(); ++k) {
+                QnBlock const& yb = pd.y[k];
                 for (auto it = brt.basis.left_lower_bound(yb.rc); it != brt.basis.end() && it->lc == yb.rc; ++it) {
                     if (spin_f != -1 && !su2::triangle(spin(yb.lc), spin_f, spin(it->rc))) continue;
-                    size_t mb = it - brt.basis.begin();
-                    emit_close(P, cur.close_gemm, ol, yb.lc, it->rc, Ref{BUF_Y, yl.off[k]}, (int32_t)yb.ls, 0, (int32_t)yb.ls, (int32_t)yb.rs, brt.blocks[mb], BUF_BRA_RP);
+                    match[k].push_back(it - brt.basis.begin());
+                    P.flops_close += 2.0 * yb.ls * it->rs * yb.rs; P.n_gemm_tasks++;
                 }
+            }
+            std::vector<Panel> panels = collect_panels(P, pd.ytasks, tl);
+            for (Panel const& pn : panels) {
+                if (match[pn.o].empty()) { P.skipped_panel_elems += (int64_t)pn.rows * pn.cols; continue; }
+                PanelRef pr;
+                if (!place_panel(P, cur.w_apply, pn, cur_y, pr)) continue;
+                QnBlock const& yb = pd.y[pn.o];
+                for (size_t mb : match[pn.o])
+                    emit_close(P, cur.close_gemm, ol, yb.lc, brt.blocks[mb].rc, pr.A, pr.lda, 0, pn.rows, pn.cols, pr.alpha, brt.blocks[mb], BUF_BRA_RP, 0, pn.dst_col);
             }
         }
         flush();
@@ -873,8 +900,12 @@ private:
         }
     }
 
-    // group W-application contributions by destination panel -> one gather-axpy per panel
-    void emit_axpy(Plan& P, AxpyList& al, std::vector<YTask> const& tasks, std::map<size_t, Layout> const& tl, Layout const& yl)
+    // W-application contributions grouped by destination panel.  Sources that reach the same panel through several
+    // MPO terms are merged (coefficients add up).
+    struct PanelSrc { Ref src; int32_t lds; double coef; };
+    struct Panel { size_t o; int32_t dst_row, dst_col, rows, cols; std::vector<PanelSrc> srcs; };
+    struct PanelRef { Ref A; int32_t lda; double alpha; };
+    std::vector<Panel> collect_panels(Plan& P, std::vector<YTask> const& tasks, std::map<size_t, Layout> const& tl)
     {
         std::vector<size_t> order(tasks.size());
         std::iota(order.begin(), order.end(), 0);
@@ -882,11 +913,10 @@ private:
             YTask const& x = tasks[a]; YTask const& y = tasks[b];
             return std::tie(x.o, x.dst_col, x.dst_row, x.rows, x.cols) < std::tie(y.o, y.dst_col, y.dst_row, y.rows, y.cols);
         });
+        std::vector<Panel> panels;
         for (size_t q = 0; q < order.size();) {
             YTask const& h = tasks[order[q]];
-            AxpyDst d; d.ldd = (int32_t)yl.basis[h.o].ls;
-            d.dst = Ref{BUF_Y, yl.off[h.o] + h.dst_row + (int64_t)h.dst_col * d.ldd};
-            d.rows = h.rows; d.cols = h.cols; d.src_begin = (int32_t)al.srcs.size();
+            Panel pn{h.o, h.dst_row, h.dst_col, h.rows, h.cols, {}};
             size_t q2 = q;
             for (; q2 < order.size(); ++q2) {
                 YTask const& t = tasks[order[q2]];
@@ -894,20 +924,54 @@ private:
                 Layout const& L = tl.at(t.bt);
                 int32_t lds = (int32_t)L.basis[t.t_block].ls;
                 int srcbuf = t_persistent[t.bt] ? BUF_TP : BUF_T;
-                al.srcs.push_back(AxpySrc{Ref{srcbuf, L.off[t.t_block] + t.src_row + (int64_t)t.src_col * lds}, lds, t.coef});
+                pn.srcs.push_back(PanelSrc{Ref{srcbuf, L.off[t.t_block] + t.src_row + (int64_t)t.src_col * lds}, lds, t.coef});
                 P.flops_w += 2.0 * t.rows * t.cols; P.n_axpy_tasks++;
             }
-            d.src_end = (int32_t)al.srcs.size();
-            al.dsts.push_back(d);
+            std::stable_sort(pn.srcs.begin(), pn.srcs.end(), [](PanelSrc const& a, PanelSrc const& b) { return std::tie(a.src.buf, a.src.off) < std::tie(b.src.buf, b.src.off); });
+            size_t o = 0;
+            for (size_t i = 0; i < pn.srcs.size(); ++i) {
+                if (o && pn.srcs[o - 1].src.buf == pn.srcs[i].src.buf && pn.srcs[o - 1].src.off == pn.srcs[i].src.off) pn.srcs[o - 1].coef += pn.srcs[i].coef;
+                else pn.srcs[o++] = pn.srcs[i];
+            }
+            pn.srcs.resize(o);
+            panels.push_back(std::move(pn));
             q = q2;
         }
+        return panels;
+    }
+    // Where the closing product finds a panel: the T panel itself (one source; its coefficient becomes the alpha of
+    // the K-segment) or a compact region of BUF_Y filled by the W kernel.  false: the panel is identically zero.
+    bool place_panel(Plan& P, AxpyList& al, Panel const& pn, int64_t& cur_y, PanelRef& pr)
+    {
+        if (pn.srcs.empty()) return false;
+        int64_t el = (int64_t)pn.rows * pn.cols;
+        if (pn.srcs.size() == 1) {
+            if (pn.srcs[0].coef == 0.) return false;
+            pr = PanelRef{pn.srcs[0].src, pn.srcs[0].lds, pn.srcs[0].coef};
+            P.direct_panel_elems += el;
+            return true;
+        }
+        cur_y = (cur_y + 1) & ~(int64_t)1;      // panels start 16-byte aligned
+        AxpyDst d; d.dst = Ref{BUF_Y, cur_y}; d.ldd = pn.rows; d.rows = pn.rows; d.cols = pn.cols;
+        d.src_begin = (int32_t)al.srcs.size();
+        for (auto const& sp : pn.srcs) al.srcs.push_back(AxpySrc{sp.src, sp.lds, sp.coef});
+        d.src_end = (int32_t)al.srcs.size();
+        al.dsts.push_back(d);
+        cur_y += el;
+        P.w_panel_elems += el; P.exec_w += 2.0 * el * (double)pn.srcs.size();
+        pr = PanelRef{d.dst, pn.rows, 1.};
+        return true;
     }
 
-
-    // Destinations fed by (nearly) the same set of source panels -> one group of at most 16 destinations.
-    // Candidates are bucketed by two min-hashes of their source sets and accepted when they share >= 50 % of the
-    // sources with the group leader; the group works on the union of the members' sources (absent pairs get a zero
-    // coefficient), so grouping never adds memory traffic, it only removes repeated reads of shared panels.
+    // Multi-source destination panels, grouped for the device:
+    //   cls 1 ("stream"): at most 4 sources; destinations with IDENTICAL source sets are put together (at most 4).
+    //                     Executed by a plain FMA streaming kernel -- pure HBM traffic, every source read once.
+    //   cls 0 ("gemm"):   more than 4 sources -- the integral-weighted sums over many bond terms.  Destinations that
+    //                     share at least half of their sources with the group leader are put together (at most 64);
+    //                     the group is evaluated as one dense product  dst[e, d] = sum_u src_u[e] * coef[u][d]  over
+    //                     the panel elements e on DMMA tiles (absent pairs get a zero coefficient), so every source
+    //                     panel is read once per group instead of once per destination.
+    // Candidates are bucketed by two min-hashes of their source sets.
     static void group_axpy(Plan& P, AxpyList& al, WList& wl)
     {
         size_t nd = al.dsts.size();
@@ -927,9 +991,6 @@ private:
                 v.push_back(std::make_pair(((int64_t)a.src.buf << 56) | a.src.off, a.coef));
             }
             std::sort(v.begin(), v.end(), [](auto const& x, auto const& y) { return x.first < y.first; });
-            size_t o = 0;   // the same panel reached through several MPO terms: coefficients add up
-            for (size_t q = 0; q < v.size(); ++q) { if (o && v[o - 1].first == v[q].first) v[o - 1].second += v[q].second; else v[o++] = v[q]; }
-            v.resize(o);
             uint64_t h1 = ~0ull, h2 = ~0ull;
             for (auto const& e : v) { h1 = std::min(h1, mixh((uint64_t)e.first, 0x1234567ull)); h2 = std::min(h2, mixh((uint64_t)e.first, 0xABCDEF01ull)); }
             keys[i] = Key{h1, h2, d.rows, d.cols, (int32_t)v.size(), i};
@@ -949,19 +1010,16 @@ private:
         for (size_t q = 0; q < nd;) {
             size_t lead = keys[q].idx;
             size_t q2 = q + 1;
-            if (!sorted[lead].empty())
-                while (q2 < nd && q2 - q < 16 && keys[q2].rows == keys[q].rows && keys[q2].cols == keys[q].cols && keys[q2].h1 == keys[q].h1) {
-                    SrcVec const& cand = sorted[keys[q2].idx];
-                    size_t c = overlap(sorted[lead], cand);
-                    if (2 * c < std::max(sorted[lead].size(), cand.size())) break;
-                    ++q2;
-                }
-            int32_t g = (int32_t)(q2 - q);
-            if (getenv("QCM_DEBUG_GROUPS") && g == 1 && sorted[lead].size() > 1000 && q2 < nd) {
+            bool stream = sorted[lead].size() <= 4;
+            size_t cap = stream ? 4 : 64;
+            while (q2 < nd && q2 - q < cap && keys[q2].rows == keys[q].rows && keys[q2].cols == keys[q].cols && keys[q2].h1 == keys[q].h1) {
                 SrcVec const& cand = sorted[keys[q2].idx];
-                fprintf(stderr, "single: rows %d cols %d n %zu h1 %llx | next rows %d cols %d n %zu h1 %llx overlap %zu | prev n %zu h1 %llx overlap %zu\n", keys[q].rows, keys[q].cols, sorted[lead].size(), (unsigned long long)keys[q].h1,
-                        keys[q2].rows, keys[q2].cols, cand.size(), (unsigned long long)keys[q2].h1, overlap(sorted[lead], cand), q ? sorted[keys[q-1].idx].size() : 0, q ? (unsigned long long)keys[q-1].h1 : 0ull, q ? overlap(sorted[lead], sorted[keys[q-1].idx]) : 0);
+                size_t c = overlap(sorted[lead], cand);
+                if (stream) { if (c != sorted[lead].size() || c != cand.size()) break; }
+                else if (cand.size() <= 4 || 2 * c < std::max(sorted[lead].size(), cand.size())) break;
+                ++q2;
             }
+            int32_t g = (int32_t)(q2 - q);
             uni.clear();
             for (auto const& e : sorted[lead]) uni.push_back(e.first);
             for (int32_t d = 1; d < g; ++d) {
@@ -976,10 +1034,11 @@ private:
                 uni.swap(tmp);
             }
             int32_t ns = (int32_t)uni.size();
-            WGroup G; G.rows = keys[q].rows; G.cols = keys[q].cols; G.n_src = ns; G.n_dst = g; G.ng = g <= 8 ? 8 : 16;
+            WGroup G; G.rows = keys[q].rows; G.cols = keys[q].cols; G.n_src = ns; G.n_dst = g; G.cls = stream ? 1 : 0;
+            G.ng = stream ? 4 : (g <= 8 ? 8 : g <= 16 ? 16 : g <= 32 ? 32 : 64);
             G.src_begin = (int32_t)wl.srcs.size(); G.dst_begin = (int32_t)wl.dsts.size(); G.coef_begin = (int64_t)wl.coefs.size();
             for (int64_t ref : uni) wl.srcs.push_back(WSrc{Ref{(int32_t)(ref >> 56), ref & (((int64_t)1 << 56) - 1)}, lds_map[ref]});
-            int32_t ns_pad = (ns + 3) / 4 * 4;
+            int32_t ns_pad = stream ? ns : (ns + 7) / 8 * 8;      // the DMMA kernel consumes sources eight at a time
             wl.coefs.resize(wl.coefs.size() + (size_t)ns_pad * G.ng, 0.);
             for (int32_t d = 0; d < g; ++d) {
                 size_t di = keys[q + d].idx;
@@ -1000,18 +1059,20 @@ private:
         AxpyList().dsts.swap(al.dsts); AxpyList().srcs.swap(al.srcs);
     }
 
-    // step 3: one K-segment A(m x k) * op(B)(k x n) into output block (lc, rc)
+    // step 3: one K-segment alpha * op(A)(m x k) * op(B)(k x n) into rows [c_row, c_row + m) of output block (lc, rc);
+    // op(B) starts at row b_k of the stored operand (a panel covers a K sub-range of the reference's product)
     void emit_close(Plan& P, GemmList& gl, Layout const& ol, Charge const& lc, Charge const& rc, Ref A, int32_t lda, int32_t ta, int32_t m, int32_t k,
-                    VBlock const& b, int bbuf)
+                    double alpha, VBlock const& b, int bbuf, int32_t c_row, int32_t b_k)
     {
         size_t cb = ol.basis.position(lc, rc);
         if (cb == ol.basis.size()) return;
-        Out o; o.C = Ref{BUF_OUT, ol.off[cb]}; o.ldc = (int32_t)ol.basis[cb].ls; o.m = m; o.n = b.rs;
+        Out o; o.C = Ref{BUF_OUT, ol.off[cb] + c_row}; o.ldc = (int32_t)ol.basis[cb].ls; o.m = m; o.n = b.rs;
         o.seg_begin = (int32_t)gl.segs.size();
-        gl.segs.push_back(Seg{A, Ref{bbuf, b.off}, lda, b.ld, m, o.n, k, ta, b.trans, b.scale});
+        int64_t boff = b.off + (b.trans ? (int64_t)b_k * b.ld : (int64_t)b_k);
+        gl.segs.push_back(Seg{A, Ref{bbuf, boff}, lda, b.ld, m, o.n, k, ta, b.trans, alpha * b.scale});
         o.seg_end = (int32_t)gl.segs.size();
         gl.outs.push_back(o);
-        P.flops_close += 2.0 * m * o.n * k; P.n_gemm_tasks++;
+        P.exec_close += 2.0 * m * o.n * k;
     }
     // outputs that target the same block become ONE output with a longer segment list (segments keep their own m, n)
     static void merge_outputs(GemmList& gl)

@@ -12,9 +12,11 @@
 //                   K-segments (the sum over MPO bond terms that hit the same symmetry sector), stages
 //                   operand tiles in shared memory and issues mma.sync.m8n8k4.f64 (DMMA).  tcgen05 has no
 //                   FP64 kind, so DMMA is the FP64 tensor path of sm_100a.
-//   k_wapply_dmma   the W application as grouped small dense products on DMMA: destination panels fed by the
-//                   same source panels share one pass over those sources (SU2 Wigner-9j couplings and
-//                   Hermitian phases are folded into the coefficients on the host)
+//   k_wstream       the W application for destination panels with 2..4 source panels (FMA streaming, HBM bound)
+//   k_wgemm         the W application for high fan-in panels as gathered dense products on DMMA: destination
+//                   panels fed by the same source panels share one pass over those sources (SU2 Wigner-9j
+//                   couplings and Hermitian phases are folded into the coefficients on the host).  Destination
+//                   panels with a single source are never formed: the closing GEMM reads the source directly.
 //   k_vec_*         solver-side BLAS-1 on device-resident vectors
 //
 // There is no CPU fallback: every entry point fails with a status when the device is not usable.
@@ -45,8 +47,8 @@ struct DSeg { long long a_off, b_off; int a_buf, b_buf, lda, ldb, m, n, k, ta, t
 struct DWork { long long c_off; int c_buf, ldc, m0, n0, m, n, seg_begin, seg_end, mode, pad; };   // mode 0 store, 1 add, 2 atomic
 struct DWSrc { long long off; int buf, lds; };
 struct DWDst { long long off; int buf, ldd; };
-struct DWGroup { int rows, cols, n_src, n_dst, ng, src_begin, dst_begin, tpc; long long coef_begin; };   // tpc = 8-row tiles per column
-struct DWWork { int group, r8, c0, pad; };
+struct DWGroup { int rows, cols, n_src, n_dst, ng, src_begin, dst_begin, cls; long long coef_begin; };
+struct DWWork { int group, e0; };   // panel elements [e0, e0 + tile) of a group (element e = row + col * rows)
 struct DCopy { long long src_off, dst_off; int src_buf, dst_buf, rows, cols, lds, ldd; };
 
 // --------------------------------------------------------------------------------------------------------
@@ -69,93 +71,6 @@ __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, doub
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// W application.  One WARP owns one work item: a strip of WT consecutive panel columns x 8 consecutive rows of a
-// group, and streams over the group's source panels four at a time.  DMMA shape: M = 8 panel rows, K = 4 sources,
-// N = 8 destinations (two N tiles in the WIDE variant for groups of 9..16 destinations).  A fragments come
-// straight from global memory (every source element is needed exactly once per group), B fragments are the
-// coefficients.  The loop is software pipelined: source descriptors are fetched two chunks ahead, source elements
-// one chunk ahead of the DMMAs that consume them.
-constexpr int W_WARPS = 4;
-template <bool WIDE>
-__global__ void __launch_bounds__(W_WARPS * 32, 5)
-k_wapply_dmma(const DWWork* __restrict__ works, int n_works, const DWGroup* __restrict__ groups, const DWSrc* __restrict__ srcs,
-              const DWDst* __restrict__ dsts, const double* __restrict__ coefs, const __grid_constant__ BufTable bufs)
-{
-    constexpr int WT = WIDE ? 4 : 8;
-    constexpr int NG = WIDE ? 16 : 8;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int wi = blockIdx.x * W_WARPS + warp;
-    if (wi >= n_works) return;
-    const DWWork w = works[wi];
-    const DWGroup g = groups[w.group];
-    const int fr = lane >> 2, fk = lane & 3;
-    const int r = w.r8 * 8 + fr;
-    const bool rok = r < g.rows;
-    const int ncv = min(WT, g.cols - w.c0);
-    const DWSrc* __restrict__ sp = srcs + g.src_begin;
-    const double* __restrict__ cp = coefs + g.coef_begin + fr;
-
-    double acc[WT][WIDE ? 2 : 1][2];
-#pragma unroll
-    for (int i = 0; i < WT; ++i)
-#pragma unroll
-        for (int j = 0; j < (WIDE ? 2 : 1); ++j) acc[i][j][0] = acc[i][j][1] = 0.;
-
-    // pipeline registers
-    const double* p_nn = nullptr; int lds_nn = 0;      // descriptor of chunk (cur + 2)
-    const double* p_n = nullptr; int lds_n = 0;        // descriptor of chunk (cur + 1)
-    double a_n[WT];                                     // elements of chunk (cur + 1)
-    double b_n[WIDE ? 2 : 1];
-    auto fetch_desc = [&](int u0, const double*& p, int& lds) {
-        const int u = u0 + fk;
-        p = nullptr; lds = 0;
-        if (u < g.n_src && rok) { DWSrc q = sp[u]; p = bufs.p[q.buf] + q.off + r + (long long)w.c0 * q.lds; lds = q.lds; }
-    };
-    auto fetch_elems = [&](int u0, const double* p, int lds, double (&a)[WT], double (&b)[WIDE ? 2 : 1]) {
-#pragma unroll
-        for (int i = 0; i < WT; ++i) a[i] = (p != nullptr && i < ncv) ? p[(long long)i * lds] : 0.;
-        const int u = u0 + fk;                         // coefficient rows are padded to a multiple of 4 sources
-        b[0] = u0 < g.n_src ? cp[(long long)u * NG] : 0.;
-        if (WIDE) b[WIDE ? 1 : 0] = u0 < g.n_src ? cp[(long long)u * NG + 8] : 0.;
-    };
-    fetch_desc(0, p_n, lds_n);
-    fetch_desc(4, p_nn, lds_nn);
-    fetch_elems(0, p_n, lds_n, a_n, b_n);
-    for (int u0 = 0; u0 < g.n_src; u0 += 4) {
-        double a[WT], b[WIDE ? 2 : 1];
-#pragma unroll
-        for (int i = 0; i < WT; ++i) a[i] = a_n[i];
-        b[0] = b_n[0];
-        if (WIDE) b[WIDE ? 1 : 0] = b_n[WIDE ? 1 : 0];
-        p_n = p_nn; lds_n = lds_nn;
-        fetch_desc(u0 + 8, p_nn, lds_nn);
-        fetch_elems(u0 + 4, p_n, lds_n, a_n, b_n);
-#pragma unroll
-        for (int i = 0; i < WT; ++i) {
-            dmma8x8x4(acc[i][0][0], acc[i][0][1], a[i], b[0]);
-            if (WIDE) dmma8x8x4(acc[i][WIDE ? 1 : 0][0], acc[i][WIDE ? 1 : 0][1], a[i], b[WIDE ? 1 : 0]);
-        }
-    }
-    // C fragment: row = panel row (lane/4), cols = destinations 2*(lane%4) + {0,1} (+8 for the second N tile)
-    if (!rok) return;
-#pragma unroll
-    for (int j = 0; j < (WIDE ? 2 : 1); ++j)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int d = j * 8 + 2 * fk + e;
-            if (d >= g.n_dst) continue;
-            const DWDst q = dsts[g.dst_begin + d];
-            double* __restrict__ o = bufs.p[q.buf] + q.off + r + (long long)w.c0 * q.ldd;
-#pragma unroll
-            for (int i = 0; i < WT; ++i)
-                if (i < ncv) o[(long long)i * q.ldd] = acc[i][j][e];
-        }
-}
-
-constexpr int KC = 16;         // K chunk staged per pipeline stage
-constexpr int SPAD = 4;        // row padding: (TM + 4) % 16 == 4 makes the fragment reads conflict free
-constexpr int STAGES = 3;
-
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool valid)
 {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -165,11 +80,167 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-// Grouped, variable-size FP64 GEMM.  CTA = WARPS_M x WARPS_N warps, each warp owns WMT x WNT DMMA tiles (8x8).
+// W application, low fan-in (at most 4 sources, at most 4 destinations with identical source sets): a streaming
+// kernel, HBM bound by construction.  One CTA = WS_TILE consecutive panel elements of one group; every thread keeps
+// WS_PT independent loads per source in flight.
+constexpr int WS_THREADS = 128, WS_PT = 8, WS_TILE = WS_THREADS * WS_PT;
+__global__ void __launch_bounds__(WS_THREADS)
+k_wstream(const DWWork* __restrict__ works, const DWGroup* __restrict__ groups, const DWSrc* __restrict__ srcs,
+          const DWDst* __restrict__ dsts, const double* __restrict__ coefs, const __grid_constant__ BufTable bufs)
+{
+    const DWWork w = works[blockIdx.x];
+    const DWGroup g = groups[w.group];
+    const int n = g.rows * g.cols;
+    const double* __restrict__ sp[4]; int sl[4]; double cf[4][4];
+    double* __restrict__ dp[4]; int dl[4];
+    bool flat = true;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        sp[u] = nullptr; sl[u] = g.rows;
+        if (u < g.n_src) { const DWSrc q = srcs[g.src_begin + u]; sp[u] = bufs.p[q.buf] + q.off; sl[u] = q.lds; flat = flat && q.lds == g.rows; }
+#pragma unroll
+        for (int d = 0; d < 4; ++d) cf[u][d] = (u < g.n_src && d < g.n_dst) ? coefs[g.coef_begin + u * 4 + d] : 0.;
+    }
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+        dp[d] = nullptr; dl[d] = g.rows;
+        if (d < g.n_dst) { const DWDst q = dsts[g.dst_begin + d]; dp[d] = bufs.p[q.buf] + q.off; dl[d] = q.ldd; flat = flat && q.ldd == g.rows; }
+    }
+    double x[WS_PT][4];
+    int rr[WS_PT], cc[WS_PT];
+#pragma unroll
+    for (int i = 0; i < WS_PT; ++i) {
+        const int e = w.e0 + threadIdx.x + i * WS_THREADS;
+        if (flat) { rr[i] = e; cc[i] = 0; } else { cc[i] = e / g.rows; rr[i] = e - cc[i] * g.rows; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[i][u] = (e < n && u < g.n_src) ? sp[u][rr[i] + (long long)cc[i] * sl[u]] : 0.;
+    }
+#pragma unroll
+    for (int i = 0; i < WS_PT; ++i) {
+        const int e = w.e0 + threadIdx.x + i * WS_THREADS;
+        if (e >= n) continue;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            if (d >= g.n_dst) continue;
+            double a = x[i][0] * cf[0][d];
+#pragma unroll
+            for (int u = 1; u < 4; ++u) a = fma(x[i][u], cf[u][d], a);
+            dp[d][rr[i] + (long long)cc[i] * dl[d]] = a;
+        }
+    }
+}
+
+// W application, high fan-in (the integral-weighted sums over many bond terms): a dense product
+//   dst[e, d] = sum_u src_u[e] * coef[u][d]      e: TE panel elements of this CTA, u: sources, d <= NG destinations
+// on DMMA tiles (M = 8 elements, K = 4 sources, N = 8 destinations).  Source elements are gathered into shared memory
+// by a WG_STAGES-deep cp.async pipeline, eight sources per stage, each source row a coalesced run of TE doubles;
+// the result is transposed through shared memory so that every destination is written in coalesced runs as well.
+constexpr int WG_TE = 128, WG_KC = 8, WG_STAGES = 3, WG_LDA = WG_TE + 4, WG_LDC = WG_TE + 2;
+template <int NG, int MF> constexpr int wg_smem_doubles()
+{
+    return (WG_STAGES * WG_KC * (WG_LDA + NG + 4) > NG * WG_LDC) ? WG_STAGES * WG_KC * (WG_LDA + NG + 4) : NG * WG_LDC;
+}
+template <int NG, int MF>
+__global__ void __launch_bounds__(WG_TE / (8 * MF) * 32)
+k_wgemm(const DWWork* __restrict__ works, const DWGroup* __restrict__ groups, const DWSrc* __restrict__ srcs,
+        const DWDst* __restrict__ dsts, const double* __restrict__ coefs, const __grid_constant__ BufTable bufs)
+{
+    constexpr int NT = WG_TE / (8 * MF) * 32, NF = NG / 8, LDB = NG + 4;
+    extern __shared__ double smem[];
+    double* As = smem;                                   // [STAGES][KC][LDA]
+    double* Bs = smem + WG_STAGES * WG_KC * WG_LDA;      // [STAGES][KC][LDB]
+    const DWWork w = works[blockIdx.x];
+    const DWGroup g = groups[w.group];
+    const int n = g.rows * g.cols;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, fr = lane >> 2, fk = lane & 3;
+    const int el = tid % WG_TE, kk0 = tid / WG_TE;       // this thread gathers element el of sources kk0, kk0 + NT/TE, ...
+    const int e = w.e0 + el;
+    const bool valid = e < n;
+    const int c = valid ? e / g.rows : 0, r = valid ? e - c * g.rows : 0;
+    const int nst = (g.n_src + WG_KC - 1) / WG_KC;
+    const DWSrc* __restrict__ sq = srcs + g.src_begin;
+    const double* __restrict__ cq = coefs + g.coef_begin;
+
+    auto issue = [&](int it) {
+        if (it < nst) {
+            const int stage = it % WG_STAGES, u0 = it * WG_KC;
+#pragma unroll
+            for (int kk = kk0; kk < WG_KC; kk += NT / WG_TE) {
+                const int u = u0 + kk;
+                const bool ok = valid && u < g.n_src;
+                const DWSrc q = sq[min(u, g.n_src - 1)];
+                const double* p = bufs.p[q.buf] + q.off;
+                cp_async8(As + (stage * WG_KC + kk) * WG_LDA + el, ok ? p + r + (long long)c * q.lds : p, ok);
+            }
+#pragma unroll
+            for (int idx = tid; idx < WG_KC * NG; idx += NT) {
+                const int kk = idx / NG, d = idx % NG;    // coefficient rows are padded to a multiple of WG_KC sources
+                cp_async8(Bs + (stage * WG_KC + kk) * LDB + d, cq + (long long)(u0 + kk) * NG + d, true);
+            }
+        }
+        cp_async_commit();
+    };
+
+    double acc[MF][NF][2];
+#pragma unroll
+    for (int i = 0; i < MF; ++i)
+#pragma unroll
+        for (int j = 0; j < NF; ++j) acc[i][j][0] = acc[i][j][1] = 0.;
+    const int nf_used = (g.n_dst + 7) / 8;
+
+#pragma unroll
+    for (int st = 0; st < WG_STAGES - 1; ++st) issue(st);
+    for (int it = 0; it < nst; ++it) {
+        cp_async_wait<WG_STAGES - 2>();
+        __syncthreads();
+        issue(it + WG_STAGES - 1);
+        const double* as = As + (it % WG_STAGES) * WG_KC * WG_LDA + warp * (8 * MF) + fr;
+        const double* bs = Bs + (it % WG_STAGES) * WG_KC * LDB + fr;
+#pragma unroll
+        for (int k4 = 0; k4 < WG_KC / 4; ++k4) {
+            double a[MF], b[NF];
+#pragma unroll
+            for (int i = 0; i < MF; ++i) a[i] = as[(k4 * 4 + fk) * WG_LDA + i * 8];
+#pragma unroll
+            for (int j = 0; j < NF; ++j) b[j] = bs[(k4 * 4 + fk) * LDB + j * 8];
+#pragma unroll
+            for (int j = 0; j < NF; ++j)
+                if (j < nf_used) {
+#pragma unroll
+                    for (int i = 0; i < MF; ++i) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                }
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    // transpose through shared memory: Cs[d][element]
+    double* Cs = smem;
+#pragma unroll
+    for (int j = 0; j < NF; ++j)
+#pragma unroll
+        for (int i = 0; i < MF; ++i)
+#pragma unroll
+            for (int x = 0; x < 2; ++x) Cs[(j * 8 + 2 * fk + x) * WG_LDC + warp * (8 * MF) + i * 8 + fr] = acc[i][j][x];
+    __syncthreads();
+    if (valid)
+        for (int d = kk0; d < g.n_dst; d += NT / WG_TE) {
+            const DWDst q = dsts[g.dst_begin + d];
+            (bufs.p[q.buf] + q.off)[r + (long long)c * q.ldd] = Cs[d * WG_LDC + el];
+        }
+}
+
+constexpr int KC = 16;         // K chunk staged per pipeline stage
+constexpr int SPAD = 4;        // row padding: (TM + 4) % 16 == 4 makes the fragment reads conflict free
+constexpr int STAGES = 3;
+
+// Grouped, variable-size FP64 GEMM.  CTA = WARPS_M x WARPS_N warps, each warp owns up to WMT x WNT DMMA tiles (8x8).
 // One CTA computes one output tile and walks the K-segments of its work item (the terms of the sum over the MPO
-// bond index that land in this symmetry sector).  Operand tiles are staged in shared memory by a STAGES-deep
-// cp.async pipeline that runs across segment borders; alpha (Hermitian phase / conjugate correction) is applied
-// to the A fragments.
+// bond index and over source panels that land in this row unit of a symmetry sector).  Operand tiles are staged in
+// shared memory by a STAGES-deep cp.async pipeline that runs across segment borders.  Symmetry blocks are ragged:
+// the 8x8 fragments of the tile that lie inside the output are distributed evenly over the warp grid at run time,
+// fragments outside are never issued, and a K chunk is consumed in steps of 4 up to the segment's real depth -- the
+// FP64 pipe only sees work that is padded to (8, 8, 4), not to the tile shape.  alpha (coefficient of a directly
+// consumed source panel, Hermitian phase, SU2 conjugate correction) scales the A fragments when it is not 1.
 constexpr int LDK = KC + 4;     // K-major rows: (KC + 4) % 16 == 4, conflict free as well
 template <int WARPS_M, int WARPS_N, int WMT, int WNT>
 __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32)
@@ -186,12 +257,19 @@ k_gemm_dmma(const DWork* __restrict__ works, const DSeg* __restrict__ segs, cons
     double* As = smem;                          // [STAGES][A_STAGE]
     double* Bs = smem + STAGES * A_STAGE;       // [STAGES][B_STAGE]
     __shared__ double alpha_s[STAGES];
-    __shared__ int flags_s[STAGES];             // bit 0: A is K-major, bit 1: B is K-major
+    __shared__ int flags_s[STAGES];             // bit 0: A is K-major, bit 1: B is K-major, bits 8..: valid depth of the chunk
 
     const DWork w = works[blockIdx.x];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp % WARPS_M, wn = warp / WARPS_M;
     const int fr = lane >> 2, fk = lane & 3;
+
+    // rows / columns of the tile that exist, in fragments, spread evenly over the warp grid
+    const int tm_eff = min(TM, w.m - w.m0), tn_eff = min(TN, w.n - w.n0);
+    const int fpw_m = ((tm_eff + 7) / 8 + WARPS_M - 1) / WARPS_M, fpw_n = ((tn_eff + 7) / 8 + WARPS_N - 1) / WARPS_N;   // <= WMT, WNT
+    const int row0 = wm * fpw_m * 8, col0 = wn * fpw_n * 8;                     // first row / column of this warp inside the tile
+    const int mt = max(0, min(fpw_m, (tm_eff - row0 + 7) / 8)), nt = max(0, min(fpw_n, (tn_eff - col0 + 7) / 8));
+    const int tm_ld = (tm_eff + 7) & ~7, tn_ld = (tn_eff + 7) & ~7;             // rows / columns the producer stages
 
     double acc[WMT][WNT][2];
 #pragma unroll
@@ -227,41 +305,42 @@ k_gemm_dmma(const DWork* __restrict__ works, const DSeg* __restrict__ segs, cons
             double* as = As + stage * A_STAGE;
             double* bs = Bs + stage * B_STAGE;
             const int krem = p_k - pk0;
+            const int kld = min(KC, (krem + 3) & ~3);           // depth the consumer will read
             if (!p_ta) {
                 const double* __restrict__ base = pA + (long long)pk0 * p_lda;
-#pragma unroll
-                for (int idx = tid; idx < TM * KC; idx += NT) {
+                for (int idx = tid; idx < TM * kld; idx += NT) {
                     const int mm = idx % TM, kk = idx / TM;
+                    if (mm >= tm_ld) continue;
                     const bool v = mm < pmrem && kk < krem;
-                    cp_async8(as + kk * LDA_S + mm, v ? base + (mm + kk * p_lda) : pA, v);
+                    cp_async8(as + kk * LDA_S + mm, v ? base + (mm + (long long)kk * p_lda) : pA, v);
                 }
             } else {
                 const double* __restrict__ base = pA + pk0;
-#pragma unroll
-                for (int idx = tid; idx < TM * KC; idx += NT) {
+                for (int idx = tid; idx < tm_ld * KC; idx += NT) {
                     const int kk = idx % KC, mm = idx / KC;
+                    if (kk >= kld) continue;
                     const bool v = mm < pmrem && kk < krem;
-                    cp_async8(as + mm * LDK + kk, v ? base + (kk + mm * p_lda) : pA, v);
+                    cp_async8(as + mm * LDK + kk, v ? base + (kk + (long long)mm * p_lda) : pA, v);
                 }
             }
             if (!p_tb) {
                 const double* __restrict__ base = pB + pk0;
-#pragma unroll
-                for (int idx = tid; idx < TN * KC; idx += NT) {
+                for (int idx = tid; idx < tn_ld * KC; idx += NT) {
                     const int kk = idx % KC, nn = idx / KC;
+                    if (kk >= kld) continue;
                     const bool v = nn < pnrem && kk < krem;
-                    cp_async8(bs + nn * LDK + kk, v ? base + (kk + nn * p_ldb) : pB, v);
+                    cp_async8(bs + nn * LDK + kk, v ? base + (kk + (long long)nn * p_ldb) : pB, v);
                 }
             } else {
                 const double* __restrict__ base = pB + (long long)pk0 * p_ldb;
-#pragma unroll
-                for (int idx = tid; idx < TN * KC; idx += NT) {
+                for (int idx = tid; idx < TN * kld; idx += NT) {
                     const int nn = idx % TN, kk = idx / TN;
+                    if (nn >= tn_ld) continue;
                     const bool v = nn < pnrem && kk < krem;
-                    cp_async8(bs + kk * LDB_S + nn, v ? base + (nn + kk * p_ldb) : pB, v);
+                    cp_async8(bs + kk * LDB_S + nn, v ? base + (nn + (long long)kk * p_ldb) : pB, v);
                 }
             }
-            if (tid == 0) { alpha_s[stage] = p_alpha; flags_s[stage] = (p_ta ? 1 : 0) | (p_tb ? 0 : 2); }
+            if (tid == 0) { alpha_s[stage] = p_alpha; flags_s[stage] = (p_ta ? 1 : 0) | (p_tb ? 0 : 2) | (kld << 8); }
             pk0 += KC;
             if (pk0 >= p_k) { ++ps; load_seg(); }
         }
@@ -285,22 +364,47 @@ k_gemm_dmma(const DWork* __restrict__ works, const DSeg* __restrict__ segs, cons
         const double* bs = Bs + stage * B_STAGE;
         const double alpha = alpha_s[stage];
         const int fl = flags_s[stage];
+        const int k4n = (fl >> 8) >> 2;
         // per-lane fragment base and strides for the two orientations
-        const int a_base = (fl & 1) ? (wm * WMT * 8 + fr) * LDK + fk : fk * LDA_S + wm * WMT * 8 + fr;
+        const int a_base = (fl & 1) ? (row0 + fr) * LDK + fk : fk * LDA_S + row0 + fr;
         const int a_ti = (fl & 1) ? 8 * LDK : 8, a_tk = (fl & 1) ? 4 : 4 * LDA_S;
-        const int b_base = (fl & 2) ? (wn * WNT * 8 + fr) * LDK + fk : fk * LDB_S + wn * WNT * 8 + fr;
+        const int b_base = (fl & 2) ? (col0 + fr) * LDK + fk : fk * LDB_S + col0 + fr;
         const int b_tj = (fl & 2) ? 8 * LDK : 8, b_tk = (fl & 2) ? 4 : 4 * LDB_S;
+        if (mt == WMT && nt == WNT) {             // full warp tile: no per-fragment tests
 #pragma unroll
-        for (int k4 = 0; k4 < KC / 4; ++k4) {
-            double a[WMT], b[WNT];
+            for (int k4 = 0; k4 < KC / 4; ++k4) {
+                if (k4 >= k4n) break;
+                double a[WMT], b[WNT];
 #pragma unroll
-            for (int i = 0; i < WMT; ++i) a[i] = alpha * as[a_base + i * a_ti + k4 * a_tk];
+                for (int i = 0; i < WMT; ++i) a[i] = as[a_base + i * a_ti + k4 * a_tk];
 #pragma unroll
-            for (int j = 0; j < WNT; ++j) b[j] = bs[b_base + j * b_tj + k4 * b_tk];
+                for (int j = 0; j < WNT; ++j) b[j] = bs[b_base + j * b_tj + k4 * b_tk];
+                if (alpha != 1.0) {
 #pragma unroll
-            for (int i = 0; i < WMT; ++i)
+                    for (int i = 0; i < WMT; ++i) a[i] *= alpha;
+                }
 #pragma unroll
-                for (int j = 0; j < WNT; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                for (int i = 0; i < WMT; ++i)
+#pragma unroll
+                    for (int j = 0; j < WNT; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            }
+        } else if (mt > 0 && nt > 0) {
+#pragma unroll
+            for (int k4 = 0; k4 < KC / 4; ++k4) {
+                if (k4 >= k4n) break;
+                double a[WMT], b[WNT];
+#pragma unroll
+                for (int i = 0; i < WMT; ++i) a[i] = i < mt ? alpha * as[a_base + i * a_ti + k4 * a_tk] : 0.;
+#pragma unroll
+                for (int j = 0; j < WNT; ++j) b[j] = j < nt ? bs[b_base + j * b_tj + k4 * b_tk] : 0.;
+#pragma unroll
+                for (int i = 0; i < WMT; ++i)
+                    if (i < mt) {
+#pragma unroll
+                        for (int j = 0; j < WNT; ++j)
+                            if (j < nt) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                    }
+            }
         }
     }
     cp_async_wait<0>();
@@ -312,8 +416,8 @@ k_gemm_dmma(const DWork* __restrict__ works, const DSeg* __restrict__ segs, cons
         for (int j = 0; j < WNT; ++j)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                int r = w.m0 + (wm * WMT + i) * 8 + fr, c = w.n0 + (wn * WNT + j) * 8 + 2 * fk + e;
-                if (r < w.m && c < w.n) {
+                int r = w.m0 + row0 + i * 8 + fr, c = w.n0 + col0 + j * 8 + 2 * fk + e;
+                if (i < mt && j < nt && r < w.m && c < w.n) {
                     double* q = C + r + (long long)c * w.ldc;
                     if (w.mode == 0) *q = acc[i][j][e];
                     else if (w.mode == 1) *q += acc[i][j][e];
@@ -387,7 +491,11 @@ struct GemmGroup
     std::vector<GemmLaunch> launches;
     int64_t n_works = 0;
 };
-struct AxpyGroup { DWWork* d_works = nullptr; DWGroup* d_groups = nullptr; DWSrc* d_srcs = nullptr; DWDst* d_dsts = nullptr; double* d_coefs = nullptr; int64_t n_works = 0, n_narrow = 0; };
+struct AxpyGroup
+{
+    DWWork* d_works = nullptr; DWGroup* d_groups = nullptr; DWSrc* d_srcs = nullptr; DWDst* d_dsts = nullptr; double* d_coefs = nullptr;
+    int64_t begin[5] = {0, 0, 0, 0, 0}, count[5] = {0, 0, 0, 0, 0};   // work ranges: [0] stream, [1..4] DMMA product with ng = 8, 16, 32, 64
+};
 struct WaveDev { GemmGroup t, c; AxpyGroup w; int64_t y_elems = 0, t_elems = 0; };
 
 struct qcm_plan_s
@@ -434,6 +542,7 @@ static struct Global
 } G;
 
 static int gemm_set_attributes();
+static int wgemm_set_attributes();
 static int ensure_ws(int slot, int64_t n)
 {
     if (n <= G.ws_elems[slot]) return 0;
@@ -467,7 +576,7 @@ extern "C" int qcm_init(int device)
     for (int i = 0; i < Global::kAux; ++i) { CU(cudaStreamCreateWithFlags(&G.aux[i], cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&G.join_ev[i], cudaEventDisableTiming)); }
     CU(cudaEventCreateWithFlags(&G.fork_ev, cudaEventDisableTiming));
     CU(cudaMalloc((void**)&G.scratch, 4096));
-    if (gemm_set_attributes()) return 1;
+    if (gemm_set_attributes() || wgemm_set_attributes()) return 1;
     G.device = device;
     G.ready = true;
     return 0;
@@ -560,15 +669,15 @@ struct TileVariant { int tm, tn, threads; double eff; };
 static const TileVariant kVariants[] = {
     {64, 128, 256, 1.00},  // 0: 2x4 warps, 4x4 tiles
     {128, 64, 256, 1.00},  // 1: 4x2 warps, 4x4
-    {64, 64, 128, 0.90},   // 2: 2x2 warps, 4x4
-    {32, 128, 128, 0.85},  // 3: 1x4 warps, 4x4
-    {128, 32, 128, 0.85},  // 4: 4x1 warps, 4x4
-    {16, 128, 128, 0.60},  // 5: 1x4 warps, 2x4
-    {128, 16, 128, 0.60},  // 6: 4x1 warps, 4x2
-    {32, 32, 128, 0.45},   // 7: 2x2 warps, 2x2
-    {16, 16, 128, 0.20},   // 8: 2x2 warps, 1x1
-    {8, 128, 128, 0.35},   // 9: 1x4 warps, 1x4
-    {128, 8, 128, 0.35},   // 10: 4x1 warps, 4x1
+    {64, 64, 128, 1.00},   // 2: 2x2 warps, 4x4
+    {32, 128, 128, 1.00},  // 3: 1x4 warps, 4x4
+    {128, 32, 128, 1.00},  // 4: 4x1 warps, 4x4
+    {16, 128, 128, 0.90},  // 5: 1x4 warps, 2x4
+    {128, 16, 128, 0.90},  // 6: 4x1 warps, 4x2
+    {32, 32, 128, 0.90},   // 7: 2x2 warps, 2x2
+    {16, 16, 128, 0.80},   // 8: 2x2 warps, 1x1
+    {8, 128, 128, 0.80},   // 9: 1x4 warps, 1x4
+    {128, 8, 128, 0.80},   // 10: 4x1 warps, 4x1
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 static size_t variant_smem(int v)
@@ -600,12 +709,30 @@ static void launch_gemm_variant(int v, int64_t n, const DWork* works, const DSeg
     }
 }
 
-static int pick_variant(int m, int n)
+// Cost model (SM cycles) of running an m x n output with `chunks` K chunks on tile variant v.  Fragments outside
+// the output are skipped by the kernel, so the FP64 pipe term counts real 8x8 fragments (16 pipe cycles per fragment
+// and k-step of 4, one DMMA per 4 cycles and SM); staging and the per-chunk barrier are partly hidden by the other
+// CTAs of the SM; every tile pays a fixed prologue / epilogue.
+static int g_force_variant = -2;
+static int pick_variant(int m, int n, int chunks)
 {
+    if (g_force_variant == -2) { const char* e = getenv("QCM_FORCE_VARIANT"); g_force_variant = e ? atoi(e) : -1; }
+    if (g_force_variant >= 0 && g_force_variant < kNumVariants) return g_force_variant;
     int best = 0; double best_cost = 1e300;
     for (int v = 0; v < kNumVariants; ++v) {
-        double tiles = (double)((m + kVariants[v].tm - 1) / kVariants[v].tm) * (double)((n + kVariants[v].tn - 1) / kVariants[v].tn);
-        double cost = tiles * kVariants[v].tm * kVariants[v].tn / kVariants[v].eff;
+        const int tm = kVariants[v].tm, tn = kVariants[v].tn;
+        double cost = 0;
+        for (int pm = 0; pm < 2; ++pm)
+            for (int pn = 0; pn < 2; ++pn) {
+                // full tiles and the ragged last row / column of tiles
+                const int cm = pm == 0 ? m / tm : (m % tm ? 1 : 0), cn = pn == 0 ? n / tn : (n % tn ? 1 : 0);
+                if (!cm || !cn) continue;
+                const int em = pm == 0 ? tm : m % tm, en = pn == 0 ? tn : n % tn;
+                const double frags = (double)((em + 7) / 8) * ((en + 7) / 8);
+                const double per_chunk = frags * 4.0 * (KC / 4) + 1.0 * (((em + 7) & ~7) + ((en + 7) & ~7)) + 120.0;
+                cost += (double)cm * cn * (chunks * per_chunk + 1200.0);
+            }
+        cost /= kVariants[v].eff;
         if (cost < best_cost) { best_cost = cost; best = v; }
     }
     return best;
@@ -636,8 +763,6 @@ static int build_gemm_group(qcm_plan_s* P, GemmGroup& g, const qcm_gemm_out* out
     for (int64_t o = 0; o < n_outs; ++o) {
         qcm_gemm_out const& out = outs[o];
         if (out.m <= 0 || out.n <= 0) continue;
-        int v = pick_variant(out.m, out.n);
-        // chunk the segment list
         std::vector<std::pair<int, int>> chunks;
         {
             int csum = 0, cb = out.seg_begin;
@@ -647,6 +772,9 @@ static int build_gemm_group(qcm_plan_s* P, GemmGroup& g, const qcm_gemm_out* out
             }
             chunks.push_back(std::make_pair(cb, out.seg_end));
         }
+        int total_chunks = 0;
+        for (int s = out.seg_begin; s < out.seg_end; ++s) total_chunks += (segs[s].k + KC - 1) / KC;
+        int v = pick_variant(out.m, out.n, std::max(1, total_chunks / (int)chunks.size()));
         int mode = chunks.size() > 1 ? 2 : base_mode;
         if (chunks.size() > 1 && base_mode == 0) return fail("internal: split-K on a store-mode output");
         for (auto const& ch : chunks)
@@ -678,26 +806,79 @@ static int build_axpy_group(qcm_plan_s* P, AxpyGroup& g, qcm_wave_desc const& wd
     std::vector<DWDst> hd((size_t)wd.n_w_dsts);
     for (int64_t i = 0; i < wd.n_w_dsts; ++i) hd[i] = DWDst{wd.w_dsts[i].dst.off, wd.w_dsts[i].dst.buf, wd.w_dsts[i].ldd};
     std::vector<DWGroup> hg((size_t)wd.n_w_groups);
-    std::vector<DWWork> hw, hw_wide;      // one work item per warp: 8 rows x WT columns of the group's panels
+    std::vector<DWWork> cls[5];
     for (int64_t i = 0; i < wd.n_w_groups; ++i) {
         qcm_w_group const& q = wd.w_groups[i];
-        if (q.ng != 8 && q.ng != 16) return fail("qcm_plan_create: W group with ng outside {8,16}");
-        if (q.n_dst > q.ng) return fail("qcm_plan_create: W group with more destinations than ng");
-        int tpc = (q.rows + 7) / 8;
-        hg[i] = DWGroup{q.rows, q.cols, q.n_src, q.n_dst, q.ng, q.src_begin, q.dst_begin, tpc, q.coef_begin};
-        const int wt = q.ng == 16 ? 4 : 8;
-        std::vector<DWWork>& dstv = q.ng == 16 ? hw_wide : hw;
-        for (int c0 = 0; c0 < q.cols; c0 += wt)
-            for (int r8 = 0; r8 < tpc; ++r8) dstv.push_back(DWWork{(int)i, r8, c0, 0});
+        int c;
+        if (q.cls == 1) {
+            if (q.n_src > 4 || q.n_dst > 4 || q.ng != 4) return fail("qcm_plan_create: stream W group outside (n_src <= 4, n_dst <= 4, ng = 4)");
+            c = 0;
+        } else {
+            c = q.ng == 8 ? 1 : q.ng == 16 ? 2 : q.ng == 32 ? 3 : q.ng == 64 ? 4 : -1;
+            if (c < 0) return fail("qcm_plan_create: W group with ng outside {8,16,32,64}");
+            if (q.n_dst > q.ng) return fail("qcm_plan_create: W group with more destinations than ng");
+        }
+        if (q.n_src < 1 || q.n_dst < 1) return fail("qcm_plan_create: empty W group");
+        if ((int64_t)q.rows * q.cols >= ((int64_t)1 << 31)) return fail("qcm_plan_create: W panel with 2^31 or more elements");
+        hg[i] = DWGroup{q.rows, q.cols, q.n_src, q.n_dst, q.ng, q.src_begin, q.dst_begin, q.cls, q.coef_begin};
+        const int n = q.rows * q.cols, tile = c == 0 ? WS_TILE : WG_TE;
+        for (int e0 = 0; e0 < n; e0 += tile) cls[c].push_back(DWWork{(int)i, e0});
     }
-    g.n_narrow = (int64_t)hw.size();
-    hw.insert(hw.end(), hw_wide.begin(), hw_wide.end());
+    std::vector<DWWork> hw;
+    for (int c = 0; c < 5; ++c) {
+        g.begin[c] = (int64_t)hw.size(); g.count[c] = (int64_t)cls[c].size();
+        hw.insert(hw.end(), cls[c].begin(), cls[c].end());
+        if (g.count[c]) P->n_launches += 1;
+    }
     std::vector<double> hc(wd.w_coefs, wd.w_coefs + wd.n_w_coefs);
-    g.n_works = (int64_t)hw.size();
     if (dev_upload(P, hw, &g.d_works) || dev_upload(P, hg, &g.d_groups) || dev_upload(P, hs, &g.d_srcs) || dev_upload(P, hd, &g.d_dsts) ||
         dev_upload(P, hc, &g.d_coefs)) return 1;
-    if (g.n_narrow) P->n_launches += 1;
-    if (g.n_works > g.n_narrow) P->n_launches += 1;
+    return 0;
+}
+
+template <int NG, int MF> static void launch_wgemm(AxpyGroup const& g, int c, BufTable const& bufs, cudaStream_t st)
+{
+    constexpr int NT = WG_TE / (8 * MF) * 32;
+    k_wgemm<NG, MF><<<(unsigned)g.count[c], NT, wg_smem_doubles<NG, MF>() * sizeof(double), st>>>(g.d_works + g.begin[c], g.d_groups, g.d_srcs, g.d_dsts, g.d_coefs, bufs);
+}
+static int wgemm_set_attributes()
+{
+    CU(cudaFuncSetAttribute(k_wgemm<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(wg_smem_doubles<8, 4>() * sizeof(double))));
+    CU(cudaFuncSetAttribute(k_wgemm<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(wg_smem_doubles<16, 4>() * sizeof(double))));
+    CU(cudaFuncSetAttribute(k_wgemm<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(wg_smem_doubles<32, 2>() * sizeof(double))));
+    CU(cudaFuncSetAttribute(k_wgemm<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(wg_smem_doubles<64, 2>() * sizeof(double))));
+    return 0;
+}
+static int run_w_group(AxpyGroup const& g, BufTable const& bufs)
+{
+    // the classes write disjoint destination panels: run them side by side
+    int n_active = 0;
+    for (int c = 0; c < 5; ++c) n_active += g.count[c] > 0;
+    if (n_active == 0) return 0;
+    const bool fork = n_active > 1;
+    if (fork) {
+        CU(cudaEventRecord(G.fork_ev, G.stream));
+        for (int i = 0; i < Global::kAux; ++i) CU(cudaStreamWaitEvent(G.aux[i], G.fork_ev, 0));
+    }
+    bool used[Global::kAux] = {false, false, false};
+    int li = 0;
+    for (int c = 4; c >= 0; --c) {       // the compute-heavy classes first
+        if (!g.count[c]) continue;
+        cudaStream_t st = G.stream;
+        if (fork && li > 0) { int a = (li - 1) % Global::kAux; st = G.aux[a]; used[a] = true; }
+        switch (c) {
+            case 0: k_wstream<<<(unsigned)g.count[0], WS_THREADS, 0, st>>>(g.d_works + g.begin[0], g.d_groups, g.d_srcs, g.d_dsts, g.d_coefs, bufs); break;
+            case 1: launch_wgemm<8, 4>(g, c, bufs, st); break;
+            case 2: launch_wgemm<16, 4>(g, c, bufs, st); break;
+            case 3: launch_wgemm<32, 2>(g, c, bufs, st); break;
+            case 4: launch_wgemm<64, 2>(g, c, bufs, st); break;
+        }
+        G.launches++; ++li;
+    }
+    if (fork)
+        for (int i = 0; i < Global::kAux; ++i)
+            if (used[i]) { CU(cudaEventRecord(G.join_ev[i], G.aux[i])); CU(cudaStreamWaitEvent(G.stream, G.join_ev[i], 0)); }
+    CU(cudaGetLastError());
     return 0;
 }
 
@@ -809,16 +990,7 @@ static int execute(qcm_plan_s* P, BufTable bufs)
         mark(3);
         if (run_gemm_group(W.t, bufs)) return 1;
         mark(4); lap(1, 3, 4);
-        if (W.y_elems) CU(cudaMemsetAsync(bufs.p[QCM_BUF_Y], 0, (size_t)W.y_elems * 8, G.stream));
-        if (W.w.n_narrow) {
-            k_wapply_dmma<false><<<(unsigned)((W.w.n_narrow + W_WARPS - 1) / W_WARPS), W_WARPS * 32, 0, G.stream>>>(W.w.d_works, (int)W.w.n_narrow, W.w.d_groups, W.w.d_srcs, W.w.d_dsts, W.w.d_coefs, bufs);
-            G.launches++;
-        }
-        if (W.w.n_works > W.w.n_narrow) {
-            int64_t nw = W.w.n_works - W.w.n_narrow;
-            k_wapply_dmma<true><<<(unsigned)((nw + W_WARPS - 1) / W_WARPS), W_WARPS * 32, 0, G.stream>>>(W.w.d_works + W.w.n_narrow, (int)nw, W.w.d_groups, W.w.d_srcs, W.w.d_dsts, W.w.d_coefs, bufs);
-            G.launches++;
-        }
+        if (run_w_group(W.w, bufs)) return 1;
         mark(5); lap(2, 4, 5);
         if (run_gemm_group(W.c, bufs)) return 1;
         mark(6); lap(3, 5, 6);

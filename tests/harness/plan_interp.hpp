@@ -51,7 +51,8 @@ inline void run_plan(plan::Plan const& P, Bufs& B)
         // poison T so that a read of a product that was not computed in this wave is caught
         std::fill(B.b[plan::BUF_T].begin(), B.b[plan::BUF_T].end(), std::nan(""));
         run_gemm(W.t_gemm, B, false);
-        std::fill(B.b[plan::BUF_Y].begin(), B.b[plan::BUF_Y].begin() + W.y_elems, 0.);
+        // Y is never zero-filled: every element the closing products read was written by the W pass of this wave
+        std::fill(B.b[plan::BUF_Y].begin(), B.b[plan::BUF_Y].end(), std::nan(""));
         for (auto const& G : W.w_groups.groups)
             for (int d = 0; d < G.n_dst; ++d) {
                 plan::WDst const& D = W.w_groups.dsts[G.dst_begin + d];
