@@ -41,11 +41,25 @@ def _headers():
 
 
 def build_cuda(force=False):
+    """Every .cu under csrc/ is one translation unit (compiled side by side), linked into libqcm_b200.so."""
+    from concurrent.futures import ThreadPoolExecutor
     os.makedirs(LIB, exist_ok=True)
+    odir = os.path.join(ROOT, "build", "obj")
+    os.makedirs(odir, exist_ok=True)
     out = os.path.join(LIB, "libqcm_b200.so")
-    src = os.path.join(CSRC, "qcm_b200.cu")
-    if force or _newer(out, [src] + _headers()):
-        _run(["nvcc"] + NVCC_FLAGS + [src, "-o", out, "-ldl"])
+    srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    deps = _headers() + glob.glob(os.path.join(CSRC, "*.cuh"))
+    objs, jobs = [], []
+    for src in srcs:
+        obj = os.path.join(odir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if force or _newer(obj, [src] + deps):
+            jobs.append(["nvcc"] + [f for f in NVCC_FLAGS if f != "-shared"] + ["-c", src, "-o", obj])
+    if jobs:
+        with ThreadPoolExecutor(max_workers=len(jobs)) as ex:
+            list(ex.map(_run, jobs))
+    if jobs or force or _newer(out, objs):
+        _run(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-o", out, "-ldl"])
     return out
 
 

@@ -20,9 +20,8 @@
 //   k_vec_*         solver-side BLAS-1 on device-resident vectors
 //
 // There is no CPU fallback: every entry point fails with a status when the device is not usable.
-#include "../../include/qcm_b200.h"
+#include "qcm_dev.cuh"
 
-#include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <algorithm>
 #include <cstdio>
@@ -40,11 +39,7 @@ static int fail(std::string const& s) { g_err = s; return 1; }
 
 struct qcm_array_s { double* p; int64_t n; };
 
-struct BufTable { double* p[QCM_BUF_COUNT]; };
-
 // device-side task records ---------------------------------------------------------------------------------
-struct DSeg { long long a_off, b_off; int a_buf, b_buf, lda, ldb, m, n, k, ta, tb, pad; double alpha; };
-struct DWork { long long c_off; int c_buf, ldc, m0, n0, m, n, seg_begin, seg_end, mode, pad; };   // mode 0 store, 1 add, 2 atomic
 struct DWSrc { long long off; int buf, lds; };
 struct DWDst { long long off; int buf, ldd; };
 struct DWGroup { int rows, cols, n_src, n_dst, ng, src_begin, dst_begin, cls; long long coef_begin; };
@@ -227,203 +222,6 @@ k_wgemm(const DWWork* __restrict__ works, const DWGroup* __restrict__ groups, co
             const DWDst q = dsts[g.dst_begin + d];
             (bufs.p[q.buf] + q.off)[r + (long long)c * q.ldd] = Cs[d * WG_LDC + el];
         }
-}
-
-constexpr int KC = 16;         // K chunk staged per pipeline stage
-constexpr int SPAD = 4;        // row padding: (TM + 4) % 16 == 4 makes the fragment reads conflict free
-constexpr int STAGES = 3;
-
-// Grouped, variable-size FP64 GEMM.  CTA = WARPS_M x WARPS_N warps, each warp owns up to WMT x WNT DMMA tiles (8x8).
-// One CTA computes one output tile and walks the K-segments of its work item (the terms of the sum over the MPO
-// bond index and over source panels that land in this row unit of a symmetry sector).  Operand tiles are staged in
-// shared memory by a STAGES-deep cp.async pipeline that runs across segment borders.  Symmetry blocks are ragged:
-// the 8x8 fragments of the tile that lie inside the output are distributed evenly over the warp grid at run time,
-// fragments outside are never issued, and a K chunk is consumed in steps of 4 up to the segment's real depth -- the
-// FP64 pipe only sees work that is padded to (8, 8, 4), not to the tile shape.  alpha (coefficient of a directly
-// consumed source panel, Hermitian phase, SU2 conjugate correction) scales the A fragments when it is not 1.
-constexpr int LDK = KC + 4;     // K-major rows: (KC + 4) % 16 == 4, conflict free as well
-template <int WARPS_M, int WARPS_N, int WMT, int WNT>
-__global__ void __launch_bounds__(WARPS_M* WARPS_N * 32)
-k_gemm_dmma(const DWork* __restrict__ works, const DSeg* __restrict__ segs, const __grid_constant__ BufTable bufs)
-{
-    constexpr int TM = WARPS_M * WMT * 8, TN = WARPS_N * WNT * 8, NT = WARPS_M * WARPS_N * 32;
-    constexpr int LDA_S = TM + SPAD, LDB_S = TN + SPAD;
-    // a staged operand tile is stored in the orientation in which global memory is contiguous:
-    //   "M-major"  [kk][mm]  when the m (resp. n) index is contiguous in memory (A not transposed, B transposed)
-    //   "K-major"  [mm][kk]  when the k index is contiguous (A transposed, B not transposed)
-    constexpr int A_STAGE = (KC * LDA_S > TM * LDK) ? KC * LDA_S : TM * LDK;
-    constexpr int B_STAGE = (KC * LDB_S > TN * LDK) ? KC * LDB_S : TN * LDK;
-    extern __shared__ double smem[];
-    double* As = smem;                          // [STAGES][A_STAGE]
-    double* Bs = smem + STAGES * A_STAGE;       // [STAGES][B_STAGE]
-    __shared__ double alpha_s[STAGES];
-    __shared__ int flags_s[STAGES];             // bit 0: A is K-major, bit 1: B is K-major, bits 8..: valid depth of the chunk
-
-    const DWork w = works[blockIdx.x];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp % WARPS_M, wn = warp / WARPS_M;
-    const int fr = lane >> 2, fk = lane & 3;
-
-    // rows / columns of the tile that exist, in fragments, spread evenly over the warp grid
-    const int tm_eff = min(TM, w.m - w.m0), tn_eff = min(TN, w.n - w.n0);
-    const int fpw_m = ((tm_eff + 7) / 8 + WARPS_M - 1) / WARPS_M, fpw_n = ((tn_eff + 7) / 8 + WARPS_N - 1) / WARPS_N;   // <= WMT, WNT
-    const int row0 = wm * fpw_m * 8, col0 = wn * fpw_n * 8;                     // first row / column of this warp inside the tile
-    const int mt = max(0, min(fpw_m, (tm_eff - row0 + 7) / 8)), nt = max(0, min(fpw_n, (tn_eff - col0 + 7) / 8));
-    const int tm_ld = (tm_eff + 7) & ~7, tn_ld = (tn_eff + 7) & ~7;             // rows / columns the producer stages
-
-    double acc[WMT][WNT][2];
-#pragma unroll
-    for (int i = 0; i < WMT; ++i)
-#pragma unroll
-        for (int j = 0; j < WNT; ++j) acc[i][j][0] = acc[i][j][1] = 0.;
-
-    // producer cursor over the flattened (segment, k-chunk) sequence
-    int ps = w.seg_begin, pk0 = 0;
-    int p_lda = 0, p_ldb = 0, p_k = 0, p_ta = 0, p_tb = 0, pmrem = 0, pnrem = 0;
-    double p_alpha = 0.;
-    const double* __restrict__ pA = nullptr;
-    const double* __restrict__ pB = nullptr;
-    int nchunks = 0;
-    auto load_seg = [&]() {
-        while (ps < w.seg_end) {
-            const DSeg sg = segs[ps];
-            pmrem = sg.m - w.m0; pnrem = sg.n - w.n0;
-            if (pmrem > 0 && pnrem > 0 && sg.k > 0) {          // segments may be smaller than the output block
-                p_lda = sg.lda; p_ldb = sg.ldb; p_k = sg.k; p_ta = sg.ta; p_tb = sg.tb; p_alpha = sg.alpha;
-                // tile origin folded into the base pointers
-                pA = bufs.p[sg.a_buf] + sg.a_off + (sg.ta ? (long long)w.m0 * sg.lda : (long long)w.m0);
-                pB = bufs.p[sg.b_buf] + sg.b_off + (sg.tb ? (long long)w.n0 : (long long)w.n0 * sg.ldb);
-                pk0 = 0;
-                return;
-            }
-            ++ps;
-        }
-    };
-    load_seg();
-    auto issue = [&](int stage) {
-        if (ps < w.seg_end) {
-            double* as = As + stage * A_STAGE;
-            double* bs = Bs + stage * B_STAGE;
-            const int krem = p_k - pk0;
-            const int kld = min(KC, (krem + 3) & ~3);           // depth the consumer will read
-            if (!p_ta) {
-                const double* __restrict__ base = pA + (long long)pk0 * p_lda;
-                for (int idx = tid; idx < TM * kld; idx += NT) {
-                    const int mm = idx % TM, kk = idx / TM;
-                    if (mm >= tm_ld) continue;
-                    const bool v = mm < pmrem && kk < krem;
-                    cp_async8(as + kk * LDA_S + mm, v ? base + (mm + (long long)kk * p_lda) : pA, v);
-                }
-            } else {
-                const double* __restrict__ base = pA + pk0;
-                for (int idx = tid; idx < tm_ld * KC; idx += NT) {
-                    const int kk = idx % KC, mm = idx / KC;
-                    if (kk >= kld) continue;
-                    const bool v = mm < pmrem && kk < krem;
-                    cp_async8(as + mm * LDK + kk, v ? base + (kk + (long long)mm * p_lda) : pA, v);
-                }
-            }
-            if (!p_tb) {
-                const double* __restrict__ base = pB + pk0;
-                for (int idx = tid; idx < tn_ld * KC; idx += NT) {
-                    const int kk = idx % KC, nn = idx / KC;
-                    if (kk >= kld) continue;
-                    const bool v = nn < pnrem && kk < krem;
-                    cp_async8(bs + nn * LDK + kk, v ? base + (kk + (long long)nn * p_ldb) : pB, v);
-                }
-            } else {
-                const double* __restrict__ base = pB + (long long)pk0 * p_ldb;
-                for (int idx = tid; idx < TN * kld; idx += NT) {
-                    const int nn = idx % TN, kk = idx / TN;
-                    if (nn >= tn_ld) continue;
-                    const bool v = nn < pnrem && kk < krem;
-                    cp_async8(bs + kk * LDB_S + nn, v ? base + (nn + (long long)kk * p_ldb) : pB, v);
-                }
-            }
-            if (tid == 0) { alpha_s[stage] = p_alpha; flags_s[stage] = (p_ta ? 1 : 0) | (p_tb ? 0 : 2) | (kld << 8); }
-            pk0 += KC;
-            if (pk0 >= p_k) { ++ps; load_seg(); }
-        }
-        cp_async_commit();
-    };
-
-    // total number of chunks this work item will consume (same walk as the producer, without loading)
-    for (int s = w.seg_begin; s < w.seg_end; ++s) {
-        const int m = segs[s].m, n = segs[s].n, k = segs[s].k;
-        if (m - w.m0 > 0 && n - w.n0 > 0 && k > 0) nchunks += (k + KC - 1) / KC;
-    }
-
-#pragma unroll
-    for (int st = 0; st < STAGES - 1; ++st) issue(st);
-    for (int it = 0; it < nchunks; ++it) {
-        cp_async_wait<STAGES - 2>();
-        __syncthreads();
-        issue((it + STAGES - 1) % STAGES);      // refills the stage consumed in the previous iteration
-        const int stage = it % STAGES;
-        const double* as = As + stage * A_STAGE;
-        const double* bs = Bs + stage * B_STAGE;
-        const double alpha = alpha_s[stage];
-        const int fl = flags_s[stage];
-        const int k4n = (fl >> 8) >> 2;
-        // per-lane fragment base and strides for the two orientations
-        const int a_base = (fl & 1) ? (row0 + fr) * LDK + fk : fk * LDA_S + row0 + fr;
-        const int a_ti = (fl & 1) ? 8 * LDK : 8, a_tk = (fl & 1) ? 4 : 4 * LDA_S;
-        const int b_base = (fl & 2) ? (col0 + fr) * LDK + fk : fk * LDB_S + col0 + fr;
-        const int b_tj = (fl & 2) ? 8 * LDK : 8, b_tk = (fl & 2) ? 4 : 4 * LDB_S;
-        if (mt == WMT && nt == WNT) {             // full warp tile: no per-fragment tests
-#pragma unroll
-            for (int k4 = 0; k4 < KC / 4; ++k4) {
-                if (k4 >= k4n) break;
-                double a[WMT], b[WNT];
-#pragma unroll
-                for (int i = 0; i < WMT; ++i) a[i] = as[a_base + i * a_ti + k4 * a_tk];
-#pragma unroll
-                for (int j = 0; j < WNT; ++j) b[j] = bs[b_base + j * b_tj + k4 * b_tk];
-                if (alpha != 1.0) {
-#pragma unroll
-                    for (int i = 0; i < WMT; ++i) a[i] *= alpha;
-                }
-#pragma unroll
-                for (int i = 0; i < WMT; ++i)
-#pragma unroll
-                    for (int j = 0; j < WNT; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-            }
-        } else if (mt > 0 && nt > 0) {
-#pragma unroll
-            for (int k4 = 0; k4 < KC / 4; ++k4) {
-                if (k4 >= k4n) break;
-                double a[WMT], b[WNT];
-#pragma unroll
-                for (int i = 0; i < WMT; ++i) a[i] = i < mt ? alpha * as[a_base + i * a_ti + k4 * a_tk] : 0.;
-#pragma unroll
-                for (int j = 0; j < WNT; ++j) b[j] = j < nt ? bs[b_base + j * b_tj + k4 * b_tk] : 0.;
-#pragma unroll
-                for (int i = 0; i < WMT; ++i)
-                    if (i < mt) {
-#pragma unroll
-                        for (int j = 0; j < WNT; ++j)
-                            if (j < nt) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-                    }
-            }
-        }
-    }
-    cp_async_wait<0>();
-    // ---- epilogue: C fragment (row = lane/4, cols = 2*(lane%4) + {0,1})
-    double* __restrict__ C = bufs.p[w.c_buf] + w.c_off;
-#pragma unroll
-    for (int i = 0; i < WMT; ++i)
-#pragma unroll
-        for (int j = 0; j < WNT; ++j)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                int r = w.m0 + row0 + i * 8 + fr, c = w.n0 + col0 + j * 8 + 2 * fk + e;
-                if (i < mt && j < nt && r < w.m && c < w.n) {
-                    double* q = C + r + (long long)c * w.ldc;
-                    if (w.mode == 0) *q = acc[i][j][e];
-                    else if (w.mode == 1) *q += acc[i][j][e];
-                    else atomicAdd(q, acc[i][j][e]);
-                }
-            }
 }
 
 // solver-side BLAS-1 --------------------------------------------------------------------------------------
@@ -665,62 +463,35 @@ extern "C" int qcm_array_zero(qcm_array_t a)
 }
 
 // ---- plan construction ----------------------------------------------------------------------------------
-struct TileVariant { int tm, tn, threads; double eff; };
-static const TileVariant kVariants[] = {
-    {64, 128, 256, 1.00},  // 0: 2x4 warps, 4x4 tiles
-    {128, 64, 256, 1.00},  // 1: 4x2 warps, 4x4
-    {64, 64, 128, 1.00},   // 2: 2x2 warps, 4x4
-    {32, 128, 128, 1.00},  // 3: 1x4 warps, 4x4
-    {128, 32, 128, 1.00},  // 4: 4x1 warps, 4x4
-    {16, 128, 128, 0.90},  // 5: 1x4 warps, 2x4
-    {128, 16, 128, 0.90},  // 6: 4x1 warps, 4x2
-    {32, 32, 128, 0.90},   // 7: 2x2 warps, 2x2
-    {16, 16, 128, 0.80},   // 8: 2x2 warps, 1x1
-    {8, 128, 128, 0.80},   // 9: 1x4 warps, 1x4
-    {128, 8, 128, 0.80},   // 10: 4x1 warps, 4x1
-};
-constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
-static size_t variant_smem(int v)
-{
-    size_t a = std::max(KC * (kVariants[v].tm + SPAD), kVariants[v].tm * LDK), b = std::max(KC * (kVariants[v].tn + SPAD), kVariants[v].tn * LDK);
-    return (size_t)STAGES * (a + b) * sizeof(double);
-}
-
-#define QCM_FOR_EACH_VARIANT(X) \
-    X(0, 2, 4, 4, 4) X(1, 4, 2, 4, 4) X(2, 2, 2, 4, 4) X(3, 1, 4, 4, 4) X(4, 4, 1, 4, 4) X(5, 1, 4, 2, 4) X(6, 4, 1, 4, 2) \
-    X(7, 2, 2, 2, 2) X(8, 2, 2, 1, 1) X(9, 1, 4, 1, 4) X(10, 4, 1, 4, 1)
-
+constexpr int KC = 16;   // K chunk of the GEMM kernels (gemm_ws.cu)
 static int gemm_set_attributes()
 {
-#define X(v, a, b, c, d) CU(cudaFuncSetAttribute(k_gemm_dmma<a, b, c, d>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)variant_smem(v)));
-    QCM_FOR_EACH_VARIANT(X)
-#undef X
+    const char* e = gemm_ws_init(G.sm_count);
+    if (e) return fail(std::string("gemm_ws_init: ") + e);
     return 0;
 }
 
-static void launch_gemm_variant(int v, int64_t n, const DWork* works, const DSeg* segs, BufTable const& bufs, cudaStream_t st)
-{
-    dim3 g((unsigned)n), b(kVariants[v].threads);
-    size_t sm = variant_smem(v);
-    switch (v) {
-#define X(vv, a, bb, c, d) case vv: k_gemm_dmma<a, bb, c, d><<<g, b, sm, st>>>(works, segs, bufs); break;
-    QCM_FOR_EACH_VARIANT(X)
-#undef X
-    }
-}
-
 // Cost model (SM cycles) of running an m x n output with `chunks` K chunks on tile variant v.  Fragments outside
-// the output are skipped by the kernel, so the FP64 pipe term counts real 8x8 fragments (16 pipe cycles per fragment
-// and k-step of 4, one DMMA per 4 cycles and SM); staging and the per-chunk barrier are partly hidden by the other
-// CTAs of the SM; every tile pays a fixed prologue / epilogue.
+// the output are skipped by the kernel, so the FP64 pipe term counts real 8x8 fragments (one DMMA per 4 cycles and
+// SM: 16 cycles per fragment and chunk of 16); a chunk also has to be staged through L2 ((rows + cols) * 128 B at
+// roughly 16 B per cycle and SM), whichever is larger bounds the chunk; every tile pays its epilogue.
 static int g_force_variant = -2;
-static int pick_variant(int m, int n, int chunks)
+static double tile_cost(int em, int en, int chunks)
+{
+    const int em8 = (em + 7) & ~7, en8 = (en + 7) & ~7;
+    const double frags = (double)(em8 / 8) * (en8 / 8);
+    const double per_chunk = std::max(16.0 * frags, 8.0 * (em8 + en8)) + 60.0;
+    return chunks * per_chunk + 4.0 * frags + 300.0;
+}
+static int pick_variant(int m, int n, int chunks, double* cost_out = nullptr)
 {
     if (g_force_variant == -2) { const char* e = getenv("QCM_FORCE_VARIANT"); g_force_variant = e ? atoi(e) : -1; }
-    if (g_force_variant >= 0 && g_force_variant < kNumVariants) return g_force_variant;
+    const int nv = gemm_ws_num_variants();
     int best = 0; double best_cost = 1e300;
-    for (int v = 0; v < kNumVariants; ++v) {
-        const int tm = kVariants[v].tm, tn = kVariants[v].tn;
+    for (int v = 0; v < nv; ++v) {
+        if (g_force_variant >= 0 && g_force_variant < nv && v != g_force_variant) continue;
+        const GemmWsVariant var = gemm_ws_variant(v);
+        const int tm = var.tm, tn = var.tn;
         double cost = 0;
         for (int pm = 0; pm < 2; ++pm)
             for (int pn = 0; pn < 2; ++pn) {
@@ -728,13 +499,12 @@ static int pick_variant(int m, int n, int chunks)
                 const int cm = pm == 0 ? m / tm : (m % tm ? 1 : 0), cn = pn == 0 ? n / tn : (n % tn ? 1 : 0);
                 if (!cm || !cn) continue;
                 const int em = pm == 0 ? tm : m % tm, en = pn == 0 ? tn : n % tn;
-                const double frags = (double)((em + 7) / 8) * ((en + 7) / 8);
-                const double per_chunk = frags * 4.0 * (KC / 4) + 1.0 * (((em + 7) & ~7) + ((en + 7) & ~7)) + 120.0;
-                cost += (double)cm * cn * (chunks * per_chunk + 1200.0);
+                cost += (double)cm * cn * tile_cost(em, en, chunks);
             }
-        cost /= kVariants[v].eff;
+        cost /= var.eff;
         if (cost < best_cost) { best_cost = cost; best = v; }
     }
+    if (cost_out) *cost_out = best_cost;
     return best;
 }
 
@@ -758,7 +528,8 @@ static int build_gemm_group(qcm_plan_s* P, GemmGroup& g, const qcm_gemm_out* out
         qcm_gemm_seg const& s = segs[i];
         hs[i] = DSeg{s.A.off, s.B.off, s.A.buf, s.B.buf, s.lda, s.ldb, s.m, s.n, s.k, s.ta, s.tb, 0, s.alpha};
     }
-    std::vector<std::vector<DWork>> per_variant(kNumVariants);
+    const int kNumVariants = gemm_ws_num_variants();
+    std::vector<std::vector<std::pair<double, DWork>>> per_variant(kNumVariants);
     const int max_chunks = 96;       // K chunks (of KC) per work item before the segment list is split
     for (int64_t o = 0; o < n_outs; ++o) {
         qcm_gemm_out const& out = outs[o];
@@ -777,20 +548,32 @@ static int build_gemm_group(qcm_plan_s* P, GemmGroup& g, const qcm_gemm_out* out
         int v = pick_variant(out.m, out.n, std::max(1, total_chunks / (int)chunks.size()));
         int mode = chunks.size() > 1 ? 2 : base_mode;
         if (chunks.size() > 1 && base_mode == 0) return fail("internal: split-K on a store-mode output");
-        for (auto const& ch : chunks)
-            for (int n0 = 0; n0 < out.n; n0 += kVariants[v].tn)
-                for (int m0 = 0; m0 < out.m; m0 += kVariants[v].tm)
-                    per_variant[v].push_back(DWork{out.C.off, out.C.buf, out.ldc, m0, n0, out.m, out.n, ch.first, ch.second, mode, 0});
+        const GemmWsVariant var = gemm_ws_variant(v);
+        for (auto const& ch : chunks) {
+            int nch = 0;
+            for (int s = ch.first; s < ch.second; ++s) nch += (segs[s].k + KC - 1) / KC;
+            for (int n0 = 0; n0 < out.n; n0 += var.tn)
+                for (int m0 = 0; m0 < out.m; m0 += var.tm)
+                    per_variant[v].push_back(std::make_pair(tile_cost(std::min(var.tm, out.m - m0), std::min(var.tn, out.n - n0), nch),
+                                                            DWork{out.C.off, out.C.buf, out.ldc, m0, n0, out.m, out.n, ch.first, ch.second, mode, 0}));
+        }
     }
+    // the persistent CTAs take work items round-robin: heaviest first, so that every CTA gets a similar mix and the
+    // launch ends on light items; the launches of a group are ordered by total cost
     std::vector<DWork> hw;
+    std::vector<std::pair<double, int>> order;
     for (int v = 0; v < kNumVariants; ++v) {
         if (per_variant[v].empty()) continue;
-        // heavy work first: better tail behaviour of the hardware scheduler
-        std::stable_sort(per_variant[v].begin(), per_variant[v].end(), [&](DWork const& a, DWork const& b) {
-            return (a.seg_end - a.seg_begin) > (b.seg_end - b.seg_begin);
-        });
+        double tot = 0;
+        for (auto const& x : per_variant[v]) tot += x.first;
+        order.push_back(std::make_pair(-tot, v));
+    }
+    std::sort(order.begin(), order.end());
+    for (auto const& ov : order) {
+        const int v = ov.second;
+        std::stable_sort(per_variant[v].begin(), per_variant[v].end(), [](std::pair<double, DWork> const& a, std::pair<double, DWork> const& b) { return a.first > b.first; });
         g.launches.push_back(GemmLaunch{v, (int64_t)hw.size(), (int64_t)per_variant[v].size()});
-        hw.insert(hw.end(), per_variant[v].begin(), per_variant[v].end());
+        for (auto const& x : per_variant[v]) hw.push_back(x.second);
     }
     g.n_works = (int64_t)hw.size();
     if (dev_upload(P, hw, &g.d_works)) return 1;
@@ -953,7 +736,7 @@ static int run_gemm_group(GemmGroup const& g, BufTable const& bufs)
     for (auto const& l : g.launches) {
         cudaStream_t st = G.stream;
         if (fork && li > 0) { int a = (li - 1) % Global::kAux; st = G.aux[a]; used[a] = true; }
-        launch_gemm_variant(l.variant, l.n_works, g.d_works + l.work_begin, g.d_segs, bufs, st);
+        gemm_ws_launch(l.variant, l.n_works, g.d_works + l.work_begin, g.d_segs, bufs, st);
         G.launches++; ++li;
     }
     if (fork)

@@ -1,6 +1,8 @@
 #!/bin/bash
-# iteration pass: parity tests, bench line(s), launch list
+# iteration pass: smoke, parity tests, bench line(s), launch list
 mkdir -p gpurun_out
+QCM_DEBUG=1 timeout 120 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -15 gpurun_out/smoke.log
+if ! grep -q "smoke 2u1" gpurun_out/smoke.log; then echo "smoke failed, stopping"; exit 1; fi
 ( time timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu.log 2>&1
 tail -5 gpurun_out/pytest_gpu.log
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_cfg2.json 2> gpurun_out/bench_cfg2.err; tail -c 2500 gpurun_out/bench_cfg2.json; tail -3 gpurun_out/bench_cfg2.err
