@@ -6,7 +6,7 @@
 // that land in the same row unit of one symmetry sector.
 //
 // One CTA per SM slot runs for the whole launch and takes work items round-robin.  Its warps are specialised:
-//   * one producer warp walks (work item -> K-segment -> K chunk of 16) and stages the operand tiles with cp.async
+//   * four producer warps walk (work item -> K-segment -> K chunk of 16) and stages the operand tiles with cp.async
 //     into a ring of shared-memory stages, in the orientation in which global memory is contiguous; completion is
 //     signalled per stage through an mbarrier (cp.async.mbarrier.arrive), together with a small descriptor (alpha,
 //     orientation, depth, output tile).  The ring runs across segment and work-item borders, so the operands of the
@@ -78,13 +78,14 @@ __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, doub
 //   row-contiguous global memory -> smem [kk][rr] (row length TR + SPAD), every cp.async of the warp covers a 256 B run
 //   k-contiguous global memory   -> smem [rr][kk] (row length LDK), two 128 B runs per cp.async
 // Rows in [rrem, r_ld) and depths in [krem, kld) are zero-filled (the consumers read r_ld rows and kld depths).
-template <int TR>
-__device__ __forceinline__ void stage_operand(double* s, const double* __restrict__ g, int ld, bool kmajor, int rrem, int r_ld, int krem, int kld, int lane)
+// The NP producer warps share a tile: warp pw takes every NP-th k row (row-contiguous case) / row pair (k-contiguous case).
+template <int TR, int NP>
+__device__ __forceinline__ void stage_operand(double* s, const double* __restrict__ g, int ld, bool kmajor, int rrem, int r_ld, int krem, int kld, int lane, int pw)
 {
     constexpr int LDS_R = TR + SPAD;
     if (!kmajor) {
 #pragma unroll 4
-        for (int kk = 0; kk < kld; ++kk) {
+        for (int kk = pw; kk < kld; kk += NP) {
             const bool kv = kk < krem;
             const double* gp = g + (long long)kk * ld + lane;
             double* sp = s + kk * LDS_R + lane;
@@ -95,16 +96,16 @@ __device__ __forceinline__ void stage_operand(double* s, const double* __restric
             }
         }
     } else {
-        const int kk = lane & 15, r0 = lane >> 4;
+        const int kk = lane & 15, r0 = (lane >> 4) + 2 * pw;
         if (kk < kld) {
             const bool kv = kk < krem;
             const double* gp = g + kk + (long long)r0 * ld;
             double* sp = s + r0 * LDK + kk;
-            const long long gstep = 2ll * ld;
+            const long long gstep = 2ll * NP * ld;
 #pragma unroll 4
-            for (int rr = r0; rr < r_ld; rr += 2) {
+            for (int rr = r0; rr < r_ld; rr += 2 * NP) {
                 cp_async8(sp, gp, kv && rr < rrem);
-                gp += gstep; sp += 2 * LDK;
+                gp += gstep; sp += 2 * NP * LDK;
             }
         }
     }
@@ -113,18 +114,20 @@ __device__ __forceinline__ void stage_operand(double* s, const double* __restric
 template <int WARPS_M, int WARPS_N, int WMT, int WNT, int STAGES>
 struct GemmWsCfg
 {
-    static constexpr int TM = WARPS_M * WMT * 8, TN = WARPS_N * WNT * 8, NW = WARPS_M * WARPS_N, NT = (NW + 1) * 32;
+    static constexpr int NP = 4;     // producer warps: one warp alone cannot keep enough cp.async requests in flight
+    static constexpr int TM = WARPS_M * WMT * 8, TN = WARPS_N * WNT * 8, NW = WARPS_M * WARPS_N, NT = (NW + NP) * 32;
     static constexpr int A_STAGE = (KC * (TM + SPAD) > TM * LDK) ? KC * (TM + SPAD) : TM * LDK;
     static constexpr int B_STAGE = (KC * (TN + SPAD) > TN * LDK) ? KC * (TN + SPAD) : TN * LDK;
     static constexpr size_t SMEM = (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(double) + STAGES * (sizeof(StageMeta) + 16);
 };
 
-template <int WARPS_M, int WARPS_N, int WMT, int WNT, int STAGES, int MINB>
-__global__ void __launch_bounds__((WARPS_M * WARPS_N + 1) * 32, MINB)
+// CREGS > 0: the consumer warps raise their register allowance to CREGS (setmaxnreg), the producer warps drop to 40
+template <int WARPS_M, int WARPS_N, int WMT, int WNT, int STAGES, int MINB, int CREGS>
+__global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
 k_gemm_ws(const DWork* __restrict__ works, int n_works, const DSeg* __restrict__ segs, const __grid_constant__ BufTable bufs)
 {
     using Cfg = GemmWsCfg<WARPS_M, WARPS_N, WMT, WNT, STAGES>;
-    constexpr int TM = Cfg::TM, TN = Cfg::TN, NW = Cfg::NW, A_STAGE = Cfg::A_STAGE, B_STAGE = Cfg::B_STAGE;
+    constexpr int TM = Cfg::TM, TN = Cfg::TN, NW = Cfg::NW, NP = Cfg::NP, A_STAGE = Cfg::A_STAGE, B_STAGE = Cfg::B_STAGE;
     constexpr int LDA_S = TM + SPAD, LDB_S = TN + SPAD;
     extern __shared__ __align__(16) double smem[];
     double* As = smem;                               // [STAGES][A_STAGE]
@@ -135,24 +138,26 @@ k_gemm_ws(const DWork* __restrict__ works, int n_works, const DSeg* __restrict__
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 33); mbar_init(&empty[s], NW); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], NP * 32 + 1); mbar_init(&empty[s], NW); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
 
-    if (warp == NW) {
-        // ------------------------------------------------------------------ producer warp
+    if (warp >= NW) {
+        // ------------------------------------------------------------------ producer warps
+        if (CREGS > 0) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+        const int pw = warp - NW;
         int stage = 0; unsigned phase = 0;
         auto publish = [&](StageMeta const& m) {
-            if (lane == 0) metas[stage] = m;
+            if (tid == NW * 32) metas[stage] = m;
             mbar_cp_async_arrive(&full[stage]);
-            if (lane == 0) mbar_arrive(&full[stage]);
+            if (tid == NW * 32) mbar_arrive(&full[stage]);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
         };
         for (int wi = blockIdx.x; wi < n_works; wi += gridDim.x) {
             const DWork w = works[wi];
             const int tm_eff = min(TM, w.m - w.m0), tn_eff = min(TN, w.n - w.n0);
-            const int tm_ld = (tm_eff + 7) & ~7, tn_ld = (tn_eff + 7) & ~7;
+            const int tm_ld = (tm_eff + WMT * 8 - 1) / (WMT * 8) * (WMT * 8), tn_ld = (tn_eff + WNT * 8 - 1) / (WNT * 8) * (WNT * 8);   // whole warp tiles
             StageMeta m;
             m.c_off = w.c_off; m.work = wi; m.c_buf_mode = w.c_buf | (w.mode << 8); m.ldc = w.ldc;
             m.m0 = w.m0; m.n0 = w.n0; m.m = w.m; m.n = w.n;
@@ -183,8 +188,8 @@ k_gemm_ws(const DWork* __restrict__ works, int n_works, const DSeg* __restrict__
                     const int krem = cur.k - pk0;
                     const int kld = min(KC, (krem + 3) & ~3);
                     mbar_wait(&empty[stage], phase ^ 1);
-                    stage_operand<TM>(As + stage * A_STAGE, a_km ? pA + pk0 : pA + (long long)pk0 * cur.lda, cur.lda, a_km, pmrem, tm_ld, krem, kld, lane);
-                    stage_operand<TN>(Bs + stage * B_STAGE, b_km ? pB + pk0 : pB + (long long)pk0 * cur.ldb, cur.ldb, b_km, pnrem, tn_ld, krem, kld, lane);
+                    stage_operand<TM, NP>(As + stage * A_STAGE, a_km ? pA + pk0 : pA + (long long)pk0 * cur.lda, cur.lda, a_km, pmrem, tm_ld, krem, kld, lane, pw);
+                    stage_operand<TN, NP>(Bs + stage * B_STAGE, b_km ? pB + pk0 : pB + (long long)pk0 * cur.ldb, cur.ldb, b_km, pnrem, tn_ld, krem, kld, lane, pw);
                     const bool last = ps == last_seg && pk0 + KC >= cur.k;
                     m.flags = (a_km ? 1 : 0) | (b_km ? 2 : 0) | first | (last ? 8 : 0) | (kld << 8);
                     first = 0;
@@ -201,10 +206,12 @@ k_gemm_ws(const DWork* __restrict__ works, int n_works, const DSeg* __restrict__
     }
 
     // ---------------------------------------------------------------------- consumer warps
+    if (CREGS > 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(CREGS > 0 ? CREGS : 24));
     const int wm = warp % WARPS_M, wn = warp / WARPS_M;
     const int fr = lane >> 2, fk = lane & 3;
+    const int row0 = wm * WMT * 8, col0 = wn * WNT * 8;      // this warp's WMT x WNT fragments inside the tile
     double acc[WMT][WNT][2];
-    int mt = 0, nt = 0, row0 = 0, col0 = 0;
+    bool active = false;                                      // warp tile intersects the output
     int stage = 0; unsigned phase = 0;
     for (;;) {
         mbar_wait(&full[stage], phase);
@@ -216,106 +223,103 @@ k_gemm_ws(const DWork* __restrict__ works, int n_works, const DSeg* __restrict__
             for (int i = 0; i < WMT; ++i)
 #pragma unroll
                 for (int j = 0; j < WNT; ++j) acc[i][j][0] = acc[i][j][1] = 0.;
-            // fragments of the tile that exist, spread evenly over the warp grid
-            const int tm_eff = min(TM, sm.m - sm.m0), tn_eff = min(TN, sm.n - sm.n0);
-            const int fpw_m = ((tm_eff + 7) / 8 + WARPS_M - 1) / WARPS_M, fpw_n = ((tn_eff + 7) / 8 + WARPS_N - 1) / WARPS_N;
-            row0 = wm * fpw_m * 8; col0 = wn * fpw_n * 8;
-            mt = max(0, min(fpw_m, (tm_eff - row0 + 7) / 8)); nt = max(0, min(fpw_n, (tn_eff - col0 + 7) / 8));
+            active = sm.m0 + row0 < sm.m && sm.n0 + col0 < sm.n;
         }
         const int k4n = fl >> 10;
-        if (k4n > 0 && mt > 0 && nt > 0) {
-            const double* as = As + stage * A_STAGE;
-            const double* bs = Bs + stage * B_STAGE;
+        if (k4n > 0 && active) {
             const double alpha = sm.alpha;
             const int a_base = (fl & 1) ? (row0 + fr) * LDK + fk : fk * LDA_S + row0 + fr;
             const int a_ti = (fl & 1) ? 8 * LDK : 8, a_tk = (fl & 1) ? 4 : 4 * LDA_S;
             const int b_base = (fl & 2) ? (col0 + fr) * LDK + fk : fk * LDB_S + col0 + fr;
             const int b_tj = (fl & 2) ? 8 * LDK : 8, b_tk = (fl & 2) ? 4 : 4 * LDB_S;
-            as += a_base; bs += b_base;
-            if (mt == WMT && nt == WNT) {
-                if (k4n == KC / 4) {
+            const double* as = As + stage * A_STAGE + a_base;
+            const double* bs = Bs + stage * B_STAGE + b_base;
+            if (k4n == KC / 4) {
 #pragma unroll
-                    for (int k4 = 0; k4 < KC / 4; ++k4) {
-                        double a[WMT], b[WNT];
+                for (int k4 = 0; k4 < KC / 4; ++k4) {
+                    double a[WMT], b[WNT];
 #pragma unroll
-                        for (int i = 0; i < WMT; ++i) a[i] = alpha * as[i * a_ti + k4 * a_tk];
+                    for (int i = 0; i < WMT; ++i) a[i] = alpha * as[i * a_ti + k4 * a_tk];
 #pragma unroll
-                        for (int j = 0; j < WNT; ++j) b[j] = bs[j * b_tj + k4 * b_tk];
+                    for (int j = 0; j < WNT; ++j) b[j] = bs[j * b_tj + k4 * b_tk];
 #pragma unroll
-                        for (int i = 0; i < WMT; ++i)
+                    for (int i = 0; i < WMT; ++i)
 #pragma unroll
-                            for (int j = 0; j < WNT; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-                    }
-                } else {
-                    for (int k4 = 0; k4 < k4n; ++k4) {
-                        double a[WMT], b[WNT];
-#pragma unroll
-                        for (int i = 0; i < WMT; ++i) a[i] = alpha * as[i * a_ti + k4 * a_tk];
-#pragma unroll
-                        for (int j = 0; j < WNT; ++j) b[j] = bs[j * b_tj + k4 * b_tk];
-#pragma unroll
-                        for (int i = 0; i < WMT; ++i)
-#pragma unroll
-                            for (int j = 0; j < WNT; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-                    }
+                        for (int j = 0; j < WNT; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
                 }
             } else {
                 for (int k4 = 0; k4 < k4n; ++k4) {
                     double a[WMT], b[WNT];
 #pragma unroll
-                    for (int i = 0; i < WMT; ++i) a[i] = i < mt ? alpha * as[i * a_ti + k4 * a_tk] : 0.;
+                    for (int i = 0; i < WMT; ++i) a[i] = alpha * as[i * a_ti + k4 * a_tk];
 #pragma unroll
-                    for (int j = 0; j < WNT; ++j) b[j] = j < nt ? bs[j * b_tj + k4 * b_tk] : 0.;
+                    for (int j = 0; j < WNT; ++j) b[j] = bs[j * b_tj + k4 * b_tk];
 #pragma unroll
                     for (int i = 0; i < WMT; ++i)
-                        if (i < mt) {
 #pragma unroll
-                            for (int j = 0; j < WNT; ++j)
-                                if (j < nt) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-                        }
+                        for (int j = 0; j < WNT; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
                 }
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        if (fl & 8) {
+        if ((fl & 8) && active) {
             // ---- epilogue: C fragment (row = lane/4, cols = 2*(lane%4) + {0,1})
-            double* __restrict__ C = bufs.p[sm.c_buf_mode & 0xff] + sm.c_off;
             const int mode = sm.c_buf_mode >> 8;
+            const int r0 = sm.m0 + row0 + fr, c0 = sm.n0 + col0 + 2 * fk;
+            double* __restrict__ q0 = bufs.p[sm.c_buf_mode & 0xff] + sm.c_off + r0 + (long long)c0 * sm.ldc;
+            const long long cstep = 8ll * sm.ldc;
+            if (sm.m0 + row0 + WMT * 8 <= sm.m && sm.n0 + col0 + WNT * 8 <= sm.n) {     // warp tile fully inside
 #pragma unroll
-            for (int i = 0; i < WMT; ++i)
+                for (int j = 0; j < WNT; ++j) {
+                    double* qj = q0 + j * cstep;
 #pragma unroll
-                for (int j = 0; j < WNT; ++j)
+                    for (int e = 0; e < 2; ++e)
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int r = sm.m0 + row0 + i * 8 + fr, c = sm.n0 + col0 + j * 8 + 2 * fk + e;
-                        if (i < mt && j < nt && r < sm.m && c < sm.n) {
-                            double* q = C + r + (long long)c * sm.ldc;
+                        for (int i = 0; i < WMT; ++i) {
+                            double* q = qj + e * sm.ldc + i * 8;
                             if (mode == 0) *q = acc[i][j][e];
                             else if (mode == 1) *q += acc[i][j][e];
                             else atomicAdd(q, acc[i][j][e]);
                         }
-                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < WNT; ++j) {
+                    double* qj = q0 + j * cstep;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+#pragma unroll
+                        for (int i = 0; i < WMT; ++i) {
+                            if (r0 + i * 8 < sm.m && c0 + j * 8 + e < sm.n) {
+                                double* q = qj + e * sm.ldc + i * 8;
+                                if (mode == 0) *q = acc[i][j][e];
+                                else if (mode == 1) *q += acc[i][j][e];
+                                else atomicAdd(q, acc[i][j][e]);
+                            }
+                        }
+                }
+            }
         }
     }
 }
 
 // ---- variant table ----------------------------------------------------------------------------------------------
-//   X(index, WARPS_M, WARPS_N, WMT, WNT, STAGES, MINB)
+//   X(index, WARPS_M, WARPS_N, WMT, WNT, STAGES, MINB, CREGS)      tile = (WARPS_M * WMT * 8) x (WARPS_N * WNT * 8)
 #define QCM_WS_VARIANTS(X) \
-    X(0, 4, 2, 4, 8, 5, 1)  /* 128 x 128 */ \
-    X(1, 2, 2, 4, 8, 3, 2)  /*  64 x 128 */ \
-    X(2, 4, 1, 4, 8, 3, 2)  /* 128 x  64 */ \
-    X(3, 2, 2, 4, 4, 3, 3)  /*  64 x  64 */ \
-    X(4, 1, 4, 4, 4, 4, 2)  /*  32 x 128 */ \
-    X(5, 4, 1, 4, 4, 4, 2)  /* 128 x  32 */ \
-    X(6, 1, 4, 2, 4, 3, 3)  /*  16 x 128 */ \
-    X(7, 4, 1, 4, 2, 3, 3)  /* 128 x  16 */ \
-    X(8, 2, 2, 2, 2, 4, 4)  /*  32 x  32 */ \
-    X(9, 2, 2, 1, 1, 4, 4)  /*  16 x  16 */ \
-    X(10, 1, 4, 1, 4, 3, 3) /*   8 x 128 */ \
-    X(11, 4, 1, 4, 1, 3, 3) /* 128 x   8 */
+    X(0, 4, 2, 4, 8, 5, 1, 232) /* 128 x 128 */ \
+    X(1, 2, 4, 4, 4, 6, 1, 0)   /*  64 x 128 */ \
+    X(2, 4, 2, 4, 4, 6, 1, 0)   /* 128 x  64 */ \
+    X(3, 1, 8, 4, 2, 7, 1, 0)   /*  32 x 128 */ \
+    X(4, 8, 1, 2, 4, 7, 1, 0)   /* 128 x  32 */ \
+    X(5, 1, 8, 2, 2, 8, 1, 0)   /*  16 x 128 */ \
+    X(6, 8, 1, 2, 2, 8, 1, 0)   /* 128 x  16 */ \
+    X(7, 1, 8, 1, 2, 8, 1, 0)   /*   8 x 128 */ \
+    X(8, 8, 1, 2, 1, 8, 1, 0)   /* 128 x   8 */ \
+    X(9, 2, 4, 4, 2, 8, 1, 0)   /*  64 x  64 */ \
+    X(10, 2, 2, 2, 2, 6, 2, 0)  /*  32 x  32 */ \
+    X(11, 2, 2, 1, 1, 6, 2, 0)  /*  16 x  16 */
 
 constexpr int kNumWs = 12;
 GemmWsVariant g_var[kNumWs];
@@ -331,12 +335,12 @@ const char* gemm_ws_init(int sm_count)
 {
     g_sms = sm_count;
     cudaError_t e;
-#define X(v, a, b, c, d, s, mb) \
+#define X(v, a, b, c, d, s, mb, cr) \
     { using Cfg = GemmWsCfg<a, b, c, d, s>; \
-      e = cudaFuncSetAttribute(k_gemm_ws<a, b, c, d, s, mb>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM); \
+      e = cudaFuncSetAttribute(k_gemm_ws<a, b, c, d, s, mb, cr>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM); \
       if (e != cudaSuccess) return cudaGetErrorString(e); \
       int occ = 0; \
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gemm_ws<a, b, c, d, s, mb>, Cfg::NT, Cfg::SMEM); \
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gemm_ws<a, b, c, d, s, mb, cr>, Cfg::NT, Cfg::SMEM); \
       if (e != cudaSuccess) return cudaGetErrorString(e); \
       if (occ < 1) return "k_gemm_ws variant does not fit on an SM"; \
       g_occ[v] = occ; g_var[v] = GemmWsVariant{Cfg::TM, Cfg::TN, Cfg::NT, 1.0}; \
@@ -353,8 +357,8 @@ void gemm_ws_launch(int v, long long n_works, const DWork* works, const DSeg* se
     if (n_works <= 0) return;
     const dim3 g((unsigned)gemm_ws_grid(v, n_works));
     switch (v) {
-#define X(vv, a, b, c, d, s, mb) \
-    case vv: { using Cfg = GemmWsCfg<a, b, c, d, s>; k_gemm_ws<a, b, c, d, s, mb><<<g, Cfg::NT, Cfg::SMEM, st>>>(works, (int)n_works, segs, bufs); break; }
+#define X(vv, a, b, c, d, s, mb, cr) \
+    case vv: { using Cfg = GemmWsCfg<a, b, c, d, s>; k_gemm_ws<a, b, c, d, s, mb, cr><<<g, Cfg::NT, Cfg::SMEM, st>>>(works, (int)n_works, segs, bufs); break; }
         QCM_WS_VARIANTS(X)
 #undef X
     }

@@ -471,11 +471,9 @@ static int gemm_set_attributes()
     return 0;
 }
 
-// Cost model (SM cycles) of running an m x n output with `chunks` K chunks on tile variant v.  Fragments outside
-// the output are skipped by the kernel, so the FP64 pipe term counts real 8x8 fragments (one DMMA per 4 cycles and
-// SM: 16 cycles per fragment and chunk of 16); a chunk also has to be staged through L2 ((rows + cols) * 128 B at
-// roughly 16 B per cycle and SM), whichever is larger bounds the chunk; every tile pays its epilogue.
-static int g_force_variant = -2;
+// Cost model (SM cycles) of one tile of em x en with `chunks` K chunks.  The FP64 pipe issues one DMMA (8x8x4) per 4
+// cycles and SM: 16 cycles per 8x8 fragment and chunk of 16; a chunk also has to be staged through L2 ((rows + cols)
+// * 128 B at roughly 16 B per cycle and SM); whichever is larger bounds the chunk; every tile pays its epilogue.
 static double tile_cost(int em, int en, int chunks)
 {
     const int em8 = (em + 7) & ~7, en8 = (en + 7) & ~7;
@@ -483,29 +481,42 @@ static double tile_cost(int em, int en, int chunks)
     const double per_chunk = std::max(16.0 * frags, 8.0 * (em8 + en8)) + 60.0;
     return chunks * per_chunk + 4.0 * frags + 300.0;
 }
-static int pick_variant(int m, int n, int chunks, double* cost_out = nullptr)
+
+// A dimension of an output block is cut into strips of 128 plus strips of {64, 32, 16, 8} (or one more 128) that
+// cover the remainder at the least modelled cost: the kernels always compute whole warp tiles, so a strip class that
+// fits the remainder tightly wastes no FP64 issue slots, while many thin strips waste operand bandwidth.
+static void cut_dimension(int len, int chunks, std::vector<std::pair<int, int>>& strips /* (offset, class) */)
 {
-    if (g_force_variant == -2) { const char* e = getenv("QCM_FORCE_VARIANT"); g_force_variant = e ? atoi(e) : -1; }
-    const int nv = gemm_ws_num_variants();
-    int best = 0; double best_cost = 1e300;
-    for (int v = 0; v < nv; ++v) {
-        if (g_force_variant >= 0 && g_force_variant < nv && v != g_force_variant) continue;
-        const GemmWsVariant var = gemm_ws_variant(v);
-        const int tm = var.tm, tn = var.tn;
-        double cost = 0;
-        for (int pm = 0; pm < 2; ++pm)
-            for (int pn = 0; pn < 2; ++pn) {
-                // full tiles and the ragged last row / column of tiles
-                const int cm = pm == 0 ? m / tm : (m % tm ? 1 : 0), cn = pn == 0 ? n / tn : (n % tn ? 1 : 0);
-                if (!cm || !cn) continue;
-                const int em = pm == 0 ? tm : m % tm, en = pn == 0 ? tn : n % tn;
-                cost += (double)cm * cn * tile_cost(em, en, chunks);
-            }
-        cost /= var.eff;
-        if (cost < best_cost) { best_cost = cost; best = v; }
+    static const int cls[5] = {8, 16, 32, 64, 128};
+    strips.clear();
+    int off = 0;
+    while (len - off >= 128) { strips.push_back(std::make_pair(off, 128)); off += 128; }
+    int r8 = (len - off + 7) / 8;      // fragments left (0..15)
+    if (r8 == 0) return;
+    // dynamic programme over "fragments still to cover"
+    double best[17]; int pick[17];
+    best[0] = 0; pick[0] = -1;
+    for (int r = 1; r <= 16; ++r) {
+        best[r] = 1e300; pick[r] = 4;
+        for (int c = 0; c < 5; ++c) {
+            const int f = cls[c] / 8;
+            const double cost = tile_cost(cls[c], 128, chunks) + best[std::max(0, r - f)];
+            if (cost < best[r]) { best[r] = cost; pick[r] = c; }
+        }
     }
-    if (cost_out) *cost_out = best_cost;
-    return best;
+    std::vector<int> sel;
+    for (int r = r8; r > 0; r = std::max(0, r - cls[pick[r]] / 8)) sel.push_back(cls[pick[r]]);
+    std::sort(sel.begin(), sel.end(), [](int a, int b) { return a > b; });
+    for (int c : sel) { strips.push_back(std::make_pair(off, c)); off += c; }
+}
+// tile variant (gemm_ws.cu table) for a (row strip class, column strip class) pair
+static int variant_for(int hr, int hc)
+{
+    if (hr == 128 && hc == 128) return 0;
+    if (hc == 128) return hr == 64 ? 1 : hr == 32 ? 3 : hr == 16 ? 5 : 7;
+    if (hr == 128) return hc == 64 ? 2 : hc == 32 ? 4 : hc == 16 ? 6 : 8;
+    const int mx = std::max(hr, hc);
+    return mx == 64 ? 9 : mx == 32 ? 10 : 11;
 }
 
 template <class T> static int dev_upload(qcm_plan_s* P, std::vector<T> const& h, T** d)
@@ -545,17 +556,23 @@ static int build_gemm_group(qcm_plan_s* P, GemmGroup& g, const qcm_gemm_out* out
         }
         int total_chunks = 0;
         for (int s = out.seg_begin; s < out.seg_end; ++s) total_chunks += (segs[s].k + KC - 1) / KC;
-        int v = pick_variant(out.m, out.n, std::max(1, total_chunks / (int)chunks.size()));
+        const int avg_chunks = std::max(1, total_chunks / (int)chunks.size());
         int mode = chunks.size() > 1 ? 2 : base_mode;
         if (chunks.size() > 1 && base_mode == 0) return fail("internal: split-K on a store-mode output");
-        const GemmWsVariant var = gemm_ws_variant(v);
+        std::vector<std::pair<int, int>> rows, cols;
+        cut_dimension(out.m, avg_chunks, rows);
+        cut_dimension(out.n, avg_chunks, cols);
         for (auto const& ch : chunks) {
             int nch = 0;
             for (int s = ch.first; s < ch.second; ++s) nch += (segs[s].k + KC - 1) / KC;
-            for (int n0 = 0; n0 < out.n; n0 += var.tn)
-                for (int m0 = 0; m0 < out.m; m0 += var.tm)
-                    per_variant[v].push_back(std::make_pair(tile_cost(std::min(var.tm, out.m - m0), std::min(var.tn, out.n - n0), nch),
-                                                            DWork{out.C.off, out.C.buf, out.ldc, m0, n0, out.m, out.n, ch.first, ch.second, mode, 0}));
+            for (auto const& cs : cols)
+                for (auto const& rs : rows) {
+                    const int v = variant_for(rs.second, cs.second);
+                    const GemmWsVariant var = gemm_ws_variant(v);
+                    // a variant tile may be larger than the strip pair (corner pieces): it is clipped by the block edge
+                    per_variant[v].push_back(std::make_pair(tile_cost(std::min(var.tm, out.m - rs.first), std::min(var.tn, out.n - cs.first), nch),
+                                                            DWork{out.C.off, out.C.buf, out.ldc, rs.first, cs.first, out.m, out.n, ch.first, ch.second, mode, 0}));
+                }
         }
     }
     // the persistent CTAs take work items round-robin: heaviest first, so that every CTA gets a similar mix and the
