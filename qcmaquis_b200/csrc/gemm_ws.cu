@@ -39,41 +39,6 @@ struct __align__(16) StageMeta
     int m0, n0, m, n;
 };
 
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* b, int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* b)
-{
-    asm volatile("{\n .reg .b64 t;\n mbarrier.arrive.shared::cta.b64 t, [%0];\n}\n" ::"r"(smem_u32(b)) : "memory");
-}
-__device__ __forceinline__ void mbar_cp_async_arrive(unsigned long long* b)
-{
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(b)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity)
-{
-    asm volatile(
-        "{\n"
-        " .reg .pred p;\n"
-        "QCM_WAIT:\n"
-        " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        " @p bra QCM_DONE;\n"
-        " bra QCM_WAIT;\n"
-        "QCM_DONE:\n"
-        "}\n" ::"r"(smem_u32(b)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool valid)
-{
-    const int bytes = valid ? 8 : 0;    // src-size 0: nothing is read, the 8 destination bytes are zero-filled
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b)
-{
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
-
 // Stage a TR x kld operand tile.  g points at (row 0, k 0) of the tile.
 //   row-contiguous global memory -> smem [kk][rr] (row length TR + SPAD), every cp.async of the warp covers a 256 B run
 //   k-contiguous global memory   -> smem [rr][kk] (row length LDK), two 128 B runs per cp.async

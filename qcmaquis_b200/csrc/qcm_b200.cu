@@ -7,16 +7,11 @@
 // critical-section reduction over the MPO bond index (abelian/site_hamil.hpp:84-86).  The host flattens
 // those loops into task arrays once per (site, direction); the kernels below execute them:
 //
-//   k_copy_panels   pairing reshapes as panel copies
-//   k_gemm_dmma     grouped, variable-size FP64 GEMM.  One CTA = one output tile; it walks a list of
-//                   K-segments (the sum over MPO bond terms that hit the same symmetry sector), stages
-//                   operand tiles in shared memory and issues mma.sync.m8n8k4.f64 (DMMA).  tcgen05 has no
-//                   FP64 kind, so DMMA is the FP64 tensor path of sm_100a.
-//   k_wstream       the W application for destination panels with 2..4 source panels (FMA streaming, HBM bound)
-//   k_wgemm         the W application for high fan-in panels as gathered dense products on DMMA: destination
-//                   panels fed by the same source panels share one pass over those sources (SU2 Wigner-9j
-//                   couplings and Hermitian phases are folded into the coefficients on the host).  Destination
-//                   panels with a single source are never formed: the closing GEMM reads the source directly.
+//   k_copy_panels   pairing reshapes as panel copies                                                   (this file)
+//   k_gemm_ws       grouped, variable-size FP64 GEMM on DMMA, persistent and warp-specialised             (gemm_ws.cu)
+//   k_wstream       the W application for destination panels with 2..4 source panels (FMA streaming)     (this file)
+//   k_wgemm_ws      the W application for high fan-in panels as gathered dense products on DMMA           (wgemm_ws.cu)
+//                   Destination panels with a single source are never formed: the closing GEMM reads the source.
 //   k_vec_*         solver-side BLAS-1 on device-resident vectors
 //
 // There is no CPU fallback: every entry point fails with a status when the device is not usable.
@@ -40,10 +35,6 @@ static int fail(std::string const& s) { g_err = s; return 1; }
 struct qcm_array_s { double* p; int64_t n; };
 
 // device-side task records ---------------------------------------------------------------------------------
-struct DWSrc { long long off; int buf, lds; };
-struct DWDst { long long off; int buf, ldd; };
-struct DWGroup { int rows, cols, n_src, n_dst, ng, src_begin, dst_begin, cls; long long coef_begin; };
-struct DWWork { int group, e0; };   // panel elements [e0, e0 + tile) of a group (element e = row + col * rows)
 struct DCopy { long long src_off, dst_off; int src_buf, dst_buf, rows, cols, lds, ldd; };
 
 // --------------------------------------------------------------------------------------------------------
@@ -59,21 +50,6 @@ __global__ void k_copy_panels(const DCopy* __restrict__ tasks, const __grid_cons
         d[r + (long long)c * t.ldd] = s[r + (long long)c * t.lds];
     }
 }
-
-__device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b)
-{
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
-
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool valid)
-{
-    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    int bytes = valid ? 8 : 0;    // src-size 0: nothing is read, the 8 destination bytes are zero-filled
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 // W application, low fan-in (at most 4 sources, at most 4 destinations with identical source sets): a streaming
 // kernel, HBM bound by construction.  One CTA = WS_TILE consecutive panel elements of one group; every thread keeps
@@ -123,105 +99,6 @@ k_wstream(const DWWork* __restrict__ works, const DWGroup* __restrict__ groups, 
             dp[d][rr[i] + (long long)cc[i] * dl[d]] = a;
         }
     }
-}
-
-// W application, high fan-in (the integral-weighted sums over many bond terms): a dense product
-//   dst[e, d] = sum_u src_u[e] * coef[u][d]      e: TE panel elements of this CTA, u: sources, d <= NG destinations
-// on DMMA tiles (M = 8 elements, K = 4 sources, N = 8 destinations).  Source elements are gathered into shared memory
-// by a WG_STAGES-deep cp.async pipeline, eight sources per stage, each source row a coalesced run of TE doubles;
-// the result is transposed through shared memory so that every destination is written in coalesced runs as well.
-constexpr int WG_TE = 128, WG_KC = 8, WG_STAGES = 3, WG_LDA = WG_TE + 4, WG_LDC = WG_TE + 2;
-template <int NG, int MF> constexpr int wg_smem_doubles()
-{
-    return (WG_STAGES * WG_KC * (WG_LDA + NG + 4) > NG * WG_LDC) ? WG_STAGES * WG_KC * (WG_LDA + NG + 4) : NG * WG_LDC;
-}
-template <int NG, int MF>
-__global__ void __launch_bounds__(WG_TE / (8 * MF) * 32)
-k_wgemm(const DWWork* __restrict__ works, const DWGroup* __restrict__ groups, const DWSrc* __restrict__ srcs,
-        const DWDst* __restrict__ dsts, const double* __restrict__ coefs, const __grid_constant__ BufTable bufs)
-{
-    constexpr int NT = WG_TE / (8 * MF) * 32, NF = NG / 8, LDB = NG + 4;
-    extern __shared__ double smem[];
-    double* As = smem;                                   // [STAGES][KC][LDA]
-    double* Bs = smem + WG_STAGES * WG_KC * WG_LDA;      // [STAGES][KC][LDB]
-    const DWWork w = works[blockIdx.x];
-    const DWGroup g = groups[w.group];
-    const int n = g.rows * g.cols;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, fr = lane >> 2, fk = lane & 3;
-    const int el = tid % WG_TE, kk0 = tid / WG_TE;       // this thread gathers element el of sources kk0, kk0 + NT/TE, ...
-    const int e = w.e0 + el;
-    const bool valid = e < n;
-    const int c = valid ? e / g.rows : 0, r = valid ? e - c * g.rows : 0;
-    const int nst = (g.n_src + WG_KC - 1) / WG_KC;
-    const DWSrc* __restrict__ sq = srcs + g.src_begin;
-    const double* __restrict__ cq = coefs + g.coef_begin;
-
-    auto issue = [&](int it) {
-        if (it < nst) {
-            const int stage = it % WG_STAGES, u0 = it * WG_KC;
-#pragma unroll
-            for (int kk = kk0; kk < WG_KC; kk += NT / WG_TE) {
-                const int u = u0 + kk;
-                const bool ok = valid && u < g.n_src;
-                const DWSrc q = sq[min(u, g.n_src - 1)];
-                const double* p = bufs.p[q.buf] + q.off;
-                cp_async8(As + (stage * WG_KC + kk) * WG_LDA + el, ok ? p + r + (long long)c * q.lds : p, ok);
-            }
-#pragma unroll
-            for (int idx = tid; idx < WG_KC * NG; idx += NT) {
-                const int kk = idx / NG, d = idx % NG;    // coefficient rows are padded to a multiple of WG_KC sources
-                cp_async8(Bs + (stage * WG_KC + kk) * LDB + d, cq + (long long)(u0 + kk) * NG + d, true);
-            }
-        }
-        cp_async_commit();
-    };
-
-    double acc[MF][NF][2];
-#pragma unroll
-    for (int i = 0; i < MF; ++i)
-#pragma unroll
-        for (int j = 0; j < NF; ++j) acc[i][j][0] = acc[i][j][1] = 0.;
-    const int nf_used = (g.n_dst + 7) / 8;
-
-#pragma unroll
-    for (int st = 0; st < WG_STAGES - 1; ++st) issue(st);
-    for (int it = 0; it < nst; ++it) {
-        cp_async_wait<WG_STAGES - 2>();
-        __syncthreads();
-        issue(it + WG_STAGES - 1);
-        const double* as = As + (it % WG_STAGES) * WG_KC * WG_LDA + warp * (8 * MF) + fr;
-        const double* bs = Bs + (it % WG_STAGES) * WG_KC * LDB + fr;
-#pragma unroll
-        for (int k4 = 0; k4 < WG_KC / 4; ++k4) {
-            double a[MF], b[NF];
-#pragma unroll
-            for (int i = 0; i < MF; ++i) a[i] = as[(k4 * 4 + fk) * WG_LDA + i * 8];
-#pragma unroll
-            for (int j = 0; j < NF; ++j) b[j] = bs[(k4 * 4 + fk) * LDB + j * 8];
-#pragma unroll
-            for (int j = 0; j < NF; ++j)
-                if (j < nf_used) {
-#pragma unroll
-                    for (int i = 0; i < MF; ++i) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-                }
-        }
-    }
-    cp_async_wait<0>();
-    __syncthreads();
-    // transpose through shared memory: Cs[d][element]
-    double* Cs = smem;
-#pragma unroll
-    for (int j = 0; j < NF; ++j)
-#pragma unroll
-        for (int i = 0; i < MF; ++i)
-#pragma unroll
-            for (int x = 0; x < 2; ++x) Cs[(j * 8 + 2 * fk + x) * WG_LDC + warp * (8 * MF) + i * 8 + fr] = acc[i][j][x];
-    __syncthreads();
-    if (valid)
-        for (int d = kk0; d < g.n_dst; d += NT / WG_TE) {
-            const DWDst q = dsts[g.dst_begin + d];
-            (bufs.p[q.buf] + q.off)[r + (long long)c * q.ldd] = Cs[d * WG_LDC + el];
-        }
 }
 
 // solver-side BLAS-1 --------------------------------------------------------------------------------------
@@ -591,6 +468,20 @@ static int build_gemm_group(qcm_plan_s* P, GemmGroup& g, const qcm_gemm_out* out
         std::stable_sort(per_variant[v].begin(), per_variant[v].end(), [](std::pair<double, DWork> const& a, std::pair<double, DWork> const& b) { return a.first > b.first; });
         g.launches.push_back(GemmLaunch{v, (int64_t)hw.size(), (int64_t)per_variant[v].size()});
         for (auto const& x : per_variant[v]) hw.push_back(x.second);
+        if (getenv("QCM_DEBUG")) {      // useful vs issued FLOPs of this launch (issued = whole warp tiles, K padded to 4)
+            const GemmWsVariant var = gemm_ws_variant(v);
+            double useful = 0, chunks_n = 0;
+            for (auto const& x : per_variant[v]) {
+                DWork const& w = x.second;
+                const int em = std::min(var.tm, w.m - w.m0), en = std::min(var.tn, w.n - w.n0);
+                for (int sgi = w.seg_begin; sgi < w.seg_end; ++sgi) {
+                    const int sm_ = std::min(em, segs[sgi].m - w.m0), sn_ = std::min(en, segs[sgi].n - w.n0);
+                    if (sm_ > 0 && sn_ > 0) { useful += 2.0 * sm_ * sn_ * segs[sgi].k; chunks_n += (segs[sgi].k + KC - 1) / KC; }
+                }
+            }
+            fprintf(stderr, "gemm launch: variant %2d (%3d x %3d) works %7zu chunks %9.0f useful %.4e flops, modelled cost %.3e cycles\n", v, var.tm, var.tn,
+                    per_variant[v].size(), chunks_n, useful, -ov.first);
+        }
     }
     g.n_works = (int64_t)hw.size();
     if (dev_upload(P, hw, &g.d_works)) return 1;
@@ -621,7 +512,7 @@ static int build_axpy_group(qcm_plan_s* P, AxpyGroup& g, qcm_wave_desc const& wd
         if (q.n_src < 1 || q.n_dst < 1) return fail("qcm_plan_create: empty W group");
         if ((int64_t)q.rows * q.cols >= ((int64_t)1 << 31)) return fail("qcm_plan_create: W panel with 2^31 or more elements");
         hg[i] = DWGroup{q.rows, q.cols, q.n_src, q.n_dst, q.ng, q.src_begin, q.dst_begin, q.cls, q.coef_begin};
-        const int n = q.rows * q.cols, tile = c == 0 ? WS_TILE : WG_TE;
+        const int n = q.rows * q.cols, tile = c == 0 ? WS_TILE : wgemm_ws_tile();
         for (int e0 = 0; e0 < n; e0 += tile) cls[c].push_back(DWWork{(int)i, e0});
     }
     std::vector<DWWork> hw;
@@ -636,17 +527,10 @@ static int build_axpy_group(qcm_plan_s* P, AxpyGroup& g, qcm_wave_desc const& wd
     return 0;
 }
 
-template <int NG, int MF> static void launch_wgemm(AxpyGroup const& g, int c, BufTable const& bufs, cudaStream_t st)
-{
-    constexpr int NT = WG_TE / (8 * MF) * 32;
-    k_wgemm<NG, MF><<<(unsigned)g.count[c], NT, wg_smem_doubles<NG, MF>() * sizeof(double), st>>>(g.d_works + g.begin[c], g.d_groups, g.d_srcs, g.d_dsts, g.d_coefs, bufs);
-}
 static int wgemm_set_attributes()
 {
-    CU(cudaFuncSetAttribute(k_wgemm<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(wg_smem_doubles<8, 4>() * sizeof(double))));
-    CU(cudaFuncSetAttribute(k_wgemm<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(wg_smem_doubles<16, 4>() * sizeof(double))));
-    CU(cudaFuncSetAttribute(k_wgemm<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(wg_smem_doubles<32, 2>() * sizeof(double))));
-    CU(cudaFuncSetAttribute(k_wgemm<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(wg_smem_doubles<64, 2>() * sizeof(double))));
+    const char* e = wgemm_ws_init(G.sm_count);
+    if (e) return fail(std::string("wgemm_ws_init: ") + e);
     return 0;
 }
 static int run_w_group(AxpyGroup const& g, BufTable const& bufs)
@@ -668,10 +552,7 @@ static int run_w_group(AxpyGroup const& g, BufTable const& bufs)
         if (fork && li > 0) { int a = (li - 1) % Global::kAux; st = G.aux[a]; used[a] = true; }
         switch (c) {
             case 0: k_wstream<<<(unsigned)g.count[0], WS_THREADS, 0, st>>>(g.d_works + g.begin[0], g.d_groups, g.d_srcs, g.d_dsts, g.d_coefs, bufs); break;
-            case 1: launch_wgemm<8, 4>(g, c, bufs, st); break;
-            case 2: launch_wgemm<16, 4>(g, c, bufs, st); break;
-            case 3: launch_wgemm<32, 2>(g, c, bufs, st); break;
-            case 4: launch_wgemm<64, 2>(g, c, bufs, st); break;
+            default: wgemm_ws_launch(c - 1, g.count[c], g.d_works + g.begin[c], g.d_groups, g.d_srcs, g.d_dsts, g.d_coefs, bufs, st); break;
         }
         G.launches++; ++li;
     }
