@@ -56,7 +56,7 @@ typedef struct { qcm_ref C; int32_t ldc, m, n, seg_begin, seg_end, pad; } qcm_ge
  * the panel elements e.  coef = W entry * scale * Wigner-9j coupling (gsl_coupling.h:177-204) * Hermitian phase,
  * zero where a destination does not use a source.  All panels of a group are rows x cols, column-major with their own
  * leading dimensions.  cls 1: n_src <= 4, n_dst <= 4, ng = 4 (FMA streaming kernel); cls 0: n_dst <= ng in
- * {8,16,32,64}, coefficient rows padded to a multiple of 8 sources (DMMA kernel). */
+ * {8,16,32,64}, coefficient rows padded with zeros to a multiple of 16 sources (DMMA kernel). */
 typedef struct { qcm_ref src; int32_t lds, pad; } qcm_w_src;
 typedef struct { qcm_ref dst; int32_t ldd, pad; } qcm_w_dst;
 typedef struct { int32_t rows, cols, n_src, n_dst, ng, src_begin, dst_begin, cls; int64_t coef_begin; } qcm_w_group;

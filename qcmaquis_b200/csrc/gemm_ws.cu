@@ -45,32 +45,36 @@ struct __align__(16) StageMeta
 // Rows in [rrem, r_ld) and depths in [krem, kld) are zero-filled (the consumers read r_ld rows and kld depths).
 // The NP producer warps share a tile: warp pw takes every NP-th k row (row-contiguous case) / row pair (k-contiguous case).
 template <int TR, int NP>
-__device__ __forceinline__ void stage_operand(double* s, const double* __restrict__ g, int ld, bool kmajor, int rrem, int r_ld, int krem, int kld, int lane, int pw)
+__device__ __forceinline__ void stage_operand(unsigned s /* shared-memory address of the stage */, const double* __restrict__ g, int ld, bool kmajor,
+                                              int rrem, int r_ld, int krem, int kld, int lane, int pw)
 {
     constexpr int LDS_R = TR + SPAD;
     if (!kmajor) {
+        int nb[(TR + 31) / 32];
+#pragma unroll
+        for (int j = 0; j < (TR + 31) / 32; ++j) nb[j] = lane + 32 * j < rrem ? 8 : 0;
+        const double* gp = g + (long long)pw * ld + lane;
+        unsigned sp = s + (pw * LDS_R + lane) * 8;
+        const long long gstep = (long long)NP * ld;
 #pragma unroll 4
         for (int kk = pw; kk < kld; kk += NP) {
             const bool kv = kk < krem;
-            const double* gp = g + (long long)kk * ld + lane;
-            double* sp = s + kk * LDS_R + lane;
 #pragma unroll
-            for (int j = 0; j < (TR + 31) / 32; ++j) {
-                const int rr = lane + 32 * j;
-                if (rr < r_ld) cp_async8(sp + 32 * j, gp + 32 * j, kv && rr < rrem);
-            }
+            for (int j = 0; j < (TR + 31) / 32; ++j)
+                if (lane + 32 * j < r_ld) cp_async8_s(sp + 32 * j * 8, gp + 32 * j, kv ? nb[j] : 0);
+            gp += gstep; sp += NP * LDS_R * 8;
         }
     } else {
         const int kk = lane & 15, r0 = (lane >> 4) + 2 * pw;
         if (kk < kld) {
-            const bool kv = kk < krem;
+            const int kb = kk < krem ? 8 : 0;
             const double* gp = g + kk + (long long)r0 * ld;
-            double* sp = s + r0 * LDK + kk;
+            unsigned sp = s + (r0 * LDK + kk) * 8;
             const long long gstep = 2ll * NP * ld;
 #pragma unroll 4
             for (int rr = r0; rr < r_ld; rr += 2 * NP) {
-                cp_async8(sp, gp, kv && rr < rrem);
-                gp += gstep; sp += 2 * NP * LDK;
+                cp_async8_s(sp, gp, rr < rrem ? kb : 0);
+                gp += gstep; sp += 2 * NP * LDK * 8;
             }
         }
     }
@@ -153,8 +157,8 @@ k_gemm_ws(const DWork* __restrict__ works, int n_works, const DSeg* __restrict__
                     const int krem = cur.k - pk0;
                     const int kld = min(KC, (krem + 3) & ~3);
                     mbar_wait(&empty[stage], phase ^ 1);
-                    stage_operand<TM, NP>(As + stage * A_STAGE, a_km ? pA + pk0 : pA + (long long)pk0 * cur.lda, cur.lda, a_km, pmrem, tm_ld, krem, kld, lane, pw);
-                    stage_operand<TN, NP>(Bs + stage * B_STAGE, b_km ? pB + pk0 : pB + (long long)pk0 * cur.ldb, cur.ldb, b_km, pnrem, tn_ld, krem, kld, lane, pw);
+                    stage_operand<TM, NP>(smem_u32(As + stage * A_STAGE), a_km ? pA + pk0 : pA + (long long)pk0 * cur.lda, cur.lda, a_km, pmrem, tm_ld, krem, kld, lane, pw);
+                    stage_operand<TN, NP>(smem_u32(Bs + stage * B_STAGE), b_km ? pB + pk0 : pB + (long long)pk0 * cur.ldb, cur.ldb, b_km, pnrem, tn_ld, krem, kld, lane, pw);
                     const bool last = ps == last_seg && pk0 + KC >= cur.k;
                     m.flags = (a_km ? 1 : 0) | (b_km ? 2 : 0) | first | (last ? 8 : 0) | (kld << 8);
                     first = 0;

@@ -1038,7 +1038,7 @@ private:
             G.ng = stream ? 4 : (g <= 8 ? 8 : g <= 16 ? 16 : g <= 32 ? 32 : 64);
             G.src_begin = (int32_t)wl.srcs.size(); G.dst_begin = (int32_t)wl.dsts.size(); G.coef_begin = (int64_t)wl.coefs.size();
             for (int64_t ref : uni) wl.srcs.push_back(WSrc{Ref{(int32_t)(ref >> 56), ref & (((int64_t)1 << 56) - 1)}, lds_map[ref]});
-            int32_t ns_pad = stream ? ns : (ns + 7) / 8 * 8;      // the DMMA kernel consumes sources eight at a time
+            int32_t ns_pad = stream ? ns : (ns + 15) / 16 * 16;   // the DMMA kernel stages sources sixteen at a time
             wl.coefs.resize(wl.coefs.size() + (size_t)ns_pad * G.ng, 0.);
             for (int32_t d = 0; d < g; ++d) {
                 size_t di = keys[q + d].idx;

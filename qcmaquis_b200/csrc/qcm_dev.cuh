@@ -48,6 +48,11 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool
     const int bytes = valid ? 8 : 0;    // src-size 0: nothing is read, the 8 destination bytes are zero-filled
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes) : "memory");
 }
+// same with a precomputed shared-memory address and byte count (0 or 8)
+__device__ __forceinline__ void cp_async8_s(unsigned smem_addr, const void* gsrc, int bytes)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(smem_addr), "l"(gsrc), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b)
 {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));

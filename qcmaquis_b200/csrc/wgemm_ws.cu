@@ -70,12 +70,13 @@ k_wgemm_ws(const DWWork* __restrict__ works, int n_works, const DWGroup* __restr
             // chunks of this work item that fall to this warp
             int c0 = (int)((pw - cnt % NP + NP) % NP);
             if (c0 < nchunks) {
-                // this lane's TE / 32 panel elements: flat index and (row, column) for panels with their own leading dimension
-                int el[TE / 32], er[TE / 32], ec[TE / 32];
+                // this lane's TE / 32 panel elements as (row, column) of the panel -- element offset inside a source is
+                // row + column * lds (= the flat index when the panel is stored with lds == rows) -- and their byte counts
+                int er[TE / 32], ec[TE / 32], nb[TE / 32];
 #pragma unroll
                 for (int j = 0; j < TE / 32; ++j) {
-                    el[j] = w.e0 + lane + 32 * j;
-                    ec[j] = el[j] / g.rows; er[j] = el[j] - ec[j] * g.rows;
+                    const int el = w.e0 + lane + 32 * j;
+                    ec[j] = el / g.rows; er[j] = el - ec[j] * g.rows; nb[j] = el < n ? 8 : 0;
                 }
                 const DWSrc* __restrict__ sq = srcs + g.src_begin;
                 const double* __restrict__ cq = coefs + g.coef_begin;
@@ -86,30 +87,33 @@ k_wgemm_ws(const DWWork* __restrict__ works, int n_works, const DWGroup* __restr
                     const long long my = cnt + c;
                     const int stage = (int)(my % STAGES);
                     const unsigned phase = (unsigned)((my / STAGES) & 1);
-                    double* as = As + stage * A_STAGE;
-                    double* bs = Bs + stage * B_STAGE;
+                    const unsigned as = smem_u32(As + stage * A_STAGE) + lane * 8;
+                    const unsigned bs = smem_u32(Bs + stage * B_STAGE);
                     bool waited = false;
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {           // two halves of eight source rows: eight descriptor loads in flight
                         DWSrc q[KC / 2];
 #pragma unroll
                         for (int t = 0; t < KC / 2; ++t) q[t] = sq[min(u0 + h * (KC / 2) + t, g.n_src - 1)];
-                        if (!waited) { mbar_wait(&empty[stage], phase ^ 1); waited = true; }
+                        if (!waited) {
+                            mbar_wait(&empty[stage], phase ^ 1); waited = true;
+                            // coefficient rows of the stage: KC * NG contiguous doubles (rows are zero-padded to a multiple of KC)
+                            const double* __restrict__ cr = cq + (long long)u0 * NG;
+#pragma unroll
+                            for (int idx = lane; idx < KC * NG; idx += 32) {
+                                const int kk = idx / NG, d = idx % NG;
+                                if (kk < kld) cp_async8_s(bs + (kk * LDB + d) * 8, cr + idx, 8);
+                            }
+                        }
 #pragma unroll
                         for (int t = 0; t < KC / 2; ++t) {
                             const int kk = h * (KC / 2) + t;
                             if (kk < kld) {
                                 const bool kv = kk < krem;
                                 const double* __restrict__ p = bufs.p[q[t].buf] + q[t].off;
-                                const bool flat = q[t].lds == g.rows;
 #pragma unroll
-                                for (int j = 0; j < TE / 32; ++j) {
-                                    const long long off = flat ? (long long)el[j] : er[j] + (long long)ec[j] * q[t].lds;
-                                    cp_async8(as + kk * LDA + lane + 32 * j, p + off, kv && el[j] < n);
-                                }
-                                const double* __restrict__ cr = cq + (long long)(u0 + kk) * NG;
-#pragma unroll
-                                for (int d = lane; d < NG; d += 32) cp_async8(bs + kk * LDB + d, cr + d, kv);
+                                for (int j = 0; j < TE / 32; ++j)
+                                    cp_async8_s(as + (kk * LDA + 32 * j) * 8, p + (er[j] + ec[j] * q[t].lds), kv ? nb[j] : 0);
                             }
                         }
                     }
