@@ -14,8 +14,9 @@ metric is quoted on, configs[2]: 24e/30o SU2U1 M=2000 two-site (one site problem
   --impl reference   the CPU oracle (restatement of the reference algorithm, OpenMP over the MPO bond index,
             OpenBLAS dgemm) on the host cores, same instance, same metric
 
-N>1: one process per GPU (torchrun); the MPO bond index is sharded across ranks and the partial sigma vectors
-are summed with one NCCL allreduce per step inside the library (strong scaling: the problem is fixed).
+N>1: one process per GPU (torchrun); the edges of the MPO bond graph are sharded across ranks by their step-1 bond
+index and the partial sigma vectors are summed with one NCCL allreduce per step inside the library (strong scaling:
+the problem is fixed; value = FLOPs of the whole problem / max-over-ranks device time).
 """
 import argparse, ctypes, json, os, subprocess, sys, tempfile, threading, time
 
@@ -95,6 +96,7 @@ def run_reference(args, cfg_name, norb, nelec, symm, M, site):
     from qcmaquis_b200 import build
     lib = ctypes.CDLL(build.build_oracle())
     lib.orc_create.restype = ctypes.c_void_p
+    lib.orc_set_threads(len(os.sched_getaffinity(0)))
     e = errbuf()
     path = make_fcidump(norb, nelec)
     h = lib.orc_create(path.encode(), symm.encode(), norb, nelec, e, 1024)
@@ -164,6 +166,7 @@ def main():
     ap.add_argument("--site", type=int, default=-1)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parity", action="store_true", help="N>1: rank 0 also runs the CPU oracle on the same instance and reports the sigma error")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3
@@ -211,7 +214,6 @@ def main():
     info = (ctypes.c_double * 32)()
     if host.qcmd_setup_site(h, site, 1, M, args.seed, local, rank, world, info, e, 1024):
         raise RuntimeError(e.value.decode())
-    flops, bytes_alg = info[0], info[4]
     psi_n, sig_n = int(info[5]), int(info[6])
     stream = torch.cuda.ExternalStream(cu.qcm_stream())
 
@@ -227,6 +229,18 @@ def main():
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    def sum_over_ranks(xs):
+        if world == 1:
+            return list(xs)
+        t = torch.tensor(list(xs), dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(v) for v in t.cpu()]
+
+    # algorithmic FLOPs of the whole problem: every rank books its share of the reference schedule exactly once
+    # (plan.hpp filter_owned), so the sum over ranks is the unsharded schedule's count whatever N is
+    flops, f_t, f_w, f_c, x_w, x_c = sum_over_ranks([info[0], info[1], info[2], info[3], info[24], info[25]])
+    bytes_alg = info[4]
 
     # ---- device-resident timing (value) ------------------------------------------------------------------
     if host.qcmd_sigma_dev(h, args.warmup, e, 1024):
@@ -301,8 +315,8 @@ def main():
             "config": {"workload": args.config, "site": site, "twosite": True, "M": M, "symmetry": symm, "parallelism": "mpo-bond-sharded x%d" % world,
                        "l2": "inputs (boundaries %.2f GB + workspaces %.2f GB) exceed L2" % ((info[7] + info[8]) * 8 / 1e9, info[12] / 1e9),
                        "mpo": "%dx%d nnz %d" % (info[16], info[17], info[18]), "sectors": int(info[14]), "largest_sector": int(info[15]),
-                       "flops_per_step": flops, "flops_split": {"step1": info[1], "w_apply": info[2], "step3": info[3]},
-                       "executed_flops": {"step1": info[1], "w_apply": info[24], "step3": info[25]},
+                       "flops_per_step": flops, "flops_split": {"step1": f_t, "w_apply": f_w, "step3": f_c},
+                       "executed_flops": {"step1": f_t, "w_apply": x_w, "step3": x_c},
                        "algorithmic_bytes": bytes_alg, "plan_seconds": info[13],
                        "w_apply_bytes": 8.0 * (info[21] + info[22]), "w_groups": int(info[23])},
             "fp64_peak_tflops": peak.value, "frac_of_fp64_peak": flops / (ms_dev * 1e-3) / 1e12 / (peak.value * world) if peak.value else None,
@@ -311,9 +325,10 @@ def main():
             "gpu_launches": int(launches)}
 
     # ---- CPU baseline + full-size parity on the same instance (rank 0, N=1 only) -------------------------
-    if world == 1 and not args.no_cpu_baseline:
+    if (world == 1 or args.parity) and rank == 0 and not args.no_cpu_baseline:
         olib = ctypes.CDLL(build.build_oracle())
         olib.orc_create.restype = ctypes.c_void_p
+        olib.orc_set_threads(len(os.sched_getaffinity(0)))
         oh = olib.orc_create(path.encode(), symm.encode(), norb, nelec, e, 1024)
         if not oh:
             raise RuntimeError(e.value.decode())

@@ -33,6 +33,8 @@ extern "C" void* orc_create(const char* fcidump, const char* symm, int L, int ne
 }
 extern "C" void orc_destroy(void* h) { delete static_cast<Orc*>(h); }
 extern "C" int orc_threads() { return omp_get_max_threads(); }
+// torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm uses all host cores like the reference's OpenMP build
+extern "C" void orc_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
 extern "C" int orc_setup_site(void* h, int site, int twosite, int M, unsigned seed, double* psi_elems, char* err, int errlen)
 {

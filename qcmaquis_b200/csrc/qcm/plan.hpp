@@ -192,7 +192,10 @@ public:
         if (structure_only) return P;
 
         // emit waves over this rank's share of b2
-        std::vector<char> mine = share_mask(pend.size(), [&](size_t i) { return estimate_cost(pend[i].y, right, pend[i].b2); });
+        std::vector<char> own = shard_sources(P, pend.size(), [&](size_t i) { return 2.0 * estimate_cost(pend[i].y, right, pend[i].b2); },
+                                              [&](size_t i) -> std::vector<size_t> const& { return pend[i].t_rows; });
+        std::vector<char> books(pend.size(), 1);
+        for (size_t i = 0; i < pend.size(); ++i) books[i] = filter_owned(own, pend[i].ytasks, pend[i].t_rows);
         Wave cur; int64_t cur_y = 0, cur_t = 0;
         auto flush = [&]() {
             if (cur.w_apply.dsts.empty() && cur.close_gemm.outs.empty() && cur.t_gemm.outs.empty()) return;
@@ -204,8 +207,8 @@ public:
             cur = Wave(); cur_y = 0; cur_t = 0;
         };
         for (size_t i = 0; i < pend.size(); ++i) {
-            if (!mine[i]) continue;
             Pending& pd = pend[i];
+            if (world > 1 && pd.ytasks.empty() && !books[i]) continue;
             int64_t need_t = 0;
             for (size_t b1 : pd.t_rows) if (!t_persistent[b1]) need_t += t_layout_size(b1);
             if ((cur_y + cur_t) > 0 && cur_y + cur_t + pd.y.total + need_t > budget) flush();
@@ -233,7 +236,7 @@ public:
                 } else
                     for (auto it = rv.basis.left_lower_bound(yb.rc); it != rv.basis.end() && it->lc == yb.rc; ++it) match[k].push_back(it - rv.basis.begin());
                 for (size_t mb : match[k])
-                    if (P.out_tensor.basis.has(yb.lc, su2_ ? yb.lc : rv.blocks[mb].rc)) { P.flops_close += 2.0 * yb.ls * rv.blocks[mb].rs * yb.rs; P.n_gemm_tasks++; }
+                    if (books[i] && P.out_tensor.basis.has(yb.lc, su2_ ? yb.lc : rv.blocks[mb].rc)) { P.flops_close += 2.0 * yb.ls * rv.blocks[mb].rs * yb.rs; P.n_gemm_tasks++; }
             }
             std::vector<Panel> panels = collect_panels(P, pd.ytasks, tl);
             for (Panel const& pn : panels) {
@@ -300,7 +303,12 @@ public:
         P.out_boundary.assign(out_bases);
         if (structure_only) return P;
 
-        std::vector<char> mine = share_mask(loop_max, [&](size_t b2) { double c = 0; for (size_t k = 0; k < pend[b2].y.size(); ++k) c += (double)pend[b2].y[k].ls * pend[b2].y[k].rs; return c; });
+        static const std::vector<size_t> no_rows;
+        std::vector<char> own = shard_sources(P, loop_max, [&](size_t b2) {
+                double c = 0; for (size_t k = 0; k < pend[b2].y.size(); ++k) c += 2.0 * (double)pend[b2].y[k].ls * pend[b2].y[k].rs * pend[b2].y[k].rs; return c; },
+            [&](size_t b2) -> std::vector<size_t> const& { return (mpo.herm_info.right_skip(b2) && isHermitian) ? no_rows : pend[b2].t_rows; });
+        std::vector<char> books(pend.size(), 1);
+        for (size_t i = 0; i < pend.size(); ++i) books[i] = filter_owned(own, pend[i].ytasks, pend[i].t_rows);
         Wave cur; int64_t cur_y = 0, cur_t = 0;
         auto flush = [&]() {
             if (cur.w_apply.dsts.empty() && cur.close_gemm.outs.empty() && cur.t_gemm.outs.empty()) return;
@@ -313,7 +321,7 @@ public:
         };
         for (size_t b2 = 0; b2 < loop_max; ++b2) {
             Pending& pd = pend[b2];
-            if (!mine[b2] || (mpo.herm_info.right_skip(b2) && isHermitian)) continue;
+            if ((world > 1 && pd.ytasks.empty() && !books[b2]) || (mpo.herm_info.right_skip(b2) && isHermitian)) continue;
             Layout ytmp; ytmp.assign(pd.y);
             int64_t need_t = 0;
             for (size_t b1 : pd.t_rows) if (!t_persistent[b1]) need_t += t_layout_size(b1);
@@ -334,7 +342,7 @@ public:
                 for (auto it = bra_lp.basis.left_lower_bound(yb.lc); it != bra_lp.basis.end() && it->lc == yb.lc; ++it) {
                     if (spin_f != -1 && !su2::triangle(spin(yb.rc), spin_f, spin(it->rc))) continue;
                     match[k].push_back(it - bra_lp.basis.begin());
-                    P.flops_close += 2.0 * yb.rs * it->rs * yb.ls; P.n_gemm_tasks++;
+                    if (books[b2]) { P.flops_close += 2.0 * yb.rs * it->rs * yb.ls; P.n_gemm_tasks++; }
                 }
             }
             std::vector<Panel> panels = collect_panels(P, pd.ytasks, tl);
@@ -400,7 +408,12 @@ public:
         P.out_boundary.assign(out_bases);
         if (structure_only) return P;
 
-        std::vector<char> mine = share_mask(loop_max, [&](size_t b1) { double c = 0; for (size_t k = 0; k < pend[b1].y.size(); ++k) c += (double)pend[b1].y[k].ls * pend[b1].y[k].rs; return c; });
+        static const std::vector<size_t> no_cols;
+        std::vector<char> own = shard_sources(P, loop_max, [&](size_t b1) {
+                double c = 0; for (size_t k = 0; k < pend[b1].y.size(); ++k) c += 2.0 * (double)pend[b1].y[k].ls * pend[b1].y[k].ls * pend[b1].y[k].rs; return c; },
+            [&](size_t b1) -> std::vector<size_t> const& { return (mpo.herm_info.left_skip(b1) && isHermitian) ? no_cols : pend[b1].t_cols; });
+        std::vector<char> books(pend.size(), 1);
+        for (size_t i = 0; i < pend.size(); ++i) books[i] = filter_owned(own, pend[i].ytasks, pend[i].t_cols);
         Wave cur; int64_t cur_y = 0, cur_t = 0;
         auto flush = [&]() {
             if (cur.w_apply.dsts.empty() && cur.close_gemm.outs.empty() && cur.t_gemm.outs.empty()) return;
@@ -415,7 +428,7 @@ public:
         VView brt; { Layout l = bra_rp; brt.build(l, true, std::vector<double>()); }
         for (size_t b1 = 0; b1 < loop_max; ++b1) {
             Pending& pd = pend[b1];
-            if (!mine[b1] || (mpo.herm_info.left_skip(b1) && isHermitian)) continue;
+            if ((world > 1 && pd.ytasks.empty() && !books[b1]) || (mpo.herm_info.left_skip(b1) && isHermitian)) continue;
             Layout ytmp; ytmp.assign(pd.y);
             int64_t need_t = 0;
             for (size_t b2 : pd.t_cols) if (!t_persistent[b2]) need_t += t_layout_size(b2);
@@ -436,7 +449,7 @@ public:
                 for (auto it = brt.basis.left_lower_bound(yb.rc); it != brt.basis.end() && it->lc == yb.rc; ++it) {
                     if (spin_f != -1 && !su2::triangle(spin(yb.lc), spin_f, spin(it->rc))) continue;
                     match[k].push_back(it - brt.basis.begin());
-                    P.flops_close += 2.0 * yb.ls * it->rs * yb.rs; P.n_gemm_tasks++;
+                    if (books[b1]) { P.flops_close += 2.0 * yb.ls * it->rs * yb.rs; P.n_gemm_tasks++; }
                 }
             }
             std::vector<Panel> panels = collect_panels(P, pd.ytasks, tl);
@@ -564,17 +577,33 @@ private:
             }
             t_basis[b1] = tb;
         }
-        // multi-use bonds are computed once up front and stay resident for all waves
-        int64_t off = 0;
+        // multi-use bonds are computed once up front and stay resident for all waves (emit_persistent, after sharding)
         for (size_t b1 = 0; b1 < B; ++b1) {
             if (b1 < mpo.row_dim() && mpo.num_row_non_zeros(b1) == 1) continue;
             if (b1 >= mpo.row_dim() || mpo.num_row_non_zeros(b1) == 0) continue;
             t_persistent[b1] = 1;
-            tp_layout[b1].assign(t_basis[b1], off);
-            off += tp_layout[b1].total;
-            emit_t_gemm(P, P.persistent_t, b1, tp_layout[b1], BUF_TP, ket_rp);
+        }
+        t_is_left = true; t_ket = ket_rp;
+    }
+    // step-1 products of the multi-use bonds this rank's share of the output index needs: laid out in BUF_TP and emitted
+    void emit_persistent(Plan& P, std::vector<char> const& needed)
+    {
+        int64_t off = 0;
+        for (size_t b = 0; b < t_basis.size(); ++b) {
+            if (!t_persistent[b] || !needed[b]) continue;
+            tp_layout[b].assign(t_basis[b], off);
+            off += tp_layout[b].total;
+            if (t_is_left) emit_t_gemm(P, P.persistent_t, b, tp_layout[b], BUF_TP, t_ket);
+            else emit_t_gemm_right(P, P.persistent_t, b, tp_layout[b], BUF_TP, t_ket);
         }
         P.tp_elems = off;
+    }
+    // FLOPs of the step-1 product of bond b (dry run of the emission)
+    double t_cost(size_t b)
+    {
+        Plan tmp; GemmList gl; Layout L; L.assign(t_basis[b], 0);
+        if (t_is_left) emit_t_gemm(tmp, gl, b, L, BUF_T, t_ket); else emit_t_gemm_right(tmp, gl, b, L, BUF_T, t_ket);
+        return tmp.flops_t;
     }
     void emit_t_gemm(Plan& P, GemmList& gl, size_t b1, Layout const& tl, int buf, Layout const& ket_rp)
     {
@@ -624,15 +653,11 @@ private:
             }
             t_basis[b2] = tb;
         }
-        int64_t off = 0;
         for (size_t b2 = 0; b2 < B; ++b2) {
             if (b2 >= mpo.col_dim() || mpo.num_col_non_zeros(b2) <= 1) continue;
             t_persistent[b2] = 1;
-            tp_layout[b2].assign(t_basis[b2], off);
-            off += tp_layout[b2].total;
-            emit_t_gemm_right(P, P.persistent_t, b2, tp_layout[b2], BUF_TP, ket_lp);
         }
-        P.tp_elems = off;
+        t_is_left = false; t_ket = ket_lp;
         ket_lp_for_right = ket_lp;
     }
     void emit_t_gemm_right(Plan& P, GemmList& gl, size_t b2, Layout const& tl, int buf, Layout const& ket_lp)
@@ -1101,21 +1126,59 @@ private:
         gl = std::move(r);
     }
 
-    // ---- sharding of the output bond index across ranks (owner computes), balanced greedily by cost
-    template <class F> std::vector<char> share_mask(size_t n, F cost)
+    // ---- sharding across ranks.  sigma = sum over the EDGES (b1, b2) of the MPO bond graph of W(b1,b2) (*) T[b1] . R[b2] is
+    // bilinear, and every result is combined by an allreduce anyway, so the edges can go to any rank.  They are sharded
+    // by the step-1 index (b1 for sigma and the left step, b2 for the right step): a rank owns a set of bonds, computes
+    // their step-1 products exactly once, and handles every edge that leaves them -- partial W sums for all output
+    // indices they feed and the closing products of those partial sums.  In the quantum-chemical MPO most output
+    // indices have a single source (their whole cost follows that source), while the few high fan-in ones (the
+    // integral-weighted sums over all operator pairs) are summed in slices, one per rank; sharding by the OUTPUT index
+    // instead makes every rank recompute nearly all step-1 products, because those few outputs need all
+    // of them.  Bonds are taken in order of decreasing cost and go to the least loaded rank; every rank runs the same
+    // deterministic assignment.  Returns own[b]; emits the step-1 products of the owned multi-use bonds.
+    template <class Cost, class Rows> std::vector<char> shard_sources(Plan& P, size_t n_out, Cost out_cost, Rows rows)
     {
-        std::vector<char> mine(n, 1);
-        if (world <= 1) return mine;
-        std::vector<std::pair<double, size_t>> c(n);
-        for (size_t i = 0; i < n; ++i) c[i] = std::make_pair(cost(i), i);
-        std::stable_sort(c.begin(), c.end(), [](auto const& a, auto const& b) { return a.first > b.first; });
+        const size_t B = t_basis.size();
+        std::vector<char> own(B, 0);
+        if (world <= 1) {
+            for (size_t i = 0; i < n_out; ++i) for (size_t b : rows(i)) own[b] = 1;
+            emit_persistent(P, own);
+            return own;
+        }
+        std::vector<double> c(B, 0.);
+        std::vector<char> used(B, 0);
+        for (size_t i = 0; i < n_out; ++i) {
+            auto const& r = rows(i);
+            if (r.empty()) continue;
+            const double share = out_cost(i) / (double)r.size();     // closing + W cost of output i, spread over its sources
+            for (size_t b : r) { c[b] += share; used[b] = 1; }
+        }
+        std::vector<std::pair<double, size_t>> order;
+        for (size_t b = 0; b < B; ++b) if (used[b]) order.push_back(std::make_pair(c[b] + t_cost(b), b));
+        std::stable_sort(order.begin(), order.end(), [](auto const& x, auto const& y) { return x.first > y.first; });
         std::vector<double> load(world, 0.);
-        for (auto const& e : c) {
+        for (auto const& e : order) {
             int r = (int)(std::min_element(load.begin(), load.end()) - load.begin());
             load[r] += e.first;
-            mine[e.second] = (r == rank);
+            own[e.second] = (r == rank);
         }
-        return mine;
+        emit_persistent(P, own);
+        return own;
+    }
+    // the tasks / step-1 rows of one output index that belong to this rank
+    // returns whether this rank books the reference's closing FLOPs of the output (it owns the first source): the
+    // algorithmic FLOP counts of the ranks then add up to exactly the unsharded schedule's
+    bool filter_owned(std::vector<char> const& own, std::vector<YTask>& tasks, std::vector<size_t>& rows) const
+    {
+        if (world <= 1) return true;
+        const bool books = rows.empty() ? rank == 0 : own[*std::min_element(rows.begin(), rows.end())] != 0;
+        size_t o = 0;
+        for (size_t i = 0; i < tasks.size(); ++i) if (own[tasks[i].bt]) tasks[o++] = tasks[i];
+        tasks.resize(o);
+        o = 0;
+        for (size_t i = 0; i < rows.size(); ++i) if (own[rows[i]]) rows[o++] = rows[i];
+        rows.resize(o);
+        return books;
     }
     double estimate_cost(Layout const& y, BoundaryLayout const&, size_t) const
     {
@@ -1133,6 +1196,7 @@ private:
     std::vector<VView> t_views;
     std::vector<char> t_persistent;
     std::vector<Layout> tp_layout;
+    bool t_is_left = true; Layout t_ket;
     Layout ket_lp_for_right;
 };
 

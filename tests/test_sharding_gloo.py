@@ -1,5 +1,5 @@
 """N>1 path on CPU: two processes (gloo), each builds ITS share of the sigma plan exactly as one GPU rank does
-(owner-computes over the MPO bond index b, plan.hpp share_mask), executes it with the plan interpreter, and the
+(the edges of the MPO bond graph sharded by their step-1 index, plan.hpp shard_sources), executes it with the plan interpreter, and the
 partial sigma vectors are summed with torch.distributed.all_reduce -- the CPU stand-in for the NCCL allreduce in
 qcm_site_hamil2.  The sum must equal the oracle's sigma; each rank's share alone must not."""
 import ctypes, os, socket, sys

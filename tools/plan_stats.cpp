@@ -17,8 +17,22 @@ int main(int argc, char** argv)
     for (size_t k = 0; k < lb.size(); ++k) lb[k] = S.left[k].basis();
     for (size_t k = 0; k < rb.size(); ++k) rb[k] = S.right[k].basis();
     plan::BoundaryLayout ll, rl; ll.assign(lb); rl.assign(rb);
-    plan::Planner pl(P.symm(), *S.mpo, true, 0, 1, (int64_t)1 << 40);
     plan::TensorDesc td{S.psi.site_dim(), S.psi.row_dim(), S.psi.col_dim(), S.psi.data().basis()};
+    if (argc > 7) {     // sharding quality: per-rank FLOPs for world sizes 1, 2, 4, 8
+        for (int world : {1, 2, 4, 8}) {
+            double mx = 0, sum = 0, t_sum = 0, alg = 0;
+            for (int r = 0; r < world; ++r) {
+                plan::Planner plr(P.symm(), *S.mpo, true, r, world, (int64_t)1 << 40);
+                plan::Plan q = plr.plan_sigma(td, ll, rl);
+                double f = q.flops_t + q.exec_w + q.exec_close;
+                mx = std::max(mx, f); sum += f; t_sum += q.flops_t; alg += q.flops();
+                printf("  world %d rank %d: step1 %.3e  W %.3e  close %.3e  total %.3e  TP %.2f GB\n", world, r, q.flops_t, q.exec_w, q.exec_close, f, q.tp_elems * 8e-9);
+            }
+            printf("world %d: max rank FLOPs %.3e, sum %.3e (step 1 %.3e); algorithmic FLOPs booked over ranks %.10e\n", world, mx, sum, t_sum, alg);
+        }
+        return 0;
+    }
+    plan::Planner pl(P.symm(), *S.mpo, true, 0, 1, (int64_t)1 << 40);
     plan::Plan pp = pl.plan_sigma(td, ll, rl);
     printf("waves %zu  flops t %.3e w %.3e close %.3e\n", pp.waves.size(), pp.flops_t, pp.flops_w, pp.flops_close);
     printf("elems: left %.3e right %.3e psi %.3e  TP %.3e  T %.3e  Y %.3e\n", (double)ll.total, (double)rl.total, (double)pp.ket_lp_elems, (double)pp.tp_elems, (double)pp.t_elems_max, (double)pp.y_elems_max);
