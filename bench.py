@@ -178,6 +178,11 @@ def main():
         run_reference(args, args.config, norb, nelec, symm, M, site)
         return
 
+    # stdout carries exactly one JSON line: whatever libraries print while the run is set up (NCCL's version banner,
+    # for one) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from qcmaquis_b200 import build
@@ -349,7 +354,8 @@ def main():
             line["parity_rel_err_vs_oracle"] = "structure mismatch: %d vs %d elements" % (int(se.value), sig_n)
         olib.orc_destroy(oh)
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     host.qcmd_destroy(h)
     if world > 1:
         cu.qcm_comm_destroy()
