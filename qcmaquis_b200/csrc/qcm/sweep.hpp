@@ -1,0 +1,238 @@
+// Host-side sweep driver above contraction::Engine, written against EngineIface so that the same code runs on the
+// B200 engine and on the CPU checker.  It is the caller of the hot path, restated so that energies per micro-iteration
+// can be compared engine against engine (north star: within 1e-8 Eh) and a sweep can be timed:
+//   * single-site optimisation loop                  dmrg/optimize/ss_optimize.hpp:60-215  (noise alpha = 0: the site
+//     tensor is re-orthogonalised by QR and the remainder is pushed into the neighbour, mpstensor.hpp normalize_left /
+//     normalize_right, multiply_from_left / multiply_from_right)
+//   * SiteProblem + ietl::mult                       dmrg/mp_tensors/siteproblem.h:22-53, optimize/ietl_lanczos_solver.h:108-115
+//   * Jacobi-Davidson, ietl_jcd_gmres = 0            ietl/jacobi.h:361-451 (driver), :123-131 (correction t = -r + (r.u / u.u) u),
+//     convergence test ietl/iteration.h (|r| <= max(rtol |theta|, atol)), defaults ietl_jcd_maxiter = 10, ietl_jcd_tol = 1e-8
+//   * boundary bookkeeping                           optimize/optimize.h:105-165 (init_left_right, boundary_left/right_step)
+// Everything dense here is small (block QR, a maxiter x maxiter eigenproblem); sigma and the boundary steps go through
+// the engine.
+#pragma once
+#include "engine_iface.hpp"
+#include <chrono>
+
+extern "C" {
+void scipy_dgeqrf_(const int* m, const int* n, double* a, const int* lda, double* tau, double* work, const int* lwork, int* info);
+void scipy_dorgqr_(const int* m, const int* n, const int* k, double* a, const int* lda, const double* tau, double* work, const int* lwork, int* info);
+void scipy_dgelqf_(const int* m, const int* n, double* a, const int* lda, double* tau, double* work, const int* lwork, int* info);
+void scipy_dorglq_(const int* m, const int* n, const int* k, double* a, const int* lda, const double* tau, double* work, const int* lwork, int* info);
+void scipy_dsyev_(const char* jobz, const char* uplo, const int* n, double* a, const int* lda, double* w, double* work, const int* lwork, int* info);
+}
+
+namespace qcm { namespace sweep {
+
+// ---- block linear algebra (block_matrix_algorithms.h: gemm :48-70, qr / lq) ------------------------------------
+inline void gemm(block_matrix const& A, block_matrix const& B, block_matrix& C)
+{
+    C.clear();
+    for (size_t k = 0; k < A.n_blocks(); ++k) {
+        QnBlock const& a = A.basis()[k];
+        for (size_t j = 0; j < B.n_blocks(); ++j) {
+            QnBlock const& b = B.basis()[j];
+            if (!(b.lc == a.rc)) continue;
+            if (a.rs != b.ls) throw std::runtime_error("sweep::gemm: inner block sizes differ");
+            Matrix c(a.ls, b.rs);
+            dgemm(A.block(k), B.block(j), 1.0, 0.0, c.data(), c.rows);
+            C.match_and_add_block(c, a.lc, b.rc);
+        }
+    }
+}
+// A = Q R per block; Q: ls x k with orthonormal columns, R: k x rs, k = min(ls, rs)
+inline void qr(block_matrix const& A, block_matrix& Q, block_matrix& R)
+{
+    Q.clear(); R.clear();
+    for (size_t b = 0; b < A.n_blocks(); ++b) {
+        Matrix a = A[b];
+        const int m = (int)a.rows, n = (int)a.cols, k = std::min(m, n);
+        std::vector<double> tau(std::max(1, k)), work(1);
+        int lwork = -1, info = 0;
+        scipy_dgeqrf_(&m, &n, a.data(), &m, tau.data(), work.data(), &lwork, &info);
+        lwork = (int)work[0]; work.resize(std::max(1, lwork));
+        scipy_dgeqrf_(&m, &n, a.data(), &m, tau.data(), work.data(), &lwork, &info);
+        if (info) throw std::runtime_error("dgeqrf failed");
+        Matrix r(k, n);
+        for (int j = 0; j < n; ++j) for (int i = 0; i <= std::min(j, k - 1); ++i) r(i, j) = a(i, j);
+        lwork = -1;
+        scipy_dorgqr_(&m, &k, &k, a.data(), &m, tau.data(), work.data(), &lwork, &info);
+        lwork = (int)work[0]; work.resize(std::max(1, lwork));
+        scipy_dorgqr_(&m, &k, &k, a.data(), &m, tau.data(), work.data(), &lwork, &info);
+        if (info) throw std::runtime_error("dorgqr failed");
+        Matrix q(m, k);
+        for (int j = 0; j < k; ++j) for (int i = 0; i < m; ++i) q(i, j) = a(i, j);
+        Q.insert_block(q, A.basis()[b].lc, A.basis()[b].rc);
+        R.insert_block(r, A.basis()[b].rc, A.basis()[b].rc);
+    }
+}
+// A = L Q per block; L: ls x k, Q: k x rs with orthonormal rows
+inline void lq(block_matrix const& A, block_matrix& L, block_matrix& Q)
+{
+    L.clear(); Q.clear();
+    for (size_t b = 0; b < A.n_blocks(); ++b) {
+        Matrix a = A[b];
+        const int m = (int)a.rows, n = (int)a.cols, k = std::min(m, n);
+        std::vector<double> tau(std::max(1, k)), work(1);
+        int lwork = -1, info = 0;
+        scipy_dgelqf_(&m, &n, a.data(), &m, tau.data(), work.data(), &lwork, &info);
+        lwork = (int)work[0]; work.resize(std::max(1, lwork));
+        scipy_dgelqf_(&m, &n, a.data(), &m, tau.data(), work.data(), &lwork, &info);
+        if (info) throw std::runtime_error("dgelqf failed");
+        Matrix l(m, k);
+        for (int j = 0; j < k; ++j) for (int i = j; i < m; ++i) l(i, j) = a(i, j);
+        lwork = -1;
+        scipy_dorglq_(&k, &n, &k, a.data(), &m, tau.data(), work.data(), &lwork, &info);
+        lwork = (int)work[0]; work.resize(std::max(1, lwork));
+        scipy_dorglq_(&k, &n, &k, a.data(), &m, tau.data(), work.data(), &lwork, &info);
+        if (info) throw std::runtime_error("dorglq failed");
+        Matrix q(k, n);
+        for (int j = 0; j < n; ++j) for (int i = 0; i < k; ++i) q(i, j) = a(i, j);
+        L.insert_block(l, A.basis()[b].lc, A.basis()[b].lc);
+        Q.insert_block(q, A.basis()[b].lc, A.basis()[b].rc);
+    }
+}
+
+// ---- MPSTensor normalisation (mpstensor.hpp normalize_left / normalize_right with the QR solver, multiply_from_*) ---
+inline block_matrix normalize_left(MPSTensor& t)
+{
+    t.make_left_paired();
+    block_matrix Q, R;
+    qr(t.data(), Q, R);
+    t.replace_left_paired(Q);
+    return R;
+}
+inline block_matrix normalize_right(MPSTensor& t)
+{
+    t.make_right_paired();
+    block_matrix L, Q;
+    lq(t.data(), L, Q);
+    t.replace_right_paired(Q);
+    return L;
+}
+inline void multiply_from_left(MPSTensor& t, block_matrix const& N)
+{
+    t.make_right_paired();
+    block_matrix tmp;
+    gemm(N, t.data(), tmp);
+    t.replace_right_paired(tmp);
+}
+inline void multiply_from_right(MPSTensor& t, block_matrix const& N)
+{
+    t.make_left_paired();
+    block_matrix tmp;
+    gemm(t.data(), N, tmp);
+    t.replace_left_paired(tmp);
+}
+// MPS::canonize(0): right-normalise sites L-1 .. 1, then normalise site 0 (mps.hpp canonize / normalize_right)
+inline void canonize_to_first(MPS& mps)
+{
+    for (size_t i = mps.size() - 1; i > 0; --i) {
+        block_matrix l = normalize_right(mps[i]);
+        multiply_from_right(mps[i - 1], l);
+    }
+    mps[0].divide_by_scalar(mps[0].scalar_norm());
+}
+
+// ---- Jacobi-Davidson on the site problem ---------------------------------------------------------------------
+inline void axpy(MPSTensor& y, double a, MPSTensor const& x)       // y += a x, blocks matched by charge
+{
+    y.make_left_paired(); x.make_left_paired();
+    block_matrix tmp = x.data();
+    tmp *= a;
+    y.data() += tmp;
+}
+struct JDResult { double theta = 0; MPSTensor vec; int n_sigma = 0; double resid = 0; };
+
+inline JDResult jacobi_davidson(EngineIface& eng, MPSTensor const& x0, Boundary const& left, Boundary const& right, MPOTensor const& mpo,
+                                int max_iter, double tol)
+{
+    std::vector<MPSTensor> V(max_iter + 1), VA(max_iter);
+    std::vector<double> M((size_t)max_iter * max_iter, 0.);
+    const double kappa = 0.25;
+    JDResult res;
+    V[0] = x0; V[0].make_left_paired();
+    int it = 0;
+    for (;;) {
+        MPSTensor& t = V[it];
+        // modified Gram-Schmidt with refinement
+        const double tau = t.scalar_norm();
+        for (int i = 0; i < it; ++i) axpy(t, -V[i].scalar_overlap(t), V[i]);
+        if (t.scalar_norm() < kappa * tau)
+            for (int i = 0; i < it; ++i) axpy(t, -V[i].scalar_overlap(t), V[i]);
+        t.divide_by_scalar(t.scalar_norm());
+        VA[it] = eng.site_hamil2(t, left, right, mpo);       // ietl::mult (y = H x; x.make_left_paired())
+        VA[it].make_left_paired(); t.make_left_paired();
+        res.n_sigma++;
+        for (int i = 0; i <= it; ++i) M[(size_t)i + (size_t)it * max_iter] = V[i].scalar_overlap(VA[it]);
+        // smallest eigenpair of the projected (it+1) x (it+1) matrix (upper triangle stored)
+        const int dim = it + 1;
+        std::vector<double> A((size_t)dim * dim), w(dim), work(std::max(1, 3 * dim));
+        for (int c = 0; c < dim; ++c) for (int r = 0; r <= c; ++r) A[(size_t)r + (size_t)c * dim] = M[(size_t)r + (size_t)c * max_iter];
+        int lwork = (int)work.size(), info = 0;
+        scipy_dsyev_("V", "U", &dim, A.data(), &dim, w.data(), work.data(), &lwork, &info);
+        if (info) throw std::runtime_error("dsyev failed in the Jacobi-Davidson subspace problem");
+        const double theta = w[0];
+        const double* s = A.data();
+        MPSTensor u = V[0]; u.multiply_by_scalar(s[0]);
+        for (int j = 1; j <= it; ++j) axpy(u, s[j], V[j]);
+        MPSTensor r = VA[0]; r.multiply_by_scalar(s[0]);
+        for (int j = 1; j <= it; ++j) axpy(r, s[j], VA[j]);
+        axpy(r, -theta, u);
+        ++it;
+        const double rn = r.scalar_norm();
+        res.theta = theta; res.resid = rn;
+        if (rn <= tol * std::abs(theta) || rn <= tol || it >= max_iter) { res.vec = u; return res; }
+        // correction without GMRES steps: t = -r + (r.u / u.u) u
+        const double dru = r.scalar_overlap(u), duu = u.scalar_overlap(u);
+        MPSTensor tn = r; tn.multiply_by_scalar(-1.);
+        axpy(tn, dru / duu, u);
+        V[it] = tn;
+    }
+}
+
+// ---- single-site sweeps ------------------------------------------------------------------------------------------
+struct SweepLog
+{
+    std::vector<double> energies;        // one per micro-iteration (site update): theta + core energy
+    std::vector<double> sweep_energy;    // last energy of every sweep
+    std::vector<double> sweep_seconds;
+    std::vector<int> n_sigma;            // sigma evaluations per micro-iteration
+    long total_sigma = 0;
+};
+
+inline SweepLog ss_sweeps(EngineIface& eng, MPO const& mpo, MPS& mps, int nsweeps, int jcd_maxiter = 10, double jcd_tol = 1e-8)
+{
+    const int L = (int)mps.size();
+    SweepLog log;
+    canonize_to_first(mps);
+    std::vector<Boundary> left(L + 1), right(L + 1);
+    left[0] = mps.left_boundary();
+    right[L] = mps.right_boundary();
+    for (int i = L - 1; i >= 0; --i) right[i] = eng.overlap_mpo_right_step(mps[i], mps[i], right[i + 1], mpo[i]);
+    for (int sweep = 0; sweep < nsweeps; ++sweep) {
+        auto t0 = std::chrono::steady_clock::now();
+        for (int _site = 0; _site < 2 * L; ++_site) {
+            const int lr = _site < L ? +1 : -1;
+            const int site = _site < L ? _site : 2 * L - _site - 1;
+            JDResult r = jacobi_davidson(eng, mps[site], left[site], right[site + 1], mpo[site], jcd_maxiter, jcd_tol);
+            mps[site] = r.vec;
+            log.energies.push_back(r.theta + mpo.core_energy);
+            log.n_sigma.push_back(r.n_sigma); log.total_sigma += r.n_sigma;
+            if (lr == +1) {
+                block_matrix t = normalize_left(mps[site]);
+                if (site < L - 1) multiply_from_left(mps[site + 1], t);
+                left[site + 1] = eng.overlap_mpo_left_step(mps[site], mps[site], left[site], mpo[site]);
+            } else {
+                block_matrix t = normalize_right(mps[site]);
+                if (site > 0) multiply_from_right(mps[site - 1], t);
+                right[site] = eng.overlap_mpo_right_step(mps[site], mps[site], right[site + 1], mpo[site]);
+            }
+        }
+        log.sweep_energy.push_back(log.energies.back());
+        log.sweep_seconds.push_back(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    }
+    return log;
+}
+
+}} // namespace qcm::sweep

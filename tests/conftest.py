@@ -13,6 +13,8 @@ def pytest_configure(config):
 
 
 def golden(name):
+    if isinstance(name, bytes):
+        return name
     return os.path.join(GOLDEN, name).encode()
 
 
@@ -42,6 +44,13 @@ class Harness:
         assert rc == 0, err.value.decode()
         return e.value, a.value
 
+    def ss_dmrg(self, f, symm, L, ne, M, nsweeps, engine, seed=42):
+        """single-site DMRG sweeps (qcm/sweep.hpp) -> (energies per micro-iteration, info)"""
+        e = (ctypes.c_double * 8192)(); n = ctypes.c_int(); info = (ctypes.c_double * 8)(); err = ctypes.create_string_buffer(1024)
+        rc = self.lib.qcmt_ss_dmrg(golden(f), symm.encode(), L, ne, M, nsweeps, seed, engine, e, 8192, ctypes.byref(n), info, err, 1024)
+        assert rc == 0, err.value.decode()
+        return list(e[:n.value]), list(info)
+
     def mpo_dims(self, f, symm, L, ne):
         dims, pairs = (ctypes.c_int * L)(), (ctypes.c_int * L)(); core = ctypes.c_double(); n = ctypes.c_int(); err = ctypes.create_string_buffer(1024)
         assert self.lib.qcmt_mpo_dims(golden(f), symm.encode(), L, ne, dims, pairs, ctypes.byref(core), err, 1024) == 0, err.value.decode()
@@ -66,3 +75,13 @@ def harness_gpu(built):
     if h.lib.qcmt_gpu_available() < 1:
         pytest.fail("a test marked gpu ran without a CUDA device: the hot path has no CPU fallback")
     return h
+
+
+@pytest.fixture(scope="session")
+def fcidump_8o8e():
+    """BASELINE config 1 system: 8 electrons in 8 orbitals, the deterministic synthetic integrals of SURVEY 8(d)"""
+    import tempfile
+    from qcmaquis_b200.fcidump import make_fcidump
+    path = os.path.join(tempfile.mkdtemp(prefix="qcm_test_"), "synth_8o8e.fcidump")
+    make_fcidump(path, 8, 8)
+    return path.encode()

@@ -6,6 +6,7 @@
 // dmrg/tests/test_mps_mpo_ops/test_siteproblem.cpp:38-95, BoundaryPropagatorElectronic.cpp:39-66.
 #include "oracle_engine.hpp"
 #include "qcm/scenarios.hpp"
+#include "qcm/sweep.hpp"
 #include "plan_interp.hpp"
 #ifdef QCMT_WITH_GPU
 #include "qcm/engine_gpu.hpp"
@@ -253,4 +254,37 @@ extern "C" int qcmt_rank_sigma(const char* fcidump, const char* symm, int L, int
         std::memcpy(buf, B.b[plan::BUF_OUT].data(), (size_t)pp.out_tensor.total * 8);
         return 0;
     } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
+}
+
+// Single-site DMRG sweeps (qcm/sweep.hpp: ss_optimize loop + Jacobi-Davidson) through an engine.
+//   engine_kind -1: CPU oracle, 0: plan interpreter, 1: qcm::GpuEngine
+// energies[0 .. *n_out): theta + core energy of every micro-iteration; info[0] sigma evaluations, [1] seconds of all
+// sweeps, [2] last energy, [3] micro-iterations per sweep
+extern "C" int qcmt_ss_dmrg(const char* fcidump, const char* symm, int L, int nelec, int Mmax, int nsweeps, unsigned seed, int engine_kind,
+                            double* energies, int n_max, int* n_out, double* info, char* err, int errlen)
+{
+    try {
+        Problem P = make_problem(fcidump, symm, L, nelec);
+        P.init_mps((size_t)Mmax, true, 0., seed);
+        std::unique_ptr<EngineIface> eng;
+        if (engine_kind < 0) eng.reset(new oracle::OracleEngine(P.params.symm));
+        else if (engine_kind == 0) eng.reset(new qcmtest::InterpEngine(P.params.symm, 1, (long long)1 << 40));
+        else {
+#ifdef QCMT_WITH_GPU
+            eng.reset(new GpuEngine(P.params.symm, 0, 0, 1));
+#else
+            throw std::runtime_error("harness built without GPU support");
+#endif
+        }
+        sweep::SweepLog log = sweep::ss_sweeps(*eng, P.mpo, P.mps, nsweeps);
+        int n = (int)std::min<size_t>(log.energies.size(), (size_t)n_max);
+        for (int i = 0; i < n; ++i) energies[i] = log.energies[i];
+        *n_out = n;
+        double secs = 0; for (double s : log.sweep_seconds) secs += s;
+        info[0] = (double)log.total_sigma; info[1] = secs; info[2] = log.energies.back(); info[3] = 2.0 * L;
+        return 0;
+    } catch (std::exception const& e) {
+        set_err(err, errlen, e.what());
+        return 1;
+    }
 }

@@ -13,14 +13,6 @@ REF = json.load(open(os.path.join(GOLDEN, "reference_values.json")))
 GPU = 1
 
 
-@pytest.fixture(scope="module")
-def fcidump_8o8e():
-    from qcmaquis_b200.fcidump import make_fcidump
-    path = os.path.join(tempfile.mkdtemp(prefix="qcm_test_"), "synth_8o8e.fcidump")
-    make_fcidump(path, 8, 8)
-    return path
-
-
 @pytest.mark.parametrize("f,L,ne", [("synth_4o4e.fcidump", 4, 4), ("synth_6o6e.fcidump", 6, 6), ("lih_4o.fcidump", 4, 2), ("benzene_6o.fcidump", 6, 6)])
 @pytest.mark.parametrize("symm", ["2u1", "su2u1", "2u1pg", "su2u1pg"])
 def test_chain_parity(harness_gpu, f, L, ne, symm):

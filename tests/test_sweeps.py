@@ -1,0 +1,59 @@
+"""Sweep-level parity: the single-site DMRG loop of qcm/sweep.hpp (ss_optimize.hpp:60-215 + Jacobi-Davidson,
+ietl/jacobi.h:361-451) is engine agnostic.  On the CPU oracle it must reproduce the reference's end-to-end energies
+(tests/golden/reference_values.json); the engine under test (plan interpreter on CPU, qcm::GpuEngine on B200) must
+then reproduce the oracle's energy of EVERY micro-iteration within 1e-8 Eh (the north star's tolerance)."""
+import json, os
+import pytest
+from conftest import GOLDEN
+
+REF = json.load(open(os.path.join(GOLDEN, "reference_values.json")))
+ORACLE, INTERP, GPU = -1, 0, 1
+E_TOL = 1e-8
+
+
+@pytest.mark.parametrize("symm", ["su2u1pg", "su2u1", "2u1pg", "2u1"])
+def test_oracle_sweeps_reach_the_reference_energies(harness_cpu, symm):
+    # dmrg/tests/test1.cpp:93 (H2, all four groups), Fixtures/LiHFixture.h:112 (single-site == two-site), H2_2e4o.TI.SS.out:70
+    e, _ = harness_cpu.ss_dmrg("h2_2o.fcidump", symm, 2, 2, 64, 3, ORACLE)
+    assert e[-1] == pytest.approx(REF["energies"]["h2_2o"]["value"], abs=E_TOL)
+    e, info = harness_cpu.ss_dmrg("lih_4o.fcidump", symm, 4, 2, 64, 4, ORACLE)
+    assert e[-1] == pytest.approx(REF["energies"]["lih_4o"]["value"], abs=E_TOL)
+    assert len(e) == 4 * 2 * 4 and info[0] >= len(e)          # one energy per site update, at least one sigma each
+    assert all(b <= a + 1e-9 for a, b in zip(e[8:], e[9:]))    # variational: monotone once the first sweep has passed
+
+
+def test_oracle_sweep_h2_four_orbitals(harness_cpu):
+    e, _ = harness_cpu.ss_dmrg("h2_4o.fcidump", "2u1pg", 4, 2, 100, 4, ORACLE)
+    assert e[-1] == pytest.approx(REF["energies"]["h2_4o"]["value"], abs=E_TOL)
+
+
+@pytest.mark.parametrize("symm", ["su2u1", "2u1"])
+@pytest.mark.parametrize("f,L,ne,M", [("lih_4o.fcidump", 4, 2, 64), ("synth_6o6e.fcidump", 6, 6, 12)])
+def test_plan_interpreter_matches_the_oracle_per_micro_iteration(harness_cpu, symm, f, L, ne, M):
+    eo, _ = harness_cpu.ss_dmrg(f, symm, L, ne, M, 2, ORACLE)
+    ei, _ = harness_cpu.ss_dmrg(f, symm, L, ne, M, 2, INTERP)
+    assert len(eo) == len(ei) == 2 * 2 * L
+    assert max(abs(a - b) for a, b in zip(eo, ei)) < 1e-10
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("symm", ["su2u1", "2u1", "su2u1pg"])
+@pytest.mark.parametrize("f,L,ne,M,ns", [("lih_4o.fcidump", 4, 2, 64, 3), ("synth_6o6e.fcidump", 6, 6, 30, 2), ("benzene_6o.fcidump", 6, 6, 40, 2)])
+def test_gpu_sweep_energies_match_the_oracle(harness_gpu, symm, f, L, ne, M, ns):
+    if symm.endswith("pg") and not f.startswith(("lih", "benzene")):
+        pytest.skip("no point group in the synthetic integrals")
+    eo, _ = harness_gpu.ss_dmrg(f, symm, L, ne, M, ns, ORACLE)
+    eg, info = harness_gpu.ss_dmrg(f, symm, L, ne, M, ns, GPU)
+    assert len(eo) == len(eg) == ns * 2 * L
+    assert max(abs(a - b) for a, b in zip(eo, eg)) < E_TOL       # every micro-iteration, not just the final energy
+    if f.startswith("lih"):
+        assert eg[-1] == pytest.approx(REF["energies"]["lih_4o"]["value"], abs=E_TOL)
+
+
+@pytest.mark.gpu
+def test_gpu_sweep_config1(harness_gpu, fcidump_8o8e):
+    """BASELINE config 1 system (8e/8o SU2U1, M=256) run end to end: sweeps on the GPU engine against the oracle"""
+    eo, io = harness_gpu.ss_dmrg(fcidump_8o8e, "su2u1", 8, 8, 256, 2, ORACLE)
+    eg, ig = harness_gpu.ss_dmrg(fcidump_8o8e, "su2u1", 8, 8, 256, 2, GPU)
+    assert len(eo) == len(eg) == 2 * 2 * 8
+    assert max(abs(a - b) for a, b in zip(eo, eg)) < E_TOL
