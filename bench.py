@@ -155,6 +155,41 @@ def reference_flops(path, symm, norb, nelec, site, M, seed):
     return f
 
 
+def sweep_measurement(host, build, device, with_cpu):
+    """Sweep level: single-site DMRG sweeps (qcm/sweep.hpp) on the B200 engine and, same driver, on the CPU oracle."""
+    results = []
+    for name, norb, nelec, symm, M, nsweeps in (("cfg1_8e8o_su2u1_M256", 8, 8, "su2u1", 256, 2), ("12e12o_su2u1_M300", 12, 12, "su2u1", 300, 1)):
+        path = make_fcidump(norb, nelec)
+        e = errbuf()
+        h = host.qcmd_create(path.encode(), symm.encode(), norb, nelec, e, 1024)
+        if not h:
+            raise RuntimeError(e.value.decode())
+        h = ctypes.c_void_p(h)
+        en = (ctypes.c_double * 4096)(); n = ctypes.c_int(); info = (ctypes.c_double * 8)()
+        if host.qcmd_ss_sweeps(h, M, nsweeps, 42, device, en, 4096, ctypes.byref(n), info, e, 1024):
+            raise RuntimeError(e.value.decode())
+        host.qcmd_destroy(h)
+        out = {"workload": "%s: %d single-site sweep(s), Jacobi-Davidson with <= 10 sigma per site, random start" % (name, nsweeps),
+               "gpu_seconds_per_sweep": info[1] / nsweeps, "sigma_evaluations": int(info[0]), "micro_iterations": n.value, "final_energy": info[2]}
+        if with_cpu:
+            olib = ctypes.CDLL(build.build_oracle())
+            olib.orc_create.restype = ctypes.c_void_p
+            olib.orc_set_threads(len(os.sched_getaffinity(0)))
+            oh = olib.orc_create(path.encode(), symm.encode(), norb, nelec, e, 1024)
+            if not oh:
+                raise RuntimeError(e.value.decode())
+            oh = ctypes.c_void_p(oh)
+            eo = (ctypes.c_double * 4096)(); no = ctypes.c_int(); io = (ctypes.c_double * 8)()
+            if olib.orc_ss_sweeps(oh, M, nsweeps, 42, eo, 4096, ctypes.byref(no), io, e, 1024):
+                raise RuntimeError(e.value.decode())
+            olib.orc_destroy(oh)
+            out["cpu_seconds_per_sweep"] = io[1] / nsweeps
+            out["cpu_cores"] = olib.orc_threads()
+            out["max_abs_energy_diff_vs_oracle"] = (max(abs(en[i] - eo[i]) for i in range(n.value)) if n.value == no.value else "length mismatch")
+        results.append(out)
+    return results
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -166,6 +201,7 @@ def main():
     ap.add_argument("--site", type=int, default=-1)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the sweep-level measurement (single-site DMRG sweeps of the 8e/8o system)")
     ap.add_argument("--parity", action="store_true", help="N>1: rank 0 also runs the CPU oracle on the same instance and reports the sigma error")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
@@ -353,6 +389,13 @@ def main():
         else:
             line["parity_rel_err_vs_oracle"] = "structure mismatch: %d vs %d elements" % (int(se.value), sig_n)
         olib.orc_destroy(oh)
+    # ---- sweep level (N=1): single-site DMRG sweeps of BASELINE config 1's system (8e/8o SU2U1, M=256) through the
+    # engine, boundaries resident in HBM, against the same driver on the CPU oracle: per-micro-iteration energies
+    if world == 1 and not args.no_sweep:
+        try:
+            line["sweep"] = sweep_measurement(host, build, local, not args.no_cpu_baseline)
+        except Exception as ex:     # the sigma line above stays valid
+            line["sweep"] = {"error": str(ex)}
     if rank == 0:
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())

@@ -5,6 +5,7 @@
 // reference's own threading model (utils/parallel/loops.hpp:11-26).
 #include "oracle_engine.hpp"
 #include "qcm/scenarios.hpp"
+#include "qcm/sweep.hpp"
 #include <cstdio>
 #include <cstring>
 #include <omp.h>
@@ -70,4 +71,22 @@ extern "C" int orc_get_sigma(void* h, double* out)
     size_t o = 0;
     for (size_t k = 0; k < D->sigma.data().n_blocks(); ++k) { auto const& v = D->sigma.data()[k].v; std::memcpy(out + o, v.data(), v.size() * 8); o += v.size(); }
     return 0;
+}
+
+// the same single-site sweeps (qcm/sweep.hpp) on the CPU oracle: the sweep-level CPU baseline and energy reference
+extern "C" int orc_ss_sweeps(void* h, int Mmax, int nsweeps, unsigned seed, double* energies, int n_max, int* n_out, double* info, char* err, int errlen)
+{
+    try {
+        Orc* D = static_cast<Orc*>(h);
+        scipy_openblas_set_num_threads(1);
+        D->P.init_mps((size_t)Mmax, true, 0., seed);
+        oracle::OracleEngine eng(D->P.symm());
+        sweep::SweepLog log = sweep::ss_sweeps(eng, D->P.mpo, D->P.mps, nsweeps);
+        int n = (int)std::min<size_t>(log.energies.size(), (size_t)n_max);
+        for (int i = 0; i < n; ++i) energies[i] = log.energies[i];
+        *n_out = n;
+        double secs = 0; for (double s : log.sweep_seconds) secs += s;
+        info[0] = (double)log.total_sigma; info[1] = secs; info[2] = log.energies.back();
+        return 0;
+    } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
 }

@@ -6,6 +6,7 @@
 // Nothing here touches oracle/.
 #include "qcm/engine_gpu.hpp"
 #include "qcm/scenarios.hpp"
+#include "qcm/sweep.hpp"
 #include <cstdio>
 #include <cstring>
 
@@ -162,4 +163,23 @@ extern "C" double qcmd_plan_flops(void* h, int site, int twosite, int M, unsigne
         plan::Plan pp = pl.plan_sigma(GpuEngine::desc_of(S.psi), ll, rl);
         return pp.flops();
     } catch (std::exception const& e) { set_err(err, errlen, e.what()); return -1.; }
+}
+
+// Single-site DMRG sweeps on the B200 engine (qcm/sweep.hpp: the reference's ss_optimize loop and Jacobi-Davidson above
+// Engine::site_hamil2 / overlap_mpo_*_step; boundaries stay in HBM between sites).
+// energies: theta + core energy per micro-iteration; info: [0] sigma evaluations [1] seconds of all sweeps [2] last energy
+extern "C" int qcmd_ss_sweeps(void* h, int Mmax, int nsweeps, unsigned seed, int device, double* energies, int n_max, int* n_out, double* info, char* err, int errlen)
+{
+    try {
+        Driver* D = static_cast<Driver*>(h);
+        D->P.init_mps((size_t)Mmax, true, 0., seed);
+        GpuEngine eng(D->P.symm(), device, 0, 1);
+        sweep::SweepLog log = sweep::ss_sweeps(eng, D->P.mpo, D->P.mps, nsweeps);
+        int n = (int)std::min<size_t>(log.energies.size(), (size_t)n_max);
+        for (int i = 0; i < n; ++i) energies[i] = log.energies[i];
+        *n_out = n;
+        double secs = 0; for (double s : log.sweep_seconds) secs += s;
+        info[0] = (double)log.total_sigma; info[1] = secs; info[2] = log.energies.back();
+        return 0;
+    } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
 }
