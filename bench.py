@@ -347,6 +347,21 @@ def main():
                 "achieved": (info[1] + info[25]) / (t_gemm * 1e-3) / 1e12, "peak": peak.value, "unit": "TFLOP/s", "traffic": None,
                 "flops_per_step": info[1] + info[25], "ms_per_step": t_gemm,
                 "peak_source": "FP64 DMMA chain probe measured live on this GPU (qcm_measure_fp64_dmma_peak); MEASURED_PEAKS.json has no FP64 entry"}
+    # DRAM traffic of that kernel family over one sigma, from the committed ncu capture of the same workload
+    # (dram__bytes_read.sum + dram__bytes_write.sum, profiles/*_traffic_*.json); null when no capture matches
+    try:
+        import glob
+        cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic_*.json")))
+        for c in reversed(cands):
+            tj = json.load(open(c))
+            if tj.get("workload") == args.config and world == 1:
+                fam = "k_gemm_ws" if roof["bound"] == "tensor" else None
+                d = tj["dram_bytes_per_sigma"]
+                roof["traffic"] = d["k_gemm_ws"] if fam else d.get("k_wgemm_ws", 0) + d.get("k_wstream", 0)
+                roof["traffic_unit"] = "bytes per sigma over all launches of the kernel (ncu, %s)" % os.path.basename(c)
+                break
+    except Exception:
+        pass
     roof["frac"] = roof["achieved"] / roof["peak"] if roof["peak"] else None
     roof["phase_ms"] = {"reshape": phases[0], "step1_gemm": phases[1], "w_apply": phases[2], "step3_gemm": phases[3], "allreduce": phases[4]}
 
