@@ -74,7 +74,7 @@ typedef struct {
 } qcm_wave_desc;
 
 typedef struct {
-    int32_t kind;                    /* 0 sigma (site_hamil2), 1 overlap_mpo_left_step, 2 overlap_mpo_right_step */
+    int32_t kind;                    /* 0 sigma (site_hamil2), 1 overlap_mpo_left_step, 2 overlap_mpo_right_step, 3 diagonal_hamiltonian */
     int32_t n_waves;
     const qcm_copy_task* pre_copies; int64_t n_pre_copies;
     const qcm_gemm_out* p_outs;      int64_t n_p_outs;     /* multi-use step-1 products -> QCM_BUF_TP */
@@ -127,6 +127,10 @@ int qcm_plan_stats(qcm_plan_t p, double* flops, int64_t* bytes, int64_t* n_launc
 int qcm_site_hamil2(qcm_plan_t p, qcm_array_t left, qcm_array_t right, const double* psi, double* sigma);
 int qcm_site_hamil2_dev(qcm_plan_t p, qcm_array_t left, qcm_array_t right, qcm_array_t psi, qcm_array_t sigma);
 int qcm_boundary_step(qcm_plan_t p, qcm_array_t in, const double* bra, const double* ket, qcm_array_t out);
+/* qcm_hdiag              replaces Engine::diagonal_hamiltonian (abelian/engine.hpp:222-227; bodies abelian/h_diag.hpp:41-168,
+ *                        non-abelian/h_diag.hpp:19-155): the diagonal of the effective Hamiltonian in the left-paired
+ *                        layout of the site tensor (plan kind 3), written to the HOST buffer `diag` (blocks back to back). */
+int qcm_hdiag(qcm_plan_t p, qcm_array_t left, qcm_array_t right, double* diag);
 
 /* device time (ms, CUDA events on the library stream) of the kernels of the last plan execution, by phase:
  * [0] reshapes, [1] step-1 GEMMs, [2] W application, [3] closing GEMMs, [4] allreduce, [5] total */

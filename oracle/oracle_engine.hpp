@@ -619,6 +619,95 @@ inline void rbtm_axpy_gemm(size_t b1, task_map& tasks, block_matrix& prod, Index
 } // namespace nonabelian
 
 // ---------------------------------------------------------------------------------------------------------
+// diagonal_hamiltonian: diag(H_eff) in the left-paired layout of x (preconditioner of the Davidson solver,
+// optimize/ietl_davidson.h:85-114).  Restated literally, quirks included:
+//   abelian  (abelian/h_diag.hpp:41-117,133-168): only op(0) of every MPO entry, the entry's scale is not applied;
+//   SU2      (non-abelian/h_diag.hpp:19-113,115-155): all ops, couplings from mod_coupling with the 2x2 case table.
+// Both read the STORED boundary blocks only: a Hermitian-skipped bond (empty entry) contributes nothing.
+namespace hdiag {
+
+inline block_matrix lbtm_diag_kernel(bool su2, size_t b2, Boundary const& left, MPOTensor const& mpo, Index const& out_left_i, Index const& left_i,
+                                     Index const& right_i, Index const& phys_i, ProductBasis const& left_pb)
+{
+    block_matrix ret;
+    for (size_t e = mpo.col_begin(b2); e < mpo.col_end(b2); ++e) {
+        size_t b1 = mpo.row_of(e);
+        auto const& access = mpo.at_entry(e);
+        size_t n_ops = su2 ? access.size() : 1;
+        for (size_t op_index = 0; op_index < n_ops; ++op_index) {
+            SiteOperator const& W = mpo.op(access[op_index].first);
+            int a = 0, k = 0, ap = 0;
+            if (su2) { a = mpo.left_spin(b1).get(); k = W.spin().get(); ap = mpo.right_spin(b2).get(); }
+            for (size_t block = 0; block < right_i.size(); ++block) {
+                Charge in_charge = right_i[block].first;
+                size_t o = ret.find_block(in_charge, in_charge);
+                if (o == ret.n_blocks()) o = ret.insert_block(Matrix(out_left_i[block].second, right_i[block].second), in_charge, in_charge);
+                for (size_t s = 0; s < phys_i.size(); ++s) {
+                    Charge phys_charge = phys_i[s].first;
+                    size_t l = left_i.position(fuse(in_charge, -phys_charge));
+                    if (l == left_i.size()) continue;
+                    Charge lc = left_i[l].first;
+                    size_t l_block = left[b1].find_block(lc, lc);
+                    if (l_block == left[b1].n_blocks()) continue;
+                    Matrix const& Lb = left[b1][l_block];
+                    std::vector<double> left_diagonal(left_i[l].second);
+                    for (size_t i = 0; i < left_diagonal.size(); ++i) left_diagonal[i] = Lb(i, i);
+                    size_t left_offset = left_pb(phys_charge, lc);
+                    for (size_t w_block = 0; w_block < W.basis().size(); ++w_block) {
+                        Charge phys_in = W.basis().left_charge(w_block), phys_out = W.basis().right_charge(w_block);
+                        if (!(phys_charge == phys_in) || !(phys_in == phys_out)) continue;
+                        double couplings[2] = {1., 1.};
+                        if (su2) {
+                            int i = spin(lc), ip = spin(in_charge), j = spin(lc), jp = spin(in_charge);
+                            int two_sp = std::abs(i - ip), two_s = std::abs(j - jp);
+                            double prefactor = std::sqrt((ip + 1.) * (j + 1.) / ((i + 1.) * (jp + 1.))) * access[op_index].second;
+                            couplings[0] = prefactor * su2::mod_coupling(j, two_s, jp, a, k, ap, i, two_sp, ip);
+                            couplings[1] = prefactor * su2::mod_coupling(j, 2, jp, a, k, ap, i, 2, ip);
+                        }
+                        for (int sp = W.sparse_ptr[w_block]; sp < W.sparse_ptr[w_block + 1]; ++sp) {
+                            SparseEntry const& en = W.sparse[sp];
+                            size_t ss1 = en.row;
+                            if (ss1 != (size_t)en.col) continue;
+                            double alfa_t = su2 ? en.coefficient * couplings[en.row_spin == 2 ? 1 : 0] : en.coefficient;
+                            Matrix& out = ret[o];
+                            for (size_t col_i = 0; col_i < right_i[block].second; ++col_i)
+                                for (size_t i = 0; i < left_diagonal.size(); ++i)
+                                    out(left_offset + ss1 * left_i[l].second + i, col_i) += left_diagonal[i] * alfa_t;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    return ret;
+}
+
+inline block_matrix diagonal_hamiltonian(SymmKind symm, Boundary const& left, Boundary const& right, MPOTensor const& mpo, MPSTensor const& x)
+{
+    const bool su2 = is_su2(symm);
+    Index const& physical_i = x.site_dim();
+    Index right_i = x.col_dim(), out_left_i = physical_i * x.row_dim();
+    common_subset(out_left_i, right_i);
+    ProductBasis out_left_pb(physical_i, x.row_dim());
+    block_matrix ret;
+    for (size_t b2 = 0; b2 < right.aux_dim(); ++b2) {
+        block_matrix lb2 = lbtm_diag_kernel(su2, b2, left, mpo, out_left_i, x.row_dim(), x.col_dim(), physical_i, out_left_pb);
+        for (size_t block = 0; block < lb2.n_blocks(); ++block) {
+            Charge in_r_charge = lb2.basis()[block].rc;
+            size_t rblock = right[b2].find_block(in_r_charge, in_r_charge);
+            if (rblock == right[b2].n_blocks()) continue;
+            Matrix m = lb2[block];
+            Matrix const& R = right[b2][rblock];
+            for (size_t c = 0; c < m.cols; ++c) for (size_t i = 0; i < m.rows; ++i) m(i, c) *= R(c, c);
+            ret.match_and_add_block(m, in_r_charge, in_r_charge);
+        }
+    }
+    return ret;
+}
+
+} // namespace hdiag
+
+// ---------------------------------------------------------------------------------------------------------
 class OracleEngine : public EngineIface
 {
 public:

@@ -93,6 +93,18 @@ public:
         return boundary_step(2, bra_tensor, ket_tensor, right, mpo, isHermitian);
     }
 
+    // ---- Engine::diagonal_hamiltonian (abelian/engine.hpp:222-227) --------------------------------------------
+    block_matrix diagonal_hamiltonian(Boundary const& left, Boundary const& right, MPOTensor const& mpo, MPSTensor const& x)
+    {
+        std::shared_ptr<DeviceBoundary> dl = mirror(left), dr = mirror(right);
+        plan::Planner planner(symm, mpo, true, 0, 1, budget);
+        plan::Plan P = planner.plan_hdiag(desc_of(x), dl->layout, dr->layout);
+        std::shared_ptr<CompiledPlan> cp = compile(P, dl->layout.total, dr->layout.total);
+        std::vector<double> diag((size_t)cp->out_elems);
+        qcm_check(qcm_hdiag(cp->handle, dl->arr, dr->arr, diag.data()), "qcm_hdiag");
+        return unflatten(cp->out_tensor, diag);
+    }
+
     // ---- HBM-resident boundary store ----------------------------------------------------------------------
     // device mirror of a boundary (uploaded on first use; boundaries produced by this engine already have one)
     std::shared_ptr<DeviceBoundary> mirror(Boundary const& b)
@@ -234,7 +246,7 @@ private:
         d.pre_copies = copies.data(); d.n_pre_copies = (int64_t)copies.size();
         d.p_outs = po.data(); d.n_p_outs = (int64_t)po.size(); d.p_segs = ps.data(); d.n_p_segs = (int64_t)ps.size();
         d.waves = waves.data();
-        int64_t out_elems = P.kind == 0 ? P.out_tensor.total : P.out_boundary.total;
+        int64_t out_elems = (P.kind == 0 || P.kind == 3) ? P.out_tensor.total : P.out_boundary.total;
         d.elems[QCM_BUF_KET_LP] = P.ket_lp_elems; d.elems[QCM_BUF_KET_RP] = P.ket_rp_elems;
         d.elems[QCM_BUF_LEFT] = left_elems; d.elems[QCM_BUF_RIGHT] = right_elems;
         d.elems[QCM_BUF_T] = P.t_elems_max; d.elems[QCM_BUF_TP] = P.tp_elems; d.elems[QCM_BUF_Y] = P.y_elems_max;

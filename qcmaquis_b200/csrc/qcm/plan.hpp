@@ -12,6 +12,7 @@
 // Block structure rules (which output blocks exist, their sizes, the descending charge order) follow the
 // reference loops literally so that the result has the same DualIndex as the CPU implementation.
 #pragma once
+#include <tuple>
 #include "mpo.hpp"
 #include "mps.hpp"
 #include <cstdint>
@@ -465,6 +466,152 @@ public:
         flush();
         merge_outputs(P.persistent_t);
         P.bytes_algorithmic = 8 * (right.total + ket_lp.total + bra_lp.total + P.out_boundary.total);
+        return P;
+    }
+
+    // -----------------------------------------------------------------------------------------------------
+    // diag(H_eff) in the left-paired layout of x (abelian/h_diag.hpp:41-168, non-abelian/h_diag.hpp:19-155):
+    //   out[(sigma, l, i), c] = sum over (b1, b2, op, diagonal W entries) alfa * L[b1](l,l)_ii * R[b2](c,c)_cc
+    // The reference forms, per b2, a matrix with identical columns and scales its columns by the right diagonal.  Here
+    // the sum over b1 is a vector per (block, b2) -- V[:, b2], formed by the W kernels from strided views of the stored
+    // left blocks (a diagonal is a 1 x m "panel" with leading dimension ld + 1) -- the right diagonals are gathered
+    // into DR[b2, :] by the panel-copy kernel, and the sum over b2 is ONE dense product V * DR per output block on the
+    // grouped GEMM.  Same quirks as the reference: abelian uses op(0) without the entry's scale; only stored boundary
+    // blocks are read (Hermitian-skipped bonds contribute nothing).  Every rank computes the whole (cheap) result.
+    Plan plan_hdiag(TensorDesc const& x, BoundaryLayout const& left, BoundaryLayout const& right)
+    {
+        Plan P; P.kind = 3; P.accumulate_out = true;
+        Index const& physical_i = x.phys_i;
+        Index right_i = x.right_i, out_left_i = physical_i * x.left_i;
+        common_subset(out_left_i, right_i);
+        ProductBasis out_left_pb(physical_i, x.left_i);
+        Index const& left_i = x.left_i;
+        // output structure: block (c, c) for every right charge with some non-empty column b2 whose right boundary has (c, c)
+        DualIndex ob;
+        std::vector<std::vector<size_t>> slots(right_i.size());        // per right_i block: the b2 that contribute
+        std::vector<std::vector<size_t>> slot_rblock(right_i.size());
+        for (size_t b2 = 0; b2 < right.aux_dim() && b2 < mpo.col_dim(); ++b2) {
+            if (mpo.col_begin(b2) == mpo.col_end(b2)) continue;
+            for (size_t block = 0; block < right_i.size(); ++block) {
+                Charge c = right_i[block].first;
+                size_t rb = right.b[b2].basis.position(c, c);
+                if (rb == right.b[b2].basis.size()) continue;
+                if (!ob.has(c, c)) ob.insert(QnBlock(c, c, out_left_i[block].second, right_i[block].second));
+                slots[block].push_back(b2); slot_rblock[block].push_back(rb);
+            }
+        }
+        P.out_tensor.assign(ob);
+        // V and DR workspaces
+        std::vector<int64_t> voff(right_i.size(), 0), droff(right_i.size(), 0);
+        int64_t vtot = 0, drtot = 0;
+        for (size_t block = 0; block < right_i.size(); ++block) {
+            voff[block] = vtot; droff[block] = drtot;
+            vtot += (int64_t)out_left_i[block].second * (int64_t)slots[block].size();
+            drtot += (int64_t)right_i[block].second * (int64_t)slots[block].size();
+        }
+        Wave wave;
+        std::map<std::tuple<size_t, size_t, int64_t>, size_t> dst_index;      // (block, slot, row offset) -> destination
+        std::vector<std::vector<AxpySrc>> dst_srcs;
+        std::vector<AxpyDst> dsts;
+        for (size_t block = 0; block < right_i.size(); ++block) {
+            Charge in_charge = right_i[block].first;
+            const int64_t rows = (int64_t)out_left_i[block].second, cols = (int64_t)right_i[block].second;
+            for (size_t kk = 0; kk < slots[block].size(); ++kk) {
+                const size_t b2 = slots[block][kk];
+                // right diagonal -> DR[kk, :]
+                {
+                    Layout const& rl = right.b[b2];
+                    size_t rb = slot_rblock[block][kk];
+                    P.pre_copies.push_back(CopyTask{Ref{BUF_RIGHT, rl.off[rb]}, Ref{BUF_TP, droff[block] + (int64_t)kk * cols}, 1, (int32_t)std::min<int64_t>(cols, rl.basis[rb].ls),
+                                                    (int32_t)rl.basis[rb].ls + 1, 1});
+                }
+                for (size_t e = mpo.col_begin(b2); e < mpo.col_end(b2); ++e) {
+                    size_t b1 = mpo.row_of(e);
+                    if (b1 >= left.aux_dim()) continue;
+                    auto const& access = mpo.at_entry(e);
+                    size_t n_ops = su2_ ? access.size() : 1;
+                    for (size_t op_index = 0; op_index < n_ops; ++op_index) {
+                        SiteOperator const& W = mpo.op(access[op_index].first);
+                        int a = 0, k = 0, ap = 0;
+                        if (su2_) { a = mpo.left_spin(b1).get(); k = W.spin().get(); ap = mpo.right_spin(b2).get(); }
+                        for (size_t s = 0; s < physical_i.size(); ++s) {
+                            Charge phys_charge = physical_i[s].first;
+                            size_t l = left_i.position(fuse(in_charge, -phys_charge));
+                            if (l == left_i.size()) continue;
+                            Charge lc = left_i[l].first;
+                            Layout const& ll = left.b[b1];
+                            size_t l_block = ll.basis.position(lc, lc);
+                            if (l_block == ll.basis.size()) continue;
+                            const int64_t m_l = (int64_t)left_i[l].second;
+                            const int64_t left_offset = (int64_t)out_left_pb(phys_charge, lc);
+                            for (size_t w_block = 0; w_block < W.basis().size(); ++w_block) {
+                                Charge phys_in = W.basis().left_charge(w_block), phys_out = W.basis().right_charge(w_block);
+                                if (!(phys_charge == phys_in) || !(phys_in == phys_out)) continue;
+                                double couplings[2] = {1., 1.};
+                                if (su2_) {
+                                    int i = spin(lc), ip = spin(in_charge), j = spin(lc), jp = spin(in_charge);
+                                    int two_sp = std::abs(i - ip), two_s = std::abs(j - jp);
+                                    double prefactor = std::sqrt((ip + 1.) * (j + 1.) / ((i + 1.) * (jp + 1.))) * access[op_index].second;
+                                    couplings[0] = prefactor * su2::mod_coupling(j, two_s, jp, a, k, ap, i, two_sp, ip);
+                                    couplings[1] = prefactor * su2::mod_coupling(j, 2, jp, a, k, ap, i, 2, ip);
+                                }
+                                for (int sp = W.sparse_ptr[w_block]; sp < W.sparse_ptr[w_block + 1]; ++sp) {
+                                    SparseEntry const& en = W.sparse[sp];
+                                    if (en.row != en.col) continue;
+                                    const double alfa = su2_ ? en.coefficient * couplings[en.row_spin == 2 ? 1 : 0] : en.coefficient;
+                                    const int64_t row_off = left_offset + (int64_t)en.row * m_l;
+                                    auto key = std::make_tuple(block, kk, row_off);
+                                    auto it = dst_index.find(key);
+                                    if (it == dst_index.end()) {
+                                        it = dst_index.emplace(key, dsts.size()).first;
+                                        AxpyDst d; d.dst = Ref{BUF_Y, voff[block] + (int64_t)kk * rows + row_off}; d.ldd = 1; d.rows = 1; d.cols = (int32_t)m_l;
+                                        d.src_begin = d.src_end = 0;
+                                        dsts.push_back(d); dst_srcs.emplace_back();
+                                    }
+                                    // the diagonal of the stored block: element i at off + i * (ld + 1)
+                                    dst_srcs[it->second].push_back(AxpySrc{Ref{BUF_LEFT, ll.off[l_block]}, (int32_t)ll.basis[l_block].ls + 1, alfa});
+                                    P.flops_w += 2.0 * (double)m_l * (double)cols;     // the reference updates every column
+                                    P.n_axpy_tasks++;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            // closing product of this block: out = V (rows x K) * DR (K x cols)
+            if (!slots[block].empty() && ob.has(in_charge, in_charge)) {
+                size_t o = P.out_tensor.basis.position(in_charge, in_charge);
+                Out out; out.C = Ref{BUF_OUT, P.out_tensor.off[o]}; out.ldc = (int32_t)rows; out.m = (int32_t)rows; out.n = (int32_t)cols;
+                out.seg_begin = (int32_t)wave.close_gemm.segs.size();
+                wave.close_gemm.segs.push_back(Seg{Ref{BUF_Y, voff[block]}, Ref{BUF_TP, droff[block]}, (int32_t)rows, (int32_t)cols, (int32_t)rows, (int32_t)cols,
+                                                   (int32_t)slots[block].size(), 0, 1, 1.0});
+                out.seg_end = (int32_t)wave.close_gemm.segs.size();
+                wave.close_gemm.outs.push_back(out);
+                P.flops_close += (double)rows * cols * (double)slots[block].size();          // the reference's column scaling + add
+                P.exec_close += 2.0 * (double)rows * cols * (double)slots[block].size();
+            }
+        }
+        // sources of equal (block, offset) inside one destination are merged; destinations -> W groups
+        for (size_t d = 0; d < dsts.size(); ++d) {
+            auto& v = dst_srcs[d];
+            std::stable_sort(v.begin(), v.end(), [](AxpySrc const& x1, AxpySrc const& x2) { return std::tie(x1.src.buf, x1.src.off) < std::tie(x2.src.buf, x2.src.off); });
+            size_t o = 0;
+            for (size_t i = 0; i < v.size(); ++i) {
+                if (o && v[o - 1].src.buf == v[i].src.buf && v[o - 1].src.off == v[i].src.off && v[o - 1].lds == v[i].lds) v[o - 1].coef += v[i].coef;
+                else v[o++] = v[i];
+            }
+            v.resize(o);
+            dsts[d].src_begin = (int32_t)wave.w_apply.srcs.size();
+            wave.w_apply.srcs.insert(wave.w_apply.srcs.end(), v.begin(), v.end());
+            dsts[d].src_end = (int32_t)wave.w_apply.srcs.size();
+            wave.w_apply.dsts.push_back(dsts[d]);
+            P.exec_w += 2.0 * dsts[d].cols * (double)v.size();
+        }
+        wave.y_elems = vtot; wave.t_elems = 0;
+        P.y_elems_max = vtot; P.tp_elems = drtot;
+        group_axpy(P, wave.w_apply, wave.w_groups);
+        P.waves.push_back(std::move(wave));
+        P.bytes_algorithmic = 8 * (left.total + right.total);
         return P;
     }
 

@@ -736,6 +736,23 @@ extern "C" int qcm_boundary_step(qcm_plan_t P, qcm_array_t in, const double* bra
     return 0;
 }
 
+extern "C" int qcm_hdiag(qcm_plan_t P, qcm_array_t left, qcm_array_t right, double* diag)
+{
+    CHECK_INIT();
+    if (!P || P->kind != 3) return fail("qcm_hdiag: plan is not a diagonal_hamiltonian plan");
+    if (check_arr(left, P->elems[QCM_BUF_LEFT], "left boundary") || check_arr(right, P->elems[QCM_BUF_RIGHT], "right boundary")) return 1;
+    if (ensure_ws(QCM_BUF_OUT, P->elems[QCM_BUF_OUT]) || ensure_ws(QCM_BUF_Y, P->elems[QCM_BUF_Y])) return 1;
+    BufTable b; memset(&b, 0, sizeof(b));
+    b.p[QCM_BUF_LEFT] = left->p; b.p[QCM_BUF_RIGHT] = right->p; b.p[QCM_BUF_OUT] = G.ws[QCM_BUF_OUT]; b.p[QCM_BUF_Y] = G.ws[QCM_BUF_Y];
+    // rows of V without contributions and the accumulating output start from zero
+    if (P->elems[QCM_BUF_OUT]) CU(cudaMemsetAsync(b.p[QCM_BUF_OUT], 0, (size_t)P->elems[QCM_BUF_OUT] * 8, G.stream));
+    if (P->elems[QCM_BUF_Y]) CU(cudaMemsetAsync(b.p[QCM_BUF_Y], 0, (size_t)P->elems[QCM_BUF_Y] * 8, G.stream));
+    if (execute(P, b)) return 1;
+    if (P->elems[QCM_BUF_OUT]) CU(cudaMemcpyAsync(diag, b.p[QCM_BUF_OUT], (size_t)P->elems[QCM_BUF_OUT] * 8, cudaMemcpyDeviceToHost, G.stream));
+    CU(cudaStreamSynchronize(G.stream));
+    return 0;
+}
+
 extern "C" int qcm_set_timing(int enabled) { G.timing = enabled != 0; return 0; }
 extern "C" int qcm_last_timing(double ms[6]) { for (int i = 0; i < 6; ++i) ms[i] = G.last_ms[i]; return 0; }
 

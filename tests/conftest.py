@@ -51,6 +51,12 @@ class Harness:
         assert rc == 0, err.value.decode()
         return list(e[:n.value]), list(info)
 
+    def hdiag_parity(self, f, symm, L, ne, M, engine, seed=42):
+        out = (ctypes.c_double * 8)(); err = ctypes.create_string_buffer(1024)
+        rc = self.lib.qcmt_hdiag_parity(golden(f), symm.encode(), L, ne, M, seed, engine, out, err, 1024)
+        assert rc == 0, err.value.decode()
+        return list(out)
+
     def mpo_dims(self, f, symm, L, ne):
         dims, pairs = (ctypes.c_int * L)(), (ctypes.c_int * L)(); core = ctypes.c_double(); n = ctypes.c_int(); err = ctypes.create_string_buffer(1024)
         assert self.lib.qcmt_mpo_dims(golden(f), symm.encode(), L, ne, dims, pairs, ctypes.byref(core), err, 1024) == 0, err.value.decode()

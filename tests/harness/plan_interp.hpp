@@ -52,7 +52,8 @@ inline void run_plan(plan::Plan const& P, Bufs& B)
         std::fill(B.b[plan::BUF_T].begin(), B.b[plan::BUF_T].end(), std::nan(""));
         run_gemm(W.t_gemm, B, false);
         // Y is never zero-filled: every element the closing products read was written by the W pass of this wave
-        std::fill(B.b[plan::BUF_Y].begin(), B.b[plan::BUF_Y].end(), std::nan(""));
+        // (the diagonal_hamiltonian plan, kind 3, is the exception: rows of V without contributions are zero, qcm_hdiag)
+        std::fill(B.b[plan::BUF_Y].begin(), B.b[plan::BUF_Y].end(), P.kind == 3 ? 0. : std::nan(""));
         for (auto const& G : W.w_groups.groups)
             for (int d = 0; d < G.n_dst; ++d) {
                 plan::WDst const& D = W.w_groups.dsts[G.dst_begin + d];
@@ -136,6 +137,17 @@ public:
         Boundary ret; ret.resize(out.aux_dim());
         for (size_t b = 0; b < out.aux_dim(); ++b) ret[b] = unflat(out.b[b], sum, 0);
         return ret;
+    }
+    block_matrix diagonal_hamiltonian(Boundary const& left, Boundary const& right, MPOTensor const& mpo, MPSTensor const& x)
+    {
+        plan::BoundaryLayout ll = layout_of(left), rl = layout_of(right);
+        plan::Planner pl(symm, mpo, true, 0, 1, budget);
+        plan::Plan P = pl.plan_hdiag(desc_of(x), ll, rl);
+        Bufs B;
+        B.b[plan::BUF_LEFT] = flat(left); B.b[plan::BUF_RIGHT] = flat(right);
+        B.b[plan::BUF_OUT].assign((size_t)P.out_tensor.total, 0.);
+        run_plan(P, B);
+        return unflat(P.out_tensor, B.b[plan::BUF_OUT], 0);
     }
     Boundary overlap_mpo_left_step(MPSTensor const& bra, MPSTensor const& ket, Boundary const& left, MPOTensor const& mpo, bool h = true) override { return step(1, bra, ket, left, mpo, h); }
     Boundary overlap_mpo_right_step(MPSTensor const& bra, MPSTensor const& ket, Boundary const& right, MPOTensor const& mpo, bool h = true) override { return step(2, bra, ket, right, mpo, h); }
