@@ -288,9 +288,13 @@ k_gemm_ws(const DWork* __restrict__ works, int n_works, const DSeg* __restrict__
     X(8, 8, 1, 2, 1, 8, 1, 0)   /* 128 x   8 */ \
     X(9, 2, 4, 4, 2, 8, 1, 0)   /*  64 x  64 */ \
     X(10, 2, 2, 2, 2, 6, 2, 0)  /*  32 x  32 */ \
-    X(11, 2, 2, 1, 1, 6, 2, 0)  /*  16 x  16 */
+    X(11, 2, 2, 1, 1, 6, 2, 0)  /*  16 x  16 */ \
+    X(12, 4, 2, 2, 2, 8, 1, 0)  /*  64 x  32 */ \
+    X(13, 2, 4, 2, 2, 8, 1, 0)  /*  32 x  64 */ \
+    X(14, 8, 1, 1, 2, 8, 1, 0)  /*  64 x  16 */ \
+    X(15, 1, 8, 2, 1, 8, 1, 0)  /*  16 x  64 */
 
-constexpr int kNumWs = 12;
+constexpr int kNumWs = 16;
 GemmWsVariant g_var[kNumWs];
 int g_occ[kNumWs];
 int g_sms = 0;

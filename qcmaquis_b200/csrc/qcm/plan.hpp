@@ -12,6 +12,9 @@
 // Block structure rules (which output blocks exist, their sizes, the descending charge order) follow the
 // reference loops literally so that the result has the same DualIndex as the CPU implementation.
 #pragma once
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <tuple>
 #include "mpo.hpp"
 #include "mps.hpp"
@@ -25,6 +28,19 @@ namespace qcm { namespace plan {
 enum Buf : int { BUF_KET_LP = 0, BUF_KET_RP, BUF_LEFT, BUF_RIGHT, BUF_T, BUF_TP, BUF_Y, BUF_OUT, BUF_BRA_LP, BUF_BRA_RP, BUF_COUNT };
 
 struct Ref { int32_t buf; int64_t off; };
+// wall-clock per planning phase, printed when QCM_PLAN_TIMING is set (development aid)
+struct PhaseTimer
+{
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    bool on = getenv("QCM_PLAN_TIMING") != nullptr;
+    void lap(const char* what)
+    {
+        if (!on) return;
+        auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "  [plan] %-28s %8.3f s\n", what, std::chrono::duration<double>(n - t).count());
+        t = n;
+    }
+};
 struct CopyTask { Ref src, dst; int32_t rows, cols, lds, ldd; };
 struct Seg { Ref A, B; int32_t lda, ldb, m, n, k, ta, tb; double alpha; };   // op(A) is m x k, op(B) is k x n
 struct Out { Ref C; int32_t ldc, m, n, seg_begin, seg_end; };
@@ -156,7 +172,9 @@ public:
         ProductBasis in_right_pb(physical_i, right_i, true);
         Index indexForTrim = ket_rp.basis.left_basis();                // bra == ket, right paired
 
+        PhaseTimer pt;
         setup_t_left(P, left, ket_rp, indexForTrim);
+        pt.lap("setup_t_left");
 
         // output structure: emulate the per-b2 products and their match_and_add_block reduction
         block_struct sigma_struct;
@@ -171,6 +189,7 @@ public:
             else y_struct_abelian_lbtm(b2, ket_rp.basis, ket_rp.basis, right_i, out_left_i, in_right_pb, out_left_pb, ybasis, pd.ytasks, pd.t_rows);
             pd.y.assign(ybasis);
         }
+        pt.lap("y_struct (all b2)");
         for (size_t b2 = 0; b2 < mpo.col_dim(); ++b2) {
             DualIndex const& ybasis = pend[b2].y.basis;
             // closing product structure (decides which sigma blocks exist, on every rank identically)
@@ -191,19 +210,24 @@ public:
         }
         P.out_tensor.assign(sigma_struct.basis);
         if (structure_only) return P;
+        pt.lap("sigma structure");
 
         // emit waves over this rank's share of b2
         std::vector<char> own = shard_sources(P, pend.size(), [&](size_t i) { return 2.0 * estimate_cost(pend[i].y, right, pend[i].b2); },
                                               [&](size_t i) -> std::vector<size_t> const& { return pend[i].t_rows; });
         std::vector<char> books(pend.size(), 1);
         for (size_t i = 0; i < pend.size(); ++i) books[i] = filter_owned(own, pend[i].ytasks, pend[i].t_rows);
+        pt.lap("sharding + persistent T");
         Wave cur; int64_t cur_y = 0, cur_t = 0;
         auto flush = [&]() {
             if (cur.w_apply.dsts.empty() && cur.close_gemm.outs.empty() && cur.t_gemm.outs.empty()) return;
             cur.y_elems = cur_y; cur.t_elems = cur_t;
             P.y_elems_max = std::max(P.y_elems_max, cur_y); P.t_elems_max = std::max(P.t_elems_max, cur_t);
+            pt.lap("emission (panels, closing)");
             merge_outputs(cur.close_gemm); merge_outputs(cur.t_gemm);
+            pt.lap("merge_outputs");
             group_axpy(P, cur.w_apply, cur.w_groups);
+            pt.lap("group_axpy");
             P.waves.push_back(std::move(cur));
             cur = Wave(); cur_y = 0; cur_t = 0;
         };

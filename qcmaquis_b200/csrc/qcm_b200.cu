@@ -349,13 +349,18 @@ static int gemm_set_attributes()
 }
 
 // Cost model (SM cycles) of one tile of em x en with `chunks` K chunks.  The FP64 pipe issues one DMMA (8x8x4) per 4
-// cycles and SM: 16 cycles per 8x8 fragment and chunk of 16; a chunk also has to be staged through L2 ((rows + cols)
-// * 128 B at roughly 16 B per cycle and SM); whichever is larger bounds the chunk; every tile pays its epilogue.
+// cycles and SM: 16 cycles per 8x8 fragment and chunk of 16; a chunk also has to be staged through L2.  For the strip
+// classes the per-chunk cost is the one MEASURED on B200 at cfg3 (profiles/r01c_counters_cfg3.txt: launch time * SMs /
+// chunks): thin strips are bound by operand traffic, not by the pipe.  Every tile pays its epilogue.
 static double tile_cost(int em, int en, int chunks)
 {
     const int em8 = (em + 7) & ~7, en8 = (en + 7) & ~7;
     const double frags = (double)(em8 / 8) * (en8 / 8);
-    const double per_chunk = std::max(16.0 * frags, 8.0 * (em8 + en8)) + 60.0;
+    auto cls = [](int x) { return x > 64 ? 128 : x > 32 ? 64 : x > 16 ? 32 : x > 8 ? 16 : 8; };
+    const int a = std::min(cls(em8), cls(en8)), b = std::max(cls(em8), cls(en8));
+    double per_chunk;
+    if (b == 128) per_chunk = a == 128 ? 4520. : a == 64 ? 2500. : a == 32 ? 1500. : a == 16 ? 1150. : 1650.;
+    else per_chunk = std::max(16.0 * frags, 8.0 * (em8 + en8)) + 300.0;
     return chunks * per_chunk + 4.0 * frags + 300.0;
 }
 
@@ -392,8 +397,9 @@ static int variant_for(int hr, int hc)
     if (hr == 128 && hc == 128) return 0;
     if (hc == 128) return hr == 64 ? 1 : hr == 32 ? 3 : hr == 16 ? 5 : 7;
     if (hr == 128) return hc == 64 ? 2 : hc == 32 ? 4 : hc == 16 ? 6 : 8;
-    const int mx = std::max(hr, hc);
-    return mx == 64 ? 9 : mx == 32 ? 10 : 11;
+    const int mx = std::max(hr, hc), mn = std::min(hr, hc);
+    if (mx == 64) return mn == 64 ? 9 : mn == 32 ? (hr == 64 ? 12 : 13) : (hr == 64 ? 14 : 15);
+    return mx == 32 ? 10 : 11;
 }
 
 template <class T> static int dev_upload(qcm_plan_s* P, std::vector<T> const& h, T** d)
