@@ -219,6 +219,10 @@ def main():
     sys.stdout.flush()
     real_stdout = os.dup(1)
     os.dup2(2, 1)
+    # torchrun exports OMP_NUM_THREADS=1; the host-side schedule builder is OpenMP-parallel: give every rank its share of
+    # the host cores (must be set before the OpenMP runtime is loaded)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        os.environ["OMP_NUM_THREADS"] = str(max(1, len(os.sched_getaffinity(0)) // int(os.environ.get("LOCAL_WORLD_SIZE", os.environ["WORLD_SIZE"]))))
     import torch
     import torch.distributed as dist
     from qcmaquis_b200 import build
