@@ -172,7 +172,7 @@ public:
         ProductBasis in_right_pb(physical_i, right_i, true);
         Index indexForTrim = ket_rp.basis.left_basis();                // bra == ket, right paired
 
-        PhaseTimer pt;
+        PhaseTimer pt; double dbg_collect = 0;
         setup_t_left(P, left, ket_rp, indexForTrim);
         pt.lap("setup_t_left");
 
@@ -218,6 +218,7 @@ public:
         std::vector<char> books(pend.size(), 1);
         for (size_t i = 0; i < pend.size(); ++i) books[i] = filter_owned(own, pend[i].ytasks, pend[i].t_rows);
         pt.lap("sharding + persistent T");
+        PanelCache pcache;
         Wave cur; int64_t cur_y = 0, cur_t = 0;
         auto flush = [&]() {
             if (cur.w_apply.dsts.empty() && cur.close_gemm.outs.empty() && cur.t_gemm.outs.empty()) return;
@@ -238,6 +239,7 @@ public:
             for (size_t b1 : pd.t_rows) if (!t_persistent[b1]) need_t += t_layout_size(b1);
             if ((cur_y + cur_t) > 0 && cur_y + cur_t + pd.y.total + need_t > budget) flush();
             // step 1 for single-use rows consumed here
+            const int64_t t_begin = cur_t;
             std::map<size_t, Layout> tl;
             for (size_t b1 : pd.t_rows) {
                 if (t_persistent[b1]) { tl[b1] = tp_layout[b1]; continue; }
@@ -263,7 +265,14 @@ public:
                 for (size_t mb : match[k])
                     if (books[i] && P.out_tensor.basis.has(yb.lc, su2_ ? yb.lc : rv.blocks[mb].rc)) { P.flops_close += 2.0 * yb.ls * rv.blocks[mb].rs * yb.rs; P.n_gemm_tasks++; }
             }
-            std::vector<Panel> panels = collect_panels(P, pd.ytasks, tl);
+            auto tq0 = std::chrono::steady_clock::now();
+            PanelCounts pcnt;
+            std::vector<Panel> panels = cached_panels(pcache, pend.size(), i, t_begin,
+                [&](size_t j) -> std::vector<size_t> const& { return pend[j].t_rows; },
+                [&](size_t j) -> std::vector<YTask> const& { return pend[j].ytasks; },
+                [&](size_t j) { return world > 1 && pend[j].ytasks.empty() && !books[j]; }, tl, pcnt);
+            P.flops_w += pcnt.flops_w; P.n_axpy_tasks += pcnt.n_axpy;
+            dbg_collect += std::chrono::duration<double>(std::chrono::steady_clock::now() - tq0).count();
             for (Panel const& pn : panels) {
                 if (match[pn.o].empty()) { P.skipped_panel_elems += (int64_t)pn.rows * pn.cols; continue; }
                 PanelRef pr;
@@ -275,6 +284,7 @@ public:
             }
         }
         flush();
+        if (pt.on) fprintf(stderr, "  [plan]   of which collect_panels %8.3f s\n", dbg_collect);
         merge_outputs(P.persistent_t);
         P.bytes_algorithmic = 8 * (left.total + right.total + 2 * ket_lp.total);
         return P;
@@ -334,6 +344,7 @@ public:
             [&](size_t b2) -> std::vector<size_t> const& { return (mpo.herm_info.right_skip(b2) && isHermitian) ? no_rows : pend[b2].t_rows; });
         std::vector<char> books(pend.size(), 1);
         for (size_t i = 0; i < pend.size(); ++i) books[i] = filter_owned(own, pend[i].ytasks, pend[i].t_rows);
+        PanelCache pcache;
         Wave cur; int64_t cur_y = 0, cur_t = 0;
         auto flush = [&]() {
             if (cur.w_apply.dsts.empty() && cur.close_gemm.outs.empty() && cur.t_gemm.outs.empty()) return;
@@ -351,6 +362,7 @@ public:
             int64_t need_t = 0;
             for (size_t b1 : pd.t_rows) if (!t_persistent[b1]) need_t += t_layout_size(b1);
             if ((cur_y + cur_t) > 0 && cur_y + cur_t + ytmp.total + need_t > budget) flush();
+            const int64_t t_begin = cur_t;
             std::map<size_t, Layout> tl;
             for (size_t b1 : pd.t_rows) {
                 if (t_persistent[b1]) { tl[b1] = tp_layout[b1]; continue; }
@@ -370,7 +382,12 @@ public:
                     if (books[b2]) { P.flops_close += 2.0 * yb.rs * it->rs * yb.ls; P.n_gemm_tasks++; }
                 }
             }
-            std::vector<Panel> panels = collect_panels(P, pd.ytasks, tl);
+            PanelCounts pcnt;
+            std::vector<Panel> panels = cached_panels(pcache, pend.size(), b2, t_begin,
+                [&](size_t j) -> std::vector<size_t> const& { return pend[j].t_rows; },
+                [&](size_t j) -> std::vector<YTask> const& { return pend[j].ytasks; },
+                [&](size_t j) { return (world > 1 && pend[j].ytasks.empty() && !books[j]) || (mpo.herm_info.right_skip(j) && isHermitian); }, tl, pcnt);
+            P.flops_w += pcnt.flops_w; P.n_axpy_tasks += pcnt.n_axpy;
             for (Panel const& pn : panels) {
                 if (match[pn.o].empty()) { P.skipped_panel_elems += (int64_t)pn.rows * pn.cols; continue; }
                 PanelRef pr;
@@ -439,6 +456,7 @@ public:
             [&](size_t b1) -> std::vector<size_t> const& { return (mpo.herm_info.left_skip(b1) && isHermitian) ? no_cols : pend[b1].t_cols; });
         std::vector<char> books(pend.size(), 1);
         for (size_t i = 0; i < pend.size(); ++i) books[i] = filter_owned(own, pend[i].ytasks, pend[i].t_cols);
+        PanelCache pcache;
         Wave cur; int64_t cur_y = 0, cur_t = 0;
         auto flush = [&]() {
             if (cur.w_apply.dsts.empty() && cur.close_gemm.outs.empty() && cur.t_gemm.outs.empty()) return;
@@ -458,6 +476,7 @@ public:
             int64_t need_t = 0;
             for (size_t b2 : pd.t_cols) if (!t_persistent[b2]) need_t += t_layout_size(b2);
             if ((cur_y + cur_t) > 0 && cur_y + cur_t + ytmp.total + need_t > budget) flush();
+            const int64_t t_begin = cur_t;
             std::map<size_t, Layout> tl;
             for (size_t b2 : pd.t_cols) {
                 if (t_persistent[b2]) { tl[b2] = tp_layout[b2]; continue; }
@@ -477,7 +496,12 @@ public:
                     if (books[b1]) { P.flops_close += 2.0 * yb.ls * it->rs * yb.rs; P.n_gemm_tasks++; }
                 }
             }
-            std::vector<Panel> panels = collect_panels(P, pd.ytasks, tl);
+            PanelCounts pcnt;
+            std::vector<Panel> panels = cached_panels(pcache, pend.size(), b1, t_begin,
+                [&](size_t j) -> std::vector<size_t> const& { return pend[j].t_cols; },
+                [&](size_t j) -> std::vector<YTask> const& { return pend[j].ytasks; },
+                [&](size_t j) { return (world > 1 && pend[j].ytasks.empty() && !books[j]) || (mpo.herm_info.left_skip(j) && isHermitian); }, tl, pcnt);
+            P.flops_w += pcnt.flops_w; P.n_axpy_tasks += pcnt.n_axpy;
             for (Panel const& pn : panels) {
                 if (match[pn.o].empty()) { P.skipped_panel_elems += (int64_t)pn.rows * pn.cols; continue; }
                 PanelRef pr;
@@ -1101,28 +1125,39 @@ private:
     struct PanelSrc { Ref src; int32_t lds; double coef; };
     struct Panel { size_t o; int32_t dst_row, dst_col, rows, cols; std::vector<PanelSrc> srcs; };
     struct PanelRef { Ref A; int32_t lda; double alpha; };
-    std::vector<Panel> collect_panels(Plan& P, std::vector<YTask> const& tasks, std::map<size_t, Layout> const& tl)
+    struct PanelCounts { double flops_w = 0; size_t n_axpy = 0; };
+    // Tasks are grouped by destination panel with a hash map (the task lists of the high fan-in outputs hold millions
+    // of entries; sorting them dominated the planning time), the panels are then put in (block, column, row) order.
+    std::vector<Panel> collect_panels(PanelCounts& cnt, std::vector<YTask> const& tasks, std::map<size_t, Layout> const& tl) const
     {
-        std::vector<size_t> order(tasks.size());
-        std::iota(order.begin(), order.end(), 0);
-        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) {
-            YTask const& x = tasks[a]; YTask const& y = tasks[b];
-            return std::tie(x.o, x.dst_col, x.dst_row, x.rows, x.cols) < std::tie(y.o, y.dst_col, y.dst_row, y.rows, y.cols);
-        });
-        std::vector<Panel> panels;
-        for (size_t q = 0; q < order.size();) {
-            YTask const& h = tasks[order[q]];
-            Panel pn{h.o, h.dst_row, h.dst_col, h.rows, h.cols, {}};
-            size_t q2 = q;
-            for (; q2 < order.size(); ++q2) {
-                YTask const& t = tasks[order[q2]];
-                if (t.o != h.o || t.dst_col != h.dst_col || t.dst_row != h.dst_row || t.rows != h.rows || t.cols != h.cols) break;
-                Layout const& L = tl.at(t.bt);
-                int32_t lds = (int32_t)L.basis[t.t_block].ls;
-                int srcbuf = t_persistent[t.bt] ? BUF_TP : BUF_T;
-                pn.srcs.push_back(PanelSrc{Ref{srcbuf, L.off[t.t_block] + t.src_row + (int64_t)t.src_col * lds}, lds, t.coef});
-                P.flops_w += 2.0 * t.rows * t.cols; P.n_axpy_tasks++;
+        struct Key
+        {
+            size_t o; int32_t dst_col, dst_row, rows, cols;
+            bool operator==(Key const& k) const { return o == k.o && dst_col == k.dst_col && dst_row == k.dst_row && rows == k.rows && cols == k.cols; }
+        };
+        struct KeyHash
+        {
+            size_t operator()(Key const& k) const
+            {
+                uint64_t h = k.o * 0x9E3779B97F4A7C15ull;
+                h ^= ((uint64_t)(uint32_t)k.dst_col << 32 | (uint32_t)k.dst_row) * 0xD6E8FEB86659FD93ull; h ^= h >> 29;
+                h ^= ((uint64_t)(uint32_t)k.rows << 32 | (uint32_t)k.cols) * 0xC2B2AE3D27D4EB4Full; h ^= h >> 32;
+                return (size_t)h;
             }
+        };
+        std::unordered_map<Key, uint32_t, KeyHash> index;
+        index.reserve(tasks.size() / 4 + 16);
+        std::vector<Panel> panels;
+        size_t last_bt = (size_t)-1; Layout const* L = nullptr; int srcbuf = 0;
+        for (YTask const& t : tasks) {
+            if (t.bt != last_bt) { L = &tl.at(t.bt); srcbuf = t_persistent[t.bt] ? BUF_TP : BUF_T; last_bt = t.bt; }
+            auto ins = index.emplace(Key{t.o, t.dst_col, t.dst_row, t.rows, t.cols}, (uint32_t)panels.size());
+            if (ins.second) panels.push_back(Panel{t.o, t.dst_row, t.dst_col, t.rows, t.cols, {}});
+            int32_t lds = (int32_t)L->basis[t.t_block].ls;
+            panels[ins.first->second].srcs.push_back(PanelSrc{Ref{srcbuf, L->off[t.t_block] + t.src_row + (int64_t)t.src_col * lds}, lds, t.coef});
+            cnt.flops_w += 2.0 * t.rows * t.cols; cnt.n_axpy++;
+        }
+        for (Panel& pn : panels) {
             std::stable_sort(pn.srcs.begin(), pn.srcs.end(), [](PanelSrc const& a, PanelSrc const& b) { return std::tie(a.src.buf, a.src.off) < std::tie(b.src.buf, b.src.off); });
             size_t o = 0;
             for (size_t i = 0; i < pn.srcs.size(); ++i) {
@@ -1130,10 +1165,60 @@ private:
                 else pn.srcs[o++] = pn.srcs[i];
             }
             pn.srcs.resize(o);
-            panels.push_back(std::move(pn));
-            q = q2;
         }
+        std::sort(panels.begin(), panels.end(), [](Panel const& x, Panel const& y) {
+            return std::tie(x.o, x.dst_col, x.dst_row, x.rows, x.cols) < std::tie(y.o, y.dst_col, y.dst_row, y.rows, y.cols);
+        });
         return panels;
+    }
+    // layouts of the step-1 products one output index needs: multi-use ones where they live in BUF_TP, single-use ones
+    // back to back in BUF_T from offset t on; returns the offset after them
+    int64_t layouts_for(std::vector<size_t> const& rows, int64_t t, std::map<size_t, Layout>& tl) const
+    {
+        for (size_t b : rows) {
+            if (t_persistent[b]) { tl[b] = tp_layout[b]; continue; }
+            Layout L; L.assign(t_basis[b], t);
+            t += L.total; tl[b] = L;
+        }
+        return t;
+    }
+    // The panels of output i.  They are computed for a batch of outputs at a time in parallel, under the assumption that
+    // no wave is flushed inside the batch (the offsets of single-use step-1 products in BUF_T then follow from a prefix
+    // sum); when the assumption fails for an output its panels are recomputed and the rest of the batch is discarded.
+    struct PanelCache { std::vector<std::vector<Panel>> panels; std::vector<PanelCounts> cnt; std::vector<int64_t> t0; size_t batch = 256; };
+    template <class RowsOf, class TasksOf, class Skip>
+    std::vector<Panel> cached_panels(PanelCache& pc, size_t n, size_t i, int64_t t_begin, RowsOf rows_of, TasksOf tasks_of, Skip skip,
+                                     std::map<size_t, Layout> const& tl, PanelCounts& cnt) const
+    {
+        if (pc.t0.empty()) { pc.t0.assign(n, -1); pc.panels.resize(n); pc.cnt.resize(n); }
+        if (pc.t0[i] < 0) {
+            const size_t hi = std::min(n, i + pc.batch);
+            int64_t t = t_begin;
+            std::vector<size_t> todo;
+            for (size_t j = i; j < hi; ++j) {
+                pc.t0[j] = -1;
+                if (skip(j)) continue;
+                pc.t0[j] = t; todo.push_back(j);
+                for (size_t b : rows_of(j)) if (!t_persistent[b]) t += t_layout_size(b);
+            }
+#pragma omp parallel for schedule(dynamic, 1)
+            for (long q = 0; q < (long)todo.size(); ++q) {
+                const size_t j = todo[(size_t)q];
+                std::map<size_t, Layout> tlj;
+                layouts_for(rows_of(j), pc.t0[j], tlj);
+                pc.cnt[j] = PanelCounts();
+                pc.panels[j] = collect_panels(pc.cnt[j], tasks_of(j), tlj);
+            }
+        }
+        if (pc.t0[i] == t_begin) {
+            cnt = pc.cnt[i];
+            std::vector<Panel> r = std::move(pc.panels[i]);
+            pc.panels[i] = std::vector<Panel>();
+            return r;
+        }
+        for (size_t j = i + 1; j < std::min(n, i + pc.batch); ++j) { pc.t0[j] = -1; pc.panels[j] = std::vector<Panel>(); }   // stale: offsets moved
+        cnt = PanelCounts();
+        return collect_panels(cnt, tasks_of(i), tl);
     }
     // Where the closing product finds a panel: the T panel itself (one source; its coefficient becomes the alpha of
     // the K-segment) or a compact region of BUF_Y filled by the W kernel.  false: the panel is identically zero.
