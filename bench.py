@@ -156,9 +156,18 @@ def reference_flops(path, symm, norb, nelec, site, M, seed):
 
 
 def sweep_measurement(host, build, device, with_cpu):
-    """Sweep level: single-site DMRG sweeps (qcm/sweep.hpp) on the B200 engine and, same driver, on the CPU oracle."""
+    """Sweep level: DMRG sweeps (qcm/sweep.hpp, qcm/twosite.hpp) on the B200 engine and, same driver, on the CPU oracle.
+    The first workload is BASELINE configs[0] as written: 8e/8o SU2U1, M=256, two-site, 4 sweeps."""
     results = []
-    for name, norb, nelec, symm, M, nsweeps in (("cfg1_8e8o_su2u1_M256", 8, 8, "su2u1", 256, 2), ("12e12o_su2u1_M300", 12, 12, "su2u1", 300, 1)):
+    workloads = (("cfg1_8e8o_su2u1_M256_twosite_4sweeps", 8, 8, "su2u1", "ts", 16, 256, 4),
+                 ("12e12o_su2u1_M300_twosite_1sweep", 12, 12, "su2u1", "ts", 60, 300, 1),
+                 ("12e12o_su2u1_M300_singlesite_1sweep", 12, 12, "su2u1", "ss", 300, 300, 1))
+    olib = None
+    if with_cpu:
+        olib = ctypes.CDLL(build.build_oracle())
+        olib.orc_create.restype = ctypes.c_void_p
+        olib.orc_set_threads(len(os.sched_getaffinity(0)))
+    for name, norb, nelec, symm, kind, M0, M, nsweeps in workloads:
         path = make_fcidump(norb, nelec)
         e = errbuf()
         h = host.qcmd_create(path.encode(), symm.encode(), norb, nelec, e, 1024)
@@ -166,21 +175,29 @@ def sweep_measurement(host, build, device, with_cpu):
             raise RuntimeError(e.value.decode())
         h = ctypes.c_void_p(h)
         en = (ctypes.c_double * 4096)(); n = ctypes.c_int(); info = (ctypes.c_double * 8)()
-        if host.qcmd_ss_sweeps(h, M, nsweeps, 42, device, en, 4096, ctypes.byref(n), info, e, 1024):
+        if kind == "ts":
+            rc = host.qcmd_ts_sweeps(h, M0, M, nsweeps, 42, device, en, 4096, ctypes.byref(n), info, e, 1024)
+        else:
+            rc = host.qcmd_ss_sweeps(h, M, nsweeps, 42, device, en, 4096, ctypes.byref(n), info, e, 1024)
+        if rc:
             raise RuntimeError(e.value.decode())
         host.qcmd_destroy(h)
-        out = {"workload": "%s: %d single-site sweep(s), Jacobi-Davidson with <= 10 sigma per site, random start" % (name, nsweeps),
+        out = {"workload": name, "driver": "two-site (TwoSiteTensor + SVD truncation)" if kind == "ts" else "single-site (QR shift)",
+               "eigensolver": "Jacobi-Davidson, <= 10 sigma per site, tol 1e-8", "start": "random MPS, M0 = %d" % M0,
                "gpu_seconds_per_sweep": info[1] / nsweeps, "sigma_evaluations": int(info[0]), "micro_iterations": n.value, "final_energy": info[2]}
-        if with_cpu:
-            olib = ctypes.CDLL(build.build_oracle())
-            olib.orc_create.restype = ctypes.c_void_p
-            olib.orc_set_threads(len(os.sched_getaffinity(0)))
+        if kind == "ts":
+            out["largest_bond_dimension"] = int(info[3])
+        if olib is not None:
             oh = olib.orc_create(path.encode(), symm.encode(), norb, nelec, e, 1024)
             if not oh:
                 raise RuntimeError(e.value.decode())
             oh = ctypes.c_void_p(oh)
             eo = (ctypes.c_double * 4096)(); no = ctypes.c_int(); io = (ctypes.c_double * 8)()
-            if olib.orc_ss_sweeps(oh, M, nsweeps, 42, eo, 4096, ctypes.byref(no), io, e, 1024):
+            if kind == "ts":
+                rc = olib.orc_ts_sweeps(oh, M0, M, nsweeps, 42, eo, 4096, ctypes.byref(no), io, e, 1024)
+            else:
+                rc = olib.orc_ss_sweeps(oh, M, nsweeps, 42, eo, 4096, ctypes.byref(no), io, e, 1024)
+            if rc:
                 raise RuntimeError(e.value.decode())
             olib.orc_destroy(oh)
             out["cpu_seconds_per_sweep"] = io[1] / nsweeps

@@ -6,6 +6,7 @@
 #include "oracle_engine.hpp"
 #include "qcm/scenarios.hpp"
 #include "qcm/sweep.hpp"
+#include "qcm/twosite.hpp"
 #include <cstdio>
 #include <cstring>
 #include <omp.h>
@@ -87,6 +88,27 @@ extern "C" int orc_ss_sweeps(void* h, int Mmax, int nsweeps, unsigned seed, doub
         *n_out = n;
         double secs = 0; for (double s : log.sweep_seconds) secs += s;
         info[0] = (double)log.total_sigma; info[1] = secs; info[2] = log.energies.back();
+        return 0;
+    } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
+}
+
+// the same two-site sweeps (qcm/twosite.hpp) on the CPU oracle
+extern "C" int orc_ts_sweeps(void* h, int M0, int Mmax, int nsweeps, unsigned seed, double* energies, int n_max, int* n_out, double* info, char* err, int errlen)
+{
+    try {
+        Orc* D = static_cast<Orc*>(h);
+        scipy_openblas_set_num_threads(1);
+        D->P.init_mps((size_t)M0, true, 0., seed);
+        oracle::OracleEngine eng(D->P.symm());
+        ts::TsParams prm; prm.Mmax = (size_t)Mmax;
+        std::vector<size_t> dims;
+        sweep::SweepLog log = ts::ts_sweeps(D->P.symm(), eng, D->P.mpo, [&](int p) -> MPOTensor const& { return D->P.twosite_mpo(p); }, D->P.mps, nsweeps, prm, &dims);
+        int n = (int)std::min<size_t>(log.energies.size(), (size_t)n_max);
+        for (int i = 0; i < n; ++i) energies[i] = log.energies[i];
+        *n_out = n;
+        double secs = 0; for (double s : log.sweep_seconds) secs += s;
+        info[0] = (double)log.total_sigma; info[1] = secs; info[2] = log.energies.back();
+        info[3] = dims.empty() ? 0. : (double)*std::max_element(dims.begin(), dims.end());
         return 0;
     } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
 }

@@ -7,6 +7,7 @@
 #include "qcm/engine_gpu.hpp"
 #include "qcm/scenarios.hpp"
 #include "qcm/sweep.hpp"
+#include "qcm/twosite.hpp"
 #include <cstdio>
 #include <cstring>
 
@@ -180,6 +181,28 @@ extern "C" int qcmd_ss_sweeps(void* h, int Mmax, int nsweeps, unsigned seed, int
         *n_out = n;
         double secs = 0; for (double s : log.sweep_seconds) secs += s;
         info[0] = (double)log.total_sigma; info[1] = secs; info[2] = log.energies.back();
+        return 0;
+    } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
+}
+
+// Two-site DMRG sweeps on the B200 engine (qcm/twosite.hpp: ts_optimize loop, TwoSiteTensor, SVD truncation to Mmax) from
+// a random MPS of bond dimension M0.  info: [0] sigma evaluations [1] seconds of all sweeps [2] last energy [3] largest bond dimension
+extern "C" int qcmd_ts_sweeps(void* h, int M0, int Mmax, int nsweeps, unsigned seed, int device, double* energies, int n_max, int* n_out, double* info,
+                              char* err, int errlen)
+{
+    try {
+        Driver* D = static_cast<Driver*>(h);
+        D->P.init_mps((size_t)M0, true, 0., seed);
+        GpuEngine eng(D->P.symm(), device, 0, 1);
+        ts::TsParams prm; prm.Mmax = (size_t)Mmax;
+        std::vector<size_t> dims;
+        sweep::SweepLog log = ts::ts_sweeps(D->P.symm(), eng, D->P.mpo, [&](int p) -> MPOTensor const& { return D->P.twosite_mpo(p); }, D->P.mps, nsweeps, prm, &dims);
+        int n = (int)std::min<size_t>(log.energies.size(), (size_t)n_max);
+        for (int i = 0; i < n; ++i) energies[i] = log.energies[i];
+        *n_out = n;
+        double secs = 0; for (double s : log.sweep_seconds) secs += s;
+        info[0] = (double)log.total_sigma; info[1] = secs; info[2] = log.energies.back();
+        info[3] = dims.empty() ? 0. : (double)*std::max_element(dims.begin(), dims.end());
         return 0;
     } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
 }

@@ -1,0 +1,396 @@
+// Two-site tensors: the data formats either side of the hot path in a two-site sweep, host code.
+//   TwoSiteTensor            dmrg/mp_tensors/twositetensor.hpp:23-31 (product of two site tensors, both-paired),
+//                            :119-139 (make_mps), :141-183 (split_mps_l2r / split_mps_r2l), :355-389 (operator<<)
+//   reshape_both_to_right    dmrg/mp_tensors/ts_reshape.h:231-289      reshape_left_to_both  ts_reshape.h:89-144
+//   reduce_right / unreduce_left (SU2: 6j recoupling of the two site spins)   dmrg/mp_tensors/ts_reduction.h:42-148,150-250
+//   svd / estimate_truncation / svd_truncate   dmrg/block_matrix/block_matrix_algorithms.h:165-185,211-260,264-335
+//   two-site sweep loop      dmrg/optimize/ts_optimize.hpp:60-270 (twosite_truncation = svd)
+// The fused two-site physical index is phys_left * phys_right; the MPO side of the same fusion is make_twosite_mpo
+// (mpo.hpp).  Everything here is O(tensor size) or block SVDs; sigma and the boundary steps go through the engine.
+#pragma once
+#include "sweep.hpp"
+#include "wigner.hpp"
+
+extern "C" void scipy_dgesdd_(const char* jobz, const int* m, const int* n, double* a, const int* lda, double* s, double* u, const int* ldu,
+                              double* vt, const int* ldvt, double* work, const int* lwork, int* iwork, int* info);
+
+namespace qcm { namespace ts {
+
+// ---- ts_reshape.h:231-289 --------------------------------------------------------------------------------------
+inline void reshape_both_to_right(Index const& physical_i_left, Index const& physical_i_right, Index const& left_i, Index const& right_i,
+                                  block_matrix const& m1, block_matrix& m2)
+{
+    m2 = block_matrix();
+    Index phys2_i = physical_i_left * physical_i_right;
+    ProductBasis phys_pb(physical_i_left, physical_i_right);
+    ProductBasis in_left(physical_i_left, left_i);
+    ProductBasis in_right(physical_i_right, right_i, true);
+    ProductBasis out_right(phys2_i, right_i, true);
+    for (size_t block = 0; block < m1.n_blocks(); ++block) {
+        Charge blc = m1.basis()[block].lc, brc = m1.basis()[block].rc;
+        Matrix const& in = m1[block];
+        for (size_t s1 = 0; s1 < physical_i_left.size(); ++s1) {
+            size_t l = left_i.position(fuse(blc, -physical_i_left[s1].first));
+            if (l == left_i.size()) continue;
+            for (size_t s2 = 0; s2 < physical_i_right.size(); ++s2) {
+                size_t r = right_i.position(fuse(brc, physical_i_right[s2].first));
+                if (r == right_i.size()) continue;
+                Charge s_charge = fuse(physical_i_left[s1].first, physical_i_right[s2].first);
+                Charge out_l_charge = left_i[l].first, out_r_charge = fuse(-s_charge, right_i[r].first);
+                if (!m2.has_block(out_l_charge, out_r_charge))
+                    m2.insert_block(Matrix(left_i[l].second, out_right.size(-s_charge, right_i[r].first)), out_l_charge, out_r_charge);
+                Matrix& out = m2(out_l_charge, out_r_charge);
+                // detail::reshape_b2r (alps_detail.hpp:112-126)
+                const size_t in_left_offset = in_left(physical_i_left[s1].first, left_i[l].first), in_right_offset = in_right(physical_i_right[s2].first, right_i[r].first);
+                const size_t out_right_offset = out_right(s_charge, right_i[r].first), out_phys_offset = phys_pb(physical_i_left[s1].first, physical_i_right[s2].first);
+                const size_t sdim1 = physical_i_left[s1].second, sdim2 = physical_i_right[s2].second, ldim = left_i[l].second, rdim = right_i[r].second;
+                for (size_t ss1 = 0; ss1 < sdim1; ++ss1)
+                    for (size_t ss2 = 0; ss2 < sdim2; ++ss2) {
+                        size_t ss_out = out_phys_offset + ss1 * sdim2 + ss2;
+                        for (size_t rr = 0; rr < rdim; ++rr)
+                            for (size_t ll = 0; ll < ldim; ++ll)
+                                out(ll, out_right_offset + ss_out * rdim + rr) = in(in_left_offset + ss1 * ldim + ll, in_right_offset + ss2 * rdim + rr);
+                    }
+            }
+        }
+    }
+}
+
+// ---- ts_reshape.h:89-144 ---------------------------------------------------------------------------------------
+inline void reshape_left_to_both(Index const& physical_i_left, Index const& physical_i_right, Index const& left_i, Index const& right_i,
+                                 block_matrix const& m1, block_matrix& m2)
+{
+    m2 = block_matrix();
+    Index phys2_i = physical_i_left * physical_i_right;
+    ProductBasis phys_pb(physical_i_left, physical_i_right);
+    ProductBasis in_left(phys2_i, left_i);
+    ProductBasis out_right(physical_i_right, right_i, true);
+    ProductBasis out_left(physical_i_left, left_i);
+    for (size_t block = 0; block < m1.n_blocks(); ++block) {
+        Charge blc = m1.basis()[block].lc, brc = m1.basis()[block].rc;
+        Matrix const& in = m1[block];
+        size_t r = right_i.position(brc);
+        if (r == right_i.size()) throw std::runtime_error("m1 matrix inconsistent with right_i.");
+        for (size_t s1 = 0; s1 < physical_i_left.size(); ++s1)
+            for (size_t s2 = 0; s2 < physical_i_right.size(); ++s2) {
+                Charge s_charge = fuse(physical_i_left[s1].first, physical_i_right[s2].first);
+                size_t l = left_i.position(fuse(blc, -s_charge));
+                if (l == left_i.size()) continue;
+                Charge out_l_charge = fuse(physical_i_left[s1].first, left_i[l].first), out_r_charge = fuse(-physical_i_right[s2].first, right_i[r].first);
+                size_t o = m2.find_block(out_l_charge, out_r_charge);
+                if (o == m2.n_blocks())
+                    o = m2.insert_block(Matrix(out_left.size(physical_i_left[s1].first, left_i[l].first), out_right.size(-physical_i_right[s2].first, right_i[r].first)),
+                                        out_l_charge, out_r_charge);
+                Matrix& out = m2[o];
+                // detail::reshape_l2b (alps_detail.hpp:78-92)
+                const size_t in_left_offset = in_left(s_charge, left_i[l].first), in_phys_offset = phys_pb(physical_i_left[s1].first, physical_i_right[s2].first);
+                const size_t out_left_offset = out_left(physical_i_left[s1].first, left_i[l].first), out_right_offset = out_right(physical_i_right[s2].first, right_i[r].first);
+                const size_t sdim1 = physical_i_left[s1].second, sdim2 = physical_i_right[s2].second, ldim = left_i[l].second, rdim = right_i[r].second;
+                for (size_t ss1 = 0; ss1 < sdim1; ++ss1)
+                    for (size_t ss2 = 0; ss2 < sdim2; ++ss2) {
+                        size_t ss_out = in_phys_offset + ss1 * sdim2 + ss2;
+                        for (size_t rr = 0; rr < rdim; ++rr)
+                            for (size_t ll = 0; ll < ldim; ++ll)
+                                out(out_left_offset + ss1 * ldim + ll, out_right_offset + ss2 * rdim + rr) = in(in_left_offset + ss_out * ldim + ll, rr);
+                    }
+            }
+    }
+}
+
+// ---- ts_reduction.h:42-148: right-paired two-site tensor, uncoupled (s1, s2) columns -> spin-coupled columns --------
+inline double recoupling(int jl, int jr, int j, int S2, int S1, int jm)
+{
+    double c = std::sqrt((j + 1.) * (jm + 1.)) * su2::wigner6j(jl, jr, j, S2, S1, jm);
+    return (((jl + jr + S1 + S2) / 2) % 2) ? -c : c;
+}
+inline Index reduce_right(Index const& physical_i_left, Index const& physical_i_right, Index const& left_i, Index const& right_i,
+                          block_matrix const& m1, block_matrix& m2)
+{
+    m2 = block_matrix();
+    Index phys2_i = physical_i_left * physical_i_right;
+    ProductBasis phys_pb(physical_i_left, physical_i_right);
+    ProductBasis in_right(phys2_i, right_i, true);
+    for (size_t block = 0; block < m1.n_blocks(); ++block) {
+        Charge lc = m1.basis()[block].lc, in_r_charge = m1.basis()[block].rc;
+        const size_t left_size = m1.basis()[block].ls;
+        size_t o = m2.insert_block(Matrix(left_size, m1.basis()[block].rs), lc, in_r_charge);
+        Matrix const& in_block = m1[block];
+        Matrix& out_block = m2[o];
+        auto reduce_r = [&](double scale, size_t in_right_offset, size_t in_phys_offset, size_t out_phys_offset, size_t sdim1, size_t sdim2, size_t ldim, size_t rdim) {
+            for (size_t ss1 = 0; ss1 < sdim1; ++ss1)
+                for (size_t ss2 = 0; ss2 < sdim2; ++ss2) {
+                    size_t ss_in = in_phys_offset + ss1 * sdim2 + ss2, ss_out = out_phys_offset + ss1 * sdim2 + ss2;
+                    const double* src = &in_block(0, in_right_offset + ss_in * rdim);
+                    double* dst = &out_block(0, in_right_offset + ss_out * rdim);
+                    for (size_t i = 0; i < ldim * rdim; ++i) dst[i] += scale * src[i];
+                }
+        };
+        for (size_t s = 0; s < phys2_i.size(); ++s) {
+            Charge s_charge = phys2_i[s].first;
+            size_t r = right_i.position(fuse(in_r_charge, s_charge));
+            if (r == right_i.size()) continue;
+            size_t in_right_offset = in_right(s_charge, right_i[r].first);
+            size_t right_size = right_i[r].second;
+            for (size_t s1 = 0; s1 < physical_i_left.size(); ++s1)
+                for (size_t s2 = 0; s2 < physical_i_right.size(); ++s2) {
+                    Charge phys_c1 = physical_i_left[s1].first, phys_c2 = physical_i_right[s2].first;
+                    if (!(s_charge == fuse(phys_c1, phys_c2))) continue;
+                    size_t in_phys_offset = phys_pb(phys_c1, phys_c2);
+                    int S1 = std::abs(spin(phys_c1)), S2 = std::abs(spin(phys_c2));
+                    int jl = spin(lc), jm = spin(lc) + spin(phys_c1), jr = spin(right_i[r].first);
+                    if (jm < 0) continue;
+                    if (jl == jr && jl > 0 && S1 == 1 && S2 == 1) {
+                        size_t base_offset = (spin(phys_c1) == 1) ? in_phys_offset : in_phys_offset - 1;
+                        for (int j = std::abs(S1 - S2); j <= std::abs(S1 + S2); j += 2) {
+                            size_t out_phys_offset = base_offset + j / 2;
+                            reduce_r(recoupling(jl, jr, j, S2, S1, jm), in_right_offset, in_phys_offset, out_phys_offset,
+                                     physical_i_left[s1].second, physical_i_right[s2].second, left_size, right_size);
+                        }
+                    } else {
+                        int j = std::abs(spin(phys_c1) + spin(phys_c2));
+                        reduce_r(recoupling(jl, jr, j, S2, S1, jm), in_right_offset, in_phys_offset, in_phys_offset,
+                                 physical_i_left[s1].second, physical_i_right[s2].second, left_size, right_size);
+                    }
+                }
+        }
+    }
+    return phys2_i;
+}
+
+// ---- ts_reduction.h:150-250: left-paired two-site tensor, spin-coupled rows -> uncoupled (s1, s2) rows -----------------
+inline Index unreduce_left(Index const& physical_i_left, Index const& physical_i_right, Index const& left_i, Index const& right_i,
+                           block_matrix const& m1, block_matrix& m2)
+{
+    m2 = block_matrix();
+    Index phys2_i = physical_i_left * physical_i_right;
+    ProductBasis phys_pb(physical_i_left, physical_i_right);
+    ProductBasis in_left(phys2_i, left_i);
+    for (size_t block = 0; block < m1.n_blocks(); ++block) {
+        Charge rc = m1.basis()[block].rc, in_l_charge = m1.basis()[block].lc;
+        const size_t right_size = m1.basis()[block].rs;
+        size_t o = m2.insert_block(Matrix(m1.basis()[block].ls, right_size), in_l_charge, rc);
+        Matrix const& in_block = m1[block];
+        Matrix& out_block = m2[o];
+        auto reduce_l = [&](double scale, size_t in_left_offset, size_t in_phys_offset, size_t out_phys_offset, size_t sdim1, size_t sdim2, size_t ldim, size_t rdim) {
+            for (size_t ss1 = 0; ss1 < sdim1; ++ss1)
+                for (size_t ss2 = 0; ss2 < sdim2; ++ss2) {
+                    size_t ss_in = in_phys_offset + ss1 * sdim2 + ss2, ss_out = out_phys_offset + ss1 * sdim2 + ss2;
+                    for (size_t rr = 0; rr < rdim; ++rr)
+                        for (size_t ll = 0; ll < ldim; ++ll)
+                            out_block(in_left_offset + ss_out * ldim + ll, rr) += scale * in_block(in_left_offset + ss_in * ldim + ll, rr);
+                }
+        };
+        for (size_t s = 0; s < phys2_i.size(); ++s) {
+            Charge s_charge = phys2_i[s].first;
+            size_t l = left_i.position(fuse(in_l_charge, -s_charge));
+            if (l == left_i.size()) continue;
+            size_t in_left_offset = in_left(s_charge, left_i[l].first);
+            for (size_t s1 = 0; s1 < physical_i_left.size(); ++s1)
+                for (size_t s2 = 0; s2 < physical_i_right.size(); ++s2) {
+                    Charge phys_c1 = physical_i_left[s1].first, phys_c2 = physical_i_right[s2].first;
+                    if (!(s_charge == fuse(phys_c1, phys_c2))) continue;
+                    size_t in_phys_offset = phys_pb(phys_c1, phys_c2);
+                    int S1 = std::abs(spin(phys_c1)), S2 = std::abs(spin(phys_c2));
+                    int jl = spin(left_i[l].first), jr = spin(rc);
+                    if (jl == jr && jl > 0 && S1 == 1 && S2 == 1) {
+                        int j = (spin(phys_c1) == 1) ? 0 : 2;
+                        size_t base_offset = (j == 0) ? in_phys_offset : in_phys_offset - 1;
+                        for (int jm = jl - 1; jm <= jl + 1; jm += 2) {
+                            size_t out_phys_offset = (jm == jl - 1) ? base_offset + 1 : base_offset;
+                            reduce_l(recoupling(jl, jr, j, S2, S1, jm), in_left_offset, in_phys_offset, out_phys_offset,
+                                     physical_i_left[s1].second, physical_i_right[s2].second, left_i[l].second, right_size);
+                        }
+                    } else {
+                        int j = std::abs(spin(phys_c1) + spin(phys_c2));
+                        int jm = jl + spin(phys_c1);
+                        if (jm < 0) continue;
+                        reduce_l(recoupling(jl, jr, j, S2, S1, jm), in_left_offset, in_phys_offset, in_phys_offset,
+                                 physical_i_left[s1].second, physical_i_right[s2].second, left_i[l].second, right_size);
+                    }
+                }
+        }
+    }
+    return phys2_i;
+}
+
+// ---- block SVD with truncation (block_matrix_algorithms.h:165-185,211-260,264-335) ----------------------------------
+struct Truncation { size_t bond_dimension = 0; double truncated_weight = 0, truncated_fraction = 0, smallest_ev = 0; };
+
+// M = U diag(S) V per block; singular values below max(rel_tol * largest, the (Mmax+1)-th largest) are dropped
+inline Truncation svd_truncate(block_matrix const& M, block_matrix& U, block_matrix& V, std::vector<std::vector<double>>& S, double rel_tol, size_t Mmax)
+{
+    const size_t nb = M.n_blocks();
+    std::vector<Matrix> us(nb), vs(nb);
+    S.assign(nb, std::vector<double>());
+    for (size_t b = 0; b < nb; ++b) {
+        Matrix a = M[b];
+        const int m = (int)a.rows, n = (int)a.cols, k = std::min(m, n);
+        us[b] = Matrix(m, k); vs[b] = Matrix(k, n); S[b].assign(k, 0.);
+        std::vector<double> work(1); std::vector<int> iwork(8 * std::max(1, k));
+        int lwork = -1, info = 0;
+        scipy_dgesdd_("S", &m, &n, a.data(), &m, S[b].data(), us[b].data(), &m, vs[b].data(), &k, work.data(), &lwork, iwork.data(), &info);
+        lwork = (int)work[0]; work.resize(std::max(1, lwork));
+        scipy_dgesdd_("S", &m, &n, a.data(), &m, S[b].data(), us[b].data(), &m, vs[b].data(), &k, work.data(), &lwork, iwork.data(), &info);
+        if (info) throw std::runtime_error("dgesdd failed");
+    }
+    // estimate_truncation
+    std::vector<double> all;
+    for (auto const& s : S) all.insert(all.end(), s.begin(), s.end());
+    if (all.empty()) throw std::runtime_error("svd_truncate: empty matrix");
+    std::sort(all.begin(), all.end(), std::greater<double>());
+    double cut = rel_tol * all[0];
+    if (all.size() > Mmax) cut = std::max(cut, all[Mmax]);
+    Truncation tr;
+    tr.smallest_ev = cut / all[0];
+    double sum1 = 0, sum2 = 0;
+    for (double x : all) { sum1 += x; sum2 += x * x; if (x < cut) { tr.truncated_fraction += x; tr.truncated_weight += x * x; } }
+    tr.truncated_fraction /= sum1; tr.truncated_weight /= sum2;
+    U.clear(); V.clear();
+    std::vector<std::vector<double>> Skept;
+    for (size_t b = 0; b < nb; ++b) {
+        size_t keep = std::find_if(S[b].begin(), S[b].end(), [cut](double x) { return x < cut; }) - S[b].begin();
+        if (keep == 0) continue;
+        Matrix u = us[b], v = vs[b];
+        u.resize(u.rows, keep); v.resize(keep, v.cols);
+        Charge lc = M.basis()[b].lc, rc = M.basis()[b].rc;
+        size_t iu = U.insert_block(u, lc, rc);
+        V.insert_block(v, lc, rc);                  // the new bond carries the block's charges on both factors (m = M.left_basis())
+        Skept.insert(Skept.begin() + iu, std::vector<double>(S[b].begin(), S[b].begin() + keep));
+        tr.bond_dimension += keep;
+    }
+    S.swap(Skept);
+    return tr;
+}
+// diag(S) * V and U * diag(S), block by block (U, V, S in the same block order)
+inline block_matrix scale_rows(block_matrix const& V, std::vector<std::vector<double>> const& S)
+{
+    block_matrix r = V;
+    for (size_t b = 0; b < r.n_blocks(); ++b) for (size_t j = 0; j < r[b].cols; ++j) for (size_t i = 0; i < r[b].rows; ++i) r[b](i, j) *= S[b][i];
+    return r;
+}
+inline block_matrix scale_cols(block_matrix const& U, std::vector<std::vector<double>> const& S)
+{
+    block_matrix r = U;
+    for (size_t b = 0; b < r.n_blocks(); ++b) for (size_t j = 0; j < r[b].cols; ++j) for (size_t i = 0; i < r[b].rows; ++i) r[b](i, j) *= S[b][j];
+    return r;
+}
+
+// ---- twositetensor.hpp ----------------------------------------------------------------------------------------------
+class TwoSiteTensor
+{
+public:
+    TwoSiteTensor(SymmKind symm, MPSTensor const& mps1, MPSTensor const& mps2)
+        : su2_(is_su2(symm)), phys_i(mps1.site_dim() * mps2.site_dim()), phys_i_left(mps1.site_dim()), phys_i_right(mps2.site_dim()),
+          left_i(mps1.row_dim()), right_i(mps2.col_dim()), storage_(Both)
+    {
+        mps1.make_left_paired(); mps2.make_right_paired();
+        sweep::gemm(mps1.data(), mps2.data(), data_);
+    }
+    // :119-139 -- the tensor the site problem works on (right-paired; SU2: spin-coupled two-site basis)
+    MPSTensor make_mps() const
+    {
+        block_matrix rp;
+        if (storage_ != Both) throw std::runtime_error("TwoSiteTensor::make_mps: tensor is not both-paired");
+        reshape_both_to_right(phys_i_left, phys_i_right, left_i, right_i, data_, rp);
+        if (!su2_) return MPSTensor(phys_i, left_i, right_i, rp, RightPaired);
+        block_matrix tmp;
+        Index phys_out = reduce_right(phys_i_left, phys_i_right, left_i, right_i, rp, tmp);
+        return MPSTensor(phys_out, left_i, right_i, tmp, RightPaired);
+    }
+    // :355-389 -- take the optimised tensor back (SU2: undo the spin coupling)
+    TwoSiteTensor& operator<<(MPSTensor const& rhs)
+    {
+        rhs.make_left_paired();
+        if (su2_) {
+            block_matrix tmp;
+            phys_i = unreduce_left(phys_i_left, phys_i_right, left_i, right_i, rhs.data(), tmp);
+            data_ = tmp;
+        } else
+            data_ = rhs.data();
+        left_i = rhs.row_dim(); right_i = rhs.col_dim();
+        storage_ = Left;
+        return *this;
+    }
+    // :141-183
+    void split_mps_l2r(size_t Mmax, double cutoff, MPSTensor& t1, MPSTensor& t2, Truncation& trunc)
+    {
+        make_both_paired();
+        block_matrix u, v; std::vector<std::vector<double>> s;
+        trunc = svd_truncate(data_, u, v, s, cutoff, Mmax);
+        t1 = MPSTensor(phys_i_left, left_i, u.right_basis(), u, LeftPaired);
+        block_matrix sv = scale_rows(v, s);
+        t2 = MPSTensor(phys_i_right, sv.left_basis(), right_i, sv, RightPaired);
+    }
+    void split_mps_r2l(size_t Mmax, double cutoff, MPSTensor& t1, MPSTensor& t2, Truncation& trunc)
+    {
+        make_both_paired();
+        block_matrix u, v; std::vector<std::vector<double>> s;
+        trunc = svd_truncate(data_, u, v, s, cutoff, Mmax);
+        t2 = MPSTensor(phys_i_right, v.left_basis(), right_i, v, RightPaired);
+        block_matrix us = scale_cols(u, s);
+        t1 = MPSTensor(phys_i_left, left_i, us.right_basis(), us, LeftPaired);
+    }
+
+private:
+    enum Storage { Both, Left };
+    void make_both_paired()
+    {
+        if (storage_ == Both) return;
+        block_matrix tmp;
+        reshape_left_to_both(phys_i_left, phys_i_right, left_i, right_i, data_, tmp);
+        data_ = tmp; storage_ = Both;
+    }
+    bool su2_;
+    Index phys_i, phys_i_left, phys_i_right, left_i, right_i;
+    block_matrix data_;
+    Storage storage_;
+};
+
+// ---- two-site sweeps (ts_optimize.hpp:60-270, twosite_truncation = svd) ------------------------------------------------
+struct TsParams { size_t Mmax = 100; double cutoff = 1e-16; int jcd_maxiter = 10; double jcd_tol = 1e-8; };
+
+template <class TsMpo>      // TsMpo(p) -> MPOTensor const& of the fused sites (p, p+1)  (ts_ops.h make_ts_cache_mpo)
+inline sweep::SweepLog ts_sweeps(SymmKind symm, EngineIface& eng, MPO const& mpo, TsMpo ts_mpo, MPS& mps, int nsweeps, TsParams const& prm,
+                                 std::vector<size_t>* bond_dims = nullptr)
+{
+    const int L = (int)mps.size();
+    sweep::SweepLog log;
+    sweep::canonize_to_first(mps);
+    std::vector<Boundary> left(L + 1), right(L + 1);
+    left[0] = mps.left_boundary();
+    right[L] = mps.right_boundary();
+    for (int i = L - 1; i >= 0; --i) right[i] = eng.overlap_mpo_right_step(mps[i], mps[i], right[i + 1], mpo[i]);
+    auto to_site = [L](int i) { return i < L ? i : 2 * L - 1 - i; };
+    for (int sw = 0; sw < nsweeps; ++sw) {
+        auto t0 = std::chrono::steady_clock::now();
+        for (int _site = 0; _site < 2 * L - 2; ++_site) {
+            int lr, site1, site2;
+            if (_site < L - 1) { lr = 1; site1 = to_site(_site); site2 = site1 + 1; }
+            else { lr = -1; site2 = to_site(_site); site1 = site2 - 1; }
+            TwoSiteTensor tst(symm, mps[site1], mps[site2]);
+            MPSTensor twin = tst.make_mps();
+            sweep::JDResult r = sweep::jacobi_davidson(eng, twin, left[site1], right[site2 + 1], ts_mpo(site1), prm.jcd_maxiter, prm.jcd_tol);
+            tst << r.vec;
+            log.energies.push_back(r.theta + mpo.core_energy);
+            log.n_sigma.push_back(r.n_sigma); log.total_sigma += r.n_sigma;
+            Truncation trunc;
+            if (lr == +1) {
+                tst.split_mps_l2r(prm.Mmax, prm.cutoff, mps[site1], mps[site2], trunc);
+                block_matrix t = sweep::normalize_left(mps[site2]);
+                if (site2 < L - 1) sweep::multiply_from_left(mps[site2 + 1], t);
+                left[site2] = eng.overlap_mpo_left_step(mps[site1], mps[site1], left[site1], mpo[site1]);
+            } else {
+                tst.split_mps_r2l(prm.Mmax, prm.cutoff, mps[site1], mps[site2], trunc);
+                block_matrix t = sweep::normalize_right(mps[site1]);
+                if (site1 > 0) sweep::multiply_from_right(mps[site1 - 1], t);
+                right[site2] = eng.overlap_mpo_right_step(mps[site2], mps[site2], right[site2 + 1], mpo[site2]);
+            }
+            if (bond_dims) bond_dims->push_back(trunc.bond_dimension);
+        }
+        log.sweep_energy.push_back(log.energies.back());
+        log.sweep_seconds.push_back(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    }
+    return log;
+}
+
+}} // namespace qcm::ts

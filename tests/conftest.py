@@ -51,6 +51,13 @@ class Harness:
         assert rc == 0, err.value.decode()
         return list(e[:n.value]), list(info)
 
+    def ts_dmrg(self, f, symm, L, ne, M0, M, nsweeps, engine, seed=42):
+        """two-site DMRG sweeps (qcm/twosite.hpp) from a random MPS of bond dimension M0, truncation to M"""
+        e = (ctypes.c_double * 8192)(); n = ctypes.c_int(); info = (ctypes.c_double * 8)(); err = ctypes.create_string_buffer(1024)
+        rc = self.lib.qcmt_ts_dmrg(golden(f), symm.encode(), L, ne, M0, M, nsweeps, seed, engine, e, 8192, ctypes.byref(n), info, err, 1024)
+        assert rc == 0, err.value.decode()
+        return list(e[:n.value]), list(info)
+
     def hdiag_parity(self, f, symm, L, ne, M, engine, seed=42):
         out = (ctypes.c_double * 8)(); err = ctypes.create_string_buffer(1024)
         rc = self.lib.qcmt_hdiag_parity(golden(f), symm.encode(), L, ne, M, seed, engine, out, err, 1024)

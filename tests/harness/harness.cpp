@@ -7,6 +7,7 @@
 #include "oracle_engine.hpp"
 #include "qcm/scenarios.hpp"
 #include "qcm/sweep.hpp"
+#include "qcm/twosite.hpp"
 #include "plan_interp.hpp"
 #ifdef QCMT_WITH_GPU
 #include "qcm/engine_gpu.hpp"
@@ -330,6 +331,41 @@ extern "C" int qcmt_hdiag_parity(const char* fcidump, const char* symm, int L, i
             mx = std::max(mx, rel_diff(d)); st &= d.structure_equal; ++n;
         }
         out[0] = n; out[1] = st; out[2] = mx; out[3] = amax;
+        return 0;
+    } catch (std::exception const& e) {
+        set_err(err, errlen, e.what());
+        return 1;
+    }
+}
+
+// Two-site DMRG sweeps (qcm/twosite.hpp: ts_optimize loop, TwoSiteTensor, SVD truncation to Mmax) through an engine.
+//   engine_kind -1: CPU oracle, 0: plan interpreter, 1: qcm::GpuEngine;  M0: bond dimension of the random start
+// energies[0 .. *n_out): per micro-iteration; info[0] sigma evaluations, [1] seconds, [2] last energy, [3] largest bond dimension kept
+extern "C" int qcmt_ts_dmrg(const char* fcidump, const char* symm, int L, int nelec, int M0, int Mmax, int nsweeps, unsigned seed, int engine_kind,
+                            double* energies, int n_max, int* n_out, double* info, char* err, int errlen)
+{
+    try {
+        Problem P = make_problem(fcidump, symm, L, nelec);
+        P.init_mps((size_t)M0, true, 0., seed);
+        std::unique_ptr<EngineIface> eng;
+        if (engine_kind < 0) eng.reset(new oracle::OracleEngine(P.params.symm));
+        else if (engine_kind == 0) eng.reset(new qcmtest::InterpEngine(P.params.symm, 1, (long long)1 << 40));
+        else {
+#ifdef QCMT_WITH_GPU
+            eng.reset(new GpuEngine(P.params.symm, 0, 0, 1));
+#else
+            throw std::runtime_error("harness built without GPU support");
+#endif
+        }
+        ts::TsParams prm; prm.Mmax = (size_t)Mmax;
+        std::vector<size_t> dims;
+        sweep::SweepLog log = ts::ts_sweeps(P.params.symm, *eng, P.mpo, [&](int p) -> MPOTensor const& { return P.twosite_mpo(p); }, P.mps, nsweeps, prm, &dims);
+        int n = (int)std::min<size_t>(log.energies.size(), (size_t)n_max);
+        for (int i = 0; i < n; ++i) energies[i] = log.energies[i];
+        *n_out = n;
+        double secs = 0; for (double s : log.sweep_seconds) secs += s;
+        info[0] = (double)log.total_sigma; info[1] = secs; info[2] = log.energies.back();
+        info[3] = dims.empty() ? 0. : (double)*std::max_element(dims.begin(), dims.end());
         return 0;
     } catch (std::exception const& e) {
         set_err(err, errlen, e.what());

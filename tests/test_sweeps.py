@@ -36,6 +36,53 @@ def test_plan_interpreter_matches_the_oracle_per_micro_iteration(harness_cpu, sy
     assert max(abs(a - b) for a, b in zip(eo, ei)) < 1e-10
 
 
+@pytest.mark.parametrize("symm", ["su2u1pg", "su2u1", "2u1pg", "2u1"])
+def test_oracle_two_site_sweeps_reach_the_reference_energies(harness_cpu, symm):
+    # two-site DMRG (ts_optimize.hpp, TwoSiteTensor + SVD truncation; SU2: 6j recoupling of the fused site) grows the
+    # bond dimension from a random M=4 state and must land on the same pinned energies (LiHFixture: SS == TS)
+    e, info = harness_cpu.ts_dmrg("h2_2o.fcidump", symm, 2, 2, 4, 64, 2, ORACLE)
+    assert e[-1] == pytest.approx(REF["energies"]["h2_2o"]["value"], abs=E_TOL)
+    e, info = harness_cpu.ts_dmrg("lih_4o.fcidump", symm, 4, 2, 4, 64, 4, ORACLE)
+    assert e[-1] == pytest.approx(REF["energies"]["lih_4o"]["value"], abs=E_TOL)
+    assert len(e) == 4 * (2 * 4 - 2)
+    e, info = harness_cpu.ts_dmrg("h2_4o.fcidump", symm, 4, 2, 4, 64, 4, ORACLE)
+    assert e[-1] == pytest.approx(REF["energies"]["h2_4o"]["value"], abs=E_TOL)
+
+
+@pytest.mark.parametrize("symm", ["su2u1", "2u1"])
+def test_two_site_truncation_and_plan_interpreter(harness_cpu, symm):
+    # truncated run (M = 10 on 6 orbitals): the plan interpreter must follow the oracle through every split
+    eo, io = harness_cpu.ts_dmrg("synth_6o6e.fcidump", symm, 6, 6, 4, 10, 2, ORACLE)
+    ei, ii = harness_cpu.ts_dmrg("synth_6o6e.fcidump", symm, 6, 6, 4, 10, 2, INTERP)
+    # estimate_truncation keeps every singular value that is not below the (Mmax+1)-th largest: up to Mmax + 1 states
+    # (block_matrix_algorithms.h:240-258), restated literally
+    assert len(eo) == len(ei) == 2 * (2 * 6 - 2) and io[3] <= 11 and io[3] == ii[3]
+    assert max(abs(a - b) for a, b in zip(eo, ei)) < 1e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("symm", ["su2u1", "2u1", "su2u1pg"])
+@pytest.mark.parametrize("f,L,ne,M0,M,ns", [("lih_4o.fcidump", 4, 2, 4, 64, 3), ("synth_6o6e.fcidump", 6, 6, 4, 16, 2), ("benzene_6o.fcidump", 6, 6, 6, 40, 2)])
+def test_gpu_two_site_sweep_energies_match_the_oracle(harness_gpu, symm, f, L, ne, M0, M, ns):
+    if symm.endswith("pg") and not f.startswith(("lih", "benzene")):
+        pytest.skip("no point group in the synthetic integrals")
+    eo, io = harness_gpu.ts_dmrg(f, symm, L, ne, M0, M, ns, ORACLE)
+    eg, ig = harness_gpu.ts_dmrg(f, symm, L, ne, M0, M, ns, GPU)
+    assert len(eo) == len(eg) == ns * (2 * L - 2) and io[3] == ig[3]
+    assert max(abs(a - b) for a, b in zip(eo, eg)) < E_TOL
+    if f.startswith("lih"):
+        assert eg[-1] == pytest.approx(REF["energies"]["lih_4o"]["value"], abs=E_TOL)
+
+
+@pytest.mark.gpu
+def test_gpu_two_site_config1(harness_gpu, fcidump_8o8e):
+    """BASELINE configs[0] as written: 8e/8o SU2U1, M=256, two-site DMRG, 4 sweeps -- GPU engine against the oracle"""
+    eo, io = harness_gpu.ts_dmrg(fcidump_8o8e, "su2u1", 8, 8, 16, 256, 4, ORACLE)
+    eg, ig = harness_gpu.ts_dmrg(fcidump_8o8e, "su2u1", 8, 8, 16, 256, 4, GPU)
+    assert len(eo) == len(eg) == 4 * (2 * 8 - 2)
+    assert max(abs(a - b) for a, b in zip(eo, eg)) < E_TOL
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("symm", ["su2u1", "2u1", "su2u1pg"])
 @pytest.mark.parametrize("f,L,ne,M,ns", [("lih_4o.fcidump", 4, 2, 64, 3), ("synth_6o6e.fcidump", 6, 6, 30, 2), ("benzene_6o.fcidump", 6, 6, 40, 2)])
