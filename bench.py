@@ -203,6 +203,8 @@ def sweep_measurement(host, build, device, with_cpu):
             out["cpu_seconds_per_sweep"] = io[1] / nsweeps
             out["cpu_cores"] = olib.orc_threads()
             out["max_abs_energy_diff_vs_oracle"] = (max(abs(en[i] - eo[i]) for i in range(n.value)) if n.value == no.value else "length mismatch")
+            if os.environ.get("QCM_DEBUG"):
+                sys.stderr.write("sweep %s: gpu/cpu energies %s\n" % (name, ["%.17g / %.17g" % (en[i], eo[i]) for i in (0, min(5, n.value - 1), n.value - 1)]))
         results.append(out)
     return results
 
