@@ -185,15 +185,24 @@ extern "C" int qcmd_ss_sweeps(void* h, int Mmax, int nsweeps, unsigned seed, int
     } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
 }
 
-// Two-site DMRG sweeps on the B200 engine (qcm/twosite.hpp: ts_optimize loop, TwoSiteTensor, SVD truncation to Mmax) from
-// a random MPS of bond dimension M0.  info: [0] sigma evaluations [1] seconds of all sweeps [2] last energy [3] largest bond dimension
+extern "C" int qcmd_ts_sweeps_ranked(void* h, int M0, int Mmax, int nsweeps, unsigned seed, int device, int rank, int world, double* energies, int n_max,
+                                     int* n_out, double* info, char* err, int errlen);
 extern "C" int qcmd_ts_sweeps(void* h, int M0, int Mmax, int nsweeps, unsigned seed, int device, double* energies, int n_max, int* n_out, double* info,
                               char* err, int errlen)
+{
+    return qcmd_ts_sweeps_ranked(h, M0, Mmax, nsweeps, seed, device, 0, 1, energies, n_max, n_out, info, err, errlen);
+}
+// Two-site DMRG sweeps on the B200 engine (qcm/twosite.hpp: ts_optimize loop, TwoSiteTensor, SVD truncation to Mmax) from
+// a random MPS of bond dimension M0.  info: [0] sigma evaluations [1] seconds of all sweeps [2] last energy [3] largest bond dimension
+extern "C" int qcmd_ts_sweeps_ranked(void* h, int M0, int Mmax, int nsweeps, unsigned seed, int device, int rank, int world, double* energies, int n_max,
+                                     int* n_out, double* info, char* err, int errlen)
 {
     try {
         Driver* D = static_cast<Driver*>(h);
         D->P.init_mps((size_t)M0, true, 0., seed);
-        GpuEngine eng(D->P.symm(), device, 0, 1);
+        // world > 1: every rank runs the same (deterministic) host driver; the engine shards each contraction and the
+        // library's allreduce hands every rank the complete sigma / boundary (qcm_comm_init must have been called)
+        GpuEngine eng(D->P.symm(), device, rank, world);
         ts::TsParams prm; prm.Mmax = (size_t)Mmax;
         std::vector<size_t> dims;
         sweep::SweepLog log = ts::ts_sweeps(D->P.symm(), eng, D->P.mpo, [&](int p) -> MPOTensor const& { return D->P.twosite_mpo(p); }, D->P.mps, nsweeps, prm, &dims);
@@ -203,6 +212,10 @@ extern "C" int qcmd_ts_sweeps(void* h, int M0, int Mmax, int nsweeps, unsigned s
         double secs = 0; for (double s : log.sweep_seconds) secs += s;
         info[0] = (double)log.total_sigma; info[1] = secs; info[2] = log.energies.back();
         info[3] = dims.empty() ? 0. : (double)*std::max_element(dims.begin(), dims.end());
+        if (getenv("QCM_DEBUG"))
+            fprintf(stderr, "two-site sweeps, host seconds: tensor %.2f | two-site MPO %.2f | eigensolver %.2f | split %.2f | boundary step %.2f ;  engine: planning %.2f | "
+                            "plan upload %.2f | sigma calls %.2f | boundary calls %.2f | flatten %.2f\n", log.phase_seconds[0], log.phase_seconds[1], log.phase_seconds[2],
+                    log.phase_seconds[3], log.phase_seconds[4], eng.seconds[0], eng.seconds[1], eng.seconds[2], eng.seconds[3], eng.seconds[4]);
         return 0;
     } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
 }

@@ -63,9 +63,14 @@ public:
         ket_tensor.make_left_paired();
         std::shared_ptr<DeviceBoundary> dl = mirror(left), dr = mirror(right);
         std::shared_ptr<CompiledPlan> cp = sigma_plan(ket_tensor, dl, dr, mpo, isHermitian);
+        Clock c0;
         std::vector<double> psi = flatten(ket_tensor.data(), cp->ket_elems), sigma((size_t)cp->out_elems);
+        seconds[4] += c0.lap();
         qcm_check(qcm_site_hamil2(cp->handle, dl->arr, dr->arr, psi.data(), sigma.data()), "qcm_site_hamil2");
-        return MPSTensor(ket_tensor.site_dim(), ket_tensor.row_dim(), ket_tensor.col_dim(), unflatten(cp->out_tensor, sigma), LeftPaired, true);
+        seconds[2] += c0.lap();
+        MPSTensor r(ket_tensor.site_dim(), ket_tensor.row_dim(), ket_tensor.col_dim(), unflatten(cp->out_tensor, sigma), LeftPaired, true);
+        seconds[4] += c0.lap();
+        return r;
     }
 
     std::shared_ptr<CompiledPlan> sigma_plan(MPSTensor const& ket_tensor, std::shared_ptr<DeviceBoundary> const& dl,
@@ -74,9 +79,12 @@ public:
         ket_tensor.make_left_paired();
         PlanKey key{&mpo, dl.get(), dr.get(), structure_hash(ket_tensor), isHermitian ? 0 : 3, dl, dr};
         for (auto& e : cache) if (e.first == key) return e.second;
+        Clock c0;
         plan::Planner planner(symm, mpo, isHermitian, rank, world, budget);
         plan::Plan P = planner.plan_sigma(desc_of(ket_tensor), dl->layout, dr->layout);
+        seconds[0] += c0.lap();
         std::shared_ptr<CompiledPlan> cp = compile(P, dl->layout.total, dr->layout.total);
+        seconds[1] += c0.lap();
         remember(key, cp);
         return cp;
     }
@@ -140,6 +148,9 @@ public:
         b.host_valid = true;
     }
     void clear_cache() { cache.clear(); }
+    // host-side time spent in this engine, by kind (seconds): [0] planning (Planner) [1] plan upload (qcm_plan_create)
+    // [2] sigma calls (H2D + kernels + D2H) [3] boundary-step calls [4] flatten / unflatten
+    double seconds[5] = {0, 0, 0, 0, 0};
     std::shared_ptr<CompiledPlan> last_plan() const { return last; }
 
     static std::vector<double> flatten(block_matrix const& m, int64_t expect)
@@ -166,6 +177,11 @@ public:
     }
 
 private:
+    struct Clock
+    {
+        std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+        double lap() { auto n = std::chrono::steady_clock::now(); double s = std::chrono::duration<double>(n - t).count(); t = n; return s; }
+    };
     struct PlanKey
     {
         const void *mpo, *a, *b; uint64_t h; int kind;
@@ -177,16 +193,21 @@ private:
     {
         bra_tensor.make_left_paired(); ket_tensor.make_left_paired();
         std::shared_ptr<DeviceBoundary> din = mirror(in);
+        Clock c0;
         plan::Planner planner(symm, mpo, isHermitian, rank, world, budget);
         plan::Plan P = kind == 1 ? planner.plan_left_step(desc_of(bra_tensor), desc_of(ket_tensor), din->layout)
                                  : planner.plan_right_step(desc_of(bra_tensor), desc_of(ket_tensor), din->layout);
+        seconds[0] += c0.lap();
         std::shared_ptr<CompiledPlan> cp = compile(P, kind == 1 ? din->layout.total : 0, kind == 2 ? din->layout.total : 0);
+        seconds[1] += c0.lap();
         last = cp;
         std::shared_ptr<DeviceBoundary> dout(new DeviceBoundary());
         dout->layout = cp->out_boundary;
         qcm_check(qcm_array_alloc(dout->layout.total, &dout->arr), "qcm_array_alloc");
         std::vector<double> bra = flatten(bra_tensor.data(), cp->bra_elems), ket = flatten(ket_tensor.data(), cp->ket_elems);
+        seconds[4] += c0.lap();
         qcm_check(qcm_boundary_step(cp->handle, din->arr, bra.data(), ket.data(), dout->arr), "qcm_boundary_step");
+        seconds[3] += c0.lap();
         Boundary ret; ret.resize(dout->layout.aux_dim());
         for (size_t b = 0; b < ret.aux_dim(); ++b) {
             DualIndex const& basis = dout->layout.b[b].basis;

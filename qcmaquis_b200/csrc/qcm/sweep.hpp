@@ -199,6 +199,9 @@ struct SweepLog
     std::vector<double> sweep_seconds;
     std::vector<int> n_sigma;            // sigma evaluations per micro-iteration
     long total_sigma = 0;
+    // two-site driver, wall seconds by phase: [0] two-site tensor (product, reshape, recoupling) [1] two-site MPO fusion
+    // [2] eigensolver (sigma calls + host vector algebra) [3] split (reshape, SVD, normalisation) [4] boundary step
+    double phase_seconds[5] = {0, 0, 0, 0, 0};
 };
 
 inline SweepLog ss_sweeps(EngineIface& eng, MPO const& mpo, MPS& mps, int nsweeps, int jcd_maxiter = 10, double jcd_tol = 1e-8)

@@ -367,9 +367,15 @@ inline sweep::SweepLog ts_sweeps(SymmKind symm, EngineIface& eng, MPO const& mpo
             int lr, site1, site2;
             if (_site < L - 1) { lr = 1; site1 = to_site(_site); site2 = site1 + 1; }
             else { lr = -1; site2 = to_site(_site); site1 = site2 - 1; }
+            auto c0 = std::chrono::steady_clock::now();
+            auto lap = [&c0]() { auto n = std::chrono::steady_clock::now(); double s = std::chrono::duration<double>(n - c0).count(); c0 = n; return s; };
             TwoSiteTensor tst(symm, mps[site1], mps[site2]);
             MPSTensor twin = tst.make_mps();
-            sweep::JDResult r = sweep::jacobi_davidson(eng, twin, left[site1], right[site2 + 1], ts_mpo(site1), prm.jcd_maxiter, prm.jcd_tol);
+            log.phase_seconds[0] += lap();
+            MPOTensor const& tsw = ts_mpo(site1);
+            log.phase_seconds[1] += lap();
+            sweep::JDResult r = sweep::jacobi_davidson(eng, twin, left[site1], right[site2 + 1], tsw, prm.jcd_maxiter, prm.jcd_tol);
+            log.phase_seconds[2] += lap();
             tst << r.vec;
             log.energies.push_back(r.theta + mpo.core_energy);
             log.n_sigma.push_back(r.n_sigma); log.total_sigma += r.n_sigma;
@@ -378,13 +384,16 @@ inline sweep::SweepLog ts_sweeps(SymmKind symm, EngineIface& eng, MPO const& mpo
                 tst.split_mps_l2r(prm.Mmax, prm.cutoff, mps[site1], mps[site2], trunc);
                 block_matrix t = sweep::normalize_left(mps[site2]);
                 if (site2 < L - 1) sweep::multiply_from_left(mps[site2 + 1], t);
+                log.phase_seconds[3] += lap();
                 left[site2] = eng.overlap_mpo_left_step(mps[site1], mps[site1], left[site1], mpo[site1]);
             } else {
                 tst.split_mps_r2l(prm.Mmax, prm.cutoff, mps[site1], mps[site2], trunc);
                 block_matrix t = sweep::normalize_right(mps[site1]);
                 if (site1 > 0) sweep::multiply_from_right(mps[site1 - 1], t);
+                log.phase_seconds[3] += lap();
                 right[site2] = eng.overlap_mpo_right_step(mps[site2], mps[site2], right[site2 + 1], mpo[site2]);
             }
+            log.phase_seconds[4] += lap();
             if (bond_dims) bond_dims->push_back(trunc.bond_dimension);
         }
         log.sweep_energy.push_back(log.energies.back());
