@@ -126,6 +126,23 @@ public:
         }
         return *this;
     }
+    // *this += a * rhs without a temporary (blocks matched by charge, missing ones inserted)
+    block_matrix& axpy(double a, block_matrix const& rhs)
+    {
+        for (size_t k = 0; k < rhs.n_blocks(); ++k) {
+            Charge r = rhs.basis_[k].lc, c = rhs.basis_[k].rc;
+            size_t j = (k < n_blocks() && basis_[k].lc == r && basis_[k].rc == c) ? k : find_block(r, c);
+            if (j < n_blocks() && data_[j].rows == rhs.data_[k].rows && data_[j].cols == rhs.data_[k].cols) {
+                double* y = data_[j].v.data(); const double* x = rhs.data_[k].v.data();
+                const size_t n = data_[j].v.size();
+                for (size_t i = 0; i < n; ++i) y[i] += a * x[i];
+            } else {
+                Matrix t = rhs.data_[k]; t *= a;
+                if (j < n_blocks()) match_and_add_block(t, r, c); else insert_block(t, r, c);
+            }
+        }
+        return *this;
+    }
     block_matrix& operator*=(double a) { for (auto& m : data_) m *= a; return *this; }
     void generate(std::function<double()> g) { for (auto& m : data_) for (auto& x : m.v) x = g(); }
     double norm_square() const { double r = 0; for (auto const& m : data_) for (double x : m.v) r += x * x; return r; }

@@ -442,13 +442,21 @@ inline MPOTensor make_twosite_mpo(SymmKind symm, MPOTensor const& mpo1, MPOTenso
     bool su2 = is_su2(symm);
     std::shared_ptr<OPTable> kron_table(new OPTable());
     std::vector<PreTerm> prempo;
-    for (size_t b1 = 0; b1 < mpo1.row_dim(); ++b1) {
-        for (size_t b3 = 0; b3 < mpo2.col_dim(); ++b3) {
-            std::vector<size_t> summands;
-            for (size_t b2 : mpo1.row(b1)) if (mpo2.has(b2, b3)) summands.push_back(b2);
-            std::map<int, SiteOperator> coupled;
-            for (size_t b2 : summands) {
-                auto const& p1 = mpo1.at(b1, b2); auto const& p2 = mpo2.at(b2, b3);
+    // The reference loops over all (b1, b3) pairs and collects the b2 that connect them (ts_ops.h:99-116).  Same
+    // products in the same order here, but found by walking row b1 of the first tensor and row b2 of the second (the
+    // pairs without a connecting b2 are never visited), and the rows b1 are fused in parallel; the fused operators are
+    // then registered serially in (b1, b3, spin) order so that the tags come out exactly as in the reference's loop.
+    const long n1 = (long)mpo1.row_dim();
+    std::vector<std::vector<std::pair<size_t, std::map<int, SiteOperator>>>> fused((size_t)n1);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (long b1l = 0; b1l < n1; ++b1l) {
+        const size_t b1 = (size_t)b1l;
+        std::map<size_t, std::map<int, SiteOperator>> acc;
+        for (size_t b2 : mpo1.row(b1)) {
+            auto const& p1 = mpo1.at(b1, b2);
+            for (size_t b3 : mpo2.row(b2)) {
+                auto const& p2 = mpo2.at(b2, b3);
+                std::map<int, SiteOperator>& coupled = acc[b3];
                 for (auto const& t1 : p1)
                     for (auto const& t2 : p2) {
                         SiteOperator const& o1 = mpo1.op(t1.first); SiteOperator const& o2 = mpo2.op(t2.first);
@@ -472,12 +480,15 @@ inline MPOTensor make_twosite_mpo(SymmKind symm, MPOTensor const& mpo1, MPOTenso
                         }
                     }
             }
-            for (auto const& kv : coupled) {
-                tag_type new_tag = kron_table->register_op(kv.second);
-                prempo.push_back(PreTerm{b1, b3, new_tag, 1.0});
-            }
         }
+        fused[b1].assign(acc.begin(), acc.end());
     }
+    for (size_t b1 = 0; b1 < (size_t)n1; ++b1)
+        for (auto const& e : fused[b1])
+            for (auto const& kv : e.second) {
+                tag_type new_tag = kron_table->register_op(kv.second);
+                prempo.push_back(PreTerm{b1, e.first, new_tag, 1.0});
+            }
     return MPOTensor(mpo1.row_dim(), mpo2.col_dim(), prempo, kron_table, mpo1.herm_info * mpo2.herm_info,
                      mpo1.row_spin_dim(), mpo2.col_spin_dim(), su2);
 }

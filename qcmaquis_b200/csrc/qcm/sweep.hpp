@@ -138,9 +138,7 @@ inline void canonize_to_first(MPS& mps)
 inline void axpy(MPSTensor& y, double a, MPSTensor const& x)       // y += a x, blocks matched by charge
 {
     y.make_left_paired(); x.make_left_paired();
-    block_matrix tmp = x.data();
-    tmp *= a;
-    y.data() += tmp;
+    y.data().axpy(a, x.data());
 }
 struct JDResult { double theta = 0; MPSTensor vec; int n_sigma = 0; double resid = 0; };
 
