@@ -175,6 +175,7 @@ extern "C" int qcmd_ss_sweeps(void* h, int Mmax, int nsweeps, unsigned seed, int
         Driver* D = static_cast<Driver*>(h);
         D->P.init_mps((size_t)Mmax, true, 0., seed);
         GpuEngine eng(D->P.symm(), device, 0, 1);
+        eng.set_cache_capacity(4 * D->P.mpo.size() + 8);
         sweep::SweepLog log = sweep::ss_sweeps(eng, D->P.mpo, D->P.mps, nsweeps);
         int n = (int)std::min<size_t>(log.energies.size(), (size_t)n_max);
         for (int i = 0; i < n; ++i) energies[i] = log.energies[i];
@@ -203,6 +204,7 @@ extern "C" int qcmd_ts_sweeps_ranked(void* h, int M0, int Mmax, int nsweeps, uns
         // world > 1: every rank runs the same (deterministic) host driver; the engine shards each contraction and the
         // library's allreduce hands every rank the complete sigma / boundary (qcm_comm_init must have been called)
         GpuEngine eng(D->P.symm(), device, rank, world);
+        eng.set_cache_capacity(4 * D->P.mpo.size() + 8);
         ts::TsParams prm; prm.Mmax = (size_t)Mmax;
         std::vector<size_t> dims;
         sweep::SweepLog log = ts::ts_sweeps(D->P.symm(), eng, D->P.mpo, [&](int p) -> MPOTensor const& { return D->P.twosite_mpo(p); }, D->P.mps, nsweeps, prm, &dims);
@@ -214,8 +216,8 @@ extern "C" int qcmd_ts_sweeps_ranked(void* h, int M0, int Mmax, int nsweeps, uns
         info[3] = dims.empty() ? 0. : (double)*std::max_element(dims.begin(), dims.end());
         if (getenv("QCM_DEBUG"))
             fprintf(stderr, "two-site sweeps, host seconds: tensor %.2f | two-site MPO %.2f | eigensolver %.2f | split %.2f | boundary step %.2f ;  engine: planning %.2f | "
-                            "plan upload %.2f | sigma calls %.2f | boundary calls %.2f | flatten %.2f\n", log.phase_seconds[0], log.phase_seconds[1], log.phase_seconds[2],
-                    log.phase_seconds[3], log.phase_seconds[4], eng.seconds[0], eng.seconds[1], eng.seconds[2], eng.seconds[3], eng.seconds[4]);
+                            "plan upload %.2f | sigma calls %.2f | boundary calls %.2f | flatten %.2f | sigma-plan cache hits %zu misses %zu\n", log.phase_seconds[0], log.phase_seconds[1], log.phase_seconds[2],
+                    log.phase_seconds[3], log.phase_seconds[4], eng.seconds[0], eng.seconds[1], eng.seconds[2], eng.seconds[3], eng.seconds[4], eng.cache_hits, eng.cache_misses);
         return 0;
     } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
 }

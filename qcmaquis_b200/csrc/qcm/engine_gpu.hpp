@@ -29,6 +29,24 @@ struct DeviceBoundary
     qcm_array_t arr = nullptr;
     plan::BoundaryLayout layout;
     ~DeviceBoundary() { if (arr) qcm_array_free(arr); }
+    // 64-bit hash of the block structure (charges and sizes of every block of every bond entry): a plan depends on the
+    // structure of its boundaries only, never on their values, so plans are keyed by it and survive from sweep to sweep
+    uint64_t structure_hash() const
+    {
+        if (hash_) return hash_;
+        uint64_t h = 1469598103934665603ull;
+        auto mix = [&](uint64_t x) { h ^= x; h *= 1099511628211ull; };
+        mix(layout.b.size());
+        for (auto const& l : layout.b) {
+            mix(l.basis.size() + 0x9E37u);
+            for (auto const& q : l.basis) { mix((uint32_t)q.lc[0]); mix((uint32_t)q.lc[1]); mix((uint32_t)q.lc[2]); mix((uint32_t)q.rc[0]); mix((uint32_t)q.rc[1]); mix((uint32_t)q.rc[2]); mix(q.ls); mix(q.rs); }
+        }
+        mix((uint64_t)layout.total);
+        hash_ = h ? h : 1;
+        return hash_;
+    }
+private:
+    mutable uint64_t hash_ = 0;
 };
 
 struct CompiledPlan
@@ -77,8 +95,9 @@ public:
                                              std::shared_ptr<DeviceBoundary> const& dr, MPOTensor const& mpo, bool isHermitian = true)
     {
         ket_tensor.make_left_paired();
-        PlanKey key{&mpo, dl.get(), dr.get(), structure_hash(ket_tensor), isHermitian ? 0 : 3, dl, dr};
-        for (auto& e : cache) if (e.first == key) return e.second;
+        PlanKey key{&mpo, dl->structure_hash(), dr->structure_hash(), structure_hash(ket_tensor), isHermitian ? 0 : 3};
+        for (auto& e : cache) if (e.first == key) { ++cache_hits; return e.second; }
+        ++cache_misses;
         Clock c0;
         plan::Planner planner(symm, mpo, isHermitian, rank, world, budget);
         plan::Plan P = planner.plan_sigma(desc_of(ket_tensor), dl->layout, dr->layout);
@@ -148,6 +167,10 @@ public:
         b.host_valid = true;
     }
     void clear_cache() { cache.clear(); }
+    // plans kept (least recently created dropped first).  A sweep driver sets this to a few times the chain length: once
+    // the bond dimensions have settled every (site, direction) finds its plan from the previous sweep.
+    void set_cache_capacity(size_t n) { cache_capacity = std::max<size_t>(1, n); while (cache.size() > cache_capacity) cache.pop_back(); }
+    size_t cache_hits = 0, cache_misses = 0;
     // host-side time spent in this engine, by kind (seconds): [0] planning (Planner) [1] plan upload (qcm_plan_create)
     // [2] sigma calls (H2D + kernels + D2H) [3] boundary-step calls [4] flatten / unflatten
     double seconds[5] = {0, 0, 0, 0, 0};
@@ -182,10 +205,10 @@ private:
         std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
         double lap() { auto n = std::chrono::steady_clock::now(); double s = std::chrono::duration<double>(n - t).count(); t = n; return s; }
     };
+    // (MPO tensor, structure of the boundaries, structure of the site tensor(s), kind): everything a plan depends on
     struct PlanKey
     {
-        const void *mpo, *a, *b; uint64_t h; int kind;
-        std::shared_ptr<void> keep_a, keep_b;   // the boundaries stay alive while their plan is cached (no address reuse)
+        const void* mpo; uint64_t a, b, h; int kind;
         bool operator==(PlanKey const& o) const { return mpo == o.mpo && a == o.a && b == o.b && h == o.h && kind == o.kind; }
     };
 
@@ -194,12 +217,18 @@ private:
         bra_tensor.make_left_paired(); ket_tensor.make_left_paired();
         std::shared_ptr<DeviceBoundary> din = mirror(in);
         Clock c0;
-        plan::Planner planner(symm, mpo, isHermitian, rank, world, budget);
-        plan::Plan P = kind == 1 ? planner.plan_left_step(desc_of(bra_tensor), desc_of(ket_tensor), din->layout)
-                                 : planner.plan_right_step(desc_of(bra_tensor), desc_of(ket_tensor), din->layout);
-        seconds[0] += c0.lap();
-        std::shared_ptr<CompiledPlan> cp = compile(P, kind == 1 ? din->layout.total : 0, kind == 2 ? din->layout.total : 0);
-        seconds[1] += c0.lap();
+        PlanKey key{&mpo, din->structure_hash(), structure_hash(bra_tensor), structure_hash(ket_tensor), (isHermitian ? 0 : 3) + kind};
+        std::shared_ptr<CompiledPlan> cp;
+        for (auto& e : cache) if (e.first == key) { cp = e.second; break; }
+        if (!cp) {
+            plan::Planner planner(symm, mpo, isHermitian, rank, world, budget);
+            plan::Plan P = kind == 1 ? planner.plan_left_step(desc_of(bra_tensor), desc_of(ket_tensor), din->layout)
+                                     : planner.plan_right_step(desc_of(bra_tensor), desc_of(ket_tensor), din->layout);
+            seconds[0] += c0.lap();
+            cp = compile(P, kind == 1 ? din->layout.total : 0, kind == 2 ? din->layout.total : 0);
+            seconds[1] += c0.lap();
+            remember(key, cp);
+        }
         last = cp;
         std::shared_ptr<DeviceBoundary> dout(new DeviceBoundary());
         dout->layout = cp->out_boundary;
@@ -299,13 +328,14 @@ private:
     void remember(PlanKey const& k, std::shared_ptr<CompiledPlan> const& cp)
     {
         cache.push_front(std::make_pair(k, cp));
-        if (cache.size() > 4) cache.pop_back();
+        while (cache.size() > cache_capacity) cache.pop_back();
     }
 
     SymmKind symm;
     int rank, world;
     int64_t budget;
     std::list<std::pair<PlanKey, std::shared_ptr<CompiledPlan>>> cache;
+    size_t cache_capacity = 4;
     std::shared_ptr<CompiledPlan> last;
 };
 

@@ -4,6 +4,9 @@
 //   TaggedMPOMaker    dmrg/models/generate_mpo/tagged_mpo_maker_optim.hpp:30-739
 //   make_twosite_mpo  dmrg/mp_tensors/ts_ops.h:36-126
 #pragma once
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include "site_operator.hpp"
 #include <array>
 #include <numeric>
@@ -447,6 +450,7 @@ inline MPOTensor make_twosite_mpo(SymmKind symm, MPOTensor const& mpo1, MPOTenso
     // pairs without a connecting b2 are never visited), and the rows b1 are fused in parallel; the fused operators are
     // then registered serially in (b1, b3, spin) order so that the tags come out exactly as in the reference's loop.
     const long n1 = (long)mpo1.row_dim();
+    auto tdbg0 = std::chrono::steady_clock::now();
     std::vector<std::vector<std::pair<size_t, std::map<int, SiteOperator>>>> fused((size_t)n1);
 #pragma omp parallel for schedule(dynamic, 4)
     for (long b1l = 0; b1l < n1; ++b1l) {
@@ -481,16 +485,21 @@ inline MPOTensor make_twosite_mpo(SymmKind symm, MPOTensor const& mpo1, MPOTenso
                     }
             }
         }
-        fused[b1].assign(acc.begin(), acc.end());
+        fused[b1].assign(std::make_move_iterator(acc.begin()), std::make_move_iterator(acc.end()));
     }
     for (size_t b1 = 0; b1 < (size_t)n1; ++b1)
-        for (auto const& e : fused[b1])
-            for (auto const& kv : e.second) {
-                tag_type new_tag = kron_table->register_op(kv.second);
-                prempo.push_back(PreTerm{b1, e.first, new_tag, 1.0});
+        for (auto& e : fused[b1])
+            for (auto& kv : e.second) {
+                kron_table->push_back(std::move(kv.second));
+                prempo.push_back(PreTerm{b1, e.first, (tag_type)kron_table->size() - 1, 1.0});
             }
-    return MPOTensor(mpo1.row_dim(), mpo2.col_dim(), prempo, kron_table, mpo1.herm_info * mpo2.herm_info,
-                     mpo1.row_spin_dim(), mpo2.col_spin_dim(), su2);
+    auto tdbg1 = std::chrono::steady_clock::now();
+    MPOTensor ret(mpo1.row_dim(), mpo2.col_dim(), prempo, kron_table, mpo1.herm_info * mpo2.herm_info,
+                  mpo1.row_spin_dim(), mpo2.col_spin_dim(), su2);
+    if (getenv("QCM_PLAN_TIMING"))
+        fprintf(stderr, "  [two-site mpo] fuse + register %.3f s, tensor construction %.3f s\n", std::chrono::duration<double>(tdbg1 - tdbg0).count(),
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - tdbg1).count());
+    return ret;
 }
 
 } // namespace qcm
