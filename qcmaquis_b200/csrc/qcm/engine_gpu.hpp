@@ -17,6 +17,8 @@
 #include "plan.hpp"
 #include <list>
 
+extern "C" void scipy_dsyev_(const char* jobz, const char* uplo, const int* n, double* a, const int* lda, double* w, double* work, const int* lwork, int* info);
+
 namespace qcm {
 
 inline void qcm_check(int status, const char* what)
@@ -73,6 +75,7 @@ public:
     {
         qcm_check(qcm_init(device), "qcm_init");
     }
+    ~GpuEngine() { for (auto a : vec_pool) qcm_array_free(a); }
 
     // ---- Engine::site_hamil2 ----------------------------------------------------------------------------
     MPSTensor site_hamil2(MPSTensor ket_tensor, Boundary const& left, Boundary const& right, MPOTensor const& mpo,
@@ -107,6 +110,79 @@ public:
         remember(key, cp);
         return cp;
     }
+
+    // ---- Jacobi-Davidson with device-resident vectors (ietl/jacobi.h:361-451, ietl_jcd_gmres = 0) ---------------------
+    // Same recurrence as the host solver (qcm/sweep.hpp), on flat device arrays: modified Gram-Schmidt with refinement,
+    // one qcm_site_hamil2_dev per iteration, the small projected eigenproblem on the host, correction t = -r + (r.u / u.u) u.
+    // psi goes up once and the eigenvector comes down once per site.  Needs sigma and psi in ONE block layout (true for
+    // a consistent site problem); otherwise the host solver is used.
+    bool jacobi_davidson(MPSTensor const& x0, Boundary const& left, Boundary const& right, MPOTensor const& mpo, int max_iter, double tol,
+                         EigenResult& res) override
+    {
+        if (!device_solver) return false;
+        x0.make_left_paired();
+        std::shared_ptr<DeviceBoundary> dl = mirror(left), dr = mirror(right);
+        std::shared_ptr<CompiledPlan> cp = sigma_plan(x0, dl, dr, mpo, true);
+        if (!(cp->out_tensor.basis == x0.data().basis()) || cp->out_elems != cp->ket_elems) return false;
+        Clock c0;
+        const int64_t n = cp->ket_elems;
+        const size_t need = 2 * (size_t)max_iter + 3;
+        if (vec_pool_n < n) { for (auto a : vec_pool) qcm_array_free(a); vec_pool.clear(); vec_pool_n = 0; }
+        while (vec_pool.size() < need) { qcm_array_t a = nullptr; qcm_check(qcm_array_alloc(n, &a), "qcm_array_alloc"); vec_pool.push_back(a); }
+        vec_pool_n = std::max(vec_pool_n, n);
+        auto V = [&](int i) { return vec_pool[(size_t)i]; };
+        auto VA = [&](int i) { return vec_pool[(size_t)max_iter + 1 + (size_t)i]; };
+        qcm_array_t u = vec_pool[2 * (size_t)max_iter + 1], r = vec_pool[2 * (size_t)max_iter + 2];
+        auto dot = [&](qcm_array_t a, qcm_array_t b) { double d = 0; qcm_check(qcm_vec_dot(a, b, n, &d), "qcm_vec_dot"); return d; };
+        auto axpy = [&](double a, qcm_array_t x, qcm_array_t y) { qcm_check(qcm_vec_axpy(a, x, y, n), "qcm_vec_axpy"); };
+        auto scal = [&](double a, qcm_array_t x) { qcm_check(qcm_vec_scal(a, x, n), "qcm_vec_scal"); };
+        auto copy = [&](qcm_array_t s_, qcm_array_t d) { qcm_check(qcm_vec_copy(s_, d, n), "qcm_vec_copy"); };
+        {
+            std::vector<double> psi = flatten(x0.data(), n);
+            qcm_check(qcm_array_upload(V(0), 0, psi.data(), n), "qcm_array_upload");
+        }
+        std::vector<double> M((size_t)max_iter * max_iter, 0.);
+        const double kappa = 0.25;
+        res = EigenResult();
+        int it = 0;
+        for (;;) {
+            qcm_array_t t = V(it);
+            const double tau = std::sqrt(dot(t, t));
+            for (int i = 0; i < it; ++i) axpy(-dot(V(i), t), V(i), t);
+            if (std::sqrt(dot(t, t)) < kappa * tau)
+                for (int i = 0; i < it; ++i) axpy(-dot(V(i), t), V(i), t);
+            scal(1. / std::sqrt(dot(t, t)), t);
+            qcm_check(qcm_site_hamil2_dev(cp->handle, dl->arr, dr->arr, t, VA(it)), "qcm_site_hamil2_dev");
+            res.n_sigma++;
+            for (int i = 0; i <= it; ++i) M[(size_t)i + (size_t)it * max_iter] = dot(V(i), VA(it));
+            const int dim = it + 1;
+            std::vector<double> A((size_t)dim * dim), w(dim), work(std::max(1, 3 * dim));
+            for (int c = 0; c < dim; ++c) for (int q = 0; q <= c; ++q) A[(size_t)q + (size_t)c * dim] = M[(size_t)q + (size_t)c * max_iter];
+            int lwork = (int)work.size(), info = 0;
+            scipy_dsyev_("V", "U", &dim, A.data(), &dim, w.data(), work.data(), &lwork, &info);
+            if (info) throw std::runtime_error("dsyev failed in the Jacobi-Davidson subspace problem");
+            const double theta = w[0];
+            const double* sv = A.data();
+            copy(V(0), u); scal(sv[0], u);
+            for (int j = 1; j <= it; ++j) axpy(sv[j], V(j), u);
+            copy(VA(0), r); scal(sv[0], r);
+            for (int j = 1; j <= it; ++j) axpy(sv[j], VA(j), r);
+            axpy(-theta, u, r);
+            ++it;
+            const double rn = std::sqrt(dot(r, r));
+            res.theta = theta; res.resid = rn;
+            if (rn <= tol * std::abs(theta) || rn <= tol || it >= max_iter) break;
+            const double dru = dot(r, u), duu = dot(u, u);
+            copy(r, V(it)); scal(-1., V(it));
+            axpy(dru / duu, u, V(it));
+        }
+        std::vector<double> out((size_t)n);
+        qcm_check(qcm_array_download(u, 0, out.data(), n), "qcm_array_download");
+        res.vec = MPSTensor(x0.site_dim(), x0.row_dim(), x0.col_dim(), unflatten(cp->out_tensor, out), LeftPaired, true);
+        seconds[2] += c0.lap();
+        return true;
+    }
+    bool device_solver = true;       // false: always leave the eigensolver to the caller (host vectors)
 
     // ---- Engine::overlap_mpo_left_step / overlap_mpo_right_step -------------------------------------------
     Boundary overlap_mpo_left_step(MPSTensor const& bra_tensor, MPSTensor const& ket_tensor, Boundary const& left, MPOTensor const& mpo,
@@ -336,6 +412,7 @@ private:
     int64_t budget;
     std::list<std::pair<PlanKey, std::shared_ptr<CompiledPlan>>> cache;
     size_t cache_capacity = 4;
+    std::vector<qcm_array_t> vec_pool; int64_t vec_pool_n = 0;      // solver vectors, reused from site to site
     std::shared_ptr<CompiledPlan> last;
 };
 

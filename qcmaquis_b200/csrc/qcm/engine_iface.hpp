@@ -8,9 +8,16 @@
 
 namespace qcm {
 
+// result of the site eigensolver (ietl::jacobi_davidson::calculate_eigenvalue, ietl/jacobi.h:361-451)
+struct EigenResult { double theta = 0; MPSTensor vec; int n_sigma = 0; double resid = 0; };
+
 struct EngineIface
 {
     virtual ~EngineIface() {}
+    // Optional: the whole Jacobi-Davidson solve of one site problem inside the engine (solver vectors resident on the
+    // device).  false: not provided for this problem, the caller runs the host solver on site_hamil2.
+    virtual bool jacobi_davidson(MPSTensor const& /*x0*/, Boundary const& /*left*/, Boundary const& /*right*/, MPOTensor const& /*mpo*/,
+                                 int /*max_iter*/, double /*tol*/, EigenResult& /*res*/) { return false; }
     // engine.hpp:196-209 -- returns a LEFT-paired tensor with phys_i/left_i/right_i of the bra (== ket here)
     virtual MPSTensor site_hamil2(MPSTensor ket_tensor, Boundary const& left, Boundary const& right,
                                   MPOTensor const& mpo, bool isHermitian = true) = 0;

@@ -140,15 +140,16 @@ inline void axpy(MPSTensor& y, double a, MPSTensor const& x)       // y += a x, 
     y.make_left_paired(); x.make_left_paired();
     y.data().axpy(a, x.data());
 }
-struct JDResult { double theta = 0; MPSTensor vec; int n_sigma = 0; double resid = 0; };
+typedef EigenResult JDResult;
 
 inline JDResult jacobi_davidson(EngineIface& eng, MPSTensor const& x0, Boundary const& left, Boundary const& right, MPOTensor const& mpo,
                                 int max_iter, double tol)
 {
+    JDResult res;
+    if (eng.jacobi_davidson(x0, left, right, mpo, max_iter, tol, res)) return res;      // solver vectors kept on the device
     std::vector<MPSTensor> V(max_iter + 1), VA(max_iter);
     std::vector<double> M((size_t)max_iter * max_iter, 0.);
     const double kappa = 0.25;
-    JDResult res;
     V[0] = x0; V[0].make_left_paired();
     int it = 0;
     for (;;) {
