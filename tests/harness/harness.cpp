@@ -372,3 +372,39 @@ extern "C" int qcmt_ts_dmrg(const char* fcidump, const char* symm, int L, int ne
         return 1;
     }
 }
+
+// Round trip of the two-site data formats on every bond of a random MPS (no engine involved):
+//   T = A[p] A[p+1] (both-paired)  ->  make_mps (right-paired; SU2: spin-coupled)  ->  operator<< (SU2: uncoupled again)
+//   ->  split without truncation  ->  product of the two new site tensors must equal T;  the norm is preserved by make_mps
+// (the 6j recoupling is orthogonal), U has orthonormal columns.
+// out[0] bonds  out[1] max rel |T' - T|  out[2] max rel | |make_mps| - |T| |  out[3] max |U^T U - 1|
+extern "C" int qcmt_twosite_roundtrip(const char* fcidump, const char* symm, int L, int nelec, int Mmax, unsigned seed, double* out, char* err, int errlen)
+{
+    try {
+        Problem P = make_problem(fcidump, symm, L, nelec);
+        P.init_mps((size_t)Mmax, true, 0., seed);
+        double d_prod = 0, d_norm = 0, d_orth = 0; int n = 0;
+        for (int p = 0; p + 1 < L; ++p) {
+            MPSTensor a = P.mps[p], b = P.mps[p + 1];
+            a.make_left_paired(); b.make_right_paired();
+            block_matrix T; sweep::gemm(a.data(), b.data(), T);
+            ts::TwoSiteTensor tst(P.params.symm, P.mps[p], P.mps[p + 1]);
+            MPSTensor twin = tst.make_mps();
+            d_norm = std::max(d_norm, std::abs(twin.scalar_norm() - std::sqrt(T.norm_square())) / std::sqrt(T.norm_square()));
+            tst << twin;
+            MPSTensor t1, t2; ts::Truncation tr;
+            tst.split_mps_l2r(100000, 0., t1, t2, tr);
+            t1.make_left_paired(); t2.make_right_paired();
+            block_matrix T2; sweep::gemm(t1.data(), t2.data(), T2);
+            d_prod = std::max(d_prod, rel_diff(compare(T2, T)));
+            block_matrix utu; { block_matrix ut; for (size_t k = 0; k < t1.data().n_blocks(); ++k) { Matrix const& m = t1.data()[k]; Matrix mt(m.cols, m.rows); for (size_t i = 0; i < m.rows; ++i) for (size_t j = 0; j < m.cols; ++j) mt(j, i) = m(i, j); ut.insert_block(mt, t1.data().basis()[k].rc, t1.data().basis()[k].lc); } sweep::gemm(ut, t1.data(), utu); }
+            for (size_t k = 0; k < utu.n_blocks(); ++k) for (size_t i = 0; i < utu[k].rows; ++i) for (size_t j = 0; j < utu[k].cols; ++j) d_orth = std::max(d_orth, std::abs(utu[k](i, j) - (i == j ? 1. : 0.)));
+            ++n;
+        }
+        out[0] = n; out[1] = d_prod; out[2] = d_norm; out[3] = d_orth;
+        return 0;
+    } catch (std::exception const& e) {
+        set_err(err, errlen, e.what());
+        return 1;
+    }
+}

@@ -37,6 +37,18 @@ def test_plan_interpreter_matches_the_oracle_per_micro_iteration(harness_cpu, sy
 
 
 @pytest.mark.parametrize("symm", ["su2u1pg", "su2u1", "2u1pg", "2u1"])
+@pytest.mark.parametrize("f,L,ne,M", [("lih_4o.fcidump", 4, 2, 20), ("synth_6o6e.fcidump", 6, 6, 12), ("benzene_6o.fcidump", 6, 6, 25)])
+def test_two_site_formats_round_trip(harness_cpu, symm, f, L, ne, M):
+    # TwoSiteTensor -> make_mps (SU2: reduce_right) -> operator<< (SU2: unreduce_left) -> SVD split reproduces the tensor
+    import ctypes
+    from conftest import golden
+    out = (ctypes.c_double * 8)(); err = ctypes.create_string_buffer(1024)
+    rc = harness_cpu.lib.qcmt_twosite_roundtrip(golden(f), symm.encode(), L, ne, M, 42, out, err, 1024)
+    assert rc == 0, err.value.decode()
+    assert out[0] == L - 1 and out[1] < 1e-12 and out[2] < 1e-12 and out[3] < 1e-12, list(out)[:4]
+
+
+@pytest.mark.parametrize("symm", ["su2u1pg", "su2u1", "2u1pg", "2u1"])
 def test_oracle_two_site_sweeps_reach_the_reference_energies(harness_cpu, symm):
     # two-site DMRG (ts_optimize.hpp, TwoSiteTensor + SVD truncation; SU2: 6j recoupling of the fused site) grows the
     # bond dimension from a random M=4 state and must land on the same pinned energies (LiHFixture: SS == TS)
