@@ -47,3 +47,31 @@ def test_product_libraries_do_not_link_the_oracle(built):
     for key in ("cuda", "host"):
         out = subprocess.run(["nm", "-D", "--defined-only", built[key]], capture_output=True, text=True).stdout
         assert "oracle" not in out and "orc_" not in out
+
+
+@pytest.mark.gpu
+def test_error_conventions_on_the_device(built):
+    """Every call returns a status; misuse is reported through qcm_last_error(), never silently computed around
+    (the C++ Engine mirror turns the status into std::runtime_error, the reference's convention on this path)."""
+    lib = ctypes.CDLL(built["cuda"], mode=ctypes.RTLD_GLOBAL)
+    lib.qcm_last_error.restype = ctypes.c_char_p
+    assert lib.qcm_init(0) == 0, lib.qcm_last_error()
+    assert lib.qcm_init(0) == 0                                    # idempotent on the same device
+    arr = ctypes.c_void_p()
+    assert lib.qcm_array_alloc(ctypes.c_int64(16), ctypes.byref(arr)) == 0
+    host = (ctypes.c_double * 32)(*range(32))
+    assert lib.qcm_array_upload(arr, ctypes.c_int64(8), host, ctypes.c_int64(16)) != 0       # 8 + 16 > 16
+    assert b"range" in lib.qcm_last_error()
+    assert lib.qcm_array_upload(arr, ctypes.c_int64(0), host, ctypes.c_int64(16)) == 0
+    back = (ctypes.c_double * 16)()
+    assert lib.qcm_array_download(arr, ctypes.c_int64(0), back, ctypes.c_int64(16)) == 0 and list(back) == [float(i) for i in range(16)]
+    # a null plan is refused by each of the engine calls
+    out = (ctypes.c_double * 16)()
+    assert lib.qcm_site_hamil2(None, arr, arr, host, out) != 0 and b"plan" in lib.qcm_last_error()
+    assert lib.qcm_boundary_step(None, arr, host, host, arr) != 0 and b"plan" in lib.qcm_last_error()
+    assert lib.qcm_hdiag(None, arr, arr, out) != 0 and b"plan" in lib.qcm_last_error()
+    # vector algebra checks sizes
+    res = ctypes.c_double()
+    assert lib.qcm_vec_dot(arr, arr, ctypes.c_int64(32), ctypes.byref(res)) != 0 and b"holds 16" in lib.qcm_last_error()
+    assert lib.qcm_vec_dot(arr, arr, ctypes.c_int64(16), ctypes.byref(res)) == 0 and res.value == sum(i * i for i in range(16))
+    assert lib.qcm_array_free(arr) == 0
