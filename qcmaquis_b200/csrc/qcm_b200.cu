@@ -183,6 +183,10 @@ struct qcm_plan_s
     double flops = 0; int64_t bytes = 0;
     int64_t n_launches = 0;
     std::vector<void*> allocs;
+    // task arrays are staged on the host while the plan is built and go to the device in ONE allocation and one copy
+    std::vector<char> staging;
+    struct PendingPtr { void** where; size_t offset; };
+    std::vector<PendingPtr> pending;
 };
 
 typedef int (*nccl_get_uid_t)(void*);
@@ -406,9 +410,23 @@ template <class T> static int dev_upload(qcm_plan_s* P, std::vector<T> const& h,
 {
     *d = nullptr;
     if (h.empty()) return 0;
-    CU(cudaMalloc((void**)d, h.size() * sizeof(T)));
-    P->allocs.push_back(*d);
-    CU(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    size_t off = (P->staging.size() + 255) & ~(size_t)255;
+    P->staging.resize(off + h.size() * sizeof(T));
+    memcpy(P->staging.data() + off, h.data(), h.size() * sizeof(T));
+    P->pending.push_back(qcm_plan_s::PendingPtr{(void**)d, off});
+    return 0;
+}
+// one cudaMalloc + one copy for all task arrays of the plan; patches the device pointers recorded by dev_upload
+static int flush_uploads(qcm_plan_s* P)
+{
+    if (P->staging.empty()) return 0;
+    char* base = nullptr;
+    CU(cudaMalloc((void**)&base, P->staging.size()));
+    P->allocs.push_back(base);
+    CU(cudaMemcpy(base, P->staging.data(), P->staging.size(), cudaMemcpyHostToDevice));
+    for (auto const& q : P->pending) *q.where = base + q.offset;
+    std::vector<char>().swap(P->staging);
+    P->pending.clear();
     return 0;
 }
 
@@ -597,6 +615,7 @@ extern "C" int qcm_plan_create(const qcm_plan_desc* d, qcm_plan_t* out)
         if (build_axpy_group(P, W.w, wd)) return bail();
         if (build_gemm_group(P, W.c, wd.c_outs, wd.n_c_outs, wd.c_segs, wd.n_c_segs, 1)) return bail();
     }
+    if (flush_uploads(P)) return bail();
     *out = P;
     return 0;
 }
