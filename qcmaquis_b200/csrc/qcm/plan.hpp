@@ -172,7 +172,7 @@ public:
         ProductBasis in_right_pb(physical_i, right_i, true);
         Index indexForTrim = ket_rp.basis.left_basis();                // bra == ket, right paired
 
-        PhaseTimer pt; double dbg_collect = 0;
+        PhaseTimer pt;
         setup_t_left(P, left, ket_rp, indexForTrim);
         pt.lap("setup_t_left");
 
@@ -265,14 +265,12 @@ public:
                 for (size_t mb : match[k])
                     if (books[i] && P.out_tensor.basis.has(yb.lc, su2_ ? yb.lc : rv.blocks[mb].rc)) { P.flops_close += 2.0 * yb.ls * rv.blocks[mb].rs * yb.rs; P.n_gemm_tasks++; }
             }
-            auto tq0 = std::chrono::steady_clock::now();
             PanelCounts pcnt;
             std::vector<Panel> panels = cached_panels(pcache, pend.size(), i, t_begin,
                 [&](size_t j) -> std::vector<size_t> const& { return pend[j].t_rows; },
                 [&](size_t j) -> std::vector<YTask> const& { return pend[j].ytasks; },
                 [&](size_t j) { return world > 1 && pend[j].ytasks.empty() && !books[j]; }, tl, pcnt);
             P.flops_w += pcnt.flops_w; P.n_axpy_tasks += pcnt.n_axpy;
-            dbg_collect += std::chrono::duration<double>(std::chrono::steady_clock::now() - tq0).count();
             for (Panel const& pn : panels) {
                 if (match[pn.o].empty()) { P.skipped_panel_elems += (int64_t)pn.rows * pn.cols; continue; }
                 PanelRef pr;
@@ -284,7 +282,6 @@ public:
             }
         }
         flush();
-        if (pt.on) fprintf(stderr, "  [plan]   of which collect_panels %8.3f s\n", dbg_collect);
         merge_outputs(P.persistent_t);
         P.bytes_algorithmic = 8 * (left.total + right.total + 2 * ket_lp.total);
         return P;
