@@ -144,8 +144,10 @@ int qcm_vec_axpy(double a, qcm_array_t x, qcm_array_t y, int64_t n);       /* y 
 int qcm_vec_scal(double a, qcm_array_t x, int64_t n);
 int qcm_vec_copy(qcm_array_t src, qcm_array_t dst, int64_t n);
 
-/* ---- multi-GPU: one process per GPU, work sharded over the MPO bond index b (the reference's omp_for axis,
- *      abelian/site_hamil.hpp:74); sigma is combined by one allreduce per call -------------------------- */
+/* ---- multi-GPU: one process per GPU.  The reference parallelises over the MPO bond index b with OpenMP
+ *      (abelian/site_hamil.hpp:74, utils/parallel/loops.hpp:11-26); here the edges (b1, b2) of the MPO bond graph are
+ *      sharded over ranks by their step-1 index when the plan is built, every rank executes its plan, and the partial
+ *      sigma vectors / boundaries are combined by one allreduce per call inside the library ------------------------- */
 int qcm_comm_unique_id(char id[128]);
 int qcm_comm_init(int rank, int world, const char id[128]);
 int qcm_comm_destroy(void);

@@ -8,8 +8,9 @@
 //     (MPO tensor, boundaries, tensor structure) and reused by every Davidson iteration at that site,
 //   * boundaries returned by the boundary steps stay in HBM (Boundary::device_mirror); the host object carries
 //     the symmetry-block structure only until download() is called,
-//   * with a communicator (one process per GPU) every rank executes its share of the MPO bond index and the
-//     library sums the partial results.
+//   * with a communicator (one process per GPU) every rank executes its share of the edges of the MPO bond graph
+//     (sharded by their step-1 index, plan.hpp shard_sources) and the library sums the partial results,
+//   * the Jacobi-Davidson solve of a site can run inside the engine with the solver vectors resident in HBM.
 // There is no CPU fallback: every failure of the device layer surfaces as std::runtime_error.
 #pragma once
 #include "../../../include/qcm_b200.h"
