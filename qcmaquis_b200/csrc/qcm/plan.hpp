@@ -1255,7 +1255,8 @@ private:
         size_t nd = al.dsts.size();
         struct Key { uint64_t h1, h2; int32_t rows, cols, n; size_t idx; };
         std::vector<Key> keys(nd);
-        typedef std::vector<std::pair<int64_t, double>> SrcVec;   // (packed src ref, coef), sorted by ref
+        struct SrcE { int64_t first; double second; int32_t lds; };   // packed src ref, coef, leading dimension
+        typedef std::vector<SrcE> SrcVec;                            // sorted by ref
         std::vector<SrcVec> sorted(nd);
         auto mixh = [](uint64_t x, uint64_t seed) { x ^= seed; x *= 0x9E3779B97F4A7C15ull; x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull; x ^= x >> 29; return x; };
 #pragma omp parallel for schedule(dynamic, 256)
@@ -1266,7 +1267,7 @@ private:
             v.reserve(d.src_end - d.src_begin);
             for (int32_t q = d.src_begin; q < d.src_end; ++q) {
                 AxpySrc const& a = al.srcs[q];
-                v.push_back(std::make_pair(((int64_t)a.src.buf << 56) | a.src.off, a.coef));
+                v.push_back(SrcE{((int64_t)a.src.buf << 56) | a.src.off, a.coef, a.lds});
             }
             std::sort(v.begin(), v.end(), [](auto const& x, auto const& y) { return x.first < y.first; });
             uint64_t h1 = ~0ull, h2 = ~0ull;
@@ -1281,10 +1282,7 @@ private:
             while (i < a.size() && j < b.size()) { if (a[i].first == b[j].first) { ++c; ++i; ++j; } else if (a[i].first < b[j].first) ++i; else ++j; }
             return c;
         };
-        std::unordered_map<int64_t, int32_t> lds_map;
-        lds_map.reserve(al.srcs.size());
-        for (auto const& a : al.srcs) lds_map[((int64_t)a.src.buf << 56) | a.src.off] = a.lds;
-        std::vector<int64_t> uni, tmp;
+        std::vector<std::pair<int64_t, int32_t>> uni, tmp;      // (packed src ref, leading dimension) of a group's sources
         for (size_t q = 0; q < nd;) {
             size_t lead = keys[q].idx;
             size_t q2 = q + 1;
@@ -1299,14 +1297,14 @@ private:
             }
             int32_t g = (int32_t)(q2 - q);
             uni.clear();
-            for (auto const& e : sorted[lead]) uni.push_back(e.first);
+            for (auto const& e : sorted[lead]) uni.push_back(std::make_pair(e.first, e.lds));
             for (int32_t d = 1; d < g; ++d) {
                 tmp.clear();
                 SrcVec const& m = sorted[keys[q + d].idx];
                 size_t i = 0, j = 0;
                 while (i < uni.size() || j < m.size()) {
-                    if (j == m.size() || (i < uni.size() && uni[i] < m[j].first)) tmp.push_back(uni[i++]);
-                    else if (i == uni.size() || m[j].first < uni[i]) tmp.push_back(m[j++].first);
+                    if (j == m.size() || (i < uni.size() && uni[i].first < m[j].first)) tmp.push_back(uni[i++]);
+                    else if (i == uni.size() || m[j].first < uni[i].first) { tmp.push_back(std::make_pair(m[j].first, m[j].lds)); ++j; }
                     else { tmp.push_back(uni[i]); ++i; ++j; }
                 }
                 uni.swap(tmp);
@@ -1315,7 +1313,7 @@ private:
             WGroup G; G.rows = keys[q].rows; G.cols = keys[q].cols; G.n_src = ns; G.n_dst = g; G.cls = stream ? 1 : 0;
             G.ng = stream ? 4 : (g <= 8 ? 8 : g <= 16 ? 16 : g <= 32 ? 32 : 64);
             G.src_begin = (int32_t)wl.srcs.size(); G.dst_begin = (int32_t)wl.dsts.size(); G.coef_begin = (int64_t)wl.coefs.size();
-            for (int64_t ref : uni) wl.srcs.push_back(WSrc{Ref{(int32_t)(ref >> 56), ref & (((int64_t)1 << 56) - 1)}, lds_map[ref]});
+            for (auto const& rf : uni) wl.srcs.push_back(WSrc{Ref{(int32_t)(rf.first >> 56), rf.first & (((int64_t)1 << 56) - 1)}, rf.second});
             int32_t ns_pad = stream ? ns : (ns + 15) / 16 * 16;   // the DMMA kernel stages sources sixteen at a time
             wl.coefs.resize(wl.coefs.size() + (size_t)ns_pad * G.ng, 0.);
             for (int32_t d = 0; d < g; ++d) {
@@ -1324,7 +1322,7 @@ private:
                 SrcVec const& m = sorted[di];
                 size_t u = 0;
                 for (auto const& e : m) {
-                    while (uni[u] != e.first) ++u;
+                    while (uni[u].first != e.first) ++u;
                     wl.coefs[(size_t)G.coef_begin + u * G.ng + d] = e.second;
                 }
             }
