@@ -45,10 +45,12 @@ struct CopyTask { Ref src, dst; int32_t rows, cols, lds, ldd; };
 struct Seg { Ref A, B; int32_t lda, ldb, m, n, k, ta, tb; double alpha; };   // op(A) is m x k, op(B) is k x n
 struct Out { Ref C; int32_t ldc, m, n, seg_begin, seg_end; };
 struct AxpySrc { Ref src; int32_t lds; double coef; };
-struct AxpyDst { Ref dst; int32_t ldd, rows, cols, src_begin, src_end; };
+struct AxpyDst { Ref dst; int32_t ldd, rows, cols; };       // its sources: AxpyList::lists at the same index
 
 struct GemmList { std::vector<Out> outs; std::vector<Seg> segs; };
-struct AxpyList { std::vector<AxpyDst> dsts; std::vector<AxpySrc> srcs; };
+// destination panels with their source lists (each list sorted by (buf, off), equal sources merged); the lists are
+// moved in from the panel collection, never copied -- at cfg3 they hold more than 10^8 (source, destination) pairs
+struct AxpyList { std::vector<AxpyDst> dsts; std::vector<std::vector<AxpySrc>> lists; };
 
 // The W application in the form the device executes: destination panels that are fed by the SAME set of source
 // panels (typical for quantum-chemistry MPOs: all bond terms that differ only by an integral value) are grouped,
@@ -271,7 +273,7 @@ public:
                 [&](size_t j) -> std::vector<YTask> const& { return pend[j].ytasks; },
                 [&](size_t j) { return world > 1 && pend[j].ytasks.empty() && !books[j]; }, tl, pcnt);
             P.flops_w += pcnt.flops_w; P.n_axpy_tasks += pcnt.n_axpy;
-            for (Panel const& pn : panels) {
+            for (Panel& pn : panels) {
                 if (match[pn.o].empty()) { P.skipped_panel_elems += (int64_t)pn.rows * pn.cols; continue; }
                 PanelRef pr;
                 if (!place_panel(P, cur.w_apply, pn, cur_y, pr)) continue;
@@ -385,7 +387,7 @@ public:
                 [&](size_t j) -> std::vector<YTask> const& { return pend[j].ytasks; },
                 [&](size_t j) { return (world > 1 && pend[j].ytasks.empty() && !books[j]) || (mpo.herm_info.right_skip(j) && isHermitian); }, tl, pcnt);
             P.flops_w += pcnt.flops_w; P.n_axpy_tasks += pcnt.n_axpy;
-            for (Panel const& pn : panels) {
+            for (Panel& pn : panels) {
                 if (match[pn.o].empty()) { P.skipped_panel_elems += (int64_t)pn.rows * pn.cols; continue; }
                 PanelRef pr;
                 if (!place_panel(P, cur.w_apply, pn, cur_y, pr)) continue;
@@ -499,7 +501,7 @@ public:
                 [&](size_t j) -> std::vector<YTask> const& { return pend[j].ytasks; },
                 [&](size_t j) { return (world > 1 && pend[j].ytasks.empty() && !books[j]) || (mpo.herm_info.left_skip(j) && isHermitian); }, tl, pcnt);
             P.flops_w += pcnt.flops_w; P.n_axpy_tasks += pcnt.n_axpy;
-            for (Panel const& pn : panels) {
+            for (Panel& pn : panels) {
                 if (match[pn.o].empty()) { P.skipped_panel_elems += (int64_t)pn.rows * pn.cols; continue; }
                 PanelRef pr;
                 if (!place_panel(P, cur.w_apply, pn, cur_y, pr)) continue;
@@ -610,7 +612,6 @@ public:
                                     if (it == dst_index.end()) {
                                         it = dst_index.emplace(key, dsts.size()).first;
                                         AxpyDst d; d.dst = Ref{BUF_Y, voff[block] + (int64_t)kk * rows + row_off}; d.ldd = 1; d.rows = 1; d.cols = (int32_t)m_l;
-                                        d.src_begin = d.src_end = 0;
                                         dsts.push_back(d); dst_srcs.emplace_back();
                                     }
                                     // the diagonal of the stored block: element i at off + i * (ld + 1)
@@ -646,11 +647,9 @@ public:
                 else v[o++] = v[i];
             }
             v.resize(o);
-            dsts[d].src_begin = (int32_t)wave.w_apply.srcs.size();
-            wave.w_apply.srcs.insert(wave.w_apply.srcs.end(), v.begin(), v.end());
-            dsts[d].src_end = (int32_t)wave.w_apply.srcs.size();
-            wave.w_apply.dsts.push_back(dsts[d]);
             P.exec_w += 2.0 * dsts[d].cols * (double)v.size();
+            wave.w_apply.dsts.push_back(dsts[d]);
+            wave.w_apply.lists.push_back(std::move(v));
         }
         wave.y_elems = vtot; wave.t_elems = 0;
         P.y_elems_max = vtot; P.tp_elems = drtot;
@@ -1119,7 +1118,7 @@ private:
 
     // W-application contributions grouped by destination panel.  Sources that reach the same panel through several
     // MPO terms are merged (coefficients add up).
-    struct PanelSrc { Ref src; int32_t lds; double coef; };
+    typedef AxpySrc PanelSrc;
     struct Panel { size_t o; int32_t dst_row, dst_col, rows, cols; std::vector<PanelSrc> srcs; };
     struct PanelRef { Ref A; int32_t lda; double alpha; };
     struct PanelCounts { double flops_w = 0; size_t n_axpy = 0; };
@@ -1219,7 +1218,7 @@ private:
     }
     // Where the closing product finds a panel: the T panel itself (one source; its coefficient becomes the alpha of
     // the K-segment) or a compact region of BUF_Y filled by the W kernel.  false: the panel is identically zero.
-    bool place_panel(Plan& P, AxpyList& al, Panel const& pn, int64_t& cur_y, PanelRef& pr)
+    bool place_panel(Plan& P, AxpyList& al, Panel& pn, int64_t& cur_y, PanelRef& pr)
     {
         if (pn.srcs.empty()) return false;
         int64_t el = (int64_t)pn.rows * pn.cols;
@@ -1231,12 +1230,10 @@ private:
         }
         cur_y = (cur_y + 1) & ~(int64_t)1;      // panels start 16-byte aligned
         AxpyDst d; d.dst = Ref{BUF_Y, cur_y}; d.ldd = pn.rows; d.rows = pn.rows; d.cols = pn.cols;
-        d.src_begin = (int32_t)al.srcs.size();
-        for (auto const& sp : pn.srcs) al.srcs.push_back(AxpySrc{sp.src, sp.lds, sp.coef});
-        d.src_end = (int32_t)al.srcs.size();
-        al.dsts.push_back(d);
-        cur_y += el;
         P.w_panel_elems += el; P.exec_w += 2.0 * el * (double)pn.srcs.size();
+        al.dsts.push_back(d);
+        al.lists.push_back(std::move(pn.srcs));
+        cur_y += el;
         pr = PanelRef{d.dst, pn.rows, 1.};
         return true;
     }
@@ -1255,23 +1252,18 @@ private:
         size_t nd = al.dsts.size();
         struct Key { uint64_t h1, h2; int32_t rows, cols, n; size_t idx; };
         std::vector<Key> keys(nd);
-        struct SrcE { int64_t first; double second; int32_t lds; };   // packed src ref, coef, leading dimension
-        typedef std::vector<SrcE> SrcVec;                            // sorted by ref
-        std::vector<SrcVec> sorted(nd);
+        // packed source reference (buffer, offset): the lists are sorted by it
+        auto ref_of = [](AxpySrc const& a) { return ((int64_t)a.src.buf << 56) | a.src.off; };
+        typedef std::vector<AxpySrc> SrcVec;
+        std::vector<SrcVec>& sorted = al.lists;
         auto mixh = [](uint64_t x, uint64_t seed) { x ^= seed; x *= 0x9E3779B97F4A7C15ull; x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull; x ^= x >> 29; return x; };
 #pragma omp parallel for schedule(dynamic, 256)
         for (long il = 0; il < (long)nd; ++il) {
             size_t i = (size_t)il;
             AxpyDst const& d = al.dsts[i];
-            SrcVec& v = sorted[i];
-            v.reserve(d.src_end - d.src_begin);
-            for (int32_t q = d.src_begin; q < d.src_end; ++q) {
-                AxpySrc const& a = al.srcs[q];
-                v.push_back(SrcE{((int64_t)a.src.buf << 56) | a.src.off, a.coef, a.lds});
-            }
-            std::sort(v.begin(), v.end(), [](auto const& x, auto const& y) { return x.first < y.first; });
+            SrcVec const& v = sorted[i];
             uint64_t h1 = ~0ull, h2 = ~0ull;
-            for (auto const& e : v) { h1 = std::min(h1, mixh((uint64_t)e.first, 0x1234567ull)); h2 = std::min(h2, mixh((uint64_t)e.first, 0xABCDEF01ull)); }
+            for (auto const& e : v) { uint64_t r = (uint64_t)ref_of(e); h1 = std::min(h1, mixh(r, 0x1234567ull)); h2 = std::min(h2, mixh(r, 0xABCDEF01ull)); }
             keys[i] = Key{h1, h2, d.rows, d.cols, (int32_t)v.size(), i};
         }
         std::sort(keys.begin(), keys.end(), [](Key const& a, Key const& b) {
@@ -1279,7 +1271,7 @@ private:
         });
         auto overlap = [&](SrcVec const& a, SrcVec const& b) {
             size_t i = 0, j = 0, c = 0;
-            while (i < a.size() && j < b.size()) { if (a[i].first == b[j].first) { ++c; ++i; ++j; } else if (a[i].first < b[j].first) ++i; else ++j; }
+            while (i < a.size() && j < b.size()) { int64_t x = ref_of(a[i]), y = ref_of(b[j]); if (x == y) { ++c; ++i; ++j; } else if (x < y) ++i; else ++j; }
             return c;
         };
         std::vector<std::pair<int64_t, int32_t>> uni, tmp;      // (packed src ref, leading dimension) of a group's sources
@@ -1297,14 +1289,14 @@ private:
             }
             int32_t g = (int32_t)(q2 - q);
             uni.clear();
-            for (auto const& e : sorted[lead]) uni.push_back(std::make_pair(e.first, e.lds));
+            for (auto const& e : sorted[lead]) uni.push_back(std::make_pair(ref_of(e), e.lds));
             for (int32_t d = 1; d < g; ++d) {
                 tmp.clear();
                 SrcVec const& m = sorted[keys[q + d].idx];
                 size_t i = 0, j = 0;
                 while (i < uni.size() || j < m.size()) {
-                    if (j == m.size() || (i < uni.size() && uni[i].first < m[j].first)) tmp.push_back(uni[i++]);
-                    else if (i == uni.size() || m[j].first < uni[i].first) { tmp.push_back(std::make_pair(m[j].first, m[j].lds)); ++j; }
+                    if (j == m.size() || (i < uni.size() && uni[i].first < ref_of(m[j]))) tmp.push_back(uni[i++]);
+                    else if (i == uni.size() || ref_of(m[j]) < uni[i].first) { tmp.push_back(std::make_pair(ref_of(m[j]), m[j].lds)); ++j; }
                     else { tmp.push_back(uni[i]); ++i; ++j; }
                 }
                 uni.swap(tmp);
@@ -1322,8 +1314,8 @@ private:
                 SrcVec const& m = sorted[di];
                 size_t u = 0;
                 for (auto const& e : m) {
-                    while (uni[u].first != e.first) ++u;
-                    wl.coefs[(size_t)G.coef_begin + u * G.ng + d] = e.second;
+                    while (uni[u].first != ref_of(e)) ++u;
+                    wl.coefs[(size_t)G.coef_begin + u * G.ng + d] = e.coef;
                 }
             }
             wl.groups.push_back(G);
@@ -1332,7 +1324,7 @@ private:
             q = q2;
         }
         P.w_elems_read += wl.elems_read; P.w_elems_written += wl.elems_written; P.w_groups += (int64_t)wl.groups.size();
-        AxpyList().dsts.swap(al.dsts); AxpyList().srcs.swap(al.srcs);
+        AxpyList().dsts.swap(al.dsts); AxpyList().lists.swap(al.lists);
     }
 
     // step 3: one K-segment alpha * op(A)(m x k) * op(B)(k x n) into rows [c_row, c_row + m) of output block (lc, rc);
