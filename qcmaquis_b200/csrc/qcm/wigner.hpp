@@ -32,7 +32,7 @@ inline long double ldelta(int a, int b, int c)
 } // namespace detail
 
 // {ja jb jc; jd je jf}, all arguments doubled
-inline double wigner6j(int ja, int jb, int jc, int jd, int je, int jf)
+inline double wigner6j_uncached(int ja, int jb, int jc, int jd, int je, int jf)
 {
     if (!triangle(ja, jb, jc) || !triangle(ja, je, jf) || !triangle(jd, jb, jf) || !triangle(jd, je, jc)) return 0.0;
     using detail::lfact; using detail::ldelta;
@@ -49,6 +49,19 @@ inline double wigner6j(int ja, int jb, int jc, int jd, int je, int jf)
         sum += (t % 2) ? -v : v;
     }
     return (double)sum;
+}
+
+// The two-site operator fusion and the two-site recoupling evaluate the same few hundred 6j symbols millions of times:
+// per-thread table (no locking), as the reference keeps its Wigner symbols in a table (gsl_coupling.h:113-144)
+inline double wigner6j(int ja, int jb, int jc, int jd, int je, int jf)
+{
+    const int args[6] = {ja, jb, jc, jd, je, jf};
+    uint64_t key = 0;
+    for (int q = 0; q < 6; ++q) { if (args[q] < 0 || args[q] > 255) return wigner6j_uncached(ja, jb, jc, jd, je, jf); key = (key << 8) | (uint64_t)args[q]; }
+    static thread_local std::unordered_map<uint64_t, double> cache;
+    auto it = cache.find(key);
+    if (it == cache.end()) it = cache.emplace(key, wigner6j_uncached(ja, jb, jc, jd, je, jf)).first;
+    return it->second;
 }
 
 // {a b c; d e f; g h i}, all arguments doubled
