@@ -408,3 +408,37 @@ extern "C" int qcmt_twosite_roundtrip(const char* fcidump, const char* symm, int
         return 1;
     }
 }
+
+// Sharding quality of the sigma plan (plan.hpp shard_sources): per-rank FLOPs for `world` ranks on a synthetic two-site problem.
+// out[0] step-1 FLOPs summed over ranks / step-1 FLOPs of the unsharded plan (1 = nothing computed twice)
+// out[1] max over ranks of executed FLOPs / (executed FLOPs of the unsharded plan / world)   (1 = perfect balance, no replication)
+// out[2] algorithmic FLOPs booked over ranks / unsharded (must be exactly 1)
+extern "C" int qcmt_shard_stats(const char* fcidump, const char* symm, int L, int nelec, int site, int M, unsigned seed, int world, double* out, char* err, int errlen)
+{
+    try {
+        Problem P = make_problem(fcidump, symm, L, nelec);
+        SyntheticSite S = make_synthetic_site(P, site, true, (size_t)M, seed);
+        S.psi.make_left_paired();
+        std::vector<DualIndex> lb(S.left.aux_dim()), rb(S.right.aux_dim());
+        for (size_t k = 0; k < lb.size(); ++k) lb[k] = S.left[k].basis();
+        for (size_t k = 0; k < rb.size(); ++k) rb[k] = S.right[k].basis();
+        plan::BoundaryLayout ll, rl; ll.assign(lb); rl.assign(rb);
+        plan::TensorDesc td{S.psi.site_dim(), S.psi.row_dim(), S.psi.col_dim(), S.psi.data().basis()};
+        plan::Planner p1(P.params.symm, *S.mpo, true, 0, 1, (int64_t)1 << 40);
+        plan::Plan full = p1.plan_sigma(td, ll, rl);
+        double t_sum = 0, mx = 0, alg = 0;
+        for (int r = 0; r < world; ++r) {
+            plan::Planner pr(P.params.symm, *S.mpo, true, r, world, (int64_t)1 << 40);
+            plan::Plan q = pr.plan_sigma(td, ll, rl);
+            t_sum += q.flops_t; alg += q.flops();
+            mx = std::max(mx, q.flops_t + q.exec_w + q.exec_close);
+        }
+        out[0] = t_sum / full.flops_t;
+        out[1] = mx / ((full.flops_t + full.exec_w + full.exec_close) / world);
+        out[2] = alg / full.flops();
+        return 0;
+    } catch (std::exception const& e) {
+        set_err(err, errlen, e.what());
+        return 1;
+    }
+}

@@ -58,3 +58,19 @@ def test_ragged_and_degenerate_inputs(harness_cpu):
             out = harness_cpu.chain_parity("synth_6o6e.fcidump", symm, 6, 6, M, seed=5)
             assert out[1] == 1 and out[4] == 1 and out[7] == 1
             assert out[2] < TOL and out[5] < TOL and out[8] < TOL
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_edge_sharding_computes_no_step1_product_twice(harness_cpu, world):
+    """the edges of the MPO bond graph are sharded by their step-1 index -- every T[b] is computed by exactly one
+    rank, the algorithmic FLOP count is booked exactly once, and the heaviest rank stays close to its fair share."""
+    import ctypes, os, tempfile
+    from qcmaquis_b200.fcidump import make_fcidump
+    path = os.path.join(tempfile.mkdtemp(prefix="qcm_test_"), "synth_12o12e.fcidump")
+    make_fcidump(path, 12, 12)
+    out = (ctypes.c_double * 4)(); err = ctypes.create_string_buffer(1024)
+    rc = harness_cpu.lib.qcmt_shard_stats(path.encode(), b"su2u1", 12, 12, 5, 300, 1, world, out, err, 1024)
+    assert rc == 0, err.value.decode()
+    assert out[0] == pytest.approx(1.0, abs=1e-12)       # step 1 is partitioned, not replicated
+    assert out[2] == pytest.approx(1.0, abs=1e-12)       # FLOPs booked once across ranks
+    assert out[1] < 1.6                                  # replication of the few high fan-in closing products only
