@@ -14,7 +14,10 @@
 // The upstream code itself cannot be built in this image (no Boost/GSL/HDF5 headers), see DESIGN.md.
 //
 // Containers (Index, block_matrix, MPSTensor, MPOTensor, Boundary) are the product's host data model
-// (qcmaquis_b200/csrc/qcm); only the algorithm is restated here.
+// (qcmaquis_b200/csrc/qcm); only the algorithm is restated here.  The sweep drivers (qcm/sweep.hpp, qcm/twosite.hpp) are
+// engine agnostic host code and run unchanged on this engine: that is how the oracle reaches the reference's pinned
+// end-to-end energies (tests/test_sweeps.py) and how sweeps on the GPU engine are checked per micro-iteration.
+// Also here: hdiag::diagonal_hamiltonian, the literal restatement of abelian/h_diag.hpp and non-abelian/h_diag.hpp.
 #pragma once
 #include "qcm/engine_iface.hpp"
 #include <omp.h>
