@@ -22,6 +22,9 @@
 #include <map>
 #include <numeric>
 #include <unordered_map>
+#ifdef _OPENMP
+#include <parallel/algorithm>
+#endif
 
 namespace qcm { namespace plan {
 
@@ -59,9 +62,19 @@ struct AxpyList { std::vector<AxpyDst> dsts; std::vector<std::vector<AxpySrc>> l
 struct WSrc { Ref src; int32_t lds; };
 struct WDst { Ref dst; int32_t ldd; };
 struct WGroup { int32_t rows, cols, n_src, n_dst, ng, cls, src_begin, dst_begin; int64_t coef_begin; };   // coef[coef_begin + u*ng + d]; cls 0: DMMA product (u padded to 8), 1: FMA stream
+// allocator whose resize() leaves new elements uninitialised: the coefficient tables (10^8 doubles at cfg3) are zeroed
+// and filled group by group in parallel instead of by one serial value-initialisation
+template <class T> struct DefaultInitAlloc : std::allocator<T>
+{
+    template <class U> struct rebind { typedef DefaultInitAlloc<U> other; };
+    DefaultInitAlloc() = default;
+    template <class U> DefaultInitAlloc(DefaultInitAlloc<U> const&) {}
+    template <class U> void construct(U* p) { ::new ((void*)p) U; }
+    template <class U, class... A> void construct(U* p, A&&... a) { ::new ((void*)p) U(std::forward<A>(a)...); }
+};
 struct WList
 {
-    std::vector<WGroup> groups; std::vector<WSrc> srcs; std::vector<WDst> dsts; std::vector<double> coefs;
+    std::vector<WGroup> groups; std::vector<WSrc> srcs; std::vector<WDst> dsts; std::vector<double, DefaultInitAlloc<double>> coefs;
     int64_t elems_read = 0, elems_written = 0;   // panel elements moved by the grouped form
 };
 
@@ -1266,62 +1279,102 @@ private:
             for (auto const& e : v) { uint64_t r = (uint64_t)ref_of(e); h1 = std::min(h1, mixh(r, 0x1234567ull)); h2 = std::min(h2, mixh(r, 0xABCDEF01ull)); }
             keys[i] = Key{h1, h2, d.rows, d.cols, (int32_t)v.size(), i};
         }
-        std::sort(keys.begin(), keys.end(), [](Key const& a, Key const& b) {
+        auto key_less = [](Key const& a, Key const& b) {
             return std::tie(a.rows, a.cols, a.h1, a.h2, a.n, a.idx) < std::tie(b.rows, b.cols, b.h1, b.h2, b.n, b.idx);
-        });
+        };
+        // a total order (idx breaks ties): the parallel sort gives the same sequence as the serial one
+#ifdef _OPENMP
+        __gnu_parallel::sort(keys.begin(), keys.end(), key_less);
+#else
+        std::sort(keys.begin(), keys.end(), key_less);
+#endif
         auto overlap = [&](SrcVec const& a, SrcVec const& b) {
             size_t i = 0, j = 0, c = 0;
             while (i < a.size() && j < b.size()) { int64_t x = ref_of(a[i]), y = ref_of(b[j]); if (x == y) { ++c; ++i; ++j; } else if (x < y) ++i; else ++j; }
             return c;
         };
-        std::vector<std::pair<int64_t, int32_t>> uni, tmp;      // (packed src ref, leading dimension) of a group's sources
-        for (size_t q = 0; q < nd;) {
-            size_t lead = keys[q].idx;
-            size_t q2 = q + 1;
-            bool stream = sorted[lead].size() <= 4;
-            size_t cap = stream ? 4 : 64;
-            while (q2 < nd && q2 - q < cap && keys[q2].rows == keys[q].rows && keys[q2].cols == keys[q].cols && keys[q2].h1 == keys[q].h1) {
-                SrcVec const& cand = sorted[keys[q2].idx];
-                size_t c = overlap(sorted[lead], cand);
-                if (stream) { if (c != sorted[lead].size() || c != cand.size()) break; }
-                else if (cand.size() <= 4 || 2 * c < std::max(sorted[lead].size(), cand.size())) break;
-                ++q2;
-            }
-            int32_t g = (int32_t)(q2 - q);
-            uni.clear();
-            for (auto const& e : sorted[lead]) uni.push_back(std::make_pair(ref_of(e), e.lds));
-            for (int32_t d = 1; d < g; ++d) {
-                tmp.clear();
-                SrcVec const& m = sorted[keys[q + d].idx];
-                size_t i = 0, j = 0;
-                while (i < uni.size() || j < m.size()) {
-                    if (j == m.size() || (i < uni.size() && uni[i].first < ref_of(m[j]))) tmp.push_back(uni[i++]);
-                    else if (i == uni.size() || ref_of(m[j]) < uni[i].first) { tmp.push_back(std::make_pair(ref_of(m[j]), m[j].lds)); ++j; }
-                    else { tmp.push_back(uni[i]); ++i; ++j; }
+        // A group never crosses a change of (rows, cols, h1): the runs of equal (rows, cols, h1) are cut into groups
+        // independently (in parallel, greedily from the front of each run, as a serial pass over all keys would), the
+        // groups get their places in the source / destination / coefficient arrays by a prefix sum, and are written
+        // out in parallel.  The result does not depend on the number of threads.
+        typedef std::vector<std::pair<int64_t, int32_t>> UniVec;   // (packed src ref, leading dimension) of a group's sources
+        struct GInfo { size_t q; int32_t g; bool stream; UniVec uni; };
+        std::vector<size_t> run_begin;
+        for (size_t q = 0; q < nd; ++q)
+            if (q == 0 || keys[q].rows != keys[q - 1].rows || keys[q].cols != keys[q - 1].cols || keys[q].h1 != keys[q - 1].h1) run_begin.push_back(q);
+        run_begin.push_back(nd);
+        const long n_runs = (long)run_begin.size() - 1;
+        std::vector<std::vector<GInfo>> per_run((size_t)std::max(n_runs, 0L));
+#pragma omp parallel for schedule(dynamic, 8)
+        for (long r = 0; r < n_runs; ++r) {
+            UniVec uni, tmp;
+            const size_t q_end = run_begin[(size_t)r + 1];
+            for (size_t q = run_begin[(size_t)r]; q < q_end;) {
+                size_t lead = keys[q].idx;
+                size_t q2 = q + 1;
+                bool stream = sorted[lead].size() <= 4;
+                size_t cap = stream ? 4 : 64;
+                while (q2 < q_end && q2 - q < cap) {
+                    SrcVec const& cand = sorted[keys[q2].idx];
+                    size_t c = overlap(sorted[lead], cand);
+                    if (stream) { if (c != sorted[lead].size() || c != cand.size()) break; }
+                    else if (cand.size() <= 4 || 2 * c < std::max(sorted[lead].size(), cand.size())) break;
+                    ++q2;
                 }
-                uni.swap(tmp);
+                int32_t g = (int32_t)(q2 - q);
+                uni.clear();
+                for (auto const& e : sorted[lead]) uni.push_back(std::make_pair(ref_of(e), e.lds));
+                for (int32_t d = 1; d < g; ++d) {
+                    tmp.clear();
+                    SrcVec const& m = sorted[keys[q + d].idx];
+                    size_t i = 0, j = 0;
+                    while (i < uni.size() || j < m.size()) {
+                        if (j == m.size() || (i < uni.size() && uni[i].first < ref_of(m[j]))) tmp.push_back(uni[i++]);
+                        else if (i == uni.size() || ref_of(m[j]) < uni[i].first) { tmp.push_back(std::make_pair(ref_of(m[j]), m[j].lds)); ++j; }
+                        else { tmp.push_back(uni[i]); ++i; ++j; }
+                    }
+                    uni.swap(tmp);
+                }
+                per_run[(size_t)r].push_back(GInfo{q, g, stream, uni});
+                q = q2;
             }
-            int32_t ns = (int32_t)uni.size();
-            WGroup G; G.rows = keys[q].rows; G.cols = keys[q].cols; G.n_src = ns; G.n_dst = g; G.cls = stream ? 1 : 0;
-            G.ng = stream ? 4 : (g <= 8 ? 8 : g <= 16 ? 16 : g <= 32 ? 32 : 64);
-            G.src_begin = (int32_t)wl.srcs.size(); G.dst_begin = (int32_t)wl.dsts.size(); G.coef_begin = (int64_t)wl.coefs.size();
-            for (auto const& rf : uni) wl.srcs.push_back(WSrc{Ref{(int32_t)(rf.first >> 56), rf.first & (((int64_t)1 << 56) - 1)}, rf.second});
-            int32_t ns_pad = stream ? ns : (ns + 15) / 16 * 16;   // the DMMA kernel stages sources sixteen at a time
-            wl.coefs.resize(wl.coefs.size() + (size_t)ns_pad * G.ng, 0.);
-            for (int32_t d = 0; d < g; ++d) {
-                size_t di = keys[q + d].idx;
-                wl.dsts.push_back(WDst{al.dsts[di].dst, al.dsts[di].ldd});
+        }
+        std::vector<GInfo*> flat;
+        for (auto& v : per_run) for (auto& gi : v) flat.push_back(&gi);
+        const size_t g_base = wl.groups.size();
+        size_t n_srcs = wl.srcs.size(), n_dsts = wl.dsts.size(), n_coefs = wl.coefs.size();
+        wl.groups.resize(g_base + flat.size());
+        for (size_t f = 0; f < flat.size(); ++f) {
+            GInfo const& gi = *flat[f];
+            int32_t ns = (int32_t)gi.uni.size(), g = gi.g;
+            WGroup G; G.rows = keys[gi.q].rows; G.cols = keys[gi.q].cols; G.n_src = ns; G.n_dst = g; G.cls = gi.stream ? 1 : 0;
+            G.ng = gi.stream ? 4 : (g <= 8 ? 8 : g <= 16 ? 16 : g <= 32 ? 32 : 64);
+            G.src_begin = (int32_t)n_srcs; G.dst_begin = (int32_t)n_dsts; G.coef_begin = (int64_t)n_coefs;
+            int32_t ns_pad = gi.stream ? ns : (ns + 15) / 16 * 16;   // the DMMA kernel stages sources sixteen at a time
+            n_srcs += (size_t)ns; n_dsts += (size_t)g; n_coefs += (size_t)ns_pad * G.ng;
+            wl.groups[g_base + f] = G;
+            wl.elems_read += (int64_t)ns * G.rows * G.cols;
+            wl.elems_written += (int64_t)g * G.rows * G.cols;
+        }
+        wl.srcs.resize(n_srcs); wl.dsts.resize(n_dsts); wl.coefs.resize(n_coefs);   // coefficients: zeroed per group below
+#pragma omp parallel for schedule(dynamic, 64)
+        for (long fl = 0; fl < (long)flat.size(); ++fl) {
+            GInfo const& gi = *flat[(size_t)fl];
+            WGroup const& G = wl.groups[g_base + (size_t)fl];
+            const size_t ns_pad = gi.stream ? gi.uni.size() : (gi.uni.size() + 15) / 16 * 16;
+            std::fill(wl.coefs.begin() + G.coef_begin, wl.coefs.begin() + G.coef_begin + (int64_t)(ns_pad * (size_t)G.ng), 0.);
+            for (size_t u = 0; u < gi.uni.size(); ++u)
+                wl.srcs[(size_t)G.src_begin + u] = WSrc{Ref{(int32_t)(gi.uni[u].first >> 56), gi.uni[u].first & (((int64_t)1 << 56) - 1)}, gi.uni[u].second};
+            for (int32_t d = 0; d < gi.g; ++d) {
+                size_t di = keys[gi.q + d].idx;
+                wl.dsts[(size_t)G.dst_begin + d] = WDst{al.dsts[di].dst, al.dsts[di].ldd};
                 SrcVec const& m = sorted[di];
                 size_t u = 0;
                 for (auto const& e : m) {
-                    while (uni[u].first != ref_of(e)) ++u;
+                    while (gi.uni[u].first != ref_of(e)) ++u;
                     wl.coefs[(size_t)G.coef_begin + u * G.ng + d] = e.coef;
                 }
             }
-            wl.groups.push_back(G);
-            wl.elems_read += (int64_t)ns * G.rows * G.cols;
-            wl.elems_written += (int64_t)g * G.rows * G.cols;
-            q = q2;
         }
         P.w_elems_read += wl.elems_read; P.w_elems_written += wl.elems_written; P.w_groups += (int64_t)wl.groups.size();
         AxpyList().dsts.swap(al.dsts); AxpyList().lists.swap(al.lists);
@@ -1347,10 +1400,12 @@ private:
     {
         std::vector<size_t> order(gl.outs.size());
         std::iota(order.begin(), order.end(), 0);
-        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) {
-            Out const& x = gl.outs[a]; Out const& y = gl.outs[b];
-            return x.C.off < y.C.off;
-        });
+        auto by_target = [&](size_t a, size_t b) { return gl.outs[a].C.off < gl.outs[b].C.off; };
+#ifdef _OPENMP
+        __gnu_parallel::stable_sort(order.begin(), order.end(), by_target);
+#else
+        std::stable_sort(order.begin(), order.end(), by_target);
+#endif
         GemmList r;
         for (size_t q = 0; q < order.size();) {
             Out o = gl.outs[order[q]];

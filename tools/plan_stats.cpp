@@ -34,6 +34,22 @@ int main(int argc, char** argv)
     }
     plan::Planner pl(P.symm(), *S.mpo, true, 0, 1, (int64_t)1 << 40);
     plan::Plan pp = pl.plan_sigma(td, ll, rl);
+    {   // digest of everything the device executes (to compare planner versions / thread counts)
+        uint64_t h = 1469598103934665603ull;
+        auto mix = [&](const void* p, size_t n) { const unsigned char* c = (const unsigned char*)p; for (size_t i = 0; i < n; ++i) { h ^= c[i]; h *= 1099511628211ull; } };
+        auto gl = [&](plan::GemmList const& g) {
+            for (auto const& o : g.outs) { mix(&o.C.buf, 4); mix(&o.C.off, 8); mix(&o.ldc, 4); mix(&o.m, 4); mix(&o.n, 4); mix(&o.seg_begin, 4); mix(&o.seg_end, 4); }
+            for (auto const& s : g.segs) { mix(&s.A.buf, 4); mix(&s.A.off, 8); mix(&s.B.buf, 4); mix(&s.B.off, 8); mix(&s.lda, 4); mix(&s.ldb, 4); mix(&s.m, 4); mix(&s.n, 4); mix(&s.k, 4); mix(&s.ta, 4); mix(&s.tb, 4); mix(&s.alpha, 8); } };
+        gl(pp.persistent_t);
+        for (auto const& W : pp.waves) {
+            gl(W.t_gemm); gl(W.close_gemm);
+            for (auto const& g : W.w_groups.groups) { mix(&g.rows, 4); mix(&g.cols, 4); mix(&g.n_src, 4); mix(&g.n_dst, 4); mix(&g.ng, 4); mix(&g.cls, 4); mix(&g.src_begin, 4); mix(&g.dst_begin, 4); mix(&g.coef_begin, 8); }
+            for (auto const& s : W.w_groups.srcs) { mix(&s.src.buf, 4); mix(&s.src.off, 8); mix(&s.lds, 4); }
+            for (auto const& d : W.w_groups.dsts) { mix(&d.dst.buf, 4); mix(&d.dst.off, 8); mix(&d.ldd, 4); }
+            mix(W.w_groups.coefs.data(), W.w_groups.coefs.size() * 8);
+        }
+        printf("plan digest %016llx\n", (unsigned long long)h);
+    }
     printf("waves %zu  flops t %.3e w %.3e close %.3e\n", pp.waves.size(), pp.flops_t, pp.flops_w, pp.flops_close);
     printf("elems: left %.3e right %.3e psi %.3e  TP %.3e  T %.3e  Y %.3e\n", (double)ll.total, (double)rl.total, (double)pp.ket_lp_elems, (double)pp.tp_elems, (double)pp.t_elems_max, (double)pp.y_elems_max);
     printf("W: groups %lld elems read %.3e written %.3e\n", (long long)pp.w_groups, (double)pp.w_elems_read, (double)pp.w_elems_written);
