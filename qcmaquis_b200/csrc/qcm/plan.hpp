@@ -961,9 +961,12 @@ private:
                            ProductBasis const& in_right_pb, ProductBasis const& out_left_pb,
                            DualIndex& ret, std::vector<YTask>& tasks, std::vector<size_t>& t_rows)
     {
-        // first pass: block structure (blocks are created lazily, in loop order, but sorted on insertion)
-        struct Raw { Charge ol, orc; int32_t dst_row, rows, cols; size_t b1, tb; int32_t src_col; double coef; };
-        std::vector<Raw> raws;
+        // Blocks are created lazily, in loop order, but sorted on insertion: a task first carries the creation number
+        // of its block (one hash lookup per (T block, W block) pair, not per operator entry) and gets the block's final
+        // position once the structure is complete.
+        std::unordered_map<std::pair<Charge, Charge>, size_t, ChargePairHash> seen;
+        std::vector<std::pair<Charge, Charge>> created;
+        const size_t first_task = tasks.size();
         for (size_t e = mpo.col_begin(b2); e < mpo.col_end(b2); ++e) {
             size_t b1 = mpo.row_of(e);
             DualIndex const& T = t_basis[b1];
@@ -984,8 +987,13 @@ private:
                         if (!su2::triangle(spin(out_r), ap, spin(out_l))) continue;
                         if (!out_left_i.has(out_l)) continue;
                         int32_t r_size = (int32_t)right_i[rb].second;
-                        if (!ret.has(out_l, out_r)) ret.insert(QnBlock(out_l, out_r, out_left_i.size_of_block(out_l), r_size));
+                        auto ins = seen.emplace(std::make_pair(out_l, out_r), created.size());
+                        if (ins.second) {
+                            created.push_back(ins.first->first);
+                            if (!ret.has(out_l, out_r)) ret.insert(QnBlock(out_l, out_r, out_left_i.size_of_block(out_l), r_size));
+                        }
                         if (structure_only) continue;
+                        const size_t cid = ins.first->second;
                         int i = spin(lc), ip = spin(out_l), j = spin(mc), jp = spin(out_r);
                         int two_sp = std::abs(i - ip), two_s = std::abs(j - jp);
                         double couplings[4];
@@ -998,7 +1006,7 @@ private:
                             if (en.row_spin == 2 && en.col_spin == 2) cn = 3; else if (en.row_spin == 2) cn = 1; else if (en.col_spin == 2) cn = 2;
                             double alfa = en.coefficient * couplings[cn];
                             if (alfa == 0.0) continue;
-                            raws.push_back(Raw{out_l, out_r, out_off + (int32_t)en.col * l_size, l_size, r_size, b1, tb, in_off + (int32_t)en.row * r_size, alfa});
+                            tasks.push_back(YTask{cid, out_off + (int32_t)en.col * l_size, 0, l_size, r_size, b1, tb, 0, in_off + (int32_t)en.row * r_size, alfa});
                             used = true;
                         }
                     }
@@ -1006,8 +1014,9 @@ private:
             }
             if (used) t_rows.push_back(b1);
         }
-        for (auto const& r : raws)
-            tasks.push_back(YTask{ret.position(r.ol, r.orc), r.dst_row, 0, r.rows, r.cols, r.b1, r.tb, 0, r.src_col, r.coef});
+        std::vector<size_t> final_pos(created.size());
+        for (size_t c = 0; c < created.size(); ++c) final_pos[c] = ret.position(created[c].first, created[c].second);
+        for (size_t t = first_task; t < tasks.size(); ++t) tasks[t].o = final_pos[tasks[t].o];
     }
 
     // ---- step 2 structure, abelian rbtm (abelian/apply_op.hpp:141-250)
