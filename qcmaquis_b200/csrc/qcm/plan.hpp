@@ -1078,9 +1078,10 @@ private:
                            ProductBasis const& in_left_pb, ProductBasis const& out_right_pb,
                            DualIndex& ret, std::vector<YTask>& tasks, std::vector<size_t>& t_cols)
     {
-        struct Raw { Charge ol, orc; int32_t dst_col, rows, cols; size_t b2, tb; int32_t src_row; double coef; };
-        std::vector<Raw> raws;
-        std::map<std::pair<Charge, Charge>, int32_t> first_l_size;   // task_capsule map order decides block creation
+        // task_capsule map order decides block creation; value: (row size of the first task, creation number).  A task
+        // first carries the creation number of its block and gets the block's final position at the end.
+        std::map<std::pair<Charge, Charge>, std::pair<int32_t, size_t>> first_l_size;
+        const size_t first_task = tasks.size();
         for (size_t b2 : mpo.row(b1)) {
             DualIndex const& T = t_basis[b2];
             bool used = false;
@@ -1101,9 +1102,8 @@ private:
                         if (!out_right_i.has(out_r)) continue;
                         int32_t l_size = (int32_t)left_i[lb].second;
                         if (structure_only) {
-                            auto key = std::make_pair(out_l, out_r);
-                            if (!first_l_size.count(key)) first_l_size[key] = -1;
-                            if (W.sparse_ptr[w + 1] > W.sparse_ptr[w] && first_l_size[key] < 0) first_l_size[key] = l_size;
+                            auto it = first_l_size.emplace(std::make_pair(out_l, out_r), std::make_pair((int32_t)-1, first_l_size.size())).first;
+                            if (W.sparse_ptr[w + 1] > W.sparse_ptr[w] && it->second.first < 0) it->second.first = l_size;
                             continue;
                         }
                         int i = spin(out_r), ip = spin(rc), j = spin(out_l), jp = spin(mc);
@@ -1113,14 +1113,15 @@ private:
                         int32_t in_off = (int32_t)in_left_pb(phys_in, out_l), out_off = (int32_t)out_right_pb(phys_out, rc);
                         int32_t r_size = (int32_t)T[tb].rs;
                         // the reference creates the map entry before looking at the operator entries (apply_op.hpp:170)
-                        if (!first_l_size.count(std::make_pair(out_l, out_r))) first_l_size[std::make_pair(out_l, out_r)] = -1;
+                        auto it = first_l_size.emplace(std::make_pair(out_l, out_r), std::make_pair((int32_t)-1, first_l_size.size())).first;
                         for (int s = W.sparse_ptr[w]; s < W.sparse_ptr[w + 1]; ++s) {
                             SparseEntry const& en = W.sparse[s];
                             int cn = 0;
                             if (en.row_spin == 2 && en.col_spin == 2) cn = 3; else if (en.row_spin == 2) cn = 1; else if (en.col_spin == 2) cn = 2;
                             double alfa = en.coefficient * couplings[cn];
-                            if (first_l_size[std::make_pair(out_l, out_r)] < 0) first_l_size[std::make_pair(out_l, out_r)] = l_size;
-                            raws.push_back(Raw{out_l, out_r, out_off + (int32_t)en.col * r_size, l_size, r_size, b2, tb, in_off + (int32_t)en.row * l_size, alfa});
+                            if (it->second.first < 0) it->second.first = l_size;
+                            if (alfa != 0.0)
+                                tasks.push_back(YTask{it->second.second, 0, out_off + (int32_t)en.col * r_size, l_size, r_size, b2, tb, in_off + (int32_t)en.row * l_size, 0, alfa});
                             used = true;
                         }
                     }
@@ -1129,13 +1130,12 @@ private:
             if (used) t_cols.push_back(b2);
         }
         for (auto const& kv : first_l_size) {
-            if (kv.second < 0) continue;   // "if (otasks.size() == 0) continue"
-            ret.insert(QnBlock(kv.first.first, kv.first.second, (size_t)kv.second, out_right_i.size_of_block(kv.first.second)));
+            if (kv.second.first < 0) continue;   // "if (otasks.size() == 0) continue"
+            ret.insert(QnBlock(kv.first.first, kv.first.second, (size_t)kv.second.first, out_right_i.size_of_block(kv.first.second)));
         }
-        for (auto const& r : raws) {
-            if (r.coef == 0.0) continue;
-            tasks.push_back(YTask{ret.position(r.ol, r.orc), 0, r.dst_col, r.rows, r.cols, r.b2, r.tb, r.src_row, 0, r.coef});
-        }
+        std::vector<size_t> final_pos(first_l_size.size(), 0);
+        for (auto const& kv : first_l_size) if (kv.second.first >= 0) final_pos[kv.second.second] = ret.position(kv.first.first, kv.first.second);
+        for (size_t t = first_task; t < tasks.size(); ++t) tasks[t].o = final_pos[tasks[t].o];
     }
 
     // W-application contributions grouped by destination panel.  Sources that reach the same panel through several
