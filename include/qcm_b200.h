@@ -83,6 +83,9 @@ typedef struct {
     int64_t elems[QCM_BUF_COUNT];    /* required size (elements) of every slot; inputs are checked, workspaces grown */
     double flops;                    /* algorithmic FLOPs of one execution (schedule-derived) */
     int64_t bytes;                   /* algorithmic bytes of one execution */
+    int32_t rank, world;             /* the sharding this plan was built for: world <= 1 means "the whole contraction" (no
+                                        collective is issued for it); world > 1 must equal the communicator's size, the
+                                        partial results are then summed inside the call */
 } qcm_plan_desc;
 
 typedef struct qcm_array_s* qcm_array_t;   /* a device-resident FP64 array */

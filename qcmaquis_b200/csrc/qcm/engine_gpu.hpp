@@ -99,8 +99,8 @@ public:
                                              std::shared_ptr<DeviceBoundary> const& dr, MPOTensor const& mpo, bool isHermitian = true)
     {
         ket_tensor.make_left_paired();
-        PlanKey key{&mpo, dl->structure_hash(), dr->structure_hash(), structure_hash(ket_tensor), isHermitian ? 0 : 3};
-        for (auto& e : cache) if (e.first == key) { ++cache_hits; return e.second; }
+        PlanKey key{mpo.uid(), dl->structure_hash(), dr->structure_hash(), structure_hash(ket_tensor), isHermitian ? 0 : 3};
+        if (std::shared_ptr<CompiledPlan> hit = lookup(key, [&](Witness const& w) { return w.matches(dl->layout, dr->layout, ket_tensor, ket_tensor); })) { ++cache_hits; return hit; }
         ++cache_misses;
         Clock c0;
         plan::Planner planner(symm, mpo, isHermitian, rank, world, budget);
@@ -108,7 +108,7 @@ public:
         seconds[0] += c0.lap();
         std::shared_ptr<CompiledPlan> cp = compile(P, dl->layout.total, dr->layout.total);
         seconds[1] += c0.lap();
-        remember(key, cp);
+        remember(key, Witness(dl->layout, dr->layout, ket_tensor, ket_tensor), cp);
         return cp;
     }
 
@@ -128,9 +128,9 @@ public:
         Clock c0;
         const int64_t n = cp->ket_elems;
         const size_t need = 2 * (size_t)max_iter + 3;
-        if (vec_pool_n < n) { for (auto a : vec_pool) qcm_array_free(a); vec_pool.clear(); vec_pool_n = 0; }
-        while (vec_pool.size() < need) { qcm_array_t a = nullptr; qcm_check(qcm_array_alloc(n, &a), "qcm_array_alloc"); vec_pool.push_back(a); }
-        vec_pool_n = std::max(vec_pool_n, n);
+        // every pool entry holds vec_pool_n elements: a larger site rebuilds the pool, a smaller one reuses it
+        if (vec_pool_n < n) { for (auto a : vec_pool) qcm_array_free(a); vec_pool.clear(); vec_pool_n = n; }
+        while (vec_pool.size() < need) { qcm_array_t a = nullptr; qcm_check(qcm_array_alloc(vec_pool_n, &a), "qcm_array_alloc"); vec_pool.push_back(a); }
         auto V = [&](int i) { return vec_pool[(size_t)i]; };
         auto VA = [&](int i) { return vec_pool[(size_t)max_iter + 1 + (size_t)i]; };
         qcm_array_t u = vec_pool[2 * (size_t)max_iter + 1], r = vec_pool[2 * (size_t)max_iter + 2];
@@ -282,11 +282,36 @@ private:
         std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
         double lap() { auto n = std::chrono::steady_clock::now(); double s = std::chrono::duration<double>(n - t).count(); t = n; return s; }
     };
-    // (MPO tensor, structure of the boundaries, structure of the site tensor(s), kind): everything a plan depends on
+    // (MPO content id, structure of the boundaries, structure of the site tensor(s), kind): everything a plan depends on.
+    // The hashes only select the candidate; a hit is confirmed by comparing the full block structures (Witness).
     struct PlanKey
     {
-        const void* mpo; uint64_t a, b, h; int kind;
+        uint64_t mpo; uint64_t a, b, h; int kind;
         bool operator==(PlanKey const& o) const { return mpo == o.mpo && a == o.a && b == o.b && h == o.h && kind == o.kind; }
+    };
+    struct Witness
+    {
+        std::vector<DualIndex> b0, b1;     // block structure of every bond entry of the boundary operand(s)
+        Index phys[2], li[2], ri[2]; DualIndex t[2];
+        Witness() {}
+        Witness(plan::BoundaryLayout const& x, plan::BoundaryLayout const& y, MPSTensor const& bra, MPSTensor const& ket)
+        {
+            for (auto const& l : x.b) b0.push_back(l.basis);
+            for (auto const& l : y.b) b1.push_back(l.basis);
+            set(0, bra); set(1, ket);
+        }
+        void set(int i, MPSTensor const& m) { phys[i] = m.site_dim(); li[i] = m.row_dim(); ri[i] = m.col_dim(); t[i] = m.data().basis(); }
+        static bool same(std::vector<DualIndex> const& v, plan::BoundaryLayout const& l)
+        {
+            if (v.size() != l.b.size()) return false;
+            for (size_t k = 0; k < v.size(); ++k) if (!(v[k] == l.b[k].basis)) return false;
+            return true;
+        }
+        bool same_tensor(int i, MPSTensor const& m) const { return phys[i] == m.site_dim() && li[i] == m.row_dim() && ri[i] == m.col_dim() && t[i] == m.data().basis(); }
+        bool matches(plan::BoundaryLayout const& x, plan::BoundaryLayout const& y, MPSTensor const& bra, MPSTensor const& ket) const
+        {
+            return same(b0, x) && same(b1, y) && same_tensor(0, bra) && same_tensor(1, ket);
+        }
     };
 
     Boundary boundary_step(int kind, MPSTensor const& bra_tensor, MPSTensor const& ket_tensor, Boundary const& in, MPOTensor const& mpo, bool isHermitian)
@@ -294,9 +319,9 @@ private:
         bra_tensor.make_left_paired(); ket_tensor.make_left_paired();
         std::shared_ptr<DeviceBoundary> din = mirror(in);
         Clock c0;
-        PlanKey key{&mpo, din->structure_hash(), structure_hash(bra_tensor), structure_hash(ket_tensor), (isHermitian ? 0 : 3) + kind};
-        std::shared_ptr<CompiledPlan> cp;
-        for (auto& e : cache) if (e.first == key) { cp = e.second; break; }
+        PlanKey key{mpo.uid(), din->structure_hash(), structure_hash(bra_tensor), structure_hash(ket_tensor), (isHermitian ? 0 : 3) + kind};
+        static const plan::BoundaryLayout no_boundary;
+        std::shared_ptr<CompiledPlan> cp = lookup(key, [&](Witness const& w) { return w.matches(din->layout, no_boundary, bra_tensor, ket_tensor); });
         if (!cp) {
             plan::Planner planner(symm, mpo, isHermitian, rank, world, budget);
             plan::Plan P = kind == 1 ? planner.plan_left_step(desc_of(bra_tensor), desc_of(ket_tensor), din->layout)
@@ -304,7 +329,7 @@ private:
             seconds[0] += c0.lap();
             cp = compile(P, kind == 1 ? din->layout.total : 0, kind == 2 ? din->layout.total : 0);
             seconds[1] += c0.lap();
-            remember(key, cp);
+            remember(key, Witness(din->layout, no_boundary, bra_tensor, ket_tensor), cp);
         }
         last = cp;
         std::shared_ptr<DeviceBoundary> dout(new DeviceBoundary());
@@ -379,6 +404,7 @@ private:
         d.elems[QCM_BUF_T] = P.t_elems_max; d.elems[QCM_BUF_TP] = P.tp_elems; d.elems[QCM_BUF_Y] = P.y_elems_max;
         d.elems[QCM_BUF_OUT] = out_elems; d.elems[QCM_BUF_BRA_LP] = P.bra_lp_elems; d.elems[QCM_BUF_BRA_RP] = P.bra_rp_elems;
         d.flops = P.flops(); d.bytes = P.bytes_algorithmic;
+        d.rank = P.rank; d.world = P.world;
         std::shared_ptr<CompiledPlan> cp(new CompiledPlan());
         qcm_check(qcm_plan_create(&d, &cp->handle), "qcm_plan_create");
         cp->out_tensor = P.out_tensor; cp->out_boundary = P.out_boundary;
@@ -402,16 +428,22 @@ private:
         for (auto const& b : t.data().basis()) { mix((uint32_t)b.lc[0]); mix((uint32_t)b.lc[1]); mix((uint32_t)b.lc[2]); mix((uint32_t)b.rc[0]); mix((uint32_t)b.rc[1]); mix((uint32_t)b.rc[2]); mix(b.ls); mix(b.rs); }
         return h;
     }
-    void remember(PlanKey const& k, std::shared_ptr<CompiledPlan> const& cp)
+    struct CacheEntry { PlanKey key; Witness witness; std::shared_ptr<CompiledPlan> plan; };
+    template <class Confirm> std::shared_ptr<CompiledPlan> lookup(PlanKey const& k, Confirm confirm)
     {
-        cache.push_front(std::make_pair(k, cp));
+        for (auto& e : cache) if (e.key == k && confirm(e.witness)) return e.plan;
+        return std::shared_ptr<CompiledPlan>();
+    }
+    void remember(PlanKey const& k, Witness w, std::shared_ptr<CompiledPlan> const& cp)
+    {
+        cache.push_front(CacheEntry{k, std::move(w), cp});
         while (cache.size() > cache_capacity) cache.pop_back();
     }
 
     SymmKind symm;
     int rank, world;
     int64_t budget;
-    std::list<std::pair<PlanKey, std::shared_ptr<CompiledPlan>>> cache;
+    std::list<CacheEntry> cache;
     size_t cache_capacity = 4;
     std::vector<qcm_array_t> vec_pool; int64_t vec_pool_n = 0;      // solver vectors, reused from site to site
     std::shared_ptr<CompiledPlan> last;

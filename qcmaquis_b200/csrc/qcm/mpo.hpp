@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include "site_operator.hpp"
 #include <array>
+#include <atomic>
 #include <numeric>
 #include <set>
 
@@ -46,12 +47,12 @@ class MPOTensor
 public:
     typedef std::vector<std::pair<tag_type, double>> terms_type;
 
-    MPOTensor() : herm_info(1, 1) {}
+    MPOTensor() : herm_info(1, 1), uid_(next_uid()) {}
     // mpotensor.hpp:10-65
     MPOTensor(size_t ld, size_t rd, std::vector<PreTerm> tags, std::shared_ptr<OPTable> tbl, Hermitian h,
               std::vector<SpinDescriptor> lspins, std::vector<SpinDescriptor> rspins, bool su2)
         : herm_info(ld, rd), left_i(ld), right_i(rd), left_spins(std::move(lspins)), right_spins(std::move(rspins)),
-          operator_table(std::move(tbl))
+          operator_table(std::move(tbl)), uid_(next_uid())
     {
         row_index.resize(ld);
         col_ptr.assign(rd + 1, 0);
@@ -110,6 +111,9 @@ public:
     size_t num_one_cols() const { return num_one_cols_; }
     size_t nnz() const { return row_idx.size(); }
     Hermitian herm_info;
+    // identity of the tensor's CONTENT: every constructed tensor gets a fresh number, copies keep it.  Plans bake the MPO
+    // coefficients in, so plan caches key on this, never on the object's address.
+    uint64_t uid() const { return uid_; }
 
 private:
     size_t left_i = 1, right_i = 1;
@@ -120,6 +124,8 @@ private:
     std::vector<terms_type> terms;
     std::vector<std::set<size_t>> row_index;
     std::shared_ptr<OPTable> operator_table;
+    uint64_t uid_ = 0;
+    static uint64_t next_uid() { static std::atomic<uint64_t> n{1}; return n.fetch_add(1); }
 };
 
 struct MPO : public std::vector<MPOTensor>

@@ -114,7 +114,8 @@ struct BoundaryLayout
 
 struct Plan
 {
-    int kind = 0;                          // 0 sigma, 1 left step, 2 right step
+    int kind = 0;                          // 0 sigma, 1 left step, 2 right step, 3 diagonal_hamiltonian
+    int rank = 0, world = 1;               // the shard this plan computes (world 1: the whole contraction)
     std::vector<CopyTask> pre_copies;      // pairing reshapes of ket / bra
     GemmList persistent_t;                 // step 1 products of multi-use bonds -> BUF_TP
     std::vector<Wave> waves;
@@ -171,7 +172,7 @@ public:
     // sigma = H_eff psi    (abelian/site_hamil.hpp:23-90, non-abelian/site_hamil.hpp:57-147)
     Plan plan_sigma(TensorDesc const& ket, BoundaryLayout const& left, BoundaryLayout const& right)
     {
-        Plan P; P.kind = 0; P.accumulate_out = true;
+        Plan P; P.kind = 0; P.accumulate_out = true; P.rank = rank; P.world = world;
         TensorDesc const& bra = ket;
         Layout ket_lp; ket_lp.assign(ket.lp_basis);
         Layout ket_rp = plan_left_to_right(ket, ket_lp, BUF_KET_LP, BUF_KET_RP, P.pre_copies);
@@ -306,7 +307,7 @@ public:
     // L'[b2] = Y[b2]^T conj(bra)      (common/move_boundary.hpp:128-187)
     Plan plan_left_step(TensorDesc const& bra, TensorDesc const& ket, BoundaryLayout const& left)
     {
-        Plan P; P.kind = 1; P.accumulate_out = false;
+        Plan P; P.kind = 1; P.accumulate_out = false; P.rank = rank; P.world = world;
         Layout ket_lp; ket_lp.assign(ket.lp_basis);
         Layout ket_rp = plan_left_to_right(ket, ket_lp, BUF_KET_LP, BUF_KET_RP, P.pre_copies);
         Layout bra_lp; bra_lp.assign(bra.lp_basis);
@@ -422,7 +423,7 @@ public:
     // R'[b1] = Y'[b1] conj(bra)^T     (common/move_boundary.hpp:189-229)
     Plan plan_right_step(TensorDesc const& bra, TensorDesc const& ket, BoundaryLayout const& right)
     {
-        Plan P; P.kind = 2; P.accumulate_out = false;
+        Plan P; P.kind = 2; P.accumulate_out = false; P.rank = rank; P.world = world;
         Layout ket_lp; ket_lp.assign(ket.lp_basis);
         Layout bra_lp; bra_lp.assign(bra.lp_basis);
         Layout bra_rp = plan_left_to_right(bra, bra_lp, BUF_BRA_LP, BUF_BRA_RP, P.pre_copies);

@@ -176,6 +176,7 @@ struct WaveDev { GemmGroup t, c; AxpyGroup w; int64_t y_elems = 0, t_elems = 0; 
 struct qcm_plan_s
 {
     int kind = 0;
+    int rank = 0, world = 1;          // sharding the plan was built for (checked against the communicator at execution)
     DCopy* d_copies = nullptr; int64_t n_copies = 0;
     GemmGroup p;
     std::vector<WaveDev> waves;
@@ -451,7 +452,8 @@ static int build_gemm_group(qcm_plan_s* P, GemmGroup& g, const qcm_gemm_out* out
             int csum = 0, cb = out.seg_begin;
             for (int s = out.seg_begin; s < out.seg_end; ++s) {
                 csum += (segs[s].k + KC - 1) / KC;
-                if (csum >= max_chunks && s + 1 < out.seg_end) { chunks.push_back(std::make_pair(cb, s + 1)); cb = s + 1; csum = 0; }
+                // only accumulating outputs are split: a store-mode output (step-1 products) runs its whole K list in one work item
+                if (base_mode == 1 && csum >= max_chunks && s + 1 < out.seg_end) { chunks.push_back(std::make_pair(cb, s + 1)); cb = s + 1; csum = 0; }
             }
             chunks.push_back(std::make_pair(cb, out.seg_end));
         }
@@ -459,7 +461,6 @@ static int build_gemm_group(qcm_plan_s* P, GemmGroup& g, const qcm_gemm_out* out
         for (int s = out.seg_begin; s < out.seg_end; ++s) total_chunks += (segs[s].k + KC - 1) / KC;
         const int avg_chunks = std::max(1, total_chunks / (int)chunks.size());
         int mode = chunks.size() > 1 ? 2 : base_mode;
-        if (chunks.size() > 1 && base_mode == 0) return fail("internal: split-K on a store-mode output");
         std::vector<std::pair<int, int>> rows, cols;
         cut_dimension(out.m, avg_chunks, rows);
         cut_dimension(out.n, avg_chunks, cols);
@@ -593,6 +594,8 @@ extern "C" int qcm_plan_create(const qcm_plan_desc* d, qcm_plan_t* out)
     if (!d || !out) return fail("qcm_plan_create: null argument");
     qcm_plan_s* P = new qcm_plan_s();
     P->kind = d->kind; P->flops = d->flops; P->bytes = d->bytes;
+    P->world = d->world > 1 ? d->world : 1; P->rank = d->world > 1 ? d->rank : 0;
+    if (P->rank < 0 || P->rank >= P->world) { delete P; return fail("qcm_plan_create: rank outside [0, world)"); }
     for (int i = 0; i < QCM_BUF_COUNT; ++i) P->elems[i] = d->elems[i];
     auto bail = [&]() { for (void* p : P->allocs) cudaFree(p); delete P; return 1; };
     {
@@ -714,18 +717,28 @@ static int check_arr(qcm_array_t a, int64_t need, const char* what)
 }
 
 static int allreduce_ptr(double* p, int64_t n);
+// a plan sharded over `world` ranks produces a partial result: it may only run under a communicator of that shape
+static int check_sharding(qcm_plan_s const* P)
+{
+    if (P->world <= 1) return 0;
+    if (P->world != G.world || P->rank != G.rank)
+        return fail("plan was built for rank " + std::to_string(P->rank) + " of " + std::to_string(P->world) + " but the communicator is rank " +
+                    std::to_string(G.rank) + " of " + std::to_string(G.world) + " (qcm_comm_init)");
+    return 0;
+}
 
 extern "C" int qcm_site_hamil2_dev(qcm_plan_t P, qcm_array_t left, qcm_array_t right, qcm_array_t psi, qcm_array_t sigma)
 {
     CHECK_INIT();
     if (!P || P->kind != 0) return fail("qcm_site_hamil2: plan is not a sigma plan");
+    if (check_sharding(P)) return 1;
     if (check_arr(left, P->elems[QCM_BUF_LEFT], "left boundary") || check_arr(right, P->elems[QCM_BUF_RIGHT], "right boundary") ||
         check_arr(psi, P->elems[QCM_BUF_KET_LP], "psi") || check_arr(sigma, P->elems[QCM_BUF_OUT], "sigma")) return 1;
     BufTable b; memset(&b, 0, sizeof(b));
     b.p[QCM_BUF_LEFT] = left->p; b.p[QCM_BUF_RIGHT] = right->p; b.p[QCM_BUF_KET_LP] = psi->p; b.p[QCM_BUF_OUT] = sigma->p;
     if (P->elems[QCM_BUF_OUT]) CU(cudaMemsetAsync(sigma->p, 0, (size_t)P->elems[QCM_BUF_OUT] * 8, G.stream));
     if (execute(P, b)) return 1;
-    if (G.world > 1) return allreduce_ptr(sigma->p, P->elems[QCM_BUF_OUT]);
+    if (P->world > 1) return allreduce_ptr(sigma->p, P->elems[QCM_BUF_OUT]);
     return 0;
 }
 
@@ -747,6 +760,7 @@ extern "C" int qcm_boundary_step(qcm_plan_t P, qcm_array_t in, const double* bra
     CHECK_INIT();
     if (!P || (P->kind != 1 && P->kind != 2)) return fail("qcm_boundary_step: plan is not a boundary plan");
     int in_slot = P->kind == 1 ? QCM_BUF_LEFT : QCM_BUF_RIGHT;
+    if (check_sharding(P)) return 1;
     if (check_arr(in, P->elems[in_slot], "input boundary") || check_arr(out, P->elems[QCM_BUF_OUT], "output boundary")) return 1;
     if (ensure_ws(QCM_BUF_KET_LP, P->elems[QCM_BUF_KET_LP]) || ensure_ws(QCM_BUF_BRA_LP, P->elems[QCM_BUF_BRA_LP])) return 1;
     if (P->elems[QCM_BUF_KET_LP]) CU(cudaMemcpyAsync(G.ws[QCM_BUF_KET_LP], ket, (size_t)P->elems[QCM_BUF_KET_LP] * 8, cudaMemcpyHostToDevice, G.stream));
@@ -756,7 +770,7 @@ extern "C" int qcm_boundary_step(qcm_plan_t P, qcm_array_t in, const double* bra
     if (out->n) CU(cudaMemsetAsync(out->p, 0, (size_t)out->n * 8, G.stream));
     if (execute(P, b)) return 1;
     // every rank computed its share of the output bond indices into a zeroed array: the sum is the full boundary
-    if (G.world > 1 && allreduce_ptr(out->p, P->elems[QCM_BUF_OUT])) return 1;
+    if (P->world > 1 && allreduce_ptr(out->p, P->elems[QCM_BUF_OUT])) return 1;
     CU(cudaStreamSynchronize(G.stream));
     return 0;
 }

@@ -78,8 +78,15 @@ def built():
 
 
 @pytest.fixture(scope="session")
-def harness_cpu(built):
-    return Harness(ctypes.CDLL(built["harness"][0]))
+def harness_cpu_path():
+    """the CPU harness (oracle + plan interpreter) needs g++ and OpenBLAS only -- no CUDA toolkit"""
+    from qcmaquis_b200 import build
+    return build.build_harness(gpu=False)[0]
+
+
+@pytest.fixture(scope="session")
+def harness_cpu(harness_cpu_path):
+    return Harness(ctypes.CDLL(harness_cpu_path))
 
 
 @pytest.fixture(scope="session")

@@ -32,11 +32,11 @@ def _worker(rank, world, port, libpath, symm, q):
 
 
 @pytest.mark.parametrize("symm", ["su2u1", "2u1"])
-def test_two_rank_sharded_sigma(built, symm):
+def test_two_rank_sharded_sigma(harness_cpu_path, symm):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
     q = ctx.SimpleQueue()
-    mp.spawn(_worker, args=(2, port, built["harness"][0], symm, q), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, harness_cpu_path, symm, q), nprocs=2, join=True)
     same_size, rel_sum, rel_part = q.get()
     assert same_size
     assert rel_sum < 1e-12          # allreduced sigma == oracle sigma
