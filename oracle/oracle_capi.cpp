@@ -112,3 +112,25 @@ extern "C" int orc_ts_sweeps(void* h, int M0, int Mmax, int nsweeps, unsigned se
         return 0;
     } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
 }
+
+// the synthetic-start two-site sweeps of qcmd_ts_sweeps_synth (driver_capi.cpp) on the CPU oracle: same starting state
+// (make_synthetic_mps), same driver, same parameters
+extern "C" int orc_ts_sweeps_synth(void* h, int M, int nsweeps, unsigned seed, int max_micro, double* energies, int n_max, int* n_out, double* info, char* err, int errlen)
+{
+    try {
+        Orc* D = static_cast<Orc*>(h);
+        scipy_openblas_set_num_threads(1);
+        D->P.mps = make_synthetic_mps(D->P, (size_t)M, seed);
+        oracle::OracleEngine eng(D->P.symm());
+        ts::TsParams prm; prm.Mmax = (size_t)M; prm.drop_stale = true; prm.max_micro_iterations = max_micro;
+        std::vector<size_t> dims;
+        sweep::SweepLog log = ts::ts_sweeps(D->P.symm(), eng, D->P.mpo, [&](int p) -> MPOTensor const& { return D->P.twosite_mpo(p); }, D->P.mps, nsweeps, prm, &dims);
+        int n = (int)std::min<size_t>(log.energies.size(), (size_t)n_max);
+        for (int i = 0; i < n; ++i) energies[i] = log.energies[i];
+        *n_out = n;
+        double secs = 0; for (double s : log.sweep_seconds) secs += s;
+        info[0] = (double)log.total_sigma; info[1] = secs; info[2] = log.energies.empty() ? 0. : log.energies.back();
+        info[3] = dims.empty() ? 0. : (double)*std::max_element(dims.begin(), dims.end());
+        return 0;
+    } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
+}

@@ -221,3 +221,41 @@ extern "C" int qcmd_ts_sweeps_ranked(void* h, int M0, int Mmax, int nsweeps, uns
         return 0;
     } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
 }
+
+// BASELINE.json's sweep-level metric at the large configurations: two-site DMRG sweeps (ts_optimize.hpp:60-270, svd
+// truncation to M, Jacobi-Davidson with the reference's defaults) started from a random MPS on the synthetic sector
+// lists (total bond dimension M at every bond, scenarios.hpp make_synthetic_mps), boundaries resident in HBM, stale
+// boundaries dropped.  world > 1: every rank drives the same deterministic host loop, the engine calls are collective.
+// max_micro > 0 bounds the LAST sweep to that many micro-iterations (for bounded measurement runs).
+// info: [0] sigma evaluations [1] seconds of all sweeps [2] last energy [3] largest bond dimension kept
+//       [4..8] driver seconds: two-site tensor, two-site MPO, eigensolver, split, boundary step
+//       [9..13] engine seconds: planning, plan upload, sigma calls (device solver incl.), boundary calls, flatten/unflatten
+//       [14] plan-cache hits [15] misses [16] sum of sigma FLOPs (this rank's share) [17] sum of boundary-step FLOPs
+//       [18] seconds before the first sweep (canonisation + initial right boundaries) [19] micro-iterations
+//       [20] seconds of the last sweep
+extern "C" int qcmd_ts_sweeps_synth(void* h, int M, int nsweeps, unsigned seed, int device, int rank, int world, int max_micro, double* energies, int n_max,
+                                    int* n_out, double* info, char* err, int errlen)
+{
+    try {
+        Driver* D = static_cast<Driver*>(h);
+        auto t0 = std::chrono::steady_clock::now();
+        D->P.mps = make_synthetic_mps(D->P, (size_t)M, seed);
+        GpuEngine eng(D->P.symm(), device, rank, world);
+        eng.set_cache_capacity(4);
+        ts::TsParams prm; prm.Mmax = (size_t)M; prm.drop_stale = true; prm.max_micro_iterations = max_micro;
+        std::vector<size_t> dims;
+        double init_s = 0;
+        sweep::SweepLog log = ts::ts_sweeps(D->P.symm(), eng, D->P.mpo, [&](int p) -> MPOTensor const& { return D->P.twosite_mpo(p); }, D->P.mps, nsweeps, prm, &dims, &init_s);
+        (void)t0;
+        int n = (int)std::min<size_t>(log.energies.size(), (size_t)n_max);
+        for (int i = 0; i < n; ++i) energies[i] = log.energies[i];
+        *n_out = n;
+        double secs = 0; for (double s : log.sweep_seconds) secs += s;
+        info[0] = (double)log.total_sigma; info[1] = secs; info[2] = log.energies.empty() ? 0. : log.energies.back();
+        info[3] = dims.empty() ? 0. : (double)*std::max_element(dims.begin(), dims.end());
+        for (int i = 0; i < 5; ++i) { info[4 + i] = log.phase_seconds[i]; info[9 + i] = eng.seconds[i]; }
+        info[14] = (double)eng.cache_hits; info[15] = (double)eng.cache_misses; info[16] = eng.sigma_flops; info[17] = eng.boundary_flops;
+        info[18] = init_s; info[19] = (double)log.energies.size(); info[20] = log.sweep_seconds.empty() ? 0. : log.sweep_seconds.back();
+        return 0;
+    } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
+}

@@ -89,6 +89,7 @@ public:
         std::vector<double> psi = flatten(ket_tensor.data(), cp->ket_elems), sigma((size_t)cp->out_elems);
         seconds[4] += c0.lap();
         qcm_check(qcm_site_hamil2(cp->handle, dl->arr, dr->arr, psi.data(), sigma.data()), "qcm_site_hamil2");
+        sigma_flops += cp->flops; ++n_sigma_calls;
         seconds[2] += c0.lap();
         MPSTensor r(ket_tensor.site_dim(), ket_tensor.row_dim(), ket_tensor.col_dim(), unflatten(cp->out_tensor, sigma), LeftPaired, true);
         seconds[4] += c0.lap();
@@ -154,7 +155,7 @@ public:
                 for (int i = 0; i < it; ++i) axpy(-dot(V(i), t), V(i), t);
             scal(1. / std::sqrt(dot(t, t)), t);
             qcm_check(qcm_site_hamil2_dev(cp->handle, dl->arr, dr->arr, t, VA(it)), "qcm_site_hamil2_dev");
-            res.n_sigma++;
+            res.n_sigma++; sigma_flops += cp->flops; ++n_sigma_calls;
             for (int i = 0; i <= it; ++i) M[(size_t)i + (size_t)it * max_iter] = dot(V(i), VA(it));
             const int dim = it + 1;
             std::vector<double> A((size_t)dim * dim), w(dim), work(std::max(1, 3 * dim));
@@ -251,6 +252,9 @@ public:
     // host-side time spent in this engine, by kind (seconds): [0] planning (Planner) [1] plan upload (qcm_plan_create)
     // [2] sigma calls (H2D + kernels + D2H) [3] boundary-step calls [4] flatten / unflatten
     double seconds[5] = {0, 0, 0, 0, 0};
+    // algorithmic FLOPs (schedule-derived, this rank's share) of the sigma evaluations / boundary steps executed so far
+    double sigma_flops = 0, boundary_flops = 0;
+    size_t n_sigma_calls = 0, n_boundary_calls = 0;
     std::shared_ptr<CompiledPlan> last_plan() const { return last; }
 
     static std::vector<double> flatten(block_matrix const& m, int64_t expect)
@@ -338,6 +342,7 @@ private:
         std::vector<double> bra = flatten(bra_tensor.data(), cp->bra_elems), ket = flatten(ket_tensor.data(), cp->ket_elems);
         seconds[4] += c0.lap();
         qcm_check(qcm_boundary_step(cp->handle, din->arr, bra.data(), ket.data(), dout->arr), "qcm_boundary_step");
+        boundary_flops += cp->flops; ++n_boundary_calls;
         seconds[3] += c0.lap();
         Boundary ret; ret.resize(dout->layout.aux_dim());
         for (size_t b = 0; b < ret.aux_dim(); ++b) {

@@ -190,6 +190,7 @@ public:
 
         PhaseTimer pt;
         setup_t_left(P, left, ket_rp, indexForTrim);
+        if (su2_) build_lbtm_tables(ket_rp, physical_i, right_i, out_left_i, in_right_pb, out_left_pb);
         pt.lap("setup_t_left");
 
         // output structure: emulate the per-b2 products and their match_and_add_block reduction
@@ -325,6 +326,7 @@ public:
         ProductBasis in_right_pb(ket.phys_i, right_i, true);
 
         setup_t_left(P, left, ket_rp, braBasis);
+        if (su2_) build_lbtm_tables(ket_rp, ket.phys_i, right_i, out_left_i, in_right_pb, out_left_pb);
 
         size_t loop_max = mpo.col_dim();
         struct Pending { size_t b2; DualIndex y; std::vector<YTask> ytasks; std::vector<size_t> t_rows; DualIndex out; };
@@ -958,49 +960,125 @@ private:
     }
 
     // ---- step 2 structure, SU2 lbtm (non-abelian/apply_op.hpp:23-101)
-    void y_struct_su2_lbtm(size_t b2, Layout const& ket_rp, Index const& right_i, Index const& out_left_i,
-                           ProductBasis const& in_right_pb, ProductBasis const& out_left_pb,
+    // Everything the reference's inner loop looks up per (T block, W block) -- the position of the output sector in
+    // right_i / out_left_i, the product-basis offsets, the spins -- depends on the T block and ONE physical charge only.
+    // It is tabulated once per distinct T block structure (the bonds of one operator type share it) and per operator
+    // (positions of its block charges in the physical index), so that the loop over (bond, term, T block, W block) does
+    // two table reads instead of six hash / binary searches.
+    struct TbPhys { int32_t rb, r_size, in_off, ol_pos, out_off; int16_t jp, ip; };   // rb.., jp: phys as phys_in; ol_pos.., ip: phys as phys_out
+    struct TbInfo { int32_t l_size; int16_t i_spin, j_spin; std::vector<TbPhys> ph; };
+    void build_lbtm_tables(Layout const& ket_rp, Index const& physical_i, Index const& right_i, Index const& out_left_i,
+                           ProductBasis const& in_right_pb, ProductBasis const& out_left_pb)
+    {
+        const size_t B = t_basis.size(), np = physical_i.size();
+        // distinct T block structures
+        t_basis_id_.assign(B, 0);
+        std::vector<size_t> reps;
+        {
+            std::unordered_map<uint64_t, std::vector<uint32_t>> by_hash;
+            for (size_t b = 0; b < B; ++b) {
+                uint64_t h = 1469598103934665603ull;
+                for (auto const& q : t_basis[b]) for (uint64_t x : {(uint64_t)(uint32_t)q.lc[0], (uint64_t)(uint32_t)q.lc[1], (uint64_t)(uint32_t)q.lc[2], (uint64_t)(uint32_t)q.rc[0],
+                                                                    (uint64_t)(uint32_t)q.rc[1], (uint64_t)(uint32_t)q.rc[2], (uint64_t)q.ls, (uint64_t)q.rs}) { h ^= x; h *= 1099511628211ull; }
+                auto& cands = by_hash[h];
+                uint32_t id = (uint32_t)-1;
+                for (uint32_t c : cands) if (t_basis[reps[c]] == t_basis[b]) { id = c; break; }
+                if (id == (uint32_t)-1) { id = (uint32_t)reps.size(); reps.push_back(b); cands.push_back(id); }
+                t_basis_id_[b] = id;
+            }
+        }
+        tbinfo_.assign(reps.size(), std::vector<TbInfo>());
+#pragma omp parallel for schedule(dynamic, 4)
+        for (long q = 0; q < (long)reps.size(); ++q) {
+            DualIndex const& T = t_basis[reps[(size_t)q]];
+            std::vector<TbInfo>& out = tbinfo_[(size_t)q];
+            out.resize(T.size());
+            for (size_t tb = 0; tb < T.size(); ++tb) {
+                Charge lc = T[tb].lc, rc = T[tb].rc;
+                Charge mc = rc;   // ket right-paired blocks are charge-diagonal: mc == rc (site_hamil.hpp:85-89, apply_op.hpp:62-63)
+                { auto it = ket_rp.basis.left_lower_bound(rc); if (it != ket_rp.basis.end()) mc = it->lc; }
+                TbInfo& ti = out[tb];
+                ti.l_size = (int32_t)T[tb].ls; ti.i_spin = (int16_t)spin(lc); ti.j_spin = (int16_t)spin(mc);
+                ti.ph.resize(np);
+                for (size_t p = 0; p < np; ++p) {
+                    Charge ph = physical_i[p].first;
+                    TbPhys& x = ti.ph[p];
+                    Charge out_r = fuse(rc, ph), out_l = fuse(lc, ph);
+                    size_t rb = right_i.position(out_r);
+                    x.rb = rb == right_i.size() ? -1 : (int32_t)rb;
+                    x.r_size = x.rb < 0 ? 0 : (int32_t)right_i[rb].second;
+                    x.in_off = x.rb < 0 ? 0 : (int32_t)in_right_pb(ph, out_r);
+                    x.jp = (int16_t)spin(out_r);
+                    size_t ol = out_left_i.position(out_l);
+                    x.ol_pos = ol == out_left_i.size() ? -1 : (int32_t)ol;
+                    x.out_off = out_left_pb.has(ph, lc) ? (int32_t)out_left_pb(ph, lc) : 0;
+                    x.ip = (int16_t)spin(out_l);
+                }
+            }
+        }
+        // positions of every operator's block charges in the physical index
+        op_phys_.clear();
+        auto tbl = mpo.get_operator_table();
+        op_phys_.resize(tbl ? tbl->size() : 0);
+        std::vector<char> seen_tag(op_phys_.size(), 0);
+        for (size_t b2 = 0; b2 < mpo.col_dim(); ++b2)
+            for (size_t e = mpo.col_begin(b2); e < mpo.col_end(b2); ++e)
+                for (auto const& term : mpo.at_entry(e)) {
+                    if (seen_tag[term.first]) continue;
+                    seen_tag[term.first] = 1;
+                    SiteOperator const& W = mpo.op(term.first);
+                    auto& v = op_phys_[term.first];
+                    v.resize(W.basis().size());
+                    for (size_t w = 0; w < W.basis().size(); ++w) {
+                        size_t pi = physical_i.position(W.basis().left_charge(w)), po = physical_i.position(W.basis().right_charge(w));
+                        if (pi == physical_i.size() || po == physical_i.size()) throw std::runtime_error("plan: operator block outside the physical index of the site");
+                        v[w] = std::make_pair((int16_t)pi, (int16_t)po);
+                    }
+                }
+        lbtm_nr_ = right_i.size(); lbtm_nol_ = out_left_i.size();
+    }
+    void y_struct_su2_lbtm(size_t b2, Layout const& /*ket_rp*/, Index const& right_i, Index const& out_left_i,
+                           ProductBasis const& /*in_right_pb*/, ProductBasis const& /*out_left_pb*/,
                            DualIndex& ret, std::vector<YTask>& tasks, std::vector<size_t>& t_rows)
     {
         // Blocks are created lazily, in loop order, but sorted on insertion: a task first carries the creation number
-        // of its block (one hash lookup per (T block, W block) pair, not per operator entry) and gets the block's final
-        // position once the structure is complete.
-        std::unordered_map<std::pair<Charge, Charge>, size_t, ChargePairHash> seen;
-        std::vector<std::pair<Charge, Charge>> created;
+        // of its block and gets the block's final position once the structure is complete.
+        std::vector<int32_t> cid_of(lbtm_nol_ * lbtm_nr_, -1);
+        std::vector<std::pair<int32_t, int32_t>> created;      // (position in out_left_i, position in right_i)
         const size_t first_task = tasks.size();
+        const int ap = mpo.right_spin(b2).get();
         for (size_t e = mpo.col_begin(b2); e < mpo.col_end(b2); ++e) {
             size_t b1 = mpo.row_of(e);
-            DualIndex const& T = t_basis[b1];
+            std::vector<TbInfo> const& TI = tbinfo_[t_basis_id_[b1]];
+            const int a = mpo.left_spin(b1).get();
             bool used = false;
             for (auto const& term : mpo.at_entry(e)) {
                 SiteOperator const& W = mpo.op(term.first);
-                int a = mpo.left_spin(b1).get(), k = W.spin().get(), ap = mpo.right_spin(b2).get();
-                for (size_t tb = 0; tb < T.size(); ++tb) {
-                    Charge lc = T[tb].lc, rc = T[tb].rc;
-                    Charge mc = rc;   // ket right-paired blocks are charge-diagonal: mc == rc (site_hamil.hpp:85-89, apply_op.hpp:62-63)
-                    { auto it = ket_rp.basis.left_lower_bound(rc); if (it != ket_rp.basis.end()) mc = it->lc; }
-                    for (size_t w = 0; w < W.basis().size(); ++w) {
-                        Charge phys_in = W.basis().left_charge(w), phys_out = W.basis().right_charge(w);
-                        Charge out_r = fuse(rc, phys_in);
-                        size_t rb = right_i.position(out_r);
-                        if (rb == right_i.size()) continue;
-                        Charge out_l = fuse(lc, phys_out);
-                        if (!su2::triangle(spin(out_r), ap, spin(out_l))) continue;
-                        if (!out_left_i.has(out_l)) continue;
-                        int32_t r_size = (int32_t)right_i[rb].second;
-                        auto ins = seen.emplace(std::make_pair(out_l, out_r), created.size());
-                        if (ins.second) {
-                            created.push_back(ins.first->first);
-                            if (!ret.has(out_l, out_r)) ret.insert(QnBlock(out_l, out_r, out_left_i.size_of_block(out_l), r_size));
+                const int k = W.spin().get();
+                std::vector<std::pair<int16_t, int16_t>> const& oph = op_phys_[term.first];
+                const size_t nw = oph.size();
+                for (size_t tb = 0; tb < TI.size(); ++tb) {
+                    TbInfo const& ti = TI[tb];
+                    for (size_t w = 0; w < nw; ++w) {
+                        TbPhys const& qi = ti.ph[oph[w].first];
+                        if (qi.rb < 0) continue;
+                        TbPhys const& qo = ti.ph[oph[w].second];
+                        if (!su2::triangle(qi.jp, ap, qo.ip)) continue;
+                        if (qo.ol_pos < 0) continue;
+                        int32_t& cslot = cid_of[(size_t)qo.ol_pos * lbtm_nr_ + qi.rb];
+                        if (cslot < 0) {
+                            cslot = (int32_t)created.size();
+                            created.push_back(std::make_pair(qo.ol_pos, qi.rb));
+                            Charge out_l = out_left_i[qo.ol_pos].first, out_r = right_i[qi.rb].first;
+                            if (!ret.has(out_l, out_r)) ret.insert(QnBlock(out_l, out_r, out_left_i[qo.ol_pos].second, (size_t)qi.r_size));
                         }
                         if (structure_only) continue;
-                        const size_t cid = ins.first->second;
-                        int i = spin(lc), ip = spin(out_l), j = spin(mc), jp = spin(out_r);
-                        int two_sp = std::abs(i - ip), two_s = std::abs(j - jp);
+                        const size_t cid = (size_t)cslot;
+                        const int i = ti.i_spin, ip = qo.ip, j = ti.j_spin, jp = qi.jp;
+                        const int two_sp = std::abs(i - ip), two_s = std::abs(j - jp);
                         double couplings[4];
                         su2::set_coupling(j, two_s, jp, a, k, ap, i, two_sp, ip, term.second, couplings);
-                        int32_t in_off = (int32_t)in_right_pb(phys_in, out_r), out_off = (int32_t)out_left_pb(phys_out, lc);
-                        int32_t l_size = (int32_t)T[tb].ls;
+                        const int32_t in_off = qi.in_off, out_off = qo.out_off, l_size = ti.l_size, r_size = qi.r_size;
                         for (int s = W.sparse_ptr[w]; s < W.sparse_ptr[w + 1]; ++s) {
                             SparseEntry const& en = W.sparse[s];
                             int cn = 0;
@@ -1016,7 +1094,7 @@ private:
             if (used) t_rows.push_back(b1);
         }
         std::vector<size_t> final_pos(created.size());
-        for (size_t c = 0; c < created.size(); ++c) final_pos[c] = ret.position(created[c].first, created[c].second);
+        for (size_t c = 0; c < created.size(); ++c) final_pos[c] = ret.position(out_left_i[created[c].first].first, right_i[created[c].second].first);
         for (size_t t = first_task; t < tasks.size(); ++t) tasks[t].o = final_pos[tasks[t].o];
     }
 
@@ -1145,39 +1223,46 @@ private:
     struct Panel { size_t o; int32_t dst_row, dst_col, rows, cols; std::vector<PanelSrc> srcs; };
     struct PanelRef { Ref A; int32_t lda; double alpha; };
     struct PanelCounts { double flops_w = 0; size_t n_axpy = 0; };
-    // Tasks are grouped by destination panel with a hash map (the task lists of the high fan-in outputs hold millions
-    // of entries; sorting them dominated the planning time), the panels are then put in (block, column, row) order.
+    // Tasks are grouped by destination panel.  A panel is identified by (Y block, first row, first column); in both
+    // directions one of the two offsets is zero, so (block, row + column) addresses a flat table directly -- no hashing,
+    // no sorting of the task list (the lists of the high fan-in outputs hold millions of entries).  Sources are counted
+    // first and every panel's list is allocated once.  The panels are then put in (block, column, row) order.
     std::vector<Panel> collect_panels(PanelCounts& cnt, std::vector<YTask> const& tasks, std::map<size_t, Layout> const& tl) const
     {
-        struct Key
-        {
-            size_t o; int32_t dst_col, dst_row, rows, cols;
-            bool operator==(Key const& k) const { return o == k.o && dst_col == k.dst_col && dst_row == k.dst_row && rows == k.rows && cols == k.cols; }
-        };
-        struct KeyHash
-        {
-            size_t operator()(Key const& k) const
-            {
-                uint64_t h = k.o * 0x9E3779B97F4A7C15ull;
-                h ^= ((uint64_t)(uint32_t)k.dst_col << 32 | (uint32_t)k.dst_row) * 0xD6E8FEB86659FD93ull; h ^= h >> 29;
-                h ^= ((uint64_t)(uint32_t)k.rows << 32 | (uint32_t)k.cols) * 0xC2B2AE3D27D4EB4Full; h ^= h >> 32;
-                return (size_t)h;
-            }
-        };
-        std::unordered_map<Key, uint32_t, KeyHash> index;
-        index.reserve(tasks.size() / 4 + 16);
         std::vector<Panel> panels;
-        size_t last_bt = (size_t)-1; Layout const* L = nullptr; int srcbuf = 0;
-        for (YTask const& t : tasks) {
-            if (t.bt != last_bt) { L = &tl.at(t.bt); srcbuf = t_persistent[t.bt] ? BUF_TP : BUF_T; last_bt = t.bt; }
-            auto ins = index.emplace(Key{t.o, t.dst_col, t.dst_row, t.rows, t.cols}, (uint32_t)panels.size());
-            if (ins.second) panels.push_back(Panel{t.o, t.dst_row, t.dst_col, t.rows, t.cols, {}});
-            int32_t lds = (int32_t)L->basis[t.t_block].ls;
-            panels[ins.first->second].srcs.push_back(PanelSrc{Ref{srcbuf, L->off[t.t_block] + t.src_row + (int64_t)t.src_col * lds}, lds, t.coef});
-            cnt.flops_w += 2.0 * t.rows * t.cols; cnt.n_axpy++;
+        if (tasks.empty()) return panels;
+        size_t n_o = 0;
+        for (YTask const& t : tasks) n_o = std::max(n_o, t.o + 1);
+        std::vector<int64_t> base(n_o + 1, 0);
+        for (YTask const& t : tasks) base[t.o + 1] = std::max(base[t.o + 1], (int64_t)t.dst_row + t.dst_col + 1);
+        for (size_t o = 0; o < n_o; ++o) base[o + 1] += base[o];
+        std::vector<int32_t> slot_panel((size_t)base[n_o], -1);
+        std::vector<uint32_t> pid(tasks.size()), count;
+        for (size_t i = 0; i < tasks.size(); ++i) {
+            YTask const& t = tasks[i];
+            int32_t& sp = slot_panel[(size_t)(base[t.o] + t.dst_row + t.dst_col)];
+            if (sp < 0) { sp = (int32_t)panels.size(); panels.push_back(Panel{t.o, t.dst_row, t.dst_col, t.rows, t.cols, {}}); count.push_back(0); }
+            else {
+                Panel const& pn = panels[(size_t)sp];
+                if (pn.dst_row != t.dst_row || pn.dst_col != t.dst_col || pn.rows != t.rows || pn.cols != t.cols)
+                    throw std::runtime_error("plan: two destination panels of different shape start at the same element");
+            }
+            pid[i] = (uint32_t)sp; count[(size_t)sp]++;
         }
+        for (size_t p = 0; p < panels.size(); ++p) panels[p].srcs.reserve(count[p]);
+        size_t last_bt = (size_t)-1; Layout const* L = nullptr; int srcbuf = 0;
+        for (size_t i = 0; i < tasks.size(); ++i) {
+            YTask const& t = tasks[i];
+            if (t.bt != last_bt) { L = &tl.at(t.bt); srcbuf = t_persistent[t.bt] ? BUF_TP : BUF_T; last_bt = t.bt; }
+            int32_t lds = (int32_t)L->basis[t.t_block].ls;
+            panels[pid[i]].srcs.push_back(PanelSrc{Ref{srcbuf, L->off[t.t_block] + t.src_row + (int64_t)t.src_col * lds}, lds, t.coef});
+            cnt.flops_w += 2.0 * t.rows * t.cols;
+        }
+        cnt.n_axpy += tasks.size();
+        auto src_less = [](PanelSrc const& a, PanelSrc const& b) { return std::tie(a.src.buf, a.src.off) < std::tie(b.src.buf, b.src.off); };
         for (Panel& pn : panels) {
-            std::stable_sort(pn.srcs.begin(), pn.srcs.end(), [](PanelSrc const& a, PanelSrc const& b) { return std::tie(a.src.buf, a.src.off) < std::tie(b.src.buf, b.src.off); });
+            // the sources of a panel arrive in bond order, i.e. mostly sorted already
+            if (!std::is_sorted(pn.srcs.begin(), pn.srcs.end(), src_less)) std::stable_sort(pn.srcs.begin(), pn.srcs.end(), src_less);
             size_t o = 0;
             for (size_t i = 0; i < pn.srcs.size(); ++i) {
                 if (o && pn.srcs[o - 1].src.buf == pn.srcs[i].src.buf && pn.srcs[o - 1].src.off == pn.srcs[i].src.off) pn.srcs[o - 1].coef += pn.srcs[i].coef;
@@ -1506,6 +1591,11 @@ private:
     std::vector<Layout> tp_layout;
     bool t_is_left = true; Layout t_ket;
     Layout ket_lp_for_right;
+    // tables of the SU2 lbtm structure pass (build_lbtm_tables)
+    std::vector<uint32_t> t_basis_id_;
+    std::vector<std::vector<TbInfo>> tbinfo_;
+    std::vector<std::vector<std::pair<int16_t, int16_t>>> op_phys_;
+    size_t lbtm_nr_ = 0, lbtm_nol_ = 0;
 };
 
 }} // namespace qcm::plan

@@ -202,6 +202,36 @@ inline SyntheticSite make_synthetic_site(Problem& P, int site, bool twosite, siz
     return S;
 }
 
+// A random MPS on the synthetic sector lists (total bond dimension M at every bond, same lists as make_synthetic_site):
+// the starting state of the sweep-level measurements at the large configurations.  Deterministic in (M, seed).
+inline MPS make_synthetic_mps(Problem const& P, size_t M, unsigned seed)
+{
+    std::vector<Index> sectors = synthetic_sectors(P, M);
+    const int L = P.params.L;
+    MPS mps; mps.resize(L);
+    std::mt19937_64 eng(1000003ull * seed + 17);
+    std::uniform_real_distribution<double> ud(-1., 1.);
+    for (int i = 0; i < L; ++i) {
+        // the right index of tensor i must be what tensor i+1 keeps as its left index: build from the left with the
+        // previous tensor's trimmed right index
+        Index li = i == 0 ? sectors[0] : mps[i - 1].col_dim();
+        mps[i] = MPSTensor(P.phys(i), li, sectors[i + 1], [&]() { return ud(eng); });
+    }
+    // trim dangling sectors from the right end (a sector of bond i+1 that tensor i+1 dropped cannot be populated)
+    for (int i = L - 2; i >= 0; --i) {
+        Index keep = mps[i + 1].row_dim();
+        if (keep == mps[i].col_dim()) continue;
+        mps[i].make_left_paired();
+        block_matrix d;
+        for (size_t k = 0; k < mps[i].data().n_blocks(); ++k) {
+            Charge rc = mps[i].data().basis()[k].rc;
+            if (keep.has(rc)) d.insert_block(mps[i].data()[k], mps[i].data().basis()[k].lc, rc);
+        }
+        mps[i] = MPSTensor(P.phys(i), mps[i].row_dim(), keep, d, LeftPaired);
+    }
+    return mps;
+}
+
 struct DiffReport { double max_abs = 0, ref_norm = 0, diff_norm = 0; int structure_equal = 1; };
 
 inline void accumulate_diff(block_matrix const& a, block_matrix const& ref, DiffReport& r)

@@ -13,6 +13,10 @@
 #pragma once
 #include "engine_iface.hpp"
 #include <chrono>
+#include <exception>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 extern "C" {
 void scipy_dgeqrf_(const int* m, const int* n, double* a, const int* lda, double* tau, double* work, const int* lwork, int* info);
@@ -25,26 +29,69 @@ void scipy_dsyev_(const char* jobz, const char* uplo, const int* n, double* a, c
 namespace qcm { namespace sweep {
 
 // ---- block linear algebra (block_matrix_algorithms.h: gemm :48-70, qr / lq) ------------------------------------
+// Blocks are independent: they are processed side by side on the host cores (one BLAS thread per block; run_blocks),
+// the few blocks that are large enough to keep all cores busy on their own go first, one at a time, with threaded BLAS.
+// Results are inserted in block order afterwards, so the outcome does not depend on the number of threads.
+extern "C" void scipy_openblas_set_num_threads(int);
+extern "C" int scipy_openblas_get_num_threads(void);
+template <class Cost, class Body> inline void run_blocks(size_t n, Cost cost, Body body, double big = 2.5e10)
+{
+    std::vector<size_t> order(n);
+    for (size_t i = 0; i < n; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return cost(a) > cost(b); });
+#ifdef _OPENMP
+    const int nt = omp_get_max_threads();
+    if (nt > 1 && !omp_in_parallel()) {
+        const int blas_before = scipy_openblas_get_num_threads();
+        size_t first_small = 0;
+        while (first_small < n && cost(order[first_small]) >= big) ++first_small;
+        if (first_small) { scipy_openblas_set_num_threads(nt); for (size_t q = 0; q < first_small; ++q) body(order[q]); }
+        scipy_openblas_set_num_threads(1);
+        std::exception_ptr err;
+#pragma omp parallel for schedule(dynamic, 1)
+        for (long q = (long)first_small; q < (long)n; ++q) {
+            try { body(order[(size_t)q]); } catch (...) {
+#pragma omp critical(qcm_run_blocks)
+                err = std::current_exception();
+            }
+        }
+        scipy_openblas_set_num_threads(blas_before);
+        if (err) std::rethrow_exception(err);
+        return;
+    }
+#endif
+    for (size_t q = 0; q < n; ++q) body(order[q]);
+}
+
 inline void gemm(block_matrix const& A, block_matrix const& B, block_matrix& C)
 {
     C.clear();
+    struct Pair { size_t k, j; Matrix c; };
+    std::vector<Pair> pairs;
     for (size_t k = 0; k < A.n_blocks(); ++k) {
         QnBlock const& a = A.basis()[k];
         for (size_t j = 0; j < B.n_blocks(); ++j) {
             QnBlock const& b = B.basis()[j];
             if (!(b.lc == a.rc)) continue;
             if (a.rs != b.ls) throw std::runtime_error("sweep::gemm: inner block sizes differ");
-            Matrix c(a.ls, b.rs);
-            dgemm(A.block(k), B.block(j), 1.0, 0.0, c.data(), c.rows);
-            C.match_and_add_block(c, a.lc, b.rc);
+            pairs.push_back(Pair{k, j, Matrix()});
         }
     }
+    run_blocks(pairs.size(), [&](size_t i) { return 2.0 * A.basis()[pairs[i].k].ls * A.basis()[pairs[i].k].rs * B.basis()[pairs[i].j].rs; },
+               [&](size_t i) {
+                   Pair& p = pairs[i];
+                   p.c = Matrix(A.basis()[p.k].ls, B.basis()[p.j].rs);
+                   dgemm(A.block(p.k), B.block(p.j), 1.0, 0.0, p.c.data(), p.c.rows);
+               });
+    for (Pair& p : pairs) C.match_and_add_block(p.c, A.basis()[p.k].lc, B.basis()[p.j].rc);
 }
 // A = Q R per block; Q: ls x k with orthonormal columns, R: k x rs, k = min(ls, rs)
 inline void qr(block_matrix const& A, block_matrix& Q, block_matrix& R)
 {
     Q.clear(); R.clear();
-    for (size_t b = 0; b < A.n_blocks(); ++b) {
+    const size_t nb = A.n_blocks();
+    std::vector<Matrix> qs(nb), rs(nb);
+    run_blocks(nb, [&](size_t b) { return 4.0 * A[b].rows * A[b].cols * std::min(A[b].rows, A[b].cols); }, [&](size_t b) {
         Matrix a = A[b];
         const int m = (int)a.rows, n = (int)a.cols, k = std::min(m, n);
         std::vector<double> tau(std::max(1, k)), work(1);
@@ -62,15 +109,20 @@ inline void qr(block_matrix const& A, block_matrix& Q, block_matrix& R)
         if (info) throw std::runtime_error("dorgqr failed");
         Matrix q(m, k);
         for (int j = 0; j < k; ++j) for (int i = 0; i < m; ++i) q(i, j) = a(i, j);
-        Q.insert_block(q, A.basis()[b].lc, A.basis()[b].rc);
-        R.insert_block(r, A.basis()[b].rc, A.basis()[b].rc);
+        qs[b] = std::move(q); rs[b] = std::move(r);
+    });
+    for (size_t b = 0; b < nb; ++b) {
+        Q.insert_block(qs[b], A.basis()[b].lc, A.basis()[b].rc);
+        R.insert_block(rs[b], A.basis()[b].rc, A.basis()[b].rc);
     }
 }
 // A = L Q per block; L: ls x k, Q: k x rs with orthonormal rows
 inline void lq(block_matrix const& A, block_matrix& L, block_matrix& Q)
 {
     L.clear(); Q.clear();
-    for (size_t b = 0; b < A.n_blocks(); ++b) {
+    const size_t nb = A.n_blocks();
+    std::vector<Matrix> ls(nb), qs(nb);
+    run_blocks(nb, [&](size_t b) { return 4.0 * A[b].rows * A[b].cols * std::min(A[b].rows, A[b].cols); }, [&](size_t b) {
         Matrix a = A[b];
         const int m = (int)a.rows, n = (int)a.cols, k = std::min(m, n);
         std::vector<double> tau(std::max(1, k)), work(1);
@@ -88,8 +140,11 @@ inline void lq(block_matrix const& A, block_matrix& L, block_matrix& Q)
         if (info) throw std::runtime_error("dorglq failed");
         Matrix q(k, n);
         for (int j = 0; j < n; ++j) for (int i = 0; i < k; ++i) q(i, j) = a(i, j);
-        L.insert_block(l, A.basis()[b].lc, A.basis()[b].lc);
-        Q.insert_block(q, A.basis()[b].lc, A.basis()[b].rc);
+        ls[b] = std::move(l); qs[b] = std::move(q);
+    });
+    for (size_t b = 0; b < nb; ++b) {
+        L.insert_block(ls[b], A.basis()[b].lc, A.basis()[b].lc);
+        Q.insert_block(qs[b], A.basis()[b].lc, A.basis()[b].rc);
     }
 }
 

@@ -222,7 +222,7 @@ inline Truncation svd_truncate(block_matrix const& M, block_matrix& U, block_mat
     const size_t nb = M.n_blocks();
     std::vector<Matrix> us(nb), vs(nb);
     S.assign(nb, std::vector<double>());
-    for (size_t b = 0; b < nb; ++b) {
+    sweep::run_blocks(nb, [&](size_t b) { double m = (double)M[b].rows, n = (double)M[b].cols; return 20.0 * m * n * std::min(m, n); }, [&](size_t b) {
         Matrix a = M[b];
         const int m = (int)a.rows, n = (int)a.cols, k = std::min(m, n);
         us[b] = Matrix(m, k); vs[b] = Matrix(k, n); S[b].assign(k, 0.);
@@ -232,7 +232,7 @@ inline Truncation svd_truncate(block_matrix const& M, block_matrix& U, block_mat
         lwork = (int)work[0]; work.resize(std::max(1, lwork));
         scipy_dgesdd_("S", &m, &n, a.data(), &m, S[b].data(), us[b].data(), &m, vs[b].data(), &k, work.data(), &lwork, iwork.data(), &info);
         if (info) throw std::runtime_error("dgesdd failed");
-    }
+    });
     // estimate_truncation
     std::vector<double> all;
     for (auto const& s : S) all.insert(all.end(), s.begin(), s.end());
@@ -347,23 +347,35 @@ private:
 };
 
 // ---- two-site sweeps (ts_optimize.hpp:60-270, twosite_truncation = svd) ------------------------------------------------
-struct TsParams { size_t Mmax = 100; double cutoff = 1e-16; int jcd_maxiter = 10; double jcd_tol = 1e-8; };
+struct TsParams
+{
+    size_t Mmax = 100; double cutoff = 1e-16; int jcd_maxiter = 10; double jcd_tol = 1e-8;
+    // A boundary that the sweep has moved past is recomputed on the way back before it is read again
+    // (optimize.h:150-165): with drop_stale its storage is released right away, so that at most L + 1 boundaries are
+    // resident at any time (the reference's storage::drop on the disk tier, utils/storage.h:176-181).
+    bool drop_stale = false;
+    // stop after this many micro-iterations of the LAST sweep (0: full sweeps); measurement aid for bounded runs
+    int max_micro_iterations = 0;
+};
 
 template <class TsMpo>      // TsMpo(p) -> MPOTensor const& of the fused sites (p, p+1)  (ts_ops.h make_ts_cache_mpo)
 inline sweep::SweepLog ts_sweeps(SymmKind symm, EngineIface& eng, MPO const& mpo, TsMpo ts_mpo, MPS& mps, int nsweeps, TsParams const& prm,
-                                 std::vector<size_t>* bond_dims = nullptr)
+                                 std::vector<size_t>* bond_dims = nullptr, double* init_seconds = nullptr)
 {
     const int L = (int)mps.size();
     sweep::SweepLog log;
+    auto t_init = std::chrono::steady_clock::now();
     sweep::canonize_to_first(mps);
     std::vector<Boundary> left(L + 1), right(L + 1);
     left[0] = mps.left_boundary();
     right[L] = mps.right_boundary();
     for (int i = L - 1; i >= 0; --i) right[i] = eng.overlap_mpo_right_step(mps[i], mps[i], right[i + 1], mpo[i]);
+    if (init_seconds) *init_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_init).count();
     auto to_site = [L](int i) { return i < L ? i : 2 * L - 1 - i; };
     for (int sw = 0; sw < nsweeps; ++sw) {
         auto t0 = std::chrono::steady_clock::now();
         for (int _site = 0; _site < 2 * L - 2; ++_site) {
+            if (prm.max_micro_iterations > 0 && sw == nsweeps - 1 && _site >= prm.max_micro_iterations) break;
             int lr, site1, site2;
             if (_site < L - 1) { lr = 1; site1 = to_site(_site); site2 = site1 + 1; }
             else { lr = -1; site2 = to_site(_site); site1 = site2 - 1; }
@@ -386,12 +398,14 @@ inline sweep::SweepLog ts_sweeps(SymmKind symm, EngineIface& eng, MPO const& mpo
                 if (site2 < L - 1) sweep::multiply_from_left(mps[site2 + 1], t);
                 log.phase_seconds[3] += lap();
                 left[site2] = eng.overlap_mpo_left_step(mps[site1], mps[site1], left[site1], mpo[site1]);
+                if (prm.drop_stale && site2 < L - 1) right[site2] = Boundary();
             } else {
                 tst.split_mps_r2l(prm.Mmax, prm.cutoff, mps[site1], mps[site2], trunc);
                 block_matrix t = sweep::normalize_right(mps[site1]);
                 if (site1 > 0) sweep::multiply_from_right(mps[site1 - 1], t);
                 log.phase_seconds[3] += lap();
                 right[site2] = eng.overlap_mpo_right_step(mps[site2], mps[site2], right[site2 + 1], mpo[site2]);
+                if (prm.drop_stale && site1 > 0) left[site2] = Boundary();
             }
             log.phase_seconds[4] += lap();
             if (bond_dims) bond_dims->push_back(trunc.bond_dimension);
