@@ -209,6 +209,38 @@ def sweep_measurement(host, build, device, with_cpu):
     return results
 
 
+def config_sweep(host, h, args, M, device, rank, world, max_over_ranks, sum_over_ranks, peak_tflops):
+    """One two-site sweep (ts_optimize.hpp:60-270 semantics: Jacobi-Davidson <= 10 sigma per site, tol 1e-8, SVD truncation
+    to M) of the benchmarked configuration on N GPUs.  Wall-clock of the sweep loop (the analogue of the reference's sweep
+    timer, ts_optimize.hpp:267-269), max over ranks; the engine's host-side seconds are reported next to it."""
+    e = errbuf()
+    en = (ctypes.c_double * 8192)(); n = ctypes.c_int(); info = (ctypes.c_double * 32)()
+    host.qcmd_ts_sweeps_synth.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_double, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]
+    if host.qcmd_ts_sweeps_synth(h, M, 1, args.seed, device, rank, world, 0, args.sweep_budget, en, 8192, ctypes.byref(n), info, e, 1024):
+        raise RuntimeError(e.value.decode())
+    norb = CONFIGS[args.config][0]
+    sweep_s = max_over_ranks(info[1])
+    f_sigma, f_bnd = sum_over_ranks([info[16], info[17]])
+    names = ["two_site_tensor", "two_site_mpo", "eigensolver", "split", "boundary_step"]
+    eng_names = ["planning", "plan_upload", "sigma_calls", "boundary_calls", "flatten"]
+    drv = {k: info[4 + i] for i, k in enumerate(names)}
+    engs = {k: info[9 + i] for i, k in enumerate(eng_names)}
+    # host-exposed time: everything of the sweep loop that is not a device call (solver incl. its sigma evaluations, boundary-step execution)
+    device_s = engs["sigma_calls"] + engs["boundary_calls"]
+    out = {"workload": "%s two-site sweep from a random MPS on the synthetic sectors (M = %d at every bond)" % (args.config, M),
+           "micro_iterations": int(info[19]), "micro_iterations_full_sweep": 2 * norb - 2, "complete": int(info[19]) == 2 * norb - 2,
+           "sweep_s": sweep_s, "init_s": info[18], "sigma_evaluations": int(info[0]), "largest_bond_dimension": int(info[3]),
+           "final_energy": info[2], "energies": [en[i] for i in range(n.value)],
+           "driver_s": drv, "engine_s": engs, "device_call_s": device_s, "host_exposed_s": max(0.0, info[1] - device_s),
+           "host_exposed_frac": max(0.0, info[1] - device_s) / info[1] if info[1] else None,
+           "plan_cache": {"hits": int(info[14]), "misses": int(info[15])},
+           "sum_flops": f_sigma + f_bnd, "sum_sigma_flops": f_sigma, "sum_boundary_flops": f_bnd,
+           "tflops_over_sweep": (f_sigma + f_bnd) / sweep_s / 1e12 if sweep_s else None,
+           "frac_of_fp64_peak": (f_sigma + f_bnd) / sweep_s / 1e12 / (peak_tflops * world) if sweep_s and peak_tflops else None}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -221,7 +253,9 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true", help="skip the sweep-level measurement (single-site DMRG sweeps of the 8e/8o system)")
-    ap.add_argument("--parity", action="store_true", help="N>1: rank 0 also runs the CPU oracle on the same instance and reports the sigma error")
+    ap.add_argument("--parity", action="store_true", help="(kept for compatibility: the oracle parity of the sigma vector is reported at every N unless --no-cpu-baseline)")
+    ap.add_argument("--no-config-sweep", action="store_true", help="skip the two-site DMRG sweep of the benchmarked configuration itself")
+    ap.add_argument("--sweep-budget", type=float, default=300.0, help="wall-clock budget (s) of the configuration sweep; it stops at a site boundary when exceeded")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3
@@ -404,7 +438,7 @@ def main():
             "gpu_launches": int(launches)}
 
     # ---- CPU baseline + full-size parity on the same instance (rank 0, N=1 only) -------------------------
-    if (world == 1 or args.parity) and rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline:
         olib = ctypes.CDLL(build.build_oracle())
         olib.orc_create.restype = ctypes.c_void_p
         olib.orc_set_threads(len(os.sched_getaffinity(0)))
@@ -427,6 +461,15 @@ def main():
         else:
             line["parity_rel_err_vs_oracle"] = "structure mismatch: %d vs %d elements" % (int(se.value), sig_n)
         olib.orc_destroy(oh)
+    barrier()   # the other ranks' host threads stay idle while rank 0 times the CPU oracle
+    # ---- sweep level, the benchmarked configuration itself (every N): one two-site DMRG sweep from a random MPS on the
+    # synthetic sector lists (total bond dimension M at every bond), boundaries resident in HBM, engine calls collective
+    host.qcmd_release_site(h)
+    if not args.no_config_sweep:
+        try:
+            line["config_sweep"] = config_sweep(host, h, args, M, local, rank, world, max_over_ranks, sum_over_ranks, peak.value)
+        except Exception as ex:
+            line["config_sweep"] = {"error": str(ex)}
     # ---- sweep level (N=1): single-site DMRG sweeps of BASELINE config 1's system (8e/8o SU2U1, M=256) through the
     # engine, boundaries resident in HBM, against the same driver on the CPU oracle: per-micro-iteration energies
     if world == 1 and not args.no_sweep:

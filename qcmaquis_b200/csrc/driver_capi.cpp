@@ -44,6 +44,15 @@ extern "C" void* qcmd_create(const char* fcidump, const char* symm, int L, int n
     } catch (std::exception const& e) { set_err(err, errlen, e.what()); return nullptr; }
 }
 extern "C" void qcmd_destroy(void* h) { delete static_cast<Driver*>(h); }
+// drops the synthetic site problem (boundaries, plan, solver vectors) of qcmd_setup_site; the MPO and the model stay
+extern "C" void qcmd_release_site(void* h)
+{
+    Driver* D = static_cast<Driver*>(h);
+    D->plan.reset(); D->dl.reset(); D->dr.reset(); D->eng.reset();
+    if (D->d_psi) { qcm_array_free(D->d_psi); D->d_psi = nullptr; }
+    if (D->d_sigma) { qcm_array_free(D->d_sigma); D->d_sigma = nullptr; }
+    D->S = SyntheticSite(); D->psi_flat = std::vector<double>();
+}
 
 extern "C" int qcmd_mpo_dims(void* h, int* dims, int* pairs)
 {
@@ -233,8 +242,8 @@ extern "C" int qcmd_ts_sweeps_ranked(void* h, int M0, int Mmax, int nsweeps, uns
 //       [14] plan-cache hits [15] misses [16] sum of sigma FLOPs (this rank's share) [17] sum of boundary-step FLOPs
 //       [18] seconds before the first sweep (canonisation + initial right boundaries) [19] micro-iterations
 //       [20] seconds of the last sweep
-extern "C" int qcmd_ts_sweeps_synth(void* h, int M, int nsweeps, unsigned seed, int device, int rank, int world, int max_micro, double* energies, int n_max,
-                                    int* n_out, double* info, char* err, int errlen)
+extern "C" int qcmd_ts_sweeps_synth(void* h, int M, int nsweeps, unsigned seed, int device, int rank, int world, int max_micro, double budget_seconds,
+                                    double* energies, int n_max, int* n_out, double* info, char* err, int errlen)
 {
     try {
         Driver* D = static_cast<Driver*>(h);
@@ -243,10 +252,24 @@ extern "C" int qcmd_ts_sweeps_synth(void* h, int M, int nsweeps, unsigned seed, 
         GpuEngine eng(D->P.symm(), device, rank, world);
         eng.set_cache_capacity(4);
         ts::TsParams prm; prm.Mmax = (size_t)M; prm.drop_stale = true; prm.max_micro_iterations = max_micro;
+        // wall-clock budget: checked at site boundaries; with several ranks the flags are summed so that all ranks stop together
+        qcm_array_t flag = nullptr;
+        if (budget_seconds > 0) {
+            if (world > 1) qcm_check(qcm_array_alloc(1, &flag), "qcm_array_alloc");
+            prm.should_stop = [&]() {
+                double over = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > budget_seconds ? 1. : 0.;
+                if (world > 1) {
+                    qcm_check(qcm_array_upload(flag, 0, &over, 1), "qcm_array_upload");
+                    qcm_check(qcm_comm_allreduce(flag, 1), "qcm_comm_allreduce");
+                    qcm_check(qcm_array_download(flag, 0, &over, 1), "qcm_array_download");
+                }
+                return over > 0.;
+            };
+        }
         std::vector<size_t> dims;
         double init_s = 0;
         sweep::SweepLog log = ts::ts_sweeps(D->P.symm(), eng, D->P.mpo, [&](int p) -> MPOTensor const& { return D->P.twosite_mpo(p); }, D->P.mps, nsweeps, prm, &dims, &init_s);
-        (void)t0;
+        if (flag) qcm_array_free(flag);
         int n = (int)std::min<size_t>(log.energies.size(), (size_t)n_max);
         for (int i = 0; i < n; ++i) energies[i] = log.energies[i];
         *n_out = n;

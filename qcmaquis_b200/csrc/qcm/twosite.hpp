@@ -9,6 +9,7 @@
 // (mpo.hpp).  Everything here is O(tensor size) or block SVDs; sigma and the boundary steps go through the engine.
 #pragma once
 #include "sweep.hpp"
+#include <functional>
 #include "wigner.hpp"
 
 extern "C" void scipy_dgesdd_(const char* jobz, const int* m, const int* n, double* a, const int* lda, double* s, double* u, const int* ldu,
@@ -356,6 +357,9 @@ struct TsParams
     bool drop_stale = false;
     // stop after this many micro-iterations of the LAST sweep (0: full sweeps); measurement aid for bounded runs
     int max_micro_iterations = 0;
+    // asked before every micro-iteration; true ends the run at that site boundary (wall-clock budgets of measurement
+    // runs; with several ranks the callee must return the same answer on all of them)
+    std::function<bool()> should_stop;
 };
 
 template <class TsMpo>      // TsMpo(p) -> MPOTensor const& of the fused sites (p, p+1)  (ts_ops.h make_ts_cache_mpo)
@@ -372,10 +376,12 @@ inline sweep::SweepLog ts_sweeps(SymmKind symm, EngineIface& eng, MPO const& mpo
     for (int i = L - 1; i >= 0; --i) right[i] = eng.overlap_mpo_right_step(mps[i], mps[i], right[i + 1], mpo[i]);
     if (init_seconds) *init_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_init).count();
     auto to_site = [L](int i) { return i < L ? i : 2 * L - 1 - i; };
-    for (int sw = 0; sw < nsweeps; ++sw) {
+    bool stopped = false;
+    for (int sw = 0; sw < nsweeps && !stopped; ++sw) {
         auto t0 = std::chrono::steady_clock::now();
         for (int _site = 0; _site < 2 * L - 2; ++_site) {
             if (prm.max_micro_iterations > 0 && sw == nsweeps - 1 && _site >= prm.max_micro_iterations) break;
+            if (prm.should_stop && prm.should_stop()) { stopped = true; break; }
             int lr, site1, site2;
             if (_site < L - 1) { lr = 1; site1 = to_site(_site); site2 = site1 + 1; }
             else { lr = -1; site2 = to_site(_site); site1 = site2 - 1; }
@@ -410,7 +416,7 @@ inline sweep::SweepLog ts_sweeps(SymmKind symm, EngineIface& eng, MPO const& mpo
             log.phase_seconds[4] += lap();
             if (bond_dims) bond_dims->push_back(trunc.bond_dimension);
         }
-        log.sweep_energy.push_back(log.energies.back());
+        log.sweep_energy.push_back(log.energies.empty() ? 0. : log.energies.back());
         log.sweep_seconds.push_back(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
     }
     return log;

@@ -179,3 +179,51 @@ def test_vector_algebra(built):
     # range errors are reported, not ignored
     assert cu.qcm_vec_dot(ax, ay, ctypes.c_int64(n + 1), ctypes.byref(r)) != 0
     cu.qcm_array_free(ax); cu.qcm_array_free(ay)
+
+
+@pytest.mark.parametrize("symm,norb,nelec,M", [("su2u1", 8, 8, 64), ("2u1", 8, 8, 48), ("su2u1", 12, 12, 100)])
+def test_synthetic_start_sweep_matches_the_oracle(built, symm, norb, nelec, M):
+    """The sweep leg of bench.py (qcmd_ts_sweeps_synth: two-site sweep from a random MPS on the synthetic sector lists, stale
+    boundaries dropped, device-resident Jacobi-Davidson) against the same driver on the CPU oracle: every micro-iteration
+    energy within 1e-8 Eh."""
+    from qcmaquis_b200.fcidump import make_fcidump
+    cu = ctypes.CDLL(built["cuda"], mode=ctypes.RTLD_GLOBAL)
+    cu.qcm_last_error.restype = ctypes.c_char_p
+    assert cu.qcm_init(0) == 0, cu.qcm_last_error()
+    host = ctypes.CDLL(built["host"]); host.qcmd_create.restype = ctypes.c_void_p
+    olib = ctypes.CDLL(built["oracle"]); olib.orc_create.restype = ctypes.c_void_p
+    path = os.path.join(tempfile.mkdtemp(prefix="qcm_test_"), "s.fcidump")
+    make_fcidump(path, norb, nelec)
+    err = ctypes.create_string_buffer(1024)
+    h = ctypes.c_void_p(host.qcmd_create(path.encode(), symm.encode(), norb, nelec, err, 1024)); assert h.value, err.value
+    oh = ctypes.c_void_p(olib.orc_create(path.encode(), symm.encode(), norb, nelec, err, 1024)); assert oh.value, err.value
+    eg = (ctypes.c_double * 4096)(); ng = ctypes.c_int(); ig = (ctypes.c_double * 32)()
+    eo = (ctypes.c_double * 4096)(); no = ctypes.c_int(); io = (ctypes.c_double * 32)()
+    host.qcmd_ts_sweeps_synth.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_double, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]
+    assert host.qcmd_ts_sweeps_synth(h, M, 2, 3, 0, 0, 1, 0, 0.0, eg, 4096, ctypes.byref(ng), ig, err, 1024) == 0, err.value
+    assert olib.orc_ts_sweeps_synth(oh, M, 2, 3, 0, eo, 4096, ctypes.byref(no), io, err, 1024) == 0, err.value
+    assert ng.value == no.value == 2 * (2 * norb - 2)
+    assert max(abs(eg[i] - eo[i]) for i in range(ng.value)) < 1e-8
+    assert int(ig[0]) == int(io[0]), "different numbers of sigma evaluations"
+    assert ig[16] > 0 and ig[17] > 0      # the engine booked its FLOPs
+    host.qcmd_destroy(h); olib.orc_destroy(oh)
+
+
+def test_sharded_plan_needs_a_matching_communicator(built):
+    """A plan built for rank r of N produces a partial result: executing it without an N-rank communicator must fail loudly
+    (the sharding lives in the plan and is checked against qcm_comm_init's state)."""
+    from qcmaquis_b200.fcidump import make_fcidump
+    cu = ctypes.CDLL(built["cuda"], mode=ctypes.RTLD_GLOBAL)
+    cu.qcm_last_error.restype = ctypes.c_char_p
+    assert cu.qcm_init(0) == 0, cu.qcm_last_error()
+    host = ctypes.CDLL(built["host"]); host.qcmd_create.restype = ctypes.c_void_p
+    path = os.path.join(tempfile.mkdtemp(prefix="qcm_test_"), "s.fcidump")
+    make_fcidump(path, 8, 8)
+    err = ctypes.create_string_buffer(1024)
+    h = ctypes.c_void_p(host.qcmd_create(path.encode(), b"su2u1", 8, 8, err, 1024)); assert h.value, err.value
+    info = (ctypes.c_double * 32)()
+    assert host.qcmd_setup_site(h, 3, 1, 64, 1, 0, 1, 2, info, err, 1024) == 0, err.value      # rank 1 of 2, no communicator
+    assert host.qcmd_sigma_dev(h, 1, err, 1024) != 0
+    assert b"communicator" in err.value
+    host.qcmd_destroy(h)
