@@ -71,6 +71,13 @@ typedef struct {
     const qcm_gemm_out* c_outs;     int64_t n_c_outs;      /* step 3 -> QCM_BUF_OUT (accumulating) */
     const qcm_gemm_seg* c_segs;     int64_t n_c_segs;
     int64_t y_elems, t_elems;
+    /* exchange wave (sharded plans only, at most one per plan, waves[0]): its W pass writes this rank's partial sums of the
+     * destination panels whose sources are spread over several ranks into QCM_BUF_Y[0, world * x_chunk_elems) -- the same
+     * layout on every rank; the region is reduce-scattered (rank r receives the complete sums of chunk r) while the
+     * remaining waves run, and this wave's closing products (they read chunk `rank`) are executed last.
+     * x_zero: the region must be zeroed before the W pass (some panels get no contribution from this rank). */
+    int64_t x_chunk_elems;
+    int32_t x_zero, pad;
 } qcm_wave_desc;
 
 typedef struct {

@@ -388,7 +388,8 @@ private:
             waves[w] = qcm_wave_desc{S.to.data(), (int64_t)S.to.size(), S.ts.data(), (int64_t)S.ts.size(),
                                      S.wg.data(), (int64_t)S.wg.size(), S.wsrc.data(), (int64_t)S.wsrc.size(), S.wd.data(), (int64_t)S.wd.size(),
                                      wl.coefs.data(), (int64_t)wl.coefs.size(),
-                                     S.co.data(), (int64_t)S.co.size(), S.cs.data(), (int64_t)S.cs.size(), W.y_elems, W.t_elems};
+                                     S.co.data(), (int64_t)S.co.size(), S.cs.data(), (int64_t)S.cs.size(), W.y_elems, W.t_elems,
+                                     W.x_chunk, W.x_zero ? 1 : 0, 0};
         }
         std::vector<qcm_gemm_out> po; std::vector<qcm_gemm_seg> ps;
         cvt(P.persistent_t, po, ps);

@@ -86,6 +86,12 @@ struct Wave
     GemmList close_gemm;  // step 3 -> BUF_OUT (accumulating for sigma, plain for boundary steps)
     int64_t y_elems = 0;  // BUF_Y elements this wave uses (compact multi-source panels; all written by the W pass before they are read)
     int64_t t_elems = 0;
+    // Exchange wave (world > 1, always waves[0]): its W pass writes this rank's PARTIAL sums of the destination panels whose
+    // sources are spread over several ranks into BUF_Y[0, world * x_chunk) -- the same layout on every rank -- the region is
+    // reduce-scattered (rank r receives the complete sums of chunk r) while the other waves run, and the closing products
+    // of chunk `rank` (close_gemm of this wave) are executed at the end of the plan.
+    int64_t x_chunk = 0;
+    bool x_zero = false;  // some exchanged panels get no contribution from this rank: the region is zeroed first
 };
 
 struct Layout   // block offsets of one block matrix inside a flat buffer
@@ -232,11 +238,34 @@ public:
         // emit waves over this rank's share of b2
         std::vector<char> own = shard_sources(P, pend.size(), [&](size_t i) { return 2.0 * estimate_cost(pend[i].y, right, pend[i].b2); },
                                               [&](size_t i) -> std::vector<size_t> const& { return pend[i].t_rows; });
+        // Y blocks of output i that take part in a closing product (same test as the emission below)
+        auto sigma_match = [&](DualIndex const& ybasis, VView const& rv, size_t k, std::vector<size_t>& m) {
+            QnBlock const& yb = ybasis[k];
+            if (su2_) {
+                size_t mb = rv.basis.position(yb.rc, yb.lc);
+                if (mb == rv.basis.size() || !out_left_i.has(yb.lc)) return;
+                m.push_back(mb);
+            } else
+                for (auto it = rv.basis.left_lower_bound(yb.rc); it != rv.basis.end() && it->lc == yb.rc; ++it) m.push_back(it - rv.basis.begin());
+        };
+        Exchange xch = plan_exchange(pend.size(), [&](size_t i) -> std::vector<YTask> const& { return pend[i].ytasks; },
+            [&](size_t i) -> std::vector<size_t> const& { return pend[i].t_rows; },
+            [&](size_t i) {
+                VView rv = right_view(right, pend[i].b2);
+                std::vector<char> u(pend[i].y.basis.size(), 0);
+                for (size_t k = 0; k < u.size(); ++k) { std::vector<size_t> m; sigma_match(pend[i].y.basis, rv, k, m); u[k] = !m.empty(); }
+                return u;
+            });
+        auto closes_some = [&](size_t i) { if (!xch.active()) return false; for (uint32_t q : xch.by_output[i]) if (xch.xp[q].chunk == rank) return true; return false; };
         std::vector<char> books(pend.size(), 1);
         for (size_t i = 0; i < pend.size(); ++i) books[i] = filter_owned(own, pend[i].ytasks, pend[i].t_rows);
         pt.lap("sharding + persistent T");
+        std::vector<char> idle(pend.size(), 0);
+        for (size_t i = 0; i < pend.size(); ++i) idle[i] = world > 1 && pend[i].ytasks.empty() && !books[i] && !closes_some(i);
         PanelCache pcache;
-        Wave cur; int64_t cur_y = 0, cur_t = 0;
+        Wave xw;
+        const int64_t y0 = xch.active() ? xch.chunk * world : 0;      // BUF_Y[0, y0) is the exchange region
+        Wave cur; int64_t cur_y = y0, cur_t = 0;
         auto flush = [&]() {
             if (cur.w_apply.dsts.empty() && cur.close_gemm.outs.empty() && cur.t_gemm.outs.empty()) return;
             cur.y_elems = cur_y; cur.t_elems = cur_t;
@@ -247,14 +276,14 @@ public:
             group_axpy(P, cur.w_apply, cur.w_groups);
             pt.lap("group_axpy");
             P.waves.push_back(std::move(cur));
-            cur = Wave(); cur_y = 0; cur_t = 0;
+            cur = Wave(); cur_y = y0; cur_t = 0;
         };
         for (size_t i = 0; i < pend.size(); ++i) {
             Pending& pd = pend[i];
-            if (world > 1 && pd.ytasks.empty() && !books[i]) continue;
+            if (idle[i]) continue;
             int64_t need_t = 0;
             for (size_t b1 : pd.t_rows) if (!t_persistent[b1]) need_t += t_layout_size(b1);
-            if ((cur_y + cur_t) > 0 && cur_y + cur_t + pd.y.total + need_t > budget) flush();
+            if ((cur_y - y0 + cur_t) > 0 && cur_y - y0 + cur_t + pd.y.total + need_t > budget) flush();
             // step 1 for single-use rows consumed here
             const int64_t t_begin = cur_t;
             std::map<size_t, Layout> tl;
@@ -273,23 +302,30 @@ public:
             std::vector<std::vector<size_t>> match(ybasis.size());
             for (size_t k = 0; k < ybasis.size(); ++k) {
                 QnBlock const& yb = ybasis[k];
-                if (su2_) {
-                    size_t mb = rv.basis.position(yb.rc, yb.lc);
-                    if (mb == rv.basis.size() || !out_left_i.has(yb.lc)) continue;
-                    match[k].push_back(mb);
-                } else
-                    for (auto it = rv.basis.left_lower_bound(yb.rc); it != rv.basis.end() && it->lc == yb.rc; ++it) match[k].push_back(it - rv.basis.begin());
+                sigma_match(ybasis, rv, k, match[k]);
                 for (size_t mb : match[k])
                     if (books[i] && P.out_tensor.basis.has(yb.lc, su2_ ? yb.lc : rv.blocks[mb].rc)) { P.flops_close += 2.0 * yb.ls * rv.blocks[mb].rs * yb.rs; P.n_gemm_tasks++; }
             }
+            // exchanged panels of this output whose complete sums arrive on this rank: closed from the exchange region
+            if (xch.active())
+                for (uint32_t q : xch.by_output[i]) {
+                    XPanel const& x = xch.xp[q];
+                    if (x.chunk != rank) continue;
+                    QnBlock const& yb = ybasis[x.o];
+                    for (size_t mb : match[x.o])
+                        emit_close(P, xw.close_gemm, P.out_tensor, yb.lc, su2_ ? yb.lc : rv.blocks[mb].rc, Ref{BUF_Y, x.off}, x.rows, 0, x.rows, x.cols, 1., rv.blocks[mb], BUF_RIGHT,
+                                   x.dst_row, 0);
+                }
             PanelCounts pcnt;
             std::vector<Panel> panels = cached_panels(pcache, pend.size(), i, t_begin,
                 [&](size_t j) -> std::vector<size_t> const& { return pend[j].t_rows; },
                 [&](size_t j) -> std::vector<YTask> const& { return pend[j].ytasks; },
-                [&](size_t j) { return world > 1 && pend[j].ytasks.empty() && !books[j]; }, tl, pcnt);
+                [&](size_t j) { return idle[j] != 0; }, tl, pcnt);
             P.flops_w += pcnt.flops_w; P.n_axpy_tasks += pcnt.n_axpy;
             for (Panel& pn : panels) {
                 if (match[pn.o].empty()) { P.skipped_panel_elems += (int64_t)pn.rows * pn.cols; continue; }
+                const long xi = xch.find(i, pn.o, pn.dst_row, pn.dst_col);
+                if (xi >= 0) { if (!pn.srcs.empty()) place_exchanged(P, xw, pn, xch.xp[(size_t)xi]); continue; }
                 PanelRef pr;
                 if (!place_panel(P, cur.w_apply, pn, cur_y, pr)) continue;
                 QnBlock const& yb = ybasis[pn.o];
@@ -299,6 +335,7 @@ public:
             }
         }
         flush();
+        finish_exchange(P, xw, xch);
         merge_outputs(P.persistent_t);
         P.bytes_algorithmic = 8 * (left.total + right.total + 2 * ket_lp.total);
         return P;
@@ -1533,8 +1570,9 @@ private:
     {
         const size_t B = t_basis.size();
         std::vector<char> own(B, 0);
+        owner_.assign(B, -1);
         if (world <= 1) {
-            for (size_t i = 0; i < n_out; ++i) for (size_t b : rows(i)) own[b] = 1;
+            for (size_t i = 0; i < n_out; ++i) for (size_t b : rows(i)) { own[b] = 1; owner_[b] = 0; }
             emit_persistent(P, own);
             return own;
         }
@@ -1554,9 +1592,112 @@ private:
             int r = (int)(std::min_element(load.begin(), load.end()) - load.begin());
             load[r] += e.first;
             own[e.second] = (r == rank);
+            owner_[e.second] = r;
+        }
+        // the step-1 products behind an output whose sources sit on several ranks are read by the exchange wave, which runs
+        // before all others: they are kept resident like the multi-use ones
+        for (size_t i = 0; i < n_out; ++i) {
+            auto const& r = rows(i);
+            bool spread = false;
+            for (size_t b : r) if (owner_[b] != owner_[r[0]]) { spread = true; break; }
+            if (spread) for (size_t b : r) t_persistent[b] = 1;
         }
         emit_persistent(P, own);
         return own;
+    }
+
+    // ---- exchange of partial W sums (world > 1).  With the edges of the MPO bond graph sharded by their step-1 index, an
+    // output fed by bonds of several ranks has its destination panels summed in slices, one per rank.  Closing every slice
+    // on its rank repeats the closing product world times (46 % extra closing FLOPs at cfg3 on 8 ranks).  Instead
+    // the slices of such panels are written into one region of BUF_Y that has the same layout on every rank, cut into
+    // `world` chunks of equal size; one reduce-scatter hands rank r the complete sums of chunk r, and rank r alone closes
+    // them.  (The reference's dead Ambient code did the same for its "exception" columns, detail/ambient.hpp:127-214.)
+    // Every rank computes the same assignment from the unsharded task lists.
+    struct XPanel { uint32_t out, o; int32_t dst_row, dst_col, rows, cols; int32_t chunk; int64_t off; };
+    struct Exchange
+    {
+        std::vector<XPanel> xp;
+        std::vector<std::unordered_map<uint64_t, uint32_t>> index;      // per output: (Y block, first row + first column) -> xp
+        std::vector<std::vector<uint32_t>> by_output;
+        int64_t chunk = 0;
+        bool active() const { return chunk > 0; }
+        static uint64_t key(size_t o, int32_t dst_row, int32_t dst_col) { return ((uint64_t)o << 32) | (uint32_t)(dst_row + dst_col); }
+        long find(size_t out, size_t o, int32_t dst_row, int32_t dst_col) const
+        {
+            if (!active() || index[out].empty()) return -1;
+            auto it = index[out].find(key(o, dst_row, dst_col));
+            return it == index[out].end() ? -1 : (long)it->second;
+        }
+    };
+    // used_blocks(i)[o]: Y block o of output i takes part in a closing product
+    template <class TasksOf, class RowsOf, class Used>
+    Exchange plan_exchange(size_t n_out, TasksOf tasks_of, RowsOf rows_of, Used used_blocks) const
+    {
+        Exchange X;
+        if (world <= 1 || getenv("QCM_NO_EXCHANGE")) return X;
+        X.index.resize(n_out); X.by_output.resize(n_out);
+        std::vector<std::vector<XPanel>> per_out(n_out);
+#pragma omp parallel for schedule(dynamic, 1)
+        for (long il = 0; il < (long)n_out; ++il) {
+            const size_t i = (size_t)il;
+            auto const& r = rows_of(i);
+            bool spread = false;
+            for (size_t b : r) if (owner_[b] != owner_[r[0]]) { spread = true; break; }
+            if (!spread) continue;
+            struct Acc { XPanel p; uint64_t mask; };
+            std::unordered_map<uint64_t, uint32_t> idx;
+            std::vector<Acc> acc;
+            for (YTask const& t : tasks_of(i)) {
+                auto ins = idx.emplace(Exchange::key(t.o, t.dst_row, t.dst_col), (uint32_t)acc.size());
+                if (ins.second) acc.push_back(Acc{XPanel{(uint32_t)i, (uint32_t)t.o, t.dst_row, t.dst_col, t.rows, t.cols, -1, 0}, 0});
+                acc[ins.first->second].mask |= (uint64_t)1 << (owner_[t.bt] & 63);
+            }
+            std::vector<char> used = used_blocks(i);
+            for (Acc const& a : acc)
+                if ((a.mask & (a.mask - 1)) != 0 && used[(size_t)a.p.o]) per_out[i].push_back(a.p);       // sources on two or more ranks
+            std::sort(per_out[i].begin(), per_out[i].end(), [](XPanel const& x, XPanel const& y) {
+                return std::tie(x.o, x.dst_col, x.dst_row) < std::tie(y.o, y.dst_col, y.dst_row); });
+        }
+        for (size_t i = 0; i < n_out; ++i) for (XPanel const& p : per_out[i]) X.xp.push_back(p);
+        if (X.xp.empty()) return X;
+        // chunks of (nearly) equal size: largest panels first, each to the least filled chunk; panels start 16-byte aligned
+        std::vector<uint32_t> order(X.xp.size());
+        std::iota(order.begin(), order.end(), 0u);
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return (int64_t)X.xp[a].rows * X.xp[a].cols > (int64_t)X.xp[b].rows * X.xp[b].cols; });
+        std::vector<int64_t> fill((size_t)world, 0);
+        for (uint32_t q : order) {
+            int c = (int)(std::min_element(fill.begin(), fill.end()) - fill.begin());
+            X.xp[q].chunk = c; X.xp[q].off = fill[c];
+            fill[c] += ((int64_t)X.xp[q].rows * X.xp[q].cols + 1) & ~(int64_t)1;
+        }
+        X.chunk = *std::max_element(fill.begin(), fill.end());
+        for (size_t q = 0; q < X.xp.size(); ++q) {
+            XPanel& p = X.xp[q];
+            p.off += (int64_t)p.chunk * X.chunk;
+            X.index[p.out].emplace(Exchange::key(p.o, p.dst_row, p.dst_col), (uint32_t)q);
+            X.by_output[p.out].push_back((uint32_t)q);
+        }
+        return X;
+    }
+    // this rank's partial sum of an exchanged panel goes to the panel's slot of the exchange region
+    void place_exchanged(Plan& P, Wave& xw, Panel& pn, XPanel const& x)
+    {
+        if (pn.rows != x.rows || pn.cols != x.cols) throw std::runtime_error("plan: exchanged panel changed shape between ranks");
+        AxpyDst d; d.dst = Ref{BUF_Y, x.off}; d.ldd = pn.rows; d.rows = pn.rows; d.cols = pn.cols;
+        P.w_panel_elems += (int64_t)pn.rows * pn.cols; P.exec_w += 2.0 * pn.rows * pn.cols * (double)pn.srcs.size();
+        xw.w_apply.dsts.push_back(d);
+        xw.w_apply.lists.push_back(std::move(pn.srcs));
+    }
+    // the exchange wave becomes waves[0]
+    void finish_exchange(Plan& P, Wave& xw, Exchange const& X)
+    {
+        if (!X.active()) return;
+        xw.x_chunk = X.chunk; xw.y_elems = X.chunk * world; xw.t_elems = 0;
+        xw.x_zero = xw.w_apply.dsts.size() < X.xp.size();
+        merge_outputs(xw.close_gemm);
+        group_axpy(P, xw.w_apply, xw.w_groups);
+        P.y_elems_max = std::max(P.y_elems_max, xw.y_elems);
+        P.waves.insert(P.waves.begin(), std::move(xw));
     }
     // the tasks / step-1 rows of one output index that belong to this rank
     // returns whether this rank books the reference's closing FLOPs of the output (it owns the first source): the
@@ -1592,6 +1733,7 @@ private:
     bool t_is_left = true; Layout t_ket;
     Layout ket_lp_for_right;
     // tables of the SU2 lbtm structure pass (build_lbtm_tables)
+    std::vector<int> owner_;            // rank that computes the step-1 product of every bond (shard_sources)
     std::vector<uint32_t> t_basis_id_;
     std::vector<std::vector<TbInfo>> tbinfo_;
     std::vector<std::vector<std::pair<int16_t, int16_t>>> op_phys_;

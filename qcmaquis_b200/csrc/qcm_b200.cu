@@ -171,7 +171,7 @@ struct AxpyGroup
     DWWork* d_works = nullptr; DWGroup* d_groups = nullptr; DWSrc* d_srcs = nullptr; DWDst* d_dsts = nullptr; double* d_coefs = nullptr;
     int64_t begin[5] = {0, 0, 0, 0, 0}, count[5] = {0, 0, 0, 0, 0};   // work ranges: [0] stream, [1..4] DMMA product with ng = 8, 16, 32, 64
 };
-struct WaveDev { GemmGroup t, c; AxpyGroup w; int64_t y_elems = 0, t_elems = 0; };
+struct WaveDev { GemmGroup t, c; AxpyGroup w; int64_t y_elems = 0, t_elems = 0, x_chunk = 0; bool x_zero = false; };
 
 struct qcm_plan_s
 {
@@ -196,6 +196,7 @@ struct NcclUid { char internal[128]; };
 typedef int (*nccl_get_uid_fn)(NcclUid*);
 typedef int (*nccl_init_rank_fn)(void**, int, NcclUid, int);
 typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*nccl_reducescatter_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 typedef int (*nccl_destroy_fn)(void*);
 typedef const char* (*nccl_errstr_fn)(int);
 
@@ -217,7 +218,8 @@ static struct Global
     cudaEvent_t ev[8];
     // nccl (resolved at run time so that single-GPU use has no NCCL dependency)
     void* nccl_lib = nullptr; void* comm = nullptr; int rank = 0, world = 1;
-    nccl_get_uid_fn f_uid = nullptr; nccl_init_rank_fn f_init = nullptr; nccl_allreduce_fn f_ar = nullptr;
+    nccl_get_uid_fn f_uid = nullptr; nccl_init_rank_fn f_init = nullptr; nccl_allreduce_fn f_ar = nullptr; nccl_reducescatter_fn f_rs = nullptr;
+    cudaStream_t comm_stream = nullptr; cudaEvent_t x_ready = nullptr, x_done = nullptr;   // exchange of partial W sums, overlapped with the local waves
     nccl_destroy_fn f_destroy = nullptr; nccl_errstr_fn f_err = nullptr;
 } G;
 
@@ -255,6 +257,8 @@ extern "C" int qcm_init(int device)
     for (auto& ev : G.ev) CU(cudaEventCreate(&ev));
     for (int i = 0; i < Global::kAux; ++i) { CU(cudaStreamCreateWithFlags(&G.aux[i], cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&G.join_ev[i], cudaEventDisableTiming)); }
     CU(cudaEventCreateWithFlags(&G.fork_ev, cudaEventDisableTiming));
+    CU(cudaStreamCreateWithFlags(&G.comm_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&G.x_ready, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&G.x_done, cudaEventDisableTiming));
     CU(cudaMalloc((void**)&G.scratch, 4096));
     if (gemm_set_attributes() || wgemm_set_attributes()) return 1;
     G.device = device;
@@ -272,6 +276,7 @@ extern "C" int qcm_finalize(void)
     for (auto& ev : G.ev) cudaEventDestroy(ev);
     for (int i = 0; i < Global::kAux; ++i) { cudaStreamDestroy(G.aux[i]); cudaEventDestroy(G.join_ev[i]); }
     cudaEventDestroy(G.fork_ev);
+    cudaEventDestroy(G.x_ready); cudaEventDestroy(G.x_done); cudaStreamDestroy(G.comm_stream);
     cudaStreamDestroy(G.stream);
     G.stream = nullptr; G.ready = false; G.device = -1;
     return 0;
@@ -613,7 +618,9 @@ extern "C" int qcm_plan_create(const qcm_plan_desc* d, qcm_plan_t* out)
     for (int w = 0; w < d->n_waves; ++w) {
         qcm_wave_desc const& wd = d->waves[w];
         WaveDev& W = P->waves[w];
-        W.y_elems = wd.y_elems; W.t_elems = wd.t_elems;
+        W.y_elems = wd.y_elems; W.t_elems = wd.t_elems; W.x_chunk = wd.x_chunk_elems; W.x_zero = wd.x_zero != 0;
+        if (W.x_chunk < 0 || (W.x_chunk > 0 && (w != 0 || P->world <= 1))) return (fail("qcm_plan_create: an exchange wave must be waves[0] of a sharded plan"), bail());
+        if (W.x_chunk * P->world > P->elems[QCM_BUF_Y]) return (fail("qcm_plan_create: exchange region larger than the Y workspace"), bail());
         if (build_gemm_group(P, W.t, wd.t_outs, wd.n_t_outs, wd.t_segs, wd.n_t_segs, 0)) return bail();
         if (build_axpy_group(P, W.w, wd)) return bail();
         if (build_gemm_group(P, W.c, wd.c_outs, wd.n_c_outs, wd.c_segs, wd.n_c_segs, 1)) return bail();
@@ -681,7 +688,7 @@ static int execute(qcm_plan_s* P, BufTable bufs)
         bufs.p[slot] = G.ws[slot];
     }
     bool tm = G.timing;
-    float acc[4] = {0, 0, 0, 0};
+    float acc[4] = {0, 0, 0, 0}, x_wait_ms = 0;
     auto mark = [&](int i) { if (tm) cudaEventRecord(G.ev[i], G.stream); };
     auto lap = [&](int phase, int i0, int i1) { if (tm) { cudaEventSynchronize(G.ev[i1]); float ms = 0; cudaEventElapsedTime(&ms, G.ev[i0], G.ev[i1]); acc[phase] += ms; } };
     mark(0);
@@ -695,8 +702,24 @@ static int execute(qcm_plan_s* P, BufTable bufs)
     mark(1); lap(0, 0, 1);
     if (run_gemm_group(P->p, bufs)) return 1;
     mark(2); lap(1, 1, 2);
+    const WaveDev* xwave = nullptr;
     for (auto const& W : P->waves) {
         mark(3);
+        if (W.x_chunk > 0) {
+            // exchange wave: partial sums -> exchange region -> reduce-scatter on the communication stream, overlapped with
+            // the waves that follow; its closing products run once the complete sums of this rank's chunk have arrived
+            if (!G.comm || G.world != P->world) return fail("exchange wave without a matching communicator");
+            if (W.x_zero) CU(cudaMemsetAsync(bufs.p[QCM_BUF_Y], 0, (size_t)W.x_chunk * P->world * 8, G.stream));
+            if (run_w_group(W.w, bufs)) return 1;
+            CU(cudaEventRecord(G.x_ready, G.stream));
+            CU(cudaStreamWaitEvent(G.comm_stream, G.x_ready, 0));
+            int r = G.f_rs(bufs.p[QCM_BUF_Y], bufs.p[QCM_BUF_Y] + (size_t)P->rank * W.x_chunk, (size_t)W.x_chunk, 8 /*ncclFloat64*/, 0 /*ncclSum*/, G.comm, G.comm_stream);
+            if (r != 0) return fail(std::string("ncclReduceScatter: ") + (G.f_err ? G.f_err(r) : "error"));
+            CU(cudaEventRecord(G.x_done, G.comm_stream));
+            xwave = &W;
+            mark(5); lap(2, 3, 5);
+            continue;
+        }
         if (run_gemm_group(W.t, bufs)) return 1;
         mark(4); lap(1, 3, 4);
         if (run_w_group(W.w, bufs)) return 1;
@@ -704,8 +727,16 @@ static int execute(qcm_plan_s* P, BufTable bufs)
         if (run_gemm_group(W.c, bufs)) return 1;
         mark(6); lap(3, 5, 6);
     }
+    if (xwave) {
+        mark(3);
+        CU(cudaStreamWaitEvent(G.stream, G.x_done, 0));
+        mark(4);
+        if (run_gemm_group(xwave->c, bufs)) return 1;
+        mark(5); lap(3, 4, 5);
+        if (tm) { cudaEventSynchronize(G.ev[4]); float ms = 0; cudaEventElapsedTime(&ms, G.ev[3], G.ev[4]); x_wait_ms = ms; }
+    }
     CU(cudaGetLastError());
-    if (tm) { for (int i = 0; i < 4; ++i) G.last_ms[i] = acc[i]; G.last_ms[4] = 0; G.last_ms[5] = acc[0] + acc[1] + acc[2] + acc[3]; }
+    if (tm) { for (int i = 0; i < 4; ++i) G.last_ms[i] = acc[i]; G.last_ms[4] = x_wait_ms; G.last_ms[5] = acc[0] + acc[1] + acc[2] + acc[3] + x_wait_ms; }
     return 0;
 }
 
@@ -845,9 +876,10 @@ static int nccl_resolve()
     G.f_uid = (nccl_get_uid_fn)dlsym(h, "ncclGetUniqueId");
     G.f_init = (nccl_init_rank_fn)dlsym(h, "ncclCommInitRank");
     G.f_ar = (nccl_allreduce_fn)dlsym(h, "ncclAllReduce");
+    G.f_rs = (nccl_reducescatter_fn)dlsym(h, "ncclReduceScatter");
     G.f_destroy = (nccl_destroy_fn)dlsym(h, "ncclCommDestroy");
     G.f_err = (nccl_errstr_fn)dlsym(h, "ncclGetErrorString");
-    if (!G.f_uid || !G.f_init || !G.f_ar || !G.f_destroy) { G.f_ar = nullptr; return fail("libnccl lacks required symbols"); }
+    if (!G.f_uid || !G.f_init || !G.f_ar || !G.f_rs || !G.f_destroy) { G.f_ar = nullptr; return fail("libnccl lacks required symbols"); }
     return 0;
 }
 extern "C" int qcm_comm_unique_id(char id[128])
@@ -885,7 +917,7 @@ static int allreduce_ptr(double* p, int64_t n)
     if (r != 0) return fail(std::string("ncclAllReduce: ") + (G.f_err ? G.f_err(r) : "error"));
     if (G.timing) {
         cudaEventRecord(G.ev[7], G.stream); cudaEventSynchronize(G.ev[7]);
-        float ms = 0; cudaEventElapsedTime(&ms, G.ev[6], G.ev[7]); G.last_ms[4] = ms; G.last_ms[5] += ms;
+        float ms = 0; cudaEventElapsedTime(&ms, G.ev[6], G.ev[7]); G.last_ms[4] += ms; G.last_ms[5] += ms;
     }
     return 0;
 }

@@ -205,7 +205,7 @@ extern "C" int qcmt_synth_parity(const char* fcidump, const char* symm, int L, i
         MPSTensor se = eng->site_hamil2(S.psi, S.left, S.right, *S.mpo);
         DiffReport d = compare(se.data(), so.data());
         out[0] = d.structure_equal; out[1] = rel_diff(d); out[2] = (double)so.data().num_elements(); out[3] = so.scalar_overlap(S.psi);
-        if (interp) { out[8] = interp->last_flops; out[9] = (double)interp->last_waves; }
+        if (interp) { out[8] = interp->last_flops; out[9] = (double)interp->last_waves; out[10] = (double)interp->last_exchange_elems; out[11] = interp->last_exec_close; }
 #ifdef QCMT_WITH_GPU
         if (engine_kind == 1) { out[8] = static_cast<GpuEngine*>(eng.get())->last_plan()->flops; out[9] = (double)static_cast<GpuEngine*>(eng.get())->last_plan()->n_waves; }
 #endif
@@ -253,6 +253,50 @@ extern "C" int qcmt_rank_sigma(const char* fcidump, const char* symm, int L, int
         B.b[plan::BUF_OUT].assign((size_t)pp.out_tensor.total, 0.);
         qcmtest::run_plan(pp, B);
         std::memcpy(buf, B.b[plan::BUF_OUT].data(), (size_t)pp.out_tensor.total * 8);
+        return 0;
+    } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
+}
+
+// The same in the phases a rank goes through when the plan has an exchange wave (world > 1): the caller plays NCCL.
+//   phase 0: plan, reshapes, resident step-1 products, W pass of the exchange wave; *n_out = elements of the exchange region
+//            (0: no exchange), *n_sigma = sigma elements
+//   phase 1: copy the exchange region (this rank's partial sums) into buf
+//   phase 2: take the reduce-scattered region from buf (only chunk `rank` is kept, the rest is poisoned)
+//   phase 3: local waves + closing products of the exchange chunk; the rank's share of sigma -> buf
+namespace { struct RankState { Problem P; SyntheticSite S; plan::Plan plan; qcmtest::Bufs B; }; std::unique_ptr<RankState> g_rank_state; }
+extern "C" int qcmt_rank_sigma_phase(int phase, const char* fcidump, const char* symm, int L, int nelec, int site, int twosite, int M, unsigned seed, int rank,
+                                     int world, double* buf, long long* n_out, long long* n_sigma, char* err, int errlen)
+{
+    try {
+        if (phase == 0) {
+            g_rank_state.reset(new RankState());
+            RankState& R = *g_rank_state;
+            R.P = make_problem(fcidump, symm, L, nelec);
+            R.S = make_synthetic_site(R.P, site, twosite != 0, (size_t)M, seed);
+            R.S.psi.make_left_paired();
+            plan::BoundaryLayout ll = qcmtest::InterpEngine::layout_of(R.S.left), rl = qcmtest::InterpEngine::layout_of(R.S.right);
+            plan::Planner pl(R.P.params.symm, *R.S.mpo, true, rank, world, (int64_t)1 << 28);
+            R.plan = pl.plan_sigma(qcmtest::InterpEngine::desc_of(R.S.psi), ll, rl);
+            R.B.b[plan::BUF_KET_LP] = qcmtest::InterpEngine::flat(R.S.psi.data()); R.B.b[plan::BUF_LEFT] = qcmtest::InterpEngine::flat(R.S.left);
+            R.B.b[plan::BUF_RIGHT] = qcmtest::InterpEngine::flat(R.S.right);
+            R.B.b[plan::BUF_OUT].assign((size_t)R.plan.out_tensor.total, 0.);
+            qcmtest::run_pre(R.plan, R.B);
+            if (qcmtest::exchange_elems(R.plan) > 0) qcmtest::run_exchange_w(R.plan, R.B);
+            *n_out = qcmtest::exchange_elems(R.plan); *n_sigma = R.plan.out_tensor.total;
+            return 0;
+        }
+        if (!g_rank_state) throw std::runtime_error("qcmt_rank_sigma_phase: phase 0 has not run");
+        RankState& R = *g_rank_state;
+        const long long xe = qcmtest::exchange_elems(R.plan);
+        if (phase == 1) { std::memcpy(buf, R.B.b[plan::BUF_Y].data(), (size_t)xe * 8); return 0; }
+        if (phase == 2) {
+            const long long C = R.plan.waves[0].x_chunk;
+            for (long long i = 0; i < xe; ++i) R.B.b[plan::BUF_Y][(size_t)i] = (i / C == rank) ? buf[i] : std::nan("");
+            return 0;
+        }
+        qcmtest::run_local(R.plan, R.B);
+        std::memcpy(buf, R.B.b[plan::BUF_OUT].data(), (size_t)R.plan.out_tensor.total * 8);
+        g_rank_state.reset();
         return 0;
     } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
 }
@@ -426,16 +470,17 @@ extern "C" int qcmt_shard_stats(const char* fcidump, const char* symm, int L, in
         plan::TensorDesc td{S.psi.site_dim(), S.psi.row_dim(), S.psi.col_dim(), S.psi.data().basis()};
         plan::Planner p1(P.params.symm, *S.mpo, true, 0, 1, (int64_t)1 << 40);
         plan::Plan full = p1.plan_sigma(td, ll, rl);
-        double t_sum = 0, mx = 0, alg = 0;
+        double t_sum = 0, mx = 0, alg = 0, close_sum = 0;
         for (int r = 0; r < world; ++r) {
             plan::Planner pr(P.params.symm, *S.mpo, true, r, world, (int64_t)1 << 40);
             plan::Plan q = pr.plan_sigma(td, ll, rl);
-            t_sum += q.flops_t; alg += q.flops();
+            t_sum += q.flops_t; alg += q.flops(); close_sum += q.exec_close;
             mx = std::max(mx, q.flops_t + q.exec_w + q.exec_close);
         }
         out[0] = t_sum / full.flops_t;
         out[1] = mx / ((full.flops_t + full.exec_w + full.exec_close) / world);
         out[2] = alg / full.flops();
+        out[3] = close_sum / full.exec_close;      // executed closing FLOPs over all ranks / unsharded plan
         return 0;
     } catch (std::exception const& e) {
         set_err(err, errlen, e.what());
