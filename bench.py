@@ -303,16 +303,23 @@ def main():
         if cu.qcm_comm_init(rank, world, idbuf):
             raise RuntimeError(cu.qcm_last_error().decode())
 
+    t_start = time.time()
+
+    def progress(what):
+        sys.stderr.write("[bench rank %d +%.1fs] %s\n" % (rank, time.time() - t_start, what)); sys.stderr.flush()
+
     e = errbuf()
     path = make_fcidump(norb, nelec)
     h = host.qcmd_create(path.encode(), symm.encode(), norb, nelec, e, 1024)
     if not h:
         raise RuntimeError(e.value.decode())
     h = ctypes.c_void_p(h)
+    progress("model + MPO built")
     info = (ctypes.c_double * 32)()
     if host.qcmd_setup_site(h, site, 1, M, args.seed, local, rank, world, info, e, 1024):
         raise RuntimeError(e.value.decode())
     psi_n, sig_n = int(info[5]), int(info[6])
+    progress("site problem planned (%.2f s) and uploaded" % info[13])
     stream = torch.cuda.ExternalStream(cu.qcm_stream())
 
     def barrier():
@@ -344,6 +351,7 @@ def main():
     if host.qcmd_sigma_dev(h, args.warmup, e, 1024):
         raise RuntimeError(e.value.decode())
     barrier()
+    progress("warm-up done")
     sampler = ClockSampler(local); sampler.start()
     l0 = cu.qcm_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -355,6 +363,7 @@ def main():
     launches = cu.qcm_launch_count() - l0
     ms_dev = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
     clocks = sampler.finish()
+    progress("timed region done: %.2f ms per sigma" % ms_dev)
 
     # ---- per-phase kernel times (same steps, CUDA events between phases) ---------------------------------
     cu.qcm_set_timing(1)
@@ -380,6 +389,7 @@ def main():
         host.qcmd_sigma_host(h, ctypes.c_void_p(psi.data_ptr()), ctypes.c_void_p(sig.data_ptr()), e, 1024)
     barrier()
     ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+    progress("phases + e2e done")
 
     peak = ctypes.c_double()
     cu.qcm_measure_fp64_dmma_peak(ctypes.byref(peak))
@@ -461,6 +471,7 @@ def main():
         else:
             line["parity_rel_err_vs_oracle"] = "structure mismatch: %d vs %d elements" % (int(se.value), sig_n)
         olib.orc_destroy(oh)
+    progress("cpu baseline / parity done")
     barrier()   # the other ranks' host threads stay idle while rank 0 times the CPU oracle
     # ---- sweep level, the benchmarked configuration itself (every N): one two-site DMRG sweep from a random MPS on the
     # synthetic sector lists (total bond dimension M at every bond), boundaries resident in HBM, engine calls collective
@@ -470,6 +481,7 @@ def main():
             line["config_sweep"] = config_sweep(host, h, args, M, local, rank, world, max_over_ranks, sum_over_ranks, peak.value)
         except Exception as ex:
             line["config_sweep"] = {"error": str(ex)}
+        progress("configuration sweep done")
     # ---- sweep level (N=1): single-site DMRG sweeps of BASELINE config 1's system (8e/8o SU2U1, M=256) through the
     # engine, boundaries resident in HBM, against the same driver on the CPU oracle: per-micro-iteration energies
     if world == 1 and not args.no_sweep:

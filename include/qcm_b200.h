@@ -150,6 +150,12 @@ int qcm_set_timing(int enabled);
 /* ---- solver-side vector algebra on device arrays (MPSTensor::scalar_overlap / scalar_norm / += / *=,
  *      mpstensor.hpp:346-395,458-522; used by ietl::dot/two_norm, ietl_lanczos_solver.h:67-102) ---------- */
 int qcm_vec_dot(qcm_array_t x, qcm_array_t y, int64_t n, double* result);
+/* k dot products results[q] = xs[q] . ys[q] with ONE host synchronisation (the Gram-Schmidt / projected-matrix columns of the
+ * Jacobi-Davidson driver, ietl/jacobi.h:361-451); the summation order is fixed, so equal inputs give bit-equal results on
+ * every rank.  out = sum_j coefs[j] xs[j] in one pass (Ritz vector and residual, jacobi.h:404-420). */
+#define QCM_MAX_DOTS 64
+int qcm_vec_dots(const qcm_array_t* xs, const qcm_array_t* ys, int k, int64_t n, double* results);
+int qcm_vec_lincomb(const qcm_array_t* xs, const double* coefs, int k, qcm_array_t out, int64_t n);
 int qcm_vec_axpy(double a, qcm_array_t x, qcm_array_t y, int64_t n);       /* y += a x */
 int qcm_vec_scal(double a, qcm_array_t x, int64_t n);
 int qcm_vec_copy(qcm_array_t src, qcm_array_t dst, int64_t n);

@@ -76,7 +76,7 @@ public:
     {
         qcm_check(qcm_init(device), "qcm_init");
     }
-    ~GpuEngine() { for (auto a : vec_pool) qcm_array_free(a); }
+    ~GpuEngine() { for (auto a : vec_pool) qcm_array_free(a); if (host_xfer) qcm_array_free(host_xfer); }
 
     // ---- Engine::site_hamil2 ----------------------------------------------------------------------------
     MPSTensor site_hamil2(MPSTensor ket_tensor, Boundary const& left, Boundary const& right, MPOTensor const& mpo,
@@ -114,75 +114,125 @@ public:
     }
 
     // ---- Jacobi-Davidson with device-resident vectors (ietl/jacobi.h:361-451, ietl_jcd_gmres = 0) ---------------------
-    // Same recurrence as the host solver (qcm/sweep.hpp), on flat device arrays: modified Gram-Schmidt with refinement,
-    // one qcm_site_hamil2_dev per iteration, the small projected eigenproblem on the host, correction t = -r + (r.u / u.u) u.
-    // psi goes up once and the eigenvector comes down once per site.  Needs sigma and psi in ONE block layout (true for
-    // a consistent site problem); otherwise the host solver is used.
+    // Same recurrence as the host solver (qcm/sweep.hpp) on flat device arrays: one qcm_site_hamil2_dev per iteration, the small
+    // projected eigenproblem on the host, correction t = -r + (r.u / u.u) u.  psi goes up once and the eigenvector comes down
+    // once per site.  Scalars reach the host in THREE batched reads per iteration (qcm_vec_dots):
+    //   (1) after sigma: the new column of the projected matrix, V_i . (H v);
+    //   (2) after the Ritz pair: r.r, r.u, u.u and V_i . r, V_i . u -- from these the Gram-Schmidt coefficients of the
+    //       correction vector follow without touching it, so the first orthogonalisation pass is ONE fused linear combination
+    //       t' = -r + a u - sum_i c_i V_i;
+    //   (3) the second pass ("twice is enough"): V_i . t' and t'.t', applied together with the normalisation in one more
+    //       linear combination.
+    // The host solver orthogonalises by modified Gram-Schmidt with conditional refinement (jacobi.h:166-186); the two-pass
+    // classical scheme spans the same Krylov space and is as stable, energies agree to rounding (tests: <= 1e-8 Eh per
+    // micro-iteration).  Needs sigma and psi in ONE block layout (true for a consistent site problem); otherwise the host
+    // solver is used.
     bool jacobi_davidson(MPSTensor const& x0, Boundary const& left, Boundary const& right, MPOTensor const& mpo, int max_iter, double tol,
                          EigenResult& res) override
     {
-        if (!device_solver) return false;
+        if (!device_solver || max_iter < 1 || 2 * max_iter + 3 > QCM_MAX_DOTS) return false;
         x0.make_left_paired();
         std::shared_ptr<DeviceBoundary> dl = mirror(left), dr = mirror(right);
         std::shared_ptr<CompiledPlan> cp = sigma_plan(x0, dl, dr, mpo, true);
         if (!(cp->out_tensor.basis == x0.data().basis()) || cp->out_elems != cp->ket_elems) return false;
         Clock c0;
         const int64_t n = cp->ket_elems;
-        const size_t need = 2 * (size_t)max_iter + 3;
+        const size_t need = 2 * (size_t)max_iter + 4;
         // every pool entry holds vec_pool_n elements: a larger site rebuilds the pool, a smaller one reuses it
         if (vec_pool_n < n) { for (auto a : vec_pool) qcm_array_free(a); vec_pool.clear(); vec_pool_n = n; }
         while (vec_pool.size() < need) { qcm_array_t a = nullptr; qcm_check(qcm_array_alloc(vec_pool_n, &a), "qcm_array_alloc"); vec_pool.push_back(a); }
-        auto V = [&](int i) { return vec_pool[(size_t)i]; };
-        auto VA = [&](int i) { return vec_pool[(size_t)max_iter + 1 + (size_t)i]; };
-        qcm_array_t u = vec_pool[2 * (size_t)max_iter + 1], r = vec_pool[2 * (size_t)max_iter + 2];
-        auto dot = [&](qcm_array_t a, qcm_array_t b) { double d = 0; qcm_check(qcm_vec_dot(a, b, n, &d), "qcm_vec_dot"); return d; };
-        auto axpy = [&](double a, qcm_array_t x, qcm_array_t y) { qcm_check(qcm_vec_axpy(a, x, y, n), "qcm_vec_axpy"); };
-        auto scal = [&](double a, qcm_array_t x) { qcm_check(qcm_vec_scal(a, x, n), "qcm_vec_scal"); };
-        auto copy = [&](qcm_array_t s_, qcm_array_t d) { qcm_check(qcm_vec_copy(s_, d, n), "qcm_vec_copy"); };
+        std::vector<qcm_array_t> V(vec_pool.begin(), vec_pool.begin() + max_iter + 1), VA(vec_pool.begin() + max_iter + 1, vec_pool.begin() + 2 * max_iter + 1);
+        qcm_array_t u = vec_pool[2 * (size_t)max_iter + 1], r = vec_pool[2 * (size_t)max_iter + 2], w = vec_pool[2 * (size_t)max_iter + 3];
+        std::vector<qcm_array_t> xs, ys; std::vector<double> d, cf;
+        // sharded runs: every rank computes the scalars from its own copy of the (bit-identical) vectors; rank 0's values are
+        // handed to all ranks anyway, so that no rank can ever take a different convergence decision
+        auto dots = [&]() {
+            d.assign(xs.size(), 0.); qcm_check(qcm_vec_dots(xs.data(), ys.data(), (int)xs.size(), n, d.data()), "qcm_vec_dots"); ++host_syncs;
+            if (world > 1) { if (rank != 0) std::fill(d.begin(), d.end(), 0.); allreduce_sum(d.data(), d.size()); }
+        };
+        auto lincomb = [&](qcm_array_t out) { qcm_check(qcm_vec_lincomb(xs.data(), cf.data(), (int)xs.size(), out, n), "qcm_vec_lincomb"); };
         {
             std::vector<double> psi = flatten(x0.data(), n);
-            qcm_check(qcm_array_upload(V(0), 0, psi.data(), n), "qcm_array_upload");
+            qcm_check(qcm_array_upload(w, 0, psi.data(), n), "qcm_array_upload");
+            xs = {w}; ys = {w}; dots();
+            xs = {w}; cf = {1. / std::sqrt(d[0])}; lincomb(V[0]);
         }
         std::vector<double> M((size_t)max_iter * max_iter, 0.);
-        const double kappa = 0.25;
         res = EigenResult();
         int it = 0;
         for (;;) {
-            qcm_array_t t = V(it);
-            const double tau = std::sqrt(dot(t, t));
-            for (int i = 0; i < it; ++i) axpy(-dot(V(i), t), V(i), t);
-            if (std::sqrt(dot(t, t)) < kappa * tau)
-                for (int i = 0; i < it; ++i) axpy(-dot(V(i), t), V(i), t);
-            scal(1. / std::sqrt(dot(t, t)), t);
-            qcm_check(qcm_site_hamil2_dev(cp->handle, dl->arr, dr->arr, t, VA(it)), "qcm_site_hamil2_dev");
+            qcm_check(qcm_site_hamil2_dev(cp->handle, dl->arr, dr->arr, V[it], VA[it]), "qcm_site_hamil2_dev");
             res.n_sigma++; sigma_flops += cp->flops; ++n_sigma_calls;
-            for (int i = 0; i <= it; ++i) M[(size_t)i + (size_t)it * max_iter] = dot(V(i), VA(it));
+            xs.assign(V.begin(), V.begin() + it + 1); ys.assign((size_t)it + 1, VA[it]); dots();                            // (1)
+            for (int i = 0; i <= it; ++i) M[(size_t)i + (size_t)it * max_iter] = d[(size_t)i];
             const int dim = it + 1;
-            std::vector<double> A((size_t)dim * dim), w(dim), work(std::max(1, 3 * dim));
+            std::vector<double> A((size_t)dim * dim), ev(dim), work(std::max(1, 3 * dim));
             for (int c = 0; c < dim; ++c) for (int q = 0; q <= c; ++q) A[(size_t)q + (size_t)c * dim] = M[(size_t)q + (size_t)c * max_iter];
             int lwork = (int)work.size(), info = 0;
-            scipy_dsyev_("V", "U", &dim, A.data(), &dim, w.data(), work.data(), &lwork, &info);
+            scipy_dsyev_("V", "U", &dim, A.data(), &dim, ev.data(), work.data(), &lwork, &info);
             if (info) throw std::runtime_error("dsyev failed in the Jacobi-Davidson subspace problem");
-            const double theta = w[0];
+            const double theta = ev[0];
             const double* sv = A.data();
-            copy(V(0), u); scal(sv[0], u);
-            for (int j = 1; j <= it; ++j) axpy(sv[j], V(j), u);
-            copy(VA(0), r); scal(sv[0], r);
-            for (int j = 1; j <= it; ++j) axpy(sv[j], VA(j), r);
-            axpy(-theta, u, r);
+            // u = sum_j s_j V_j ;  r = sum_j s_j (H V_j) - theta u
+            xs.assign(V.begin(), V.begin() + dim); cf.assign(sv, sv + dim); lincomb(u);
+            xs.assign(VA.begin(), VA.begin() + dim); xs.insert(xs.end(), V.begin(), V.begin() + dim);
+            cf.assign(sv, sv + dim); for (int j = 0; j < dim; ++j) cf.push_back(-theta * sv[j]);
+            lincomb(r);
+            xs = {r, r, u}; ys = {r, u, u};
+            for (int i = 0; i < dim; ++i) { xs.push_back(V[i]); ys.push_back(r); }
+            for (int i = 0; i < dim; ++i) { xs.push_back(V[i]); ys.push_back(u); }
+            dots();                                                                                                          // (2)
             ++it;
-            const double rn = std::sqrt(dot(r, r));
+            const double rn = std::sqrt(d[0]);
             res.theta = theta; res.resid = rn;
             if (rn <= tol * std::abs(theta) || rn <= tol || it >= max_iter) break;
-            const double dru = dot(r, u), duu = dot(u, u);
-            copy(r, V(it)); scal(-1., V(it));
-            axpy(dru / duu, u, V(it));
+            // correction without GMRES steps, t = -r + (r.u / u.u) u, orthogonalised against V_0 .. V_{it-1} in two passes
+            const double alpha = d[1] / d[2];
+            xs = {r, u}; cf = {-1., alpha};
+            for (int i = 0; i < dim; ++i) { xs.push_back(V[i]); cf.push_back(-(-d[3 + (size_t)i] + alpha * d[3 + (size_t)dim + (size_t)i])); }
+            lincomb(w);
+            xs.assign(V.begin(), V.begin() + dim); ys.assign((size_t)dim, w); xs.push_back(w); ys.push_back(w); dots();      // (3)
+            double nrm2 = d[(size_t)dim];
+            for (int i = 0; i < dim; ++i) nrm2 -= d[(size_t)i] * d[(size_t)i];
+            const double inv = 1. / std::sqrt(nrm2 > 0 ? nrm2 : d[(size_t)dim]);
+            xs = {w}; cf = {inv};
+            for (int i = 0; i < dim; ++i) { xs.push_back(V[i]); cf.push_back(-d[(size_t)i] * inv); }
+            lincomb(V[it]);
         }
         std::vector<double> out((size_t)n);
+        if (world > 1) {       // every rank continues from rank 0's eigenvector
+            if (rank != 0) qcm_check(qcm_array_zero(u), "qcm_array_zero");
+            qcm_check(qcm_comm_allreduce(u, n), "qcm_comm_allreduce");
+        }
         qcm_check(qcm_array_download(u, 0, out.data(), n), "qcm_array_download");
         res.vec = MPSTensor(x0.site_dim(), x0.row_dim(), x0.col_dim(), unflatten(cp->out_tensor, out), LeftPaired, true);
         seconds[2] += c0.lap();
         return true;
+    }
+    size_t host_syncs = 0;           // batched scalar reads of the device solver (three per Jacobi-Davidson iteration)
+    // ---- host-side collectives of a sharded sweep (EngineIface) --------------------------------------------------------
+    int comm_rank() const override { return rank; }
+    int comm_world() const override { return world; }
+    void allreduce_sum(double* buf, size_t n) override
+    {
+        if (world <= 1 || n == 0) return;
+        int64_t have = 0;
+        if (host_xfer) qcm_array_size(host_xfer, &have);
+        if (have < (int64_t)n) { if (host_xfer) qcm_array_free(host_xfer); host_xfer = nullptr; qcm_check(qcm_array_alloc((int64_t)n + (int64_t)n / 4, &host_xfer), "qcm_array_alloc"); }
+        qcm_check(qcm_array_upload(host_xfer, 0, buf, (int64_t)n), "qcm_array_upload");
+        qcm_check(qcm_comm_allreduce(host_xfer, (int64_t)n), "qcm_comm_allreduce");
+        qcm_check(qcm_array_download(host_xfer, 0, buf, (int64_t)n), "qcm_array_download");
+    }
+    void assert_consistent(uint64_t fp, const char* what) override
+    {
+        if (world <= 1) return;
+        // 16-bit pieces h_q of the fingerprint: all ranks agree  <=>  world * sum(h_q^2) == (sum h_q)^2 for every piece
+        double v[8];
+        for (int q = 0; q < 4; ++q) { double h = (double)((fp >> (16 * q)) & 0xffffu); v[q] = h; v[4 + q] = h * h; }
+        allreduce_sum(v, 8);
+        for (int q = 0; q < 4; ++q)
+            if ((double)world * v[4 + q] != v[q] * v[q])
+                throw std::runtime_error(std::string("the ranks of the sharded sweep have diverged (") + what + "): the host-side state must be bit-identical on all ranks");
     }
     bool device_solver = true;       // false: always leave the eigensolver to the caller (host vectors)
 
@@ -452,6 +502,7 @@ private:
     std::list<CacheEntry> cache;
     size_t cache_capacity = 4;
     std::vector<qcm_array_t> vec_pool; int64_t vec_pool_n = 0;      // solver vectors, reused from site to site
+    qcm_array_t host_xfer = nullptr;                                // staging array of allreduce_sum
     std::shared_ptr<CompiledPlan> last;
 };
 

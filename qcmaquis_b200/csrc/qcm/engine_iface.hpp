@@ -26,6 +26,14 @@ struct EngineIface
                                            MPOTensor const& mpo, bool isHermitian = true) = 0;
     virtual Boundary overlap_mpo_right_step(MPSTensor const& bra_tensor, MPSTensor const& ket_tensor, Boundary const& right,
                                             MPOTensor const& mpo, bool isHermitian = true) = 0;
+    // ---- one process per GPU: the host side of a sweep runs on every rank.  Work that is the same on all ranks (the block
+    // SVDs of the two-site split) is divided among them and the pieces are combined with allreduce_sum (every rank adds its
+    // pieces into a zero buffer, so all ranks end up with bit-identical data); assert_consistent makes a sweep fail loudly,
+    // on every rank, when the ranks' host states have diverged (a collective with mismatched sizes would hang instead).
+    virtual int comm_rank() const { return 0; }
+    virtual int comm_world() const { return 1; }
+    virtual void allreduce_sum(double* /*buf*/, size_t /*n*/) {}
+    virtual void assert_consistent(uint64_t /*fingerprint*/, const char* /*what*/) {}
 };
 
 } // namespace qcm

@@ -1114,7 +1114,8 @@ private:
                         const int i = ti.i_spin, ip = qo.ip, j = ti.j_spin, jp = qi.jp;
                         const int two_sp = std::abs(i - ip), two_s = std::abs(j - jp);
                         double couplings[4];
-                        su2::set_coupling(j, two_s, jp, a, k, ap, i, two_sp, ip, term.second, couplings);
+                        if (const double* cv = su2::coupling_table(j, jp, i, ip, a, k, ap)) { for (int q = 0; q < 4; ++q) couplings[q] = cv[q] * term.second; }
+                        else su2::set_coupling(j, two_s, jp, a, k, ap, i, two_sp, ip, term.second, couplings);
                         const int32_t in_off = qi.in_off, out_off = qo.out_off, l_size = ti.l_size, r_size = qi.r_size;
                         for (int s = W.sparse_ptr[w]; s < W.sparse_ptr[w + 1]; ++s) {
                             SparseEntry const& en = W.sparse[s];

@@ -9,6 +9,7 @@
 // (mpo.hpp).  Everything here is O(tensor size) or block SVDs; sigma and the boundary steps go through the engine.
 #pragma once
 #include "sweep.hpp"
+#include <cstring>
 #include <functional>
 #include "wigner.hpp"
 
@@ -217,13 +218,29 @@ inline Index unreduce_left(Index const& physical_i_left, Index const& physical_i
 // ---- block SVD with truncation (block_matrix_algorithms.h:165-185,211-260,264-335) ----------------------------------
 struct Truncation { size_t bond_dimension = 0; double truncated_weight = 0, truncated_fraction = 0, smallest_ev = 0; };
 
-// M = U diag(S) V per block; singular values below max(rel_tol * largest, the (Mmax+1)-th largest) are dropped
-inline Truncation svd_truncate(block_matrix const& M, block_matrix& U, block_matrix& V, std::vector<std::vector<double>>& S, double rel_tol, size_t Mmax)
+// M = U diag(S) V per block; singular values below max(rel_tol * largest, the (Mmax+1)-th largest) are dropped.
+// With several ranks (eng->comm_world() > 1) the blocks are divided among the ranks, largest first to the least loaded one,
+// and the factors are combined with one allreduce of a zero-padded buffer: the split costs 1/world of the host time per
+// rank and every rank holds bit-identical factors, whatever its BLAS threads did.
+inline Truncation svd_truncate(block_matrix const& M, block_matrix& U, block_matrix& V, std::vector<std::vector<double>>& S, double rel_tol, size_t Mmax,
+                               EngineIface* eng = nullptr)
 {
     const size_t nb = M.n_blocks();
     std::vector<Matrix> us(nb), vs(nb);
     S.assign(nb, std::vector<double>());
-    sweep::run_blocks(nb, [&](size_t b) { double m = (double)M[b].rows, n = (double)M[b].cols; return 20.0 * m * n * std::min(m, n); }, [&](size_t b) {
+    const int world = eng ? eng->comm_world() : 1, rank = eng ? eng->comm_rank() : 0;
+    auto cost = [&](size_t b) { double m = (double)M[b].rows, n = (double)M[b].cols; return 20.0 * m * n * std::min(m, n); };
+    std::vector<int> owner(nb, 0);
+    std::vector<size_t> mine;
+    {
+        std::vector<size_t> order(nb);
+        std::iota(order.begin(), order.end(), (size_t)0);
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return cost(a) > cost(b); });
+        std::vector<double> load((size_t)world, 0.);
+        for (size_t b : order) { int r = (int)(std::min_element(load.begin(), load.end()) - load.begin()); owner[b] = r; load[(size_t)r] += cost(b); if (r == rank) mine.push_back(b); }
+    }
+    sweep::run_blocks(mine.size(), [&](size_t q) { return cost(mine[q]); }, [&](size_t q) {
+        const size_t b = mine[q];
         Matrix a = M[b];
         const int m = (int)a.rows, n = (int)a.cols, k = std::min(m, n);
         us[b] = Matrix(m, k); vs[b] = Matrix(k, n); S[b].assign(k, 0.);
@@ -234,6 +251,24 @@ inline Truncation svd_truncate(block_matrix const& M, block_matrix& U, block_mat
         scipy_dgesdd_("S", &m, &n, a.data(), &m, S[b].data(), us[b].data(), &m, vs[b].data(), &k, work.data(), &lwork, iwork.data(), &info);
         if (info) throw std::runtime_error("dgesdd failed");
     });
+    if (world > 1) {
+        std::vector<size_t> off(nb + 1, 0);
+        for (size_t b = 0; b < nb; ++b) { size_t m = M[b].rows, n = M[b].cols, k = std::min(m, n); off[b + 1] = off[b] + m * k + k + k * n; }
+        std::vector<double> buf(off[nb], 0.);
+        for (size_t b : mine) {
+            double* p = buf.data() + off[b];
+            p = std::copy(us[b].v.begin(), us[b].v.end(), p); p = std::copy(S[b].begin(), S[b].end(), p); std::copy(vs[b].v.begin(), vs[b].v.end(), p);
+        }
+        eng->allreduce_sum(buf.data(), buf.size());
+        for (size_t b = 0; b < nb; ++b) {
+            const size_t m = M[b].rows, n = M[b].cols, k = std::min(m, n);
+            const double* p = buf.data() + off[b];
+            us[b] = Matrix(m, k); vs[b] = Matrix(k, n); S[b].assign(k, 0.);
+            std::copy(p, p + m * k, us[b].v.begin()); p += m * k;
+            std::copy(p, p + k, S[b].begin()); p += k;
+            std::copy(p, p + k * n, vs[b].v.begin());
+        }
+    }
     // estimate_truncation
     std::vector<double> all;
     for (auto const& s : S) all.insert(all.end(), s.begin(), s.end());
@@ -313,20 +348,20 @@ public:
         return *this;
     }
     // :141-183
-    void split_mps_l2r(size_t Mmax, double cutoff, MPSTensor& t1, MPSTensor& t2, Truncation& trunc)
+    void split_mps_l2r(size_t Mmax, double cutoff, MPSTensor& t1, MPSTensor& t2, Truncation& trunc, EngineIface* eng = nullptr)
     {
         make_both_paired();
         block_matrix u, v; std::vector<std::vector<double>> s;
-        trunc = svd_truncate(data_, u, v, s, cutoff, Mmax);
+        trunc = svd_truncate(data_, u, v, s, cutoff, Mmax, eng);
         t1 = MPSTensor(phys_i_left, left_i, u.right_basis(), u, LeftPaired);
         block_matrix sv = scale_rows(v, s);
         t2 = MPSTensor(phys_i_right, sv.left_basis(), right_i, sv, RightPaired);
     }
-    void split_mps_r2l(size_t Mmax, double cutoff, MPSTensor& t1, MPSTensor& t2, Truncation& trunc)
+    void split_mps_r2l(size_t Mmax, double cutoff, MPSTensor& t1, MPSTensor& t2, Truncation& trunc, EngineIface* eng = nullptr)
     {
         make_both_paired();
         block_matrix u, v; std::vector<std::vector<double>> s;
-        trunc = svd_truncate(data_, u, v, s, cutoff, Mmax);
+        trunc = svd_truncate(data_, u, v, s, cutoff, Mmax, eng);
         t2 = MPSTensor(phys_i_right, v.left_basis(), right_i, v, RightPaired);
         block_matrix us = scale_cols(u, s);
         t1 = MPSTensor(phys_i_left, left_i, us.right_basis(), us, LeftPaired);
@@ -398,15 +433,25 @@ inline sweep::SweepLog ts_sweeps(SymmKind symm, EngineIface& eng, MPO const& mpo
             log.energies.push_back(r.theta + mpo.core_energy);
             log.n_sigma.push_back(r.n_sigma); log.total_sigma += r.n_sigma;
             Truncation trunc;
+            // all ranks of a sharded run must hold the same state here: same solver history, same structure about to be split
+            {
+                uint64_t fp = 1469598103934665603ull;
+                auto mix = [&](uint64_t x) { fp ^= x; fp *= 1099511628211ull; };
+                mix((uint64_t)r.n_sigma); mix((uint64_t)_site);
+                r.vec.make_left_paired();
+                for (auto const& q : r.vec.data().basis()) { mix(q.ls); mix(q.rs); }
+                double th = r.theta; uint64_t bits; std::memcpy(&bits, &th, 8); mix(bits);
+                eng.assert_consistent(fp, "eigensolver result");
+            }
             if (lr == +1) {
-                tst.split_mps_l2r(prm.Mmax, prm.cutoff, mps[site1], mps[site2], trunc);
+                tst.split_mps_l2r(prm.Mmax, prm.cutoff, mps[site1], mps[site2], trunc, &eng);
                 block_matrix t = sweep::normalize_left(mps[site2]);
                 if (site2 < L - 1) sweep::multiply_from_left(mps[site2 + 1], t);
                 log.phase_seconds[3] += lap();
                 left[site2] = eng.overlap_mpo_left_step(mps[site1], mps[site1], left[site1], mpo[site1]);
                 if (prm.drop_stale && site2 < L - 1) right[site2] = Boundary();
             } else {
-                tst.split_mps_r2l(prm.Mmax, prm.cutoff, mps[site1], mps[site2], trunc);
+                tst.split_mps_r2l(prm.Mmax, prm.cutoff, mps[site1], mps[site2], trunc, &eng);
                 block_matrix t = sweep::normalize_right(mps[site1]);
                 if (site1 > 0) sweep::multiply_from_right(mps[site1 - 1], t);
                 log.phase_seconds[3] += lap();
@@ -414,6 +459,13 @@ inline sweep::SweepLog ts_sweeps(SymmKind symm, EngineIface& eng, MPO const& mpo
                 if (prm.drop_stale && site1 > 0) left[site2] = Boundary();
             }
             log.phase_seconds[4] += lap();
+            {
+                uint64_t fp = 1469598103934665603ull;
+                auto mix = [&](uint64_t x) { fp ^= x; fp *= 1099511628211ull; };
+                mix(trunc.bond_dimension);
+                for (auto const& e : mps[site1].col_dim()) mix(e.second);
+                eng.assert_consistent(fp, "bond structure after the split");
+            }
             if (bond_dims) bond_dims->push_back(trunc.bond_dimension);
         }
         log.sweep_energy.push_back(log.energies.empty() ? 0. : log.energies.back());

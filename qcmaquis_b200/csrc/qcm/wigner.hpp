@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <stdexcept>
 #include <unordered_map>
+#include <vector>
 
 namespace qcm { namespace su2 {
 
@@ -118,6 +119,21 @@ inline void set_coupling(int a, int b, int c, int d, int e, int f, int g, int h,
         it = cache.emplace(key, en).first;
     }
     for (int q = 0; q < 4; ++q) couplings[q] = it->second.v[q] * init;
+}
+
+// The planner asks for the couplings of one (T block, W block) pair millions of times per plan, for a few hundred distinct
+// spin combinations: a small direct-mapped per-thread cache (it stays in L1/L2) in front of set_coupling's hash map.
+// Values are those of set_coupling with init == 1; the caller multiplies by the term's scale exactly as set_coupling does.
+inline const double* coupling_table(int j, int jp, int i, int ip, int a, int k, int ap)
+{
+    if ((unsigned)j > 255u || (unsigned)jp > 255u || (unsigned)i > 255u || (unsigned)ip > 255u || (unsigned)a > 15u || (unsigned)k > 15u || (unsigned)ap > 15u) return nullptr;
+    const uint64_t key = 1 + (((((((uint64_t)j << 8 | (uint64_t)jp) << 8 | (uint64_t)i) << 8 | (uint64_t)ip) << 4 | (uint64_t)a) << 4 | (uint64_t)k) << 4 | (uint64_t)ap);
+    struct Entry { uint64_t key; double v[4]; };
+    constexpr size_t N = 2048;
+    static thread_local Entry cache[N];
+    Entry& e = cache[(key * 0x9E3779B97F4A7C15ull) >> 53];
+    if (e.key != key) { set_coupling(j, std::abs(j - jp), jp, a, k, ap, i, std::abs(i - ip), ip, 1.0, e.v); e.key = key; }
+    return e.v;
 }
 
 // non-abelian/gemm.hpp:17-46; lspin/rspin = SU2 spin components of the block's left/right charge

@@ -22,6 +22,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -102,7 +103,11 @@ k_wstream(const DWWork* __restrict__ works, const DWGroup* __restrict__ groups, 
 }
 
 // solver-side BLAS-1 --------------------------------------------------------------------------------------
-__global__ void k_vec_dot(const double* __restrict__ x, const double* __restrict__ y, long long n, double* out)
+// Dot products are reduced in a FIXED order (per-thread strided sums -> warp shuffles -> one partial per block -> one block
+// sums the partials): the result depends on (n, grid) only, never on scheduling, so every rank of a sharded run computes
+// bit-identical solver scalars from bit-identical vectors and all ranks take the same convergence decisions.
+constexpr int DOT_THREADS = 256, DOT_MAX_BLOCKS = 1024;
+__global__ void __launch_bounds__(DOT_THREADS) k_vec_dot_partial(const double* __restrict__ x, const double* __restrict__ y, long long n, double* __restrict__ partial)
 {
     double s = 0.;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) s = fma(x[i], y[i], s);
@@ -113,7 +118,23 @@ __global__ void k_vec_dot(const double* __restrict__ x, const double* __restrict
     if (threadIdx.x < 32) {
         s = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.;
         for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-        if (threadIdx.x == 0) atomicAdd(out, s);
+        if (threadIdx.x == 0) partial[blockIdx.x] = s;
+    }
+}
+// out[q] = sum of partial[q * stride .. q * stride + n_partial) for q = blockIdx.x
+__global__ void __launch_bounds__(DOT_THREADS) k_vec_dot_final(const double* __restrict__ partial, int n_partial, int stride, double* __restrict__ out)
+{
+    const double* p = partial + (size_t)blockIdx.x * stride;
+    double s = 0.;
+    for (int i = threadIdx.x; i < n_partial; i += blockDim.x) s += p[i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    __shared__ double sh[32];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.;
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) out[blockIdx.x] = s;
     }
 }
 __global__ void k_vec_axpy(double a, const double* __restrict__ x, double* __restrict__ y, long long n)
@@ -184,8 +205,8 @@ struct qcm_plan_s
     double flops = 0; int64_t bytes = 0;
     int64_t n_launches = 0;
     std::vector<void*> allocs;
-    // task arrays are staged on the host while the plan is built and go to the device in ONE allocation and one copy
-    std::vector<char> staging;
+    // task arrays are staged in the library's pinned buffer while the plan is built and go to the device in ONE allocation and one copy
+    int64_t task_bytes = 0;
     struct PendingPtr { void** where; size_t offset; };
     std::vector<PendingPtr> pending;
 };
@@ -213,6 +234,9 @@ static struct Global
     double* ws[QCM_BUF_COUNT] = {nullptr};
     int64_t ws_elems[QCM_BUF_COUNT] = {0};
     double* scratch = nullptr;          // small device scalar area
+    double* dot_partial = nullptr;      // per-block partial sums of qcm_vec_dots + the results
+    static constexpr int kLcSlots = 64;
+    char* lc_args = nullptr; unsigned lc_next = 0;   // argument slots of qcm_vec_lincomb
     bool timing = false;
     double last_ms[6] = {0, 0, 0, 0, 0, 0};
     cudaEvent_t ev[8];
@@ -273,6 +297,10 @@ extern "C" int qcm_finalize(void)
     for (int i = 0; i < QCM_BUF_COUNT; ++i) if (G.ws[i]) { cudaFree(G.ws[i]); G.ws[i] = nullptr; G.ws_elems[i] = 0; }
     if (G.scratch) cudaFree(G.scratch);
     G.scratch = nullptr;
+    if (G.dot_partial) cudaFree(G.dot_partial);
+    G.dot_partial = nullptr;
+    if (G.lc_args) cudaFree(G.lc_args);
+    G.lc_args = nullptr;
     for (auto& ev : G.ev) cudaEventDestroy(ev);
     for (int i = 0; i < Global::kAux; ++i) { cudaStreamDestroy(G.aux[i]); cudaEventDestroy(G.join_ev[i]); }
     cudaEventDestroy(G.fork_ev);
@@ -412,26 +440,60 @@ static int variant_for(int hr, int hc)
     return mx == 32 ? 10 : 11;
 }
 
-template <class T> static int dev_upload(qcm_plan_s* P, std::vector<T> const& h, T** d)
+// Task arrays go to the device in ONE allocation and one copy.  They are gathered in a pinned host buffer owned by the
+// library (grown on demand, reused by every plan): the copy then runs at PCIe speed instead of through the driver's
+// pageable staging, and the large arrays (the W coefficient tables, 0.4 GB for a cfg3 centre site) are copied exactly once
+// on the host, by several threads.
+static struct PinnedStage { char* p = nullptr; size_t cap = 0, used = 0; } g_pin;
+static int pin_reserve(size_t need)
 {
-    *d = nullptr;
-    if (h.empty()) return 0;
-    size_t off = (P->staging.size() + 255) & ~(size_t)255;
-    P->staging.resize(off + h.size() * sizeof(T));
-    memcpy(P->staging.data() + off, h.data(), h.size() * sizeof(T));
-    P->pending.push_back(qcm_plan_s::PendingPtr{(void**)d, off});
+    if (need <= g_pin.cap) return 0;
+    size_t cap = std::max(need + need / 4, (size_t)1 << 24);
+    char* q = nullptr;
+    cudaError_t e = cudaHostAlloc((void**)&q, cap, cudaHostAllocDefault);
+    if (e != cudaSuccess) { cap = need; e = cudaHostAlloc((void**)&q, cap, cudaHostAllocDefault); }
+    if (e != cudaSuccess) return fail(std::string("pinned staging buffer of ") + std::to_string(need) + " bytes: " + cudaGetErrorString(e));
+    if (g_pin.used) memcpy(q, g_pin.p, g_pin.used);
+    if (g_pin.p) cudaFreeHost(g_pin.p);
+    g_pin.p = q; g_pin.cap = cap;
     return 0;
 }
+static void big_memcpy(char* dst, const char* src, size_t n)
+{
+    const size_t kMin = (size_t)32 << 20;
+    if (n < 2 * kMin) { memcpy(dst, src, n); return; }
+    const int nt = (int)std::min<size_t>(8, n / kMin);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) {
+        size_t b = n * t / nt, e = n * (t + 1) / nt;
+        th.emplace_back([=]() { memcpy(dst + b, src + b, e - b); });
+    }
+    for (auto& x : th) x.join();
+}
+static int dev_upload_raw(qcm_plan_s* P, const void* src, size_t bytes, void** d)
+{
+    *d = nullptr;
+    if (bytes == 0) return 0;
+    size_t off = (g_pin.used + 255) & ~(size_t)255;
+    if (pin_reserve(off + bytes)) return 1;
+    big_memcpy(g_pin.p + off, (const char*)src, bytes);
+    g_pin.used = off + bytes;
+    P->pending.push_back(qcm_plan_s::PendingPtr{d, off});
+    return 0;
+}
+template <class T> static int dev_upload(qcm_plan_s* P, std::vector<T> const& h, T** d) { return dev_upload_raw(P, h.data(), h.size() * sizeof(T), (void**)d); }
 // one cudaMalloc + one copy for all task arrays of the plan; patches the device pointers recorded by dev_upload
 static int flush_uploads(qcm_plan_s* P)
 {
-    if (P->staging.empty()) return 0;
+    if (g_pin.used == 0) return 0;
     char* base = nullptr;
-    CU(cudaMalloc((void**)&base, P->staging.size()));
+    CU(cudaMalloc((void**)&base, g_pin.used));
     P->allocs.push_back(base);
-    CU(cudaMemcpy(base, P->staging.data(), P->staging.size(), cudaMemcpyHostToDevice));
+    P->task_bytes = (int64_t)g_pin.used;
+    CU(cudaMemcpyAsync(base, g_pin.p, g_pin.used, cudaMemcpyHostToDevice, G.stream));
+    CU(cudaStreamSynchronize(G.stream));
     for (auto const& q : P->pending) *q.where = base + q.offset;
-    std::vector<char>().swap(P->staging);
+    g_pin.used = 0;
     P->pending.clear();
     return 0;
 }
@@ -551,9 +613,8 @@ static int build_axpy_group(qcm_plan_s* P, AxpyGroup& g, qcm_wave_desc const& wd
         hw.insert(hw.end(), cls[c].begin(), cls[c].end());
         if (g.count[c]) P->n_launches += 1;
     }
-    std::vector<double> hc(wd.w_coefs, wd.w_coefs + wd.n_w_coefs);
     if (dev_upload(P, hw, &g.d_works) || dev_upload(P, hg, &g.d_groups) || dev_upload(P, hs, &g.d_srcs) || dev_upload(P, hd, &g.d_dsts) ||
-        dev_upload(P, hc, &g.d_coefs)) return 1;
+        dev_upload_raw(P, wd.w_coefs, (size_t)wd.n_w_coefs * sizeof(double), (void**)&g.d_coefs)) return 1;
     return 0;
 }
 
@@ -597,7 +658,10 @@ extern "C" int qcm_plan_create(const qcm_plan_desc* d, qcm_plan_t* out)
 {
     CHECK_INIT();
     if (!d || !out) return fail("qcm_plan_create: null argument");
+    static std::mutex plan_mutex;      // the pinned staging buffer is shared
+    std::lock_guard<std::mutex> lock(plan_mutex);
     qcm_plan_s* P = new qcm_plan_s();
+    g_pin.used = 0;
     P->kind = d->kind; P->flops = d->flops; P->bytes = d->bytes;
     P->world = d->world > 1 ? d->world : 1; P->rank = d->world > 1 ? d->rank : 0;
     if (P->rank < 0 || P->rank >= P->world) { delete P; return fail("qcm_plan_create: rank outside [0, world)"); }
@@ -702,6 +766,15 @@ static int execute(qcm_plan_s* P, BufTable bufs)
     mark(1); lap(0, 0, 1);
     if (run_gemm_group(P->p, bufs)) return 1;
     mark(2); lap(1, 1, 2);
+    // QCM_SYNC_DEBUG: synchronise and report after every phase (localises a stuck kernel or collective)
+    static const bool dbg = getenv("QCM_SYNC_DEBUG") != nullptr;
+    auto checkpoint = [&](const char* what) -> int {
+        if (!dbg) return 0;
+        cudaError_t e1 = cudaStreamSynchronize(G.stream);
+        fprintf(stderr, "[qcm rank %d] %s: %s\n", G.rank, what, cudaGetErrorString(e1)); fflush(stderr);
+        return e1 == cudaSuccess ? 0 : fail(std::string(what) + ": " + cudaGetErrorString(e1));
+    };
+    if (checkpoint("reshape + resident step-1 products")) return 1;
     const WaveDev* xwave = nullptr;
     for (auto const& W : P->waves) {
         mark(3);
@@ -711,11 +784,13 @@ static int execute(qcm_plan_s* P, BufTable bufs)
             if (!G.comm || G.world != P->world) return fail("exchange wave without a matching communicator");
             if (W.x_zero) CU(cudaMemsetAsync(bufs.p[QCM_BUF_Y], 0, (size_t)W.x_chunk * P->world * 8, G.stream));
             if (run_w_group(W.w, bufs)) return 1;
+            if (checkpoint("exchange wave: W pass")) return 1;
             CU(cudaEventRecord(G.x_ready, G.stream));
             CU(cudaStreamWaitEvent(G.comm_stream, G.x_ready, 0));
             int r = G.f_rs(bufs.p[QCM_BUF_Y], bufs.p[QCM_BUF_Y] + (size_t)P->rank * W.x_chunk, (size_t)W.x_chunk, 8 /*ncclFloat64*/, 0 /*ncclSum*/, G.comm, G.comm_stream);
             if (r != 0) return fail(std::string("ncclReduceScatter: ") + (G.f_err ? G.f_err(r) : "error"));
             CU(cudaEventRecord(G.x_done, G.comm_stream));
+            if (dbg) { cudaError_t e2 = cudaStreamSynchronize(G.comm_stream); fprintf(stderr, "[qcm rank %d] reduce-scatter of %lld x %d elements: %s\n", G.rank, (long long)W.x_chunk, P->world, cudaGetErrorString(e2)); fflush(stderr); }
             xwave = &W;
             mark(5); lap(2, 3, 5);
             continue;
@@ -726,12 +801,14 @@ static int execute(qcm_plan_s* P, BufTable bufs)
         mark(5); lap(2, 4, 5);
         if (run_gemm_group(W.c, bufs)) return 1;
         mark(6); lap(3, 5, 6);
+        if (checkpoint("local wave")) return 1;
     }
     if (xwave) {
         mark(3);
         CU(cudaStreamWaitEvent(G.stream, G.x_done, 0));
         mark(4);
         if (run_gemm_group(xwave->c, bufs)) return 1;
+        if (checkpoint("closing products of the exchange chunk")) return 1;
         mark(5); lap(3, 4, 5);
         if (tm) { cudaEventSynchronize(G.ev[4]); float ms = 0; cudaEventElapsedTime(&ms, G.ev[3], G.ev[4]); x_wait_ms = ms; }
     }
@@ -827,14 +904,55 @@ extern "C" int qcm_set_timing(int enabled) { G.timing = enabled != 0; return 0; 
 extern "C" int qcm_last_timing(double ms[6]) { for (int i = 0; i < 6; ++i) ms[i] = G.last_ms[i]; return 0; }
 
 // ---- BLAS-1 ---------------------------------------------------------------------------------------------
-extern "C" int qcm_vec_dot(qcm_array_t x, qcm_array_t y, int64_t n, double* result)
+static int dot_blocks(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>(DOT_MAX_BLOCKS, (n + DOT_THREADS * 8 - 1) / (DOT_THREADS * 8))); }
+extern "C" int qcm_vec_dots(const qcm_array_t* xs, const qcm_array_t* ys, int k, int64_t n, double* results)
 {
     CHECK_INIT();
-    if (check_arr(x, n, "x") || check_arr(y, n, "y")) return 1;
-    CU(cudaMemsetAsync(G.scratch, 0, 8, G.stream));
-    if (n) { k_vec_dot<<<std::max(1, std::min(G.sm_count * 4, (int)((n + 255) / 256))), 256, 0, G.stream>>>(x->p, y->p, n, G.scratch); G.launches++; }
-    CU(cudaMemcpyAsync(result, G.scratch, 8, cudaMemcpyDeviceToHost, G.stream));
+    if (k < 0 || k > QCM_MAX_DOTS) return fail("qcm_vec_dots: between 0 and QCM_MAX_DOTS pairs per call");
+    if (k == 0) return 0;
+    for (int q = 0; q < k; ++q) if (check_arr(xs[q], n, "x") || check_arr(ys[q], n, "y")) return 1;
+    if (!G.dot_partial) CU(cudaMalloc((void**)&G.dot_partial, (size_t)(QCM_MAX_DOTS * (DOT_MAX_BLOCKS + 1)) * sizeof(double)));
+    const int nb = dot_blocks(n);
+    double* out = G.dot_partial + (size_t)QCM_MAX_DOTS * DOT_MAX_BLOCKS;
+    if (n == 0) { for (int q = 0; q < k; ++q) results[q] = 0.; return 0; }
+    for (int q = 0; q < k; ++q) {
+        k_vec_dot_partial<<<nb, DOT_THREADS, 0, G.stream>>>(xs[q]->p, ys[q]->p, n, G.dot_partial + (size_t)q * DOT_MAX_BLOCKS);
+        G.launches++;
+    }
+    k_vec_dot_final<<<k, DOT_THREADS, 0, G.stream>>>(G.dot_partial, nb, DOT_MAX_BLOCKS, out);
+    G.launches++;
+    CU(cudaMemcpyAsync(results, out, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
     CU(cudaStreamSynchronize(G.stream));
+    return 0;
+}
+extern "C" int qcm_vec_dot(qcm_array_t x, qcm_array_t y, int64_t n, double* result) { return qcm_vec_dots(&x, &y, 1, n, result); }
+// out = sum_j coefs[j] * xs[j]   (out may not alias any xs[j])
+__global__ void k_vec_lincomb(const double* const* __restrict__ xs, const double* __restrict__ coefs, int k, double* __restrict__ out, long long n)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double s = 0.;
+        for (int j = 0; j < k; ++j) s = fma(coefs[j], xs[j][i], s);
+        out[i] = s;
+    }
+}
+extern "C" int qcm_vec_lincomb(const qcm_array_t* xs, const double* coefs, int k, qcm_array_t out, int64_t n)
+{
+    CHECK_INIT();
+    if (k < 1 || k > QCM_MAX_DOTS) return fail("qcm_vec_lincomb: between 1 and QCM_MAX_DOTS terms per call");
+    if (check_arr(out, n, "out")) return 1;
+    for (int q = 0; q < k; ++q) { if (check_arr(xs[q], n, "x")) return 1; if (xs[q] == out) return fail("qcm_vec_lincomb: out aliases an input"); }
+    if (n == 0) return 0;
+    // arguments travel through a small device area; the previous call's kernel may still read it: one slot per call, round robin
+    if (!G.lc_args) CU(cudaMalloc((void**)&G.lc_args, (size_t)Global::kLcSlots * QCM_MAX_DOTS * 16));
+    char* slot = G.lc_args + (size_t)(G.lc_next++ % Global::kLcSlots) * QCM_MAX_DOTS * 16;
+    const double* hp[QCM_MAX_DOTS]; double hc[QCM_MAX_DOTS];
+    for (int q = 0; q < k; ++q) { hp[q] = xs[q]->p; hc[q] = coefs[q]; }
+    if (G.lc_next % Global::kLcSlots == 0) CU(cudaStreamSynchronize(G.stream));      // slots are reused only after the stream drained
+    CU(cudaMemcpyAsync(slot, hp, (size_t)k * 8, cudaMemcpyHostToDevice, G.stream));
+    CU(cudaMemcpyAsync(slot + QCM_MAX_DOTS * 8, hc, (size_t)k * 8, cudaMemcpyHostToDevice, G.stream));
+    k_vec_lincomb<<<std::max(1, std::min(G.sm_count * 8, (int)((n + 255) / 256))), 256, 0, G.stream>>>((const double* const*)slot, (const double*)(slot + QCM_MAX_DOTS * 8), k, out->p, n);
+    G.launches++;
+    CU(cudaGetLastError());
     return 0;
 }
 extern "C" int qcm_vec_axpy(double a, qcm_array_t x, qcm_array_t y, int64_t n)

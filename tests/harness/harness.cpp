@@ -487,3 +487,68 @@ extern "C" int qcmt_shard_stats(const char* fcidump, const char* symm, int L, in
         return 1;
     }
 }
+
+// The two-site split with its block SVDs divided among `world` ranks (twosite.hpp svd_truncate, EngineIface::allreduce_sum),
+// emulated in one process: pass 1 collects every rank's zero-padded buffer, pass 2 hands each rank the sum, as the allreduce
+// does.  out[0] = bonds checked, out[1] = 1 if every rank ends up with bit-identical factors, out[2] = largest relative
+// difference of U diag(S) V to the single-rank split, out[3] = 1 if the kept bond structure equals the single-rank one.
+namespace {
+struct FakeCommEngine : public qcm::EngineIface
+{
+    int r, w; std::vector<double>* slot; std::vector<double> const* total;
+    FakeCommEngine(int r_, int w_, std::vector<double>* s, std::vector<double> const* t) : r(r_), w(w_), slot(s), total(t) {}
+    qcm::MPSTensor site_hamil2(qcm::MPSTensor, qcm::Boundary const&, qcm::Boundary const&, qcm::MPOTensor const&, bool) override { throw std::runtime_error("not used"); }
+    qcm::Boundary overlap_mpo_left_step(qcm::MPSTensor const&, qcm::MPSTensor const&, qcm::Boundary const&, qcm::MPOTensor const&, bool) override { throw std::runtime_error("not used"); }
+    qcm::Boundary overlap_mpo_right_step(qcm::MPSTensor const&, qcm::MPSTensor const&, qcm::Boundary const&, qcm::MPOTensor const&, bool) override { throw std::runtime_error("not used"); }
+    int comm_rank() const override { return r; }
+    int comm_world() const override { return w; }
+    void allreduce_sum(double* buf, size_t n) override
+    {
+        if (total) { if (total->size() != n) throw std::runtime_error("ranks disagree on the buffer size"); std::copy(total->begin(), total->end(), buf); }
+        else slot->assign(buf, buf + n);
+    }
+};
+}
+extern "C" int qcmt_sharded_split(const char* fcidump, const char* symm, int L, int nelec, int Mmax, unsigned seed, int world, double* out, char* err, int errlen)
+{
+    try {
+        Problem P = make_problem(fcidump, symm, L, nelec);
+        P.init_mps((size_t)Mmax, true, 0., seed);
+        int n = 0; double identical = 1, same_struct = 1, worst = 0;
+        for (int p = 0; p + 1 < L; ++p) {
+            ts::TwoSiteTensor tst(P.params.symm, P.mps[p], P.mps[p + 1]);
+            MPSTensor twin = tst.make_mps();
+            tst << twin;
+            const size_t keep = (size_t)std::max(1, Mmax / 2);
+            MPSTensor a1, b1; ts::Truncation t1;
+            { ts::TwoSiteTensor c = tst; c.split_mps_l2r(keep, 1e-16, a1, b1, t1); }
+            std::vector<std::vector<double>> parts((size_t)world);
+            for (int r = 0; r < world; ++r) {
+                FakeCommEngine e(r, world, &parts[(size_t)r], nullptr);
+                ts::TwoSiteTensor c = tst; MPSTensor a, b; ts::Truncation t; c.split_mps_l2r(keep, 1e-16, a, b, t, &e);
+            }
+            std::vector<double> total(parts[0].size(), 0.);
+            for (auto const& v : parts) { if (v.size() != total.size()) throw std::runtime_error("ranks disagree on the buffer size"); for (size_t i = 0; i < v.size(); ++i) total[i] += v[i]; }
+            std::vector<MPSTensor> as, bs;
+            for (int r = 0; r < world; ++r) {
+                FakeCommEngine e(r, world, nullptr, &total);
+                ts::TwoSiteTensor c = tst; MPSTensor a, b; ts::Truncation t; c.split_mps_l2r(keep, 1e-16, a, b, t, &e);
+                a.make_left_paired(); b.make_right_paired();
+                as.push_back(a); bs.push_back(b);
+                if (t.bond_dimension != t1.bond_dimension) same_struct = 0;
+            }
+            for (int r = 1; r < world; ++r) {
+                if (!(as[(size_t)r].data().basis() == as[0].data().basis()) || !(bs[(size_t)r].data().basis() == bs[0].data().basis())) { identical = 0; continue; }
+                for (size_t k = 0; k < as[0].data().n_blocks(); ++k) if (as[(size_t)r].data()[k].v != as[0].data()[k].v) identical = 0;
+                for (size_t k = 0; k < bs[0].data().n_blocks(); ++k) if (bs[(size_t)r].data()[k].v != bs[0].data()[k].v) identical = 0;
+            }
+            a1.make_left_paired(); b1.make_right_paired();
+            if (!(as[0].data().basis() == a1.data().basis())) same_struct = 0;
+            block_matrix T1, T2; sweep::gemm(a1.data(), b1.data(), T1); sweep::gemm(as[0].data(), bs[0].data(), T2);
+            worst = std::max(worst, rel_diff(compare(T2, T1)));
+            ++n;
+        }
+        out[0] = n; out[1] = identical; out[2] = worst; out[3] = same_struct;
+        return 0;
+    } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
+}

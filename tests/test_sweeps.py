@@ -4,7 +4,7 @@ ietl/jacobi.h:361-451) is engine agnostic.  On the CPU oracle it must reproduce 
 then reproduce the oracle's energy of EVERY micro-iteration within 1e-8 Eh (the north star's tolerance)."""
 import json, os
 import pytest
-from conftest import GOLDEN
+from conftest import GOLDEN, golden
 
 REF = json.load(open(os.path.join(GOLDEN, "reference_values.json")))
 ORACLE, INTERP, GPU = -1, 0, 1
@@ -116,3 +116,19 @@ def test_gpu_sweep_config1(harness_gpu, fcidump_8o8e):
     eg, ig = harness_gpu.ss_dmrg(fcidump_8o8e, "su2u1", 8, 8, 256, 2, GPU)
     assert len(eo) == len(eg) == 2 * 2 * 8
     assert max(abs(a - b) for a, b in zip(eo, eg)) < E_TOL
+
+
+@pytest.mark.parametrize("symm", ["su2u1", "2u1"])
+@pytest.mark.parametrize("world", [2, 3])
+def test_split_with_block_svds_divided_among_ranks(harness_cpu, symm, world):
+    """N>1 host path of a sweep: every rank computes the SVDs of its share of the blocks, the factors are combined by an
+    allreduce of zero-padded buffers (twosite.hpp svd_truncate) -- all ranks must end up with bit-identical tensors and the
+    same truncated bond structure as the single-rank split."""
+    import ctypes
+    out = (ctypes.c_double * 4)(); err = ctypes.create_string_buffer(1024)
+    f = golden("synth_6o6e.fcidump")
+    assert harness_cpu.lib.qcmt_sharded_split(f, symm.encode(), 6, 6, 16, 5, world, out, err, 1024) == 0, err.value.decode()
+    assert out[0] == 5
+    assert out[1] == 1, "ranks hold different factors"
+    assert out[3] == 1, "bond structure differs from the single-rank split"
+    assert out[2] < 1e-12

@@ -26,8 +26,8 @@ int main(int argc, char** argv)
                 plan::Plan q = plr.plan_sigma(td, ll, rl);
                 double f = q.flops_t + q.exec_w + q.exec_close;
                 mx = std::max(mx, f); sum += f; t_sum += q.flops_t; alg += q.flops();
-                printf("  world %d rank %d: step1 %.3e  W %.3e  close %.3e  total %.3e  TP %.2f GB  exchange region %.2f GB (chunk %.3f GB)\n", world, r, q.flops_t, q.exec_w, q.exec_close, f,
-                       q.tp_elems * 8e-9, (!q.waves.empty() ? q.waves[0].x_chunk * world * 8e-9 : 0.), (!q.waves.empty() ? q.waves[0].x_chunk * 8e-9 : 0.));
+                printf("  world %d rank %d: step1 %.3e  W %.3e  close %.3e  total %.3e  TP %.2f GB  exchange region %.2f GB (chunk %.3f GB = %lld elements)\n", world, r, q.flops_t, q.exec_w, q.exec_close, f,
+                       q.tp_elems * 8e-9, (!q.waves.empty() ? q.waves[0].x_chunk * world * 8e-9 : 0.), (!q.waves.empty() ? q.waves[0].x_chunk * 8e-9 : 0.), (long long)(!q.waves.empty() ? q.waves[0].x_chunk : 0));
             }
             printf("world %d: max rank FLOPs %.3e, sum %.3e (step 1 %.3e); algorithmic FLOPs booked over ranks %.10e\n", world, mx, sum, t_sum, alg);
         }
