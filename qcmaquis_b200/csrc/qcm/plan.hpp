@@ -201,15 +201,20 @@ public:
 
         // output structure: emulate the per-b2 products and their match_and_add_block reduction
         block_struct sigma_struct;
-        struct Pending { size_t b2; Layout y; std::vector<YTask> ytasks; std::vector<size_t> t_rows; };
+        struct Pending { size_t b2; Layout y; std::vector<size_t> t_rows; std::vector<std::vector<uint32_t>> block_bonds; };
         std::vector<Pending> pend(mpo.col_dim());
         int n_b2 = (int)mpo.col_dim();
+        // pass A: structure of every Y[b2], the bonds that contribute to it and (sharded plans) the bonds behind every block
+        auto walk = [&](size_t b2, DualIndex& ybasis, std::vector<YTask>& tasks, std::vector<size_t>& rows, YOpts const& o) {
+            if (su2_) y_struct_su2_lbtm(b2, ket_rp, right_i, out_left_i, in_right_pb, out_left_pb, ybasis, tasks, rows, o);
+            else y_struct_abelian_lbtm(b2, ket_rp.basis, ket_rp.basis, right_i, out_left_i, in_right_pb, out_left_pb, ybasis, tasks, rows, o);
+        };
 #pragma omp parallel for schedule(dynamic, 4)
         for (int b2 = 0; b2 < n_b2; ++b2) {
             Pending& pd = pend[b2]; pd.b2 = (size_t)b2;
-            DualIndex ybasis;
-            if (su2_) y_struct_su2_lbtm(b2, ket_rp, right_i, out_left_i, in_right_pb, out_left_pb, ybasis, pd.ytasks, pd.t_rows);
-            else y_struct_abelian_lbtm(b2, ket_rp.basis, ket_rp.basis, right_i, out_left_i, in_right_pb, out_left_pb, ybasis, pd.ytasks, pd.t_rows);
+            DualIndex ybasis; std::vector<YTask> none;
+            YOpts o; o.emit_tasks = false; o.block_bonds = world > 1 ? &pd.block_bonds : nullptr;
+            walk((size_t)b2, ybasis, none, pd.t_rows, o);
             pd.y.assign(ybasis);
         }
         pt.lap("y_struct (all b2)");
@@ -248,20 +253,37 @@ public:
             } else
                 for (auto it = rv.basis.left_lower_bound(yb.rc); it != rv.basis.end() && it->lc == yb.rc; ++it) m.push_back(it - rv.basis.begin());
         };
-        Exchange xch = plan_exchange(pend.size(), [&](size_t i) -> std::vector<YTask> const& { return pend[i].ytasks; },
-            [&](size_t i) -> std::vector<size_t> const& { return pend[i].t_rows; },
+        // row units of Y block o of output i: one panel per (physical state, left sector) -- the same panels the W tasks address
+        auto units_of = [&](size_t i, size_t o, std::vector<XPanel>& out) {
+            QnBlock const& yb = pend[i].y.basis[o];
+            for (size_t p = 0; p < physical_i.size(); ++p) {
+                size_t l = left_i.position(fuse(yb.lc, -physical_i[p].first));
+                if (l == left_i.size() || !out_left_pb.has(physical_i[p].first, left_i[l].first)) continue;
+                const int32_t off = (int32_t)out_left_pb(physical_i[p].first, left_i[l].first), ls = (int32_t)left_i[l].second;
+                for (size_t c = 0; c < physical_i[p].second; ++c) out.push_back(XPanel{(uint32_t)i, (uint32_t)o, off + (int32_t)c * ls, 0, ls, (int32_t)yb.rs, -1, 0});
+            }
+        };
+        Exchange xch = plan_exchange(pend.size(), [&](size_t i) -> std::vector<std::vector<uint32_t>> const& { return pend[i].block_bonds; },
             [&](size_t i) {
                 VView rv = right_view(right, pend[i].b2);
                 std::vector<char> u(pend[i].y.basis.size(), 0);
                 for (size_t k = 0; k < u.size(); ++k) { std::vector<size_t> m; sigma_match(pend[i].y.basis, rv, k, m); u[k] = !m.empty(); }
                 return u;
-            });
+            }, units_of);
         auto closes_some = [&](size_t i) { if (!xch.active()) return false; for (uint32_t q : xch.by_output[i]) if (xch.xp[q].chunk == rank) return true; return false; };
         std::vector<char> books(pend.size(), 1);
-        for (size_t i = 0; i < pend.size(); ++i) books[i] = filter_owned(own, pend[i].ytasks, pend[i].t_rows);
+        for (size_t i = 0; i < pend.size(); ++i) books[i] = filter_owned(own, pend[i].t_rows);
         pt.lap("sharding + persistent T");
         std::vector<char> idle(pend.size(), 0);
-        for (size_t i = 0; i < pend.size(); ++i) idle[i] = world > 1 && pend[i].ytasks.empty() && !books[i] && !closes_some(i);
+        for (size_t i = 0; i < pend.size(); ++i) idle[i] = world > 1 && pend[i].t_rows.empty() && !books[i] && !closes_some(i);
+        // pass B, output by output: the tasks of the bonds this rank owns, into the calling thread's scratch buffer
+        YOpts emit_own; emit_own.own = world > 1 ? &own : nullptr;
+        auto gen_tasks = [&](size_t j, std::vector<YTask>& scratch) -> std::vector<YTask> const& {
+            scratch.clear();
+            DualIndex yb; std::vector<size_t> rows;
+            walk(pend[j].b2, yb, scratch, rows, emit_own);
+            return scratch;
+        };
         PanelCache pcache;
         Wave xw;
         const int64_t y0 = xch.active() ? xch.chunk * world : 0;      // BUF_Y[0, y0) is the exchange region
@@ -318,8 +340,7 @@ public:
                 }
             PanelCounts pcnt;
             std::vector<Panel> panels = cached_panels(pcache, pend.size(), i, t_begin,
-                [&](size_t j) -> std::vector<size_t> const& { return pend[j].t_rows; },
-                [&](size_t j) -> std::vector<YTask> const& { return pend[j].ytasks; },
+                [&](size_t j) -> std::vector<size_t> const& { return pend[j].t_rows; }, gen_tasks,
                 [&](size_t j) { return idle[j] != 0; }, tl, pcnt);
             P.flops_w += pcnt.flops_w; P.n_axpy_tasks += pcnt.n_axpy;
             for (Panel& pn : panels) {
@@ -437,7 +458,7 @@ public:
             PanelCounts pcnt;
             std::vector<Panel> panels = cached_panels(pcache, pend.size(), b2, t_begin,
                 [&](size_t j) -> std::vector<size_t> const& { return pend[j].t_rows; },
-                [&](size_t j) -> std::vector<YTask> const& { return pend[j].ytasks; },
+                [&](size_t j, std::vector<YTask>&) -> std::vector<YTask> const& { return pend[j].ytasks; },
                 [&](size_t j) { return (world > 1 && pend[j].ytasks.empty() && !books[j]) || (mpo.herm_info.right_skip(j) && isHermitian); }, tl, pcnt);
             P.flops_w += pcnt.flops_w; P.n_axpy_tasks += pcnt.n_axpy;
             for (Panel& pn : panels) {
@@ -551,7 +572,7 @@ public:
             PanelCounts pcnt;
             std::vector<Panel> panels = cached_panels(pcache, pend.size(), b1, t_begin,
                 [&](size_t j) -> std::vector<size_t> const& { return pend[j].t_cols; },
-                [&](size_t j) -> std::vector<YTask> const& { return pend[j].ytasks; },
+                [&](size_t j, std::vector<YTask>&) -> std::vector<YTask> const& { return pend[j].ytasks; },
                 [&](size_t j) { return (world > 1 && pend[j].ytasks.empty() && !books[j]) || (mpo.herm_info.left_skip(j) && isHermitian); }, tl, pcnt);
             P.flops_w += pcnt.flops_w; P.n_axpy_tasks += pcnt.n_axpy;
             for (Panel& pn : panels) {
@@ -722,6 +743,18 @@ private:
             if (p == basis.size()) basis.insert(QnBlock(lc, rc, ls, rs));
             else { basis[p].ls = std::max(basis[p].ls, ls); basis[p].rs = std::max(basis[p].rs, rs); }
         }
+    };
+    // What a walk over the W-application loops of one output index is asked to produce.  The block structure of Y (and the
+    // order in which its blocks are created) always comes out.  The planner walks every output twice: once for the structure,
+    // the bonds that really contribute and -- for sharded plans -- which bonds touch which Y block (pass A, cheap), and once,
+    // output by output inside the emission, for the tasks of the bonds this rank owns (pass B); the task list of an output
+    // lives in a per-thread scratch buffer only until its panels are collected.
+    struct YOpts
+    {
+        bool emit_tasks;                                     // false: structure and used bonds only
+        std::vector<char> const* own;                        // tasks only for these bonds
+        std::vector<std::vector<uint32_t>>* block_bonds;     // per Y block (final position): the bonds that touch it, ascending
+        YOpts() : emit_tasks(true), own(nullptr), block_bonds(nullptr) {}
     };
     // one W-application contribution: dst panel in Y block `o`, source panel in T[bt] block `t_block`
     struct YTask { size_t o; int32_t dst_row, dst_col, rows, cols; size_t bt, t_block; int32_t src_row, src_col; double coef; };
@@ -942,8 +975,9 @@ private:
     // ---- step 2 structure, abelian lbtm (abelian/apply_op.hpp:23-139)
     void y_struct_abelian_lbtm(size_t b2, DualIndex const& /*ket_basis*/, DualIndex const& /*bra_basis*/, Index const& right_i, Index const& out_left_i,
                                ProductBasis const& in_right_pb, ProductBasis const& out_left_pb,
-                               DualIndex& ret, std::vector<YTask>& tasks, std::vector<size_t>& t_rows)
+                               DualIndex& ret, std::vector<YTask>& tasks, std::vector<size_t>& t_rows, YOpts const& opts = YOpts())
     {
+        std::vector<std::pair<std::pair<Charge, Charge>, uint32_t>> touches;      // (block, bond), only when asked for
         for (size_t e = mpo.col_begin(b2); e < mpo.col_end(b2); ++e) {   // allocate
             size_t b1 = mpo.row_of(e);
             DualIndex const& T = t_basis[b1];
@@ -956,21 +990,28 @@ private:
                     Charge out_r = right_i[r].first, out_l = fuse(out_r, total_delta);
                     if (!out_left_i.has(out_l)) continue;
                     if (!ret.has(out_l, out_r)) ret.insert(QnBlock(out_l, out_r, out_left_i.size_of_block(out_l), right_i[r].second));
+                    if (opts.block_bonds) touches.push_back(std::make_pair(std::make_pair(out_l, out_r), (uint32_t)b1));
                 }
             }
+        }
+        if (opts.block_bonds) {
+            opts.block_bonds->assign(ret.size(), std::vector<uint32_t>());
+            for (auto const& t : touches) { auto& v = (*opts.block_bonds)[ret.position(t.first.first, t.first.second)]; if (v.empty() || v.back() != t.second) v.push_back(t.second); }
         }
         if (structure_only) return;
         for (size_t e = mpo.col_begin(b2); e < mpo.col_end(b2); ++e) {   // execute
             size_t b1 = mpo.row_of(e);
             DualIndex const& T = t_basis[b1];
             if (T.size() == 0) continue;
+            const bool emit = opts.emit_tasks && (!opts.own || (*opts.own)[b1]);
+            if (!emit && opts.emit_tasks) continue;                      // pass B: somebody else's bond
             bool used = false;
             for (auto const& term : mpo.at_entry(e)) {
                 SiteOperator const& W = mpo.op(term.first);
                 if (W.n_blocks() == 0) continue;
                 Charge T_delta = delta_of(T);
                 Charge total_delta = fuse(delta_of(W.basis()), -T_delta);
-                for (size_t r = 0; r < right_i.size(); ++r) {
+                for (size_t r = 0; r < right_i.size() && (emit || !used); ++r) {
                     Charge out_r = right_i[r].first, out_l = fuse(out_r, total_delta);
                     if (!out_left_i.has(out_l)) continue;
                     int32_t r_size = (int32_t)right_i[r].second;
@@ -986,7 +1027,7 @@ private:
                             for (size_t s2 = 0; s2 < W[w].cols; ++s2) {
                                 double alfa = W[w](s1, s2) * term.second;
                                 if (alfa == 0.0) continue;   // the reference adds 0*x here
-                                tasks.push_back(YTask{o, out_off + (int32_t)s2 * ldim, 0, ldim, r_size, b1, tb, 0, in_off + (int32_t)s1 * r_size, alfa});
+                                if (emit) tasks.push_back(YTask{o, out_off + (int32_t)s2 * ldim, 0, ldim, r_size, b1, tb, 0, in_off + (int32_t)s1 * r_size, alfa});
                                 used = true;
                             }
                     }
@@ -1076,8 +1117,9 @@ private:
     }
     void y_struct_su2_lbtm(size_t b2, Layout const& /*ket_rp*/, Index const& right_i, Index const& out_left_i,
                            ProductBasis const& /*in_right_pb*/, ProductBasis const& /*out_left_pb*/,
-                           DualIndex& ret, std::vector<YTask>& tasks, std::vector<size_t>& t_rows)
+                           DualIndex& ret, std::vector<YTask>& tasks, std::vector<size_t>& t_rows, YOpts const& opts = YOpts())
     {
+        std::vector<std::vector<uint32_t>> touched;           // per created block: bonds that touch it
         // Blocks are created lazily, in loop order, but sorted on insertion: a task first carries the creation number
         // of its block and gets the block's final position once the structure is complete.
         std::vector<int32_t> cid_of(lbtm_nol_ * lbtm_nr_, -1);
@@ -1089,6 +1131,8 @@ private:
             std::vector<TbInfo> const& TI = tbinfo_[t_basis_id_[b1]];
             const int a = mpo.left_spin(b1).get();
             bool used = false;
+            const bool emit = !structure_only && opts.emit_tasks && (!opts.own || (*opts.own)[b1]);
+            const bool probe = !structure_only && !opts.emit_tasks;      // pass A: does this bond contribute at all?
             for (auto const& term : mpo.at_entry(e)) {
                 SiteOperator const& W = mpo.op(term.first);
                 const int k = W.spin().get();
@@ -1108,8 +1152,10 @@ private:
                             created.push_back(std::make_pair(qo.ol_pos, qi.rb));
                             Charge out_l = out_left_i[qo.ol_pos].first, out_r = right_i[qi.rb].first;
                             if (!ret.has(out_l, out_r)) ret.insert(QnBlock(out_l, out_r, out_left_i[qo.ol_pos].second, (size_t)qi.r_size));
+                            if (opts.block_bonds) touched.emplace_back();
                         }
-                        if (structure_only) continue;
+                        if (opts.block_bonds) { auto& v = touched[(size_t)cslot]; if (v.empty() || v.back() != (uint32_t)b1) v.push_back((uint32_t)b1); }
+                        if (!emit && !(probe && !used)) continue;
                         const size_t cid = (size_t)cslot;
                         const int i = ti.i_spin, ip = qo.ip, j = ti.j_spin, jp = qi.jp;
                         const int two_sp = std::abs(i - ip), two_s = std::abs(j - jp);
@@ -1123,8 +1169,9 @@ private:
                             if (en.row_spin == 2 && en.col_spin == 2) cn = 3; else if (en.row_spin == 2) cn = 1; else if (en.col_spin == 2) cn = 2;
                             double alfa = en.coefficient * couplings[cn];
                             if (alfa == 0.0) continue;
-                            tasks.push_back(YTask{cid, out_off + (int32_t)en.col * l_size, 0, l_size, r_size, b1, tb, 0, in_off + (int32_t)en.row * r_size, alfa});
                             used = true;
+                            if (!emit) break;
+                            tasks.push_back(YTask{cid, out_off + (int32_t)en.col * l_size, 0, l_size, r_size, b1, tb, 0, in_off + (int32_t)en.row * r_size, alfa});
                         }
                     }
                 }
@@ -1134,6 +1181,10 @@ private:
         std::vector<size_t> final_pos(created.size());
         for (size_t c = 0; c < created.size(); ++c) final_pos[c] = ret.position(out_left_i[created[c].first].first, right_i[created[c].second].first);
         for (size_t t = first_task; t < tasks.size(); ++t) tasks[t].o = final_pos[tasks[t].o];
+        if (opts.block_bonds) {
+            opts.block_bonds->assign(ret.size(), std::vector<uint32_t>());
+            for (size_t c = 0; c < created.size(); ++c) (*opts.block_bonds)[final_pos[c]] = std::move(touched[c]);
+        }
     }
 
     // ---- step 2 structure, abelian rbtm (abelian/apply_op.hpp:141-250)
@@ -1328,6 +1379,8 @@ private:
     // no wave is flushed inside the batch (the offsets of single-use step-1 products in BUF_T then follow from a prefix
     // sum); when the assumption fails for an output its panels are recomputed and the rest of the batch is discarded.
     struct PanelCache { std::vector<std::vector<Panel>> panels; std::vector<PanelCounts> cnt; std::vector<int64_t> t0; size_t batch = 256; };
+    // tasks_of(j, scratch) returns the task list of output j -- either a stored one or one it generates into `scratch`
+    static std::vector<YTask>& task_scratch() { static thread_local std::vector<YTask> v; return v; }
     template <class RowsOf, class TasksOf, class Skip>
     std::vector<Panel> cached_panels(PanelCache& pc, size_t n, size_t i, int64_t t_begin, RowsOf rows_of, TasksOf tasks_of, Skip skip,
                                      std::map<size_t, Layout> const& tl, PanelCounts& cnt) const
@@ -1343,13 +1396,15 @@ private:
                 pc.t0[j] = t; todo.push_back(j);
                 for (size_t b : rows_of(j)) if (!t_persistent[b]) t += t_layout_size(b);
             }
+            // the outputs fed by many bonds first: they take a thousand times longer than the rest
+            std::stable_sort(todo.begin(), todo.end(), [&](size_t a, size_t b) { return rows_of(a).size() > rows_of(b).size(); });
 #pragma omp parallel for schedule(dynamic, 1)
             for (long q = 0; q < (long)todo.size(); ++q) {
                 const size_t j = todo[(size_t)q];
                 std::map<size_t, Layout> tlj;
                 layouts_for(rows_of(j), pc.t0[j], tlj);
                 pc.cnt[j] = PanelCounts();
-                pc.panels[j] = collect_panels(pc.cnt[j], tasks_of(j), tlj);
+                pc.panels[j] = collect_panels(pc.cnt[j], tasks_of(j, task_scratch()), tlj);
             }
         }
         if (pc.t0[i] == t_begin) {
@@ -1360,7 +1415,7 @@ private:
         }
         for (size_t j = i + 1; j < std::min(n, i + pc.batch); ++j) { pc.t0[j] = -1; pc.panels[j] = std::vector<Panel>(); }   // stale: offsets moved
         cnt = PanelCounts();
-        return collect_panels(cnt, tasks_of(i), tl);
+        return collect_panels(cnt, tasks_of(i, task_scratch()), tl);
     }
     // Where the closing product finds a panel: the T panel itself (one source; its coefficient becomes the alpha of
     // the K-segment) or a compact region of BUF_Y filled by the W kernel.  false: the panel is identically zero.
@@ -1630,32 +1685,29 @@ private:
             return it == index[out].end() ? -1 : (long)it->second;
         }
     };
-    // used_blocks(i)[o]: Y block o of output i takes part in a closing product
-    template <class TasksOf, class RowsOf, class Used>
-    Exchange plan_exchange(size_t n_out, TasksOf tasks_of, RowsOf rows_of, Used used_blocks) const
+    // block_bonds(i)[o]: the bonds that touch Y block o of output i; used_blocks(i)[o]: the block takes part in a closing
+    // product; units_of(i, o, out): the row (column) units of the block -- the panels the W tasks address.  A block fed by
+    // bonds of two or more ranks is exchanged as a whole.
+    template <class BlockBonds, class Used, class Units>
+    Exchange plan_exchange(size_t n_out, BlockBonds block_bonds, Used used_blocks, Units units_of) const
     {
         Exchange X;
         if (world <= 1 || getenv("QCM_NO_EXCHANGE")) return X;
         X.index.resize(n_out); X.by_output.resize(n_out);
         std::vector<std::vector<XPanel>> per_out(n_out);
-#pragma omp parallel for schedule(dynamic, 1)
+#pragma omp parallel for schedule(dynamic, 8)
         for (long il = 0; il < (long)n_out; ++il) {
             const size_t i = (size_t)il;
-            auto const& r = rows_of(i);
-            bool spread = false;
-            for (size_t b : r) if (owner_[b] != owner_[r[0]]) { spread = true; break; }
-            if (!spread) continue;
-            struct Acc { XPanel p; uint64_t mask; };
-            std::unordered_map<uint64_t, uint32_t> idx;
-            std::vector<Acc> acc;
-            for (YTask const& t : tasks_of(i)) {
-                auto ins = idx.emplace(Exchange::key(t.o, t.dst_row, t.dst_col), (uint32_t)acc.size());
-                if (ins.second) acc.push_back(Acc{XPanel{(uint32_t)i, (uint32_t)t.o, t.dst_row, t.dst_col, t.rows, t.cols, -1, 0}, 0});
-                acc[ins.first->second].mask |= (uint64_t)1 << (owner_[t.bt] & 63);
+            auto const& bb = block_bonds(i);
+            std::vector<char> used;
+            for (size_t o = 0; o < bb.size(); ++o) {
+                if (bb[o].empty()) continue;
+                bool spread = false;
+                for (uint32_t b : bb[o]) if (owner_[b] != owner_[bb[o][0]]) { spread = true; break; }
+                if (!spread) continue;
+                if (used.empty()) used = used_blocks(i);
+                if (used[o]) units_of(i, o, per_out[i]);
             }
-            std::vector<char> used = used_blocks(i);
-            for (Acc const& a : acc)
-                if ((a.mask & (a.mask - 1)) != 0 && used[(size_t)a.p.o]) per_out[i].push_back(a.p);       // sources on two or more ranks
             std::sort(per_out[i].begin(), per_out[i].end(), [](XPanel const& x, XPanel const& y) {
                 return std::tie(x.o, x.dst_col, x.dst_row) < std::tie(y.o, y.dst_col, y.dst_row); });
         }
@@ -1703,6 +1755,7 @@ private:
     // the tasks / step-1 rows of one output index that belong to this rank
     // returns whether this rank books the reference's closing FLOPs of the output (it owns the first source): the
     // algorithmic FLOP counts of the ranks then add up to exactly the unsharded schedule's
+    bool filter_owned(std::vector<char> const& own, std::vector<size_t>& rows) const { std::vector<YTask> none; return filter_owned(own, none, rows); }
     bool filter_owned(std::vector<char> const& own, std::vector<YTask>& tasks, std::vector<size_t>& rows) const
     {
         if (world <= 1) return true;
