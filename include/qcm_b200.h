@@ -169,6 +169,72 @@ int qcm_comm_init(int rank, int world, const char id[128]);
 int qcm_comm_destroy(void);
 int qcm_comm_allreduce(qcm_array_t a, int64_t n);
 
+/* ---- problem descriptors: plan a contraction INSIDE the library from plain arrays ------------------------------------------
+ * The entry points above take finished task arrays.  The ones below take the PROBLEM -- the MPO site tensor in CSC form, its
+ * operator table as sparse entries, bond spins and Hermitian maps, and the block structures of the site tensor(s) and the
+ * boundaries -- and run the schedule builder (qcmaquis_b200/csrc/qcm/plan.hpp) inside libqcm_b200.so.  A QCMaquis-side binding
+ * is then a flattening of MPOTensor<Matrix,SymmGroup> (mp_tensors/mpotensor.h:23-107: row/col_dim, the CSC arrays of
+ * mpotensor.hpp:10-65, at(b1,b2) -> (tag, scale) lists, left/right_spin, herm_info), of its OPTable entries
+ * (block_matrix/site_operator.h: basis(), spin(), get_sparse() -- sparse_operator.h:16-46 (row, col, row_spin, col_spin,
+ * coefficient) per block) and of DualIndex / Index lists (dual_index.h:122-338, indexing_stable.hpp); see INTEGRATION.md.
+ * Charges are (c0, c1, irrep) as in nu1pg.h:26-84; groups without point group pass irrep = 0. */
+typedef struct { int32_t c[3]; } qcm_charge;
+typedef struct { qcm_charge q; int64_t size; } qcm_sector;                 /* one entry of an Index<SymmGroup> */
+typedef struct { qcm_charge lc, rc; int64_t ls, rs; } qcm_block;           /* one entry of a DualIndex<SymmGroup> */
+enum { QCM_SYMM_2U1 = 0, QCM_SYMM_2U1PG = 1, QCM_SYMM_SU2U1 = 2, QCM_SYMM_SU2U1PG = 3 };
+
+typedef struct {
+    int32_t spin_twoS, spin_in, spin_out;      /* SpinDescriptor(twoS, in, out), spin_descriptor.h:49-66; zeros for abelian groups */
+    int32_t n_blocks;
+    const qcm_block* blocks;                   /* op.basis(), DualIndex order */
+    const int32_t* entry_ptr;                  /* n_blocks + 1: block b owns entries [entry_ptr[b], entry_ptr[b+1]) */
+    const int32_t* row; const int32_t* col;    /* position inside the block */
+    const int32_t* row_spin; const int32_t* col_spin;   /* two-site spin labels J, J' of the entry (SU2); NULL: |spin(charge)| */
+    const double* coef;
+} qcm_site_op_desc;
+
+typedef struct {
+    int32_t symm;                              /* QCM_SYMM_* */
+    int32_t n_ops;
+    const qcm_site_op_desc* ops;               /* the operator table; terms refer to it by index (tag) */
+    int64_t row_dim, col_dim, nnz;
+    const int64_t* col_ptr;                    /* col_dim + 1 (CSC): entries of column b2, ascending b1 */
+    const int64_t* row_idx;                    /* nnz */
+    const int64_t* term_ptr;                   /* nnz + 1: entry e owns terms [term_ptr[e], term_ptr[e+1]) in at(b1,b2) order */
+    const int32_t* term_op; const double* term_scale;
+    const int32_t* left_spin; const int32_t* right_spin;        /* 2S of every bond index (row_dim / col_dim values); NULL for abelian groups */
+    const int64_t* left_herm; const int64_t* right_herm;        /* Hermitian::LeftHerm / RightHerm (mpotensor_detail.h:118-168); NULL: no pairs */
+    const int32_t* left_phase; const int32_t* right_phase;
+} qcm_mpo_desc;
+
+typedef struct {                               /* block structure of one MPSTensor; its data travel as left-paired blocks back to back */
+    int32_t n_phys, n_left, n_right, n_blocks;
+    const qcm_sector* phys; const qcm_sector* left; const qcm_sector* right;   /* site_dim(), row_dim(), col_dim() */
+    const qcm_block* blocks;                   /* data().basis() after make_left_paired() */
+} qcm_tensor_desc;
+
+typedef struct {                               /* block structure of a Boundary: entry b owns blocks [block_ptr[b], block_ptr[b+1]) */
+    int64_t aux_dim;
+    const int64_t* block_ptr;
+    const qcm_block* blocks;
+} qcm_boundary_desc;
+
+typedef struct qcm_mpo_s* qcm_mpo_t;
+int qcm_mpo_upload(const qcm_mpo_desc* d, qcm_mpo_t* out);      /* once per MPO site tensor (or fused two-site tensor) */
+int qcm_mpo_free(qcm_mpo_t m);
+/* rank/world: the shard to plan (0, 1: the whole contraction); ws_budget_elems: workspace budget in elements (0: default) */
+int qcm_plan_sigma(qcm_mpo_t m, const qcm_tensor_desc* ket, const qcm_boundary_desc* left, const qcm_boundary_desc* right,
+                   int rank, int world, int64_t ws_budget_elems, qcm_plan_t* out);
+int qcm_plan_left_step(qcm_mpo_t m, const qcm_tensor_desc* bra, const qcm_tensor_desc* ket, const qcm_boundary_desc* left,
+                       int rank, int world, int64_t ws_budget_elems, qcm_plan_t* out);
+int qcm_plan_right_step(qcm_mpo_t m, const qcm_tensor_desc* bra, const qcm_tensor_desc* ket, const qcm_boundary_desc* right,
+                        int rank, int world, int64_t ws_budget_elems, qcm_plan_t* out);
+/* block structure of the result of a plan made by the three calls above: sigma (aux_dim 1) or the new boundary.
+ * qcm_plan_out_size: number of bond entries, blocks and elements; qcm_plan_out_blocks: block_ptr (aux_dim + 1), the blocks in
+ * DualIndex order and the element offset of every block inside the output array. */
+int qcm_plan_out_size(qcm_plan_t p, int64_t* aux_dim, int64_t* n_blocks, int64_t* n_elems);
+int qcm_plan_out_blocks(qcm_plan_t p, int64_t* block_ptr, qcm_block* blocks, int64_t* elem_off);
+
 /* ---- measured FP64 peaks (roofline denominators; not part of the contraction path) ------------------ */
 int qcm_measure_fp64_fma_peak(double* tflops);     /* register-resident DFMA chains on all SMs */
 int qcm_measure_fp64_dmma_peak(double* tflops);    /* register-resident mma.sync m8n8k4 f64 chains */

@@ -55,11 +55,17 @@ def build_cuda(force=False):
         objs.append(obj)
         if force or _newer(obj, [src] + deps):
             jobs.append(["nvcc"] + [f for f in NVCC_FLAGS if f != "-shared"] + ["-c", src, "-o", obj])
+    # host-side translation units of the same library (the schedule builder behind the descriptor entry points): g++, OpenMP
+    for src in sorted(glob.glob(os.path.join(CSRC, "plan_capi.cpp"))):
+        obj = os.path.join(odir, os.path.basename(src)[:-4] + ".o")
+        objs.append(obj)
+        if force or _newer(obj, [src] + deps):
+            jobs.append(["g++", "-O2", "-std=c++17", "-fopenmp", "-fPIC", "-I", CSRC, "-I", "/usr/local/cuda/include", "-c", src, "-o", obj])
     if jobs:
         with ThreadPoolExecutor(max_workers=len(jobs)) as ex:
             list(ex.map(_run, jobs))
     if jobs or force or _newer(out, objs):
-        _run(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-o", out, "-ldl"])
+        _run(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-o", out, "-ldl", "-lgomp"])
     return out
 
 

@@ -279,6 +279,11 @@ extern "C" int qcmd_ts_sweeps_synth(void* h, int M, int nsweeps, unsigned seed, 
         for (int i = 0; i < 5; ++i) { info[4 + i] = log.phase_seconds[i]; info[9 + i] = eng.seconds[i]; }
         info[14] = (double)eng.cache_hits; info[15] = (double)eng.cache_misses; info[16] = eng.sigma_flops; info[17] = eng.boundary_flops;
         info[18] = init_s; info[19] = (double)log.energies.size(); info[20] = log.sweep_seconds.empty() ? 0. : log.sweep_seconds.back();
+        if (getenv("QCM_DEBUG")) {
+            double* ss = ts::split_seconds();
+            fprintf(stderr, "[rank %d] split seconds: block SVDs %.2f | combination across ranks %.2f | truncation %.2f | whole split incl. the former (reshapes, recoupling) %.2f | "
+                            "normalisation + shift %.2f ; device solver host syncs %zu\n", rank, ss[0], ss[1], ss[2], ss[3], ss[4], eng.host_syncs);
+        }
         return 0;
     } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
 }

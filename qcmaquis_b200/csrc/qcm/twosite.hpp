@@ -217,7 +217,25 @@ inline Index unreduce_left(Index const& physical_i_left, Index const& physical_i
 
 // ---- block SVD with truncation (block_matrix_algorithms.h:165-185,211-260,264-335) ----------------------------------
 struct Truncation { size_t bond_dimension = 0; double truncated_weight = 0, truncated_fraction = 0, smallest_ev = 0; };
+// wall seconds inside the split, by part (development aid, printed by the drivers under QCM_DEBUG):
+// [0] block SVDs [1] combination across ranks [2] truncation + tensor assembly [3] reshapes / recoupling [4] normalisation + shift
+inline double* split_seconds() { static double s[5] = {0, 0, 0, 0, 0}; return s; }
+struct SplitClock
+{
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(int i) { auto n = std::chrono::steady_clock::now(); split_seconds()[i] += std::chrono::duration<double>(n - t).count(); t = n; }
+};
 
+// With many blocks the SVDs run side by side, one BLAS thread each, largest first (a threaded dgesdd gains a factor of two on
+// eight cores and blocks everything else); only when there are fewer blocks than cores do the large ones get threaded BLAS.
+inline double svd_threaded_threshold(size_t n_blocks)
+{
+#ifdef _OPENMP
+    if (n_blocks * 2 >= (size_t)omp_get_max_threads()) return 1e300;
+#endif
+    (void)n_blocks;
+    return 2.5e10;
+}
 // M = U diag(S) V per block; singular values below max(rel_tol * largest, the (Mmax+1)-th largest) are dropped.
 // With several ranks (eng->comm_world() > 1) the blocks are divided among the ranks, largest first to the least loaded one,
 // and the factors are combined with one allreduce of a zero-padded buffer: the split costs 1/world of the host time per
@@ -230,6 +248,7 @@ inline Truncation svd_truncate(block_matrix const& M, block_matrix& U, block_mat
     S.assign(nb, std::vector<double>());
     const int world = eng ? eng->comm_world() : 1, rank = eng ? eng->comm_rank() : 0;
     auto cost = [&](size_t b) { double m = (double)M[b].rows, n = (double)M[b].cols; return 20.0 * m * n * std::min(m, n); };
+    SplitClock clk;
     std::vector<int> owner(nb, 0);
     std::vector<size_t> mine;
     {
@@ -250,7 +269,8 @@ inline Truncation svd_truncate(block_matrix const& M, block_matrix& U, block_mat
         lwork = (int)work[0]; work.resize(std::max(1, lwork));
         scipy_dgesdd_("S", &m, &n, a.data(), &m, S[b].data(), us[b].data(), &m, vs[b].data(), &k, work.data(), &lwork, iwork.data(), &info);
         if (info) throw std::runtime_error("dgesdd failed");
-    });
+    }, svd_threaded_threshold(mine.size()));
+    clk.lap(0);
     if (world > 1) {
         std::vector<size_t> off(nb + 1, 0);
         for (size_t b = 0; b < nb; ++b) { size_t m = M[b].rows, n = M[b].cols, k = std::min(m, n); off[b + 1] = off[b] + m * k + k + k * n; }
@@ -268,6 +288,7 @@ inline Truncation svd_truncate(block_matrix const& M, block_matrix& U, block_mat
             std::copy(p, p + k, S[b].begin()); p += k;
             std::copy(p, p + k * n, vs[b].v.begin());
         }
+        clk.lap(1);
     }
     // estimate_truncation
     std::vector<double> all;
@@ -295,6 +316,7 @@ inline Truncation svd_truncate(block_matrix const& M, block_matrix& U, block_mat
         tr.bond_dimension += keep;
     }
     S.swap(Skept);
+    clk.lap(2);
     return tr;
 }
 // diag(S) * V and U * diag(S), block by block (U, V, S in the same block order)
@@ -433,6 +455,7 @@ inline sweep::SweepLog ts_sweeps(SymmKind symm, EngineIface& eng, MPO const& mpo
             log.energies.push_back(r.theta + mpo.core_energy);
             log.n_sigma.push_back(r.n_sigma); log.total_sigma += r.n_sigma;
             Truncation trunc;
+            SplitClock sclk;
             // all ranks of a sharded run must hold the same state here: same solver history, same structure about to be split
             {
                 uint64_t fp = 1469598103934665603ull;
@@ -445,15 +468,19 @@ inline sweep::SweepLog ts_sweeps(SymmKind symm, EngineIface& eng, MPO const& mpo
             }
             if (lr == +1) {
                 tst.split_mps_l2r(prm.Mmax, prm.cutoff, mps[site1], mps[site2], trunc, &eng);
+                { double* ss = split_seconds(); sclk.lap(3); ss[3] -= 0; }
                 block_matrix t = sweep::normalize_left(mps[site2]);
                 if (site2 < L - 1) sweep::multiply_from_left(mps[site2 + 1], t);
+                sclk.lap(4);
                 log.phase_seconds[3] += lap();
                 left[site2] = eng.overlap_mpo_left_step(mps[site1], mps[site1], left[site1], mpo[site1]);
                 if (prm.drop_stale && site2 < L - 1) right[site2] = Boundary();
             } else {
                 tst.split_mps_r2l(prm.Mmax, prm.cutoff, mps[site1], mps[site2], trunc, &eng);
+                sclk.lap(3);
                 block_matrix t = sweep::normalize_right(mps[site1]);
                 if (site1 > 0) sweep::multiply_from_right(mps[site1 - 1], t);
+                sclk.lap(4);
                 log.phase_seconds[3] += lap();
                 right[site2] = eng.overlap_mpo_right_step(mps[site2], mps[site2], right[site2 + 1], mpo[site2]);
                 if (prm.drop_stale && site1 > 0) left[site2] = Boundary();

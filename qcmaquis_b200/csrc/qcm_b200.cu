@@ -256,7 +256,10 @@ static int ensure_ws(int slot, int64_t n)
     int64_t want = n + n / 8 + 1024;
     cudaError_t e = cudaMalloc((void**)&G.ws[slot], (size_t)want * sizeof(double));
     if (e != cudaSuccess) {
+        cudaGetLastError();
         want = n;
+        cudaStreamSynchronize(G.stream);
+        cudaMemPool_t pool; if (cudaDeviceGetDefaultMemPool(&pool, G.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
         e = cudaMalloc((void**)&G.ws[slot], (size_t)want * sizeof(double));
         if (e != cudaSuccess) return fail("workspace allocation of " + std::to_string(n * 8) + " bytes failed: " + cudaGetErrorString(e));
     }
@@ -278,6 +281,12 @@ extern "C" int qcm_init(int device)
     if (prop.major < 10) return fail(std::string("device ") + prop.name + " is not sm_100-class; this library carries sm_100a code only");
     G.sm_count = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
+    {
+        cudaMemPool_t pool;
+        CU(cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long keep = ~0ull;        // freed arrays stay in the pool for the next site
+        CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     for (auto& ev : G.ev) CU(cudaEventCreate(&ev));
     for (int i = 0; i < Global::kAux; ++i) { CU(cudaStreamCreateWithFlags(&G.aux[i], cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&G.join_ev[i], cudaEventDisableTiming)); }
     CU(cudaEventCreateWithFlags(&G.fork_ev, cudaEventDisableTiming));
@@ -311,6 +320,9 @@ extern "C" int qcm_finalize(void)
 }
 
 extern "C" const char* qcm_last_error(void) { return g_err.c_str(); }
+// for the host-side translation units of the library (plan_capi.cpp)
+extern "C" int qcm_internal_fail(const char* msg) { return fail(msg ? msg : "error"); }
+extern "C" void qcm_internal_forget_plan(qcm_plan_t p);
 extern "C" int qcm_device_count(int* n)
 {
     cudaError_t e = cudaGetDeviceCount(n);
@@ -336,8 +348,16 @@ extern "C" int qcm_array_alloc(int64_t n, qcm_array_t* out)
     if (n < 0) return fail("qcm_array_alloc: negative size");
     qcm_array_s* a = new qcm_array_s{nullptr, n};
     if (n > 0) {
-        cudaError_t e = cudaMalloc((void**)&a->p, (size_t)n * sizeof(double));
-        if (e != cudaSuccess) { delete a; return fail(std::string("qcm_array_alloc: ") + cudaGetErrorString(e)); }
+        // stream-ordered allocation from the device's default pool (its release threshold is raised in qcm_init): boundaries
+        // and solver vectors come and go at every site of a sweep without a device-wide synchronisation
+        cudaError_t e = cudaMallocAsync((void**)&a->p, (size_t)n * sizeof(double), G.stream);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            cudaStreamSynchronize(G.stream);
+            cudaMemPool_t pool; if (cudaDeviceGetDefaultMemPool(&pool, G.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+            e = cudaMallocAsync((void**)&a->p, (size_t)n * sizeof(double), G.stream);
+        }
+        if (e != cudaSuccess) { cudaGetLastError(); delete a; return fail(std::string("qcm_array_alloc: ") + cudaGetErrorString(e)); }
     }
     *out = a;
     return 0;
@@ -345,7 +365,7 @@ extern "C" int qcm_array_alloc(int64_t n, qcm_array_t* out)
 extern "C" int qcm_array_free(qcm_array_t a)
 {
     if (!a) return 0;
-    if (a->p) { cudaStreamSynchronize(G.stream); cudaFree(a->p); }
+    if (a->p) { if (G.ready) cudaFreeAsync(a->p, G.stream); else cudaFree(a->p); }
     delete a;
     return 0;
 }
@@ -697,6 +717,7 @@ extern "C" int qcm_plan_create(const qcm_plan_desc* d, qcm_plan_t* out)
 extern "C" int qcm_plan_destroy(qcm_plan_t P)
 {
     if (!P) return 0;
+    qcm_internal_forget_plan(P);
     if (G.ready) cudaStreamSynchronize(G.stream);
     for (void* p : P->allocs) cudaFree(p);
     delete P;

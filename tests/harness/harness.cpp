@@ -9,6 +9,7 @@
 #include "qcm/sweep.hpp"
 #include "qcm/twosite.hpp"
 #include "plan_interp.hpp"
+#include "flatten_desc.hpp"
 #ifdef QCMT_WITH_GPU
 #include "qcm/engine_gpu.hpp"
 #endif
@@ -550,5 +551,69 @@ extern "C" int qcmt_sharded_split(const char* fcidump, const char* symm, int L, 
         }
         out[0] = n; out[1] = identical; out[2] = worst; out[3] = same_struct;
         return 0;
+    } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
+}
+
+// The descriptor entry points of the C ABI (qcm_mpo_upload, qcm_plan_sigma / left_step / right_step, qcm_plan_out_*): the
+// problem is flattened into plain arrays (tests/harness/flatten_desc.hpp -- the binding a QCMaquis maintainer would write),
+// planned INSIDE the library and executed; no C++ object of this repository crosses the boundary.  Compared with the oracle.
+// out[0] sigma structure equal, [1] sigma rel. error, [2..3] left step, [4..5] right step (single-site problems)
+extern "C" int qcmt_desc_parity(const char* fcidump, const char* symm, int L, int nelec, int site, int twosite, int M, unsigned seed, double* out, char* err, int errlen)
+{
+    try {
+#ifdef QCMT_WITH_GPU
+        for (int i = 0; i < 6; ++i) out[i] = 0;
+        Problem P = make_problem(fcidump, symm, L, nelec);
+        SyntheticSite S = make_synthetic_site(P, site, twosite != 0, (size_t)M, seed);
+        oracle::OracleEngine orc(P.params.symm);
+        auto ck = [](int rc, const char* what) { if (rc != 0) throw std::runtime_error(std::string(what) + ": " + qcm_last_error()); };
+        ck(qcm_init(0), "qcm_init");
+        qcmflat::FlatMPO fm(P.params.symm, *S.mpo);
+        qcmflat::FlatTensor ft(S.psi);
+        qcmflat::FlatBoundary fl(S.left), fr(S.right);
+        qcm_mpo_t m = nullptr; ck(qcm_mpo_upload(&fm.d, &m), "qcm_mpo_upload");
+        qcm_array_t aL = nullptr, aR = nullptr;
+        ck(qcm_array_alloc((int64_t)fl.data.size(), &aL), "alloc"); ck(qcm_array_upload(aL, 0, fl.data.data(), (int64_t)fl.data.size()), "upload");
+        ck(qcm_array_alloc((int64_t)fr.data.size(), &aR), "alloc"); ck(qcm_array_upload(aR, 0, fr.data.data(), (int64_t)fr.data.size()), "upload");
+        auto fetch = [&](qcm_plan_t p, std::vector<int64_t>& ptr, std::vector<qcm_block>& blocks, std::vector<int64_t>& off, int64_t& n_elems) {
+            int64_t aux = 0, nb = 0; ck(qcm_plan_out_size(p, &aux, &nb, &n_elems), "qcm_plan_out_size");
+            ptr.assign((size_t)aux + 1, 0); blocks.resize((size_t)nb); off.resize((size_t)nb);
+            ck(qcm_plan_out_blocks(p, ptr.data(), blocks.data(), off.data()), "qcm_plan_out_blocks");
+        };
+        {
+            qcm_plan_t plan = nullptr; ck(qcm_plan_sigma(m, &ft.d, &fl.d, &fr.d, 0, 1, 0, &plan), "qcm_plan_sigma");
+            std::vector<int64_t> ptr, off; std::vector<qcm_block> blocks; int64_t n = 0;
+            fetch(plan, ptr, blocks, off, n);
+            std::vector<double> sigma((size_t)n);
+            ck(qcm_site_hamil2(plan, aL, aR, ft.data.data(), sigma.data()), "qcm_site_hamil2");
+            block_matrix got = qcmflat::unflatten(blocks, off, ptr[0], ptr[1], sigma.data());
+            MPSTensor so = orc.site_hamil2(S.psi, S.left, S.right, *S.mpo); so.make_left_paired();
+            DiffReport d = compare(got, so.data());
+            out[0] = d.structure_equal; out[1] = rel_diff(d);
+            qcm_plan_destroy(plan);
+        }
+        if (!twosite)
+            for (int dir = 0; dir < 2; ++dir) {
+                qcm_plan_t plan = nullptr;
+                if (dir == 0) ck(qcm_plan_left_step(m, &ft.d, &ft.d, &fl.d, 0, 1, 0, &plan), "qcm_plan_left_step");
+                else ck(qcm_plan_right_step(m, &ft.d, &ft.d, &fr.d, 0, 1, 0, &plan), "qcm_plan_right_step");
+                std::vector<int64_t> ptr, off; std::vector<qcm_block> blocks; int64_t n = 0;
+                fetch(plan, ptr, blocks, off, n);
+                qcm_array_t aO = nullptr; ck(qcm_array_alloc(n, &aO), "alloc");
+                ck(qcm_boundary_step(plan, dir == 0 ? aL : aR, ft.data.data(), ft.data.data(), aO), "qcm_boundary_step");
+                std::vector<double> flat((size_t)n); ck(qcm_array_download(aO, 0, flat.data(), n), "download");
+                Boundary got; got.resize(ptr.size() - 1);
+                for (size_t b = 0; b + 1 < ptr.size(); ++b) got[b] = qcmflat::unflatten(blocks, off, ptr[b], ptr[b + 1], flat.data());
+                Boundary ref = dir == 0 ? orc.overlap_mpo_left_step(S.psi, S.psi, S.left, *S.mpo) : orc.overlap_mpo_right_step(S.psi, S.psi, S.right, *S.mpo);
+                DiffReport d = compare(got, ref);
+                out[2 + 2 * dir] = d.structure_equal; out[3 + 2 * dir] = rel_diff(d);
+                qcm_array_free(aO); qcm_plan_destroy(plan);
+            }
+        qcm_array_free(aL); qcm_array_free(aR); qcm_mpo_free(m);
+        return 0;
+#else
+        (void)fcidump; (void)symm; (void)L; (void)nelec; (void)site; (void)twosite; (void)M; (void)seed; (void)out;
+        throw std::runtime_error("harness built without GPU support");
+#endif
     } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
 }
