@@ -617,3 +617,30 @@ extern "C" int qcmt_desc_parity(const char* fcidump, const char* symm, int L, in
 #endif
     } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
 }
+
+// Single-site sweeps from the reference's `init_type = const` state (mps_initializers.h:85-97: every allowed sector capped at
+// init_bond_dimension, all entries 1, every site tensor normalised): RNG free, so the reference's own printed energies are
+// a known answer for solver + sigma + boundary chain.  n_sigma[i] = Jacobi-Davidson iterations of micro-iteration i.
+extern "C" int qcmt_ss_dmrg_const(const char* fcidump, const char* symm, int L, int nelec, int init_bond_dimension, int nsweeps, int engine_kind,
+                                  double* energies, int* n_sigma, int n_max, int* n_out, char* err, int errlen)
+{
+    try {
+        Problem P = make_problem(fcidump, symm, L, nelec);
+        P.init_mps((size_t)init_bond_dimension, false, 1., 0);
+        std::unique_ptr<EngineIface> eng;
+        if (engine_kind < 0) eng.reset(new oracle::OracleEngine(P.params.symm));
+        else if (engine_kind == 0) eng.reset(new qcmtest::InterpEngine(P.params.symm, 1, (long long)1 << 40));
+        else {
+#ifdef QCMT_WITH_GPU
+            eng.reset(new GpuEngine(P.params.symm, 0, 0, 1));
+#else
+            throw std::runtime_error("harness built without GPU support");
+#endif
+        }
+        sweep::SweepLog log = sweep::ss_sweeps(*eng, P.mpo, P.mps, nsweeps);
+        int n = (int)std::min<size_t>(log.energies.size(), (size_t)n_max);
+        for (int i = 0; i < n; ++i) { energies[i] = log.energies[i]; n_sigma[i] = log.n_sigma[i]; }
+        *n_out = n;
+        return 0;
+    } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
+}
