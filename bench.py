@@ -451,6 +451,7 @@ def main():
     if rank == 0 and not args.no_cpu_baseline:
         olib = ctypes.CDLL(build.build_oracle())
         olib.orc_create.restype = ctypes.c_void_p
+        omp_before = olib.orc_threads()          # the oracle shares this process's OpenMP runtime: give the cores back afterwards
         olib.orc_set_threads(len(os.sched_getaffinity(0)))
         oh = olib.orc_create(path.encode(), symm.encode(), norb, nelec, e, 1024)
         if not oh:
@@ -471,6 +472,7 @@ def main():
         else:
             line["parity_rel_err_vs_oracle"] = "structure mismatch: %d vs %d elements" % (int(se.value), sig_n)
         olib.orc_destroy(oh)
+        olib.orc_set_threads(omp_before)
     progress("cpu baseline / parity done")
     barrier()   # the other ranks' host threads stay idle while rank 0 times the CPU oracle
     # ---- sweep level, the benchmarked configuration itself (every N): one two-site DMRG sweep from a random MPS on the

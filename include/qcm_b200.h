@@ -116,6 +116,16 @@ int qcm_array_upload(qcm_array_t a, int64_t off, const double* host, int64_t n);
 int qcm_array_download(qcm_array_t a, int64_t off, double* host, int64_t n);
 int qcm_array_zero(qcm_array_t a);
 void* qcm_array_devptr(qcm_array_t a);
+/* ---- spill tier: HBM <-> pinned host memory (the roles of storage::disk::evict / prefetch / fetch, utils/storage.h:113-185,
+ * 254-327, with host memory in place of the scratch directory).  qcm_array_evict copies the whole array to `pinned_host`
+ * (from qcm_pinned_alloc) on the library's copy stream and releases the device memory, stream-ordered after the work queued so
+ * far; the handle stays valid but the array may not be used until qcm_array_prefetch has been called, which allocates device
+ * memory again and uploads asynchronously -- work queued later on the library stream waits for the upload, the host never does. */
+int qcm_pinned_alloc(int64_t n_elems, double** out);
+int qcm_pinned_free(double* p);
+int qcm_array_evict(qcm_array_t a, double* pinned_host);
+int qcm_array_prefetch(qcm_array_t a, const double* pinned_host);
+int qcm_array_resident(qcm_array_t a, int* resident);
 
 /* ---- plans ----------------------------------------------------------------------------------------- */
 int qcm_plan_create(const qcm_plan_desc* desc, qcm_plan_t* out);

@@ -241,17 +241,20 @@ extern "C" int qcmd_ts_sweeps_ranked(void* h, int M0, int Mmax, int nsweeps, uns
 //       [9..13] engine seconds: planning, plan upload, sigma calls (device solver incl.), boundary calls, flatten/unflatten
 //       [14] plan-cache hits [15] misses [16] sum of sigma FLOPs (this rank's share) [17] sum of boundary-step FLOPs
 //       [18] seconds before the first sweep (canonisation + initial right boundaries) [19] micro-iterations
-//       [20] seconds of the last sweep
+//       [20] seconds of the last sweep [21] boundaries evicted to pinned host memory [22] prefetched back (QCM_SPILL)
 extern "C" int qcmd_ts_sweeps_synth(void* h, int M, int nsweeps, unsigned seed, int device, int rank, int world, int max_micro, double budget_seconds,
                                     double* energies, int n_max, int* n_out, double* info, char* err, int errlen)
 {
     try {
         Driver* D = static_cast<Driver*>(h);
         auto t0 = std::chrono::steady_clock::now();
+        // one process per GPU: the host BLAS gets the same share of the cores as OpenMP (its default is all of them, per process)
+        sweep::scipy_openblas_set_num_threads(omp_get_max_threads());
         D->P.mps = make_synthetic_mps(D->P, (size_t)M, seed);
         GpuEngine eng(D->P.symm(), device, rank, world);
         eng.set_cache_capacity(4);
         ts::TsParams prm; prm.Mmax = (size_t)M; prm.drop_stale = true; prm.max_micro_iterations = max_micro;
+        prm.spill = getenv("QCM_SPILL") != nullptr;      // boundaries the sweep has left behind move to pinned host memory
         // wall-clock budget: checked at site boundaries; with several ranks the flags are summed so that all ranks stop together
         qcm_array_t flag = nullptr;
         if (budget_seconds > 0) {
@@ -279,6 +282,7 @@ extern "C" int qcmd_ts_sweeps_synth(void* h, int M, int nsweeps, unsigned seed, 
         for (int i = 0; i < 5; ++i) { info[4 + i] = log.phase_seconds[i]; info[9 + i] = eng.seconds[i]; }
         info[14] = (double)eng.cache_hits; info[15] = (double)eng.cache_misses; info[16] = eng.sigma_flops; info[17] = eng.boundary_flops;
         info[18] = init_s; info[19] = (double)log.energies.size(); info[20] = log.sweep_seconds.empty() ? 0. : log.sweep_seconds.back();
+        info[21] = (double)eng.n_evicted; info[22] = (double)eng.n_prefetched;
         if (getenv("QCM_DEBUG")) {
             double* ss = ts::split_seconds();
             fprintf(stderr, "[rank %d] split seconds: block SVDs %.2f | combination across ranks %.2f | truncation %.2f | whole split incl. the former (reshapes, recoupling) %.2f | "

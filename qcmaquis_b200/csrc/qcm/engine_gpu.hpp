@@ -28,11 +28,37 @@ inline void qcm_check(int status, const char* what)
     if (status != 0) throw std::runtime_error(std::string(what) + ": " + qcm_last_error());
 }
 
+// pinned host buffers of the spill tier: page-locking gigabytes takes longer than copying them, so buffers are recycled
+struct SpillPool
+{
+    std::vector<std::pair<int64_t, double*>> free_list;
+    double* take(int64_t n, int64_t& cap)
+    {
+        size_t best = free_list.size();
+        for (size_t i = 0; i < free_list.size(); ++i)
+            if (free_list[i].first >= n && (best == free_list.size() || free_list[i].first < free_list[best].first)) best = i;
+        if (best != free_list.size()) { double* p = free_list[best].second; cap = free_list[best].first; free_list.erase(free_list.begin() + best); return p; }
+        double* p = nullptr; cap = n + n / 8;
+        qcm_check_status(qcm_pinned_alloc(cap, &p));
+        return p;
+    }
+    void give(double* p, int64_t cap) { if (p) free_list.push_back(std::make_pair(cap, p)); }
+    static void qcm_check_status(int rc) { if (rc != 0) throw std::runtime_error(std::string("qcm_pinned_alloc: ") + qcm_last_error()); }
+    ~SpillPool() { for (auto& e : free_list) qcm_pinned_free(e.second); }
+};
+
 struct DeviceBoundary
 {
     qcm_array_t arr = nullptr;
     plan::BoundaryLayout layout;
-    ~DeviceBoundary() { if (arr) qcm_array_free(arr); }
+    double* spill = nullptr; int64_t spill_cap = 0;     // pinned host copy while the boundary is evicted from HBM
+    std::shared_ptr<SpillPool> pool;
+    bool evicted = false;
+    ~DeviceBoundary()
+    {
+        if (arr) qcm_array_free(arr);
+        if (spill) { if (evicted) qcm_sync(); if (pool) pool->give(spill, spill_cap); else qcm_pinned_free(spill); }
+    }
     // 64-bit hash of the block structure (charges and sizes of every block of every bond entry): a plan depends on the
     // structure of its boundaries only, never on their values, so plans are keyed by it and survive from sweep to sweep
     uint64_t structure_hash() const
@@ -211,6 +237,28 @@ public:
         return true;
     }
     size_t host_syncs = 0;           // batched scalar reads of the device solver (three per Jacobi-Davidson iteration)
+    // ---- spill tier: the storage::disk protocol of the reference's sweep drivers (utils/storage.h:113-185: prefetch / evict /
+    // drop, called around every site by optimize.h:119-165) with pinned host memory as the backing store.  evict() queues a
+    // device-to-host copy on the library's copy stream and gives the HBM back; prefetch() queues the upload; both return at
+    // once.  A boundary that is used while evicted is fetched on the spot.
+    void evict(Boundary const& b) override
+    {
+        std::shared_ptr<DeviceBoundary> d = std::static_pointer_cast<DeviceBoundary>(b.device_mirror);
+        if (!d || d->evicted || d->layout.total == 0) return;
+        if (!d->spill) { d->pool = spill_pool; d->spill = spill_pool->take(d->layout.total, d->spill_cap); }
+        qcm_check(qcm_array_evict(d->arr, d->spill), "qcm_array_evict");
+        d->evicted = true; ++n_evicted;
+    }
+    void prefetch(Boundary const& b) override
+    {
+        std::shared_ptr<DeviceBoundary> d = std::static_pointer_cast<DeviceBoundary>(b.device_mirror);
+        if (!d || !d->evicted) return;
+        qcm_check(qcm_array_prefetch(d->arr, d->spill), "qcm_array_prefetch");
+        d->evicted = false; ++n_prefetched;
+    }
+    size_t n_evicted = 0, n_prefetched = 0;
+    std::shared_ptr<SpillPool> spill_pool{new SpillPool()};
+
     // ---- host-side collectives of a sharded sweep (EngineIface) --------------------------------------------------------
     int comm_rank() const override { return rank; }
     int comm_world() const override { return world; }
@@ -265,7 +313,7 @@ public:
     // device mirror of a boundary (uploaded on first use; boundaries produced by this engine already have one)
     std::shared_ptr<DeviceBoundary> mirror(Boundary const& b)
     {
-        if (b.device_mirror) return std::static_pointer_cast<DeviceBoundary>(b.device_mirror);
+        if (b.device_mirror) { prefetch(b); return std::static_pointer_cast<DeviceBoundary>(b.device_mirror); }
         if (!b.host_valid) throw std::runtime_error("GpuEngine: boundary has neither host data nor a device mirror");
         std::shared_ptr<DeviceBoundary> d(new DeviceBoundary());
         std::vector<DualIndex> bases(b.aux_dim());
@@ -286,6 +334,7 @@ public:
         if (b.host_valid) return;
         std::shared_ptr<DeviceBoundary> d = std::static_pointer_cast<DeviceBoundary>(b.device_mirror);
         if (!d) throw std::runtime_error("GpuEngine::download: no device mirror");
+        prefetch(b);
         std::vector<double> flat((size_t)d->layout.total);
         qcm_check(qcm_array_download(d->arr, 0, flat.data(), d->layout.total), "qcm_array_download");
         for (size_t k = 0; k < b.aux_dim(); ++k)

@@ -26,6 +26,10 @@ struct EngineIface
                                            MPOTensor const& mpo, bool isHermitian = true) = 0;
     virtual Boundary overlap_mpo_right_step(MPSTensor const& bra_tensor, MPSTensor const& ket_tensor, Boundary const& right,
                                             MPOTensor const& mpo, bool isHermitian = true) = 0;
+    // ---- boundary storage protocol of the sweep drivers (utils/storage.h:113-185: storage::disk::prefetch / evict; drop is the
+    // destruction of the Boundary).  Engines that keep boundaries in a fast tier move them here; the default does nothing.
+    virtual void prefetch(Boundary const& /*b*/) {}
+    virtual void evict(Boundary const& /*b*/) {}
     // ---- one process per GPU: the host side of a sweep runs on every rank.  Work that is the same on all ranks (the block
     // SVDs of the two-site split) is divided among them and the pieces are combined with allreduce_sum (every rank adds its
     // pieces into a zero buffer, so all ranks end up with bit-identical data); assert_consistent makes a sweep fail loudly,

@@ -412,6 +412,10 @@ struct TsParams
     // (optimize.h:150-165): with drop_stale its storage is released right away, so that at most L + 1 boundaries are
     // resident at any time (the reference's storage::drop on the disk tier, utils/storage.h:176-181).
     bool drop_stale = false;
+    // storage protocol of ts_optimize.hpp:92-118: the boundaries of the next site are prefetched while this site is solved,
+    // the one the sweep leaves behind is evicted (it is needed again only on the way back); with spill the engine keeps
+    // three to four boundaries in its fast tier instead of L + 1
+    bool spill = false;
     // stop after this many micro-iterations of the LAST sweep (0: full sweeps); measurement aid for bounded runs
     int max_micro_iterations = 0;
     // asked before every micro-iteration; true ends the run at that site boundary (wall-clock budgets of measurement
@@ -430,7 +434,10 @@ inline sweep::SweepLog ts_sweeps(SymmKind symm, EngineIface& eng, MPO const& mpo
     std::vector<Boundary> left(L + 1), right(L + 1);
     left[0] = mps.left_boundary();
     right[L] = mps.right_boundary();
-    for (int i = L - 1; i >= 0; --i) right[i] = eng.overlap_mpo_right_step(mps[i], mps[i], right[i + 1], mpo[i]);
+    for (int i = L - 1; i >= 0; --i) {
+        right[i] = eng.overlap_mpo_right_step(mps[i], mps[i], right[i + 1], mpo[i]);
+        if (prm.spill && i + 1 < L) eng.evict(right[i + 1]);
+    }
     if (init_seconds) *init_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_init).count();
     auto to_site = [L](int i) { return i < L ? i : 2 * L - 1 - i; };
     bool stopped = false;
@@ -444,6 +451,11 @@ inline sweep::SweepLog ts_sweeps(SymmKind symm, EngineIface& eng, MPO const& mpo
             else { lr = -1; site2 = to_site(_site); site1 = site2 - 1; }
             auto c0 = std::chrono::steady_clock::now();
             auto lap = [&c0]() { auto n = std::chrono::steady_clock::now(); double s = std::chrono::duration<double>(n - c0).count(); c0 = n; return s; };
+            if (prm.spill) {
+                eng.prefetch(left[site1]); eng.prefetch(right[site2 + 1]);
+                if (lr == +1 && site2 + 2 <= L) eng.prefetch(right[site2 + 2]);
+                if (lr == -1 && site1 >= 1) eng.prefetch(left[site1 - 1]);
+            }
             TwoSiteTensor tst(symm, mps[site1], mps[site2]);
             MPSTensor twin = tst.make_mps();
             log.phase_seconds[0] += lap();
@@ -475,6 +487,7 @@ inline sweep::SweepLog ts_sweeps(SymmKind symm, EngineIface& eng, MPO const& mpo
                 log.phase_seconds[3] += lap();
                 left[site2] = eng.overlap_mpo_left_step(mps[site1], mps[site1], left[site1], mpo[site1]);
                 if (prm.drop_stale && site2 < L - 1) right[site2] = Boundary();
+                if (prm.spill && site1 > 0) eng.evict(left[site1]);
             } else {
                 tst.split_mps_r2l(prm.Mmax, prm.cutoff, mps[site1], mps[site2], trunc, &eng);
                 sclk.lap(3);
@@ -484,6 +497,7 @@ inline sweep::SweepLog ts_sweeps(SymmKind symm, EngineIface& eng, MPO const& mpo
                 log.phase_seconds[3] += lap();
                 right[site2] = eng.overlap_mpo_right_step(mps[site2], mps[site2], right[site2 + 1], mpo[site2]);
                 if (prm.drop_stale && site1 > 0) left[site2] = Boundary();
+                if (prm.spill && site2 + 1 < L) eng.evict(right[site2 + 1]);
             }
             log.phase_seconds[4] += lap();
             {

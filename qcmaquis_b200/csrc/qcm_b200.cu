@@ -33,7 +33,7 @@ static int fail(std::string const& s) { g_err = s; return 1; }
 #define CU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e__)); } while (0)
 #define CHECK_INIT() do { if (!G.ready) return fail("qcm_init has not been called (or failed): no usable CUDA device"); } while (0)
 
-struct qcm_array_s { double* p; int64_t n; };
+struct qcm_array_s { double* p; int64_t n; bool resident = true; cudaEvent_t ready = nullptr; bool pending = false; };
 
 // device-side task records ---------------------------------------------------------------------------------
 struct DCopy { long long src_off, dst_off; int src_buf, dst_buf, rows, cols, lds, ldd; };
@@ -244,6 +244,7 @@ static struct Global
     void* nccl_lib = nullptr; void* comm = nullptr; int rank = 0, world = 1;
     nccl_get_uid_fn f_uid = nullptr; nccl_init_rank_fn f_init = nullptr; nccl_allreduce_fn f_ar = nullptr; nccl_reducescatter_fn f_rs = nullptr;
     cudaStream_t comm_stream = nullptr; cudaEvent_t x_ready = nullptr, x_done = nullptr;   // exchange of partial W sums, overlapped with the local waves
+    cudaStream_t copy_stream = nullptr; cudaEvent_t spill_ev = nullptr;                    // spill tier (qcm_array_evict / prefetch)
     nccl_destroy_fn f_destroy = nullptr; nccl_errstr_fn f_err = nullptr;
 } G;
 
@@ -291,6 +292,8 @@ extern "C" int qcm_init(int device)
     for (int i = 0; i < Global::kAux; ++i) { CU(cudaStreamCreateWithFlags(&G.aux[i], cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&G.join_ev[i], cudaEventDisableTiming)); }
     CU(cudaEventCreateWithFlags(&G.fork_ev, cudaEventDisableTiming));
     CU(cudaStreamCreateWithFlags(&G.comm_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&G.copy_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&G.spill_ev, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&G.x_ready, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&G.x_done, cudaEventDisableTiming));
     CU(cudaMalloc((void**)&G.scratch, 4096));
     if (gemm_set_attributes() || wgemm_set_attributes()) return 1;
@@ -314,6 +317,7 @@ extern "C" int qcm_finalize(void)
     for (int i = 0; i < Global::kAux; ++i) { cudaStreamDestroy(G.aux[i]); cudaEventDestroy(G.join_ev[i]); }
     cudaEventDestroy(G.fork_ev);
     cudaEventDestroy(G.x_ready); cudaEventDestroy(G.x_done); cudaStreamDestroy(G.comm_stream);
+    cudaStreamSynchronize(G.copy_stream); cudaStreamDestroy(G.copy_stream); cudaEventDestroy(G.spill_ev);
     cudaStreamDestroy(G.stream);
     G.stream = nullptr; G.ready = false; G.device = -1;
     return 0;
@@ -346,7 +350,7 @@ extern "C" int qcm_array_alloc(int64_t n, qcm_array_t* out)
 {
     CHECK_INIT();
     if (n < 0) return fail("qcm_array_alloc: negative size");
-    qcm_array_s* a = new qcm_array_s{nullptr, n};
+    qcm_array_s* a = new qcm_array_s(); a->p = nullptr; a->n = n;
     if (n > 0) {
         // stream-ordered allocation from the device's default pool (its release threshold is raised in qcm_init): boundaries
         // and solver vectors come and go at every site of a sweep without a device-wide synchronisation
@@ -366,7 +370,53 @@ extern "C" int qcm_array_free(qcm_array_t a)
 {
     if (!a) return 0;
     if (a->p) { if (G.ready) cudaFreeAsync(a->p, G.stream); else cudaFree(a->p); }
+    if (a->ready) cudaEventDestroy(a->ready);
     delete a;
+    return 0;
+}
+// ---- spill tier ---------------------------------------------------------------------------------------------
+extern "C" int qcm_pinned_alloc(int64_t n, double** out)
+{
+    CHECK_INIT();
+    if (n < 0 || !out) return fail("qcm_pinned_alloc: bad argument");
+    *out = nullptr;
+    if (n == 0) return 0;
+    CU(cudaHostAlloc((void**)out, (size_t)n * sizeof(double), cudaHostAllocDefault));
+    return 0;
+}
+extern "C" int qcm_pinned_free(double* p) { if (p) cudaFreeHost(p); return 0; }
+extern "C" int qcm_array_resident(qcm_array_t a, int* resident) { if (!a || !resident) return fail("null argument"); *resident = a->resident ? 1 : 0; return 0; }
+extern "C" int qcm_array_evict(qcm_array_t a, double* host)
+{
+    CHECK_INIT();
+    if (!a) return fail("qcm_array_evict: null array");
+    if (!a->resident) return 0;
+    if (a->n > 0) {
+        if (!host) return fail("qcm_array_evict: null host buffer");
+        // after everything queued on the compute stream (the array's producers and readers), on the copy stream
+        CU(cudaEventRecord(G.spill_ev, G.stream));
+        CU(cudaStreamWaitEvent(G.copy_stream, G.spill_ev, 0));
+        CU(cudaMemcpyAsync(host, a->p, (size_t)a->n * sizeof(double), cudaMemcpyDeviceToHost, G.copy_stream));
+        CU(cudaFreeAsync(a->p, G.copy_stream));
+        a->p = nullptr;
+    }
+    a->resident = false; a->pending = false;
+    return 0;
+}
+extern "C" int qcm_array_prefetch(qcm_array_t a, const double* host)
+{
+    CHECK_INIT();
+    if (!a) return fail("qcm_array_prefetch: null array");
+    if (a->resident) return 0;
+    if (a->n > 0) {
+        if (!host) return fail("qcm_array_prefetch: null host buffer");
+        CU(cudaMallocAsync((void**)&a->p, (size_t)a->n * sizeof(double), G.copy_stream));
+        CU(cudaMemcpyAsync(a->p, host, (size_t)a->n * sizeof(double), cudaMemcpyHostToDevice, G.copy_stream));
+        if (!a->ready) CU(cudaEventCreateWithFlags(&a->ready, cudaEventDisableTiming));
+        CU(cudaEventRecord(a->ready, G.copy_stream));
+        a->pending = true;
+    }
+    a->resident = true;
     return 0;
 }
 extern "C" int qcm_array_size(qcm_array_t a, int64_t* n) { if (!a) return fail("null array"); *n = a->n; return 0; }
@@ -376,6 +426,8 @@ extern "C" int qcm_array_upload(qcm_array_t a, int64_t off, const double* host, 
     CHECK_INIT();
     if (!a || off < 0 || n < 0 || off + n > a->n) return fail("qcm_array_upload: range outside the array");
     if (n == 0) return 0;
+    if (!a->resident) return fail("qcm_array_upload: the array has been evicted");
+    if (a->pending) { CU(cudaStreamWaitEvent(G.stream, a->ready, 0)); a->pending = false; }
     CU(cudaMemcpyAsync(a->p + off, host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, G.stream));
     CU(cudaStreamSynchronize(G.stream));
     return 0;
@@ -385,6 +437,8 @@ extern "C" int qcm_array_download(qcm_array_t a, int64_t off, double* host, int6
     CHECK_INIT();
     if (!a || off < 0 || n < 0 || off + n > a->n) return fail("qcm_array_download: range outside the array");
     if (n == 0) return 0;
+    if (!a->resident) return fail("qcm_array_download: the array has been evicted");
+    if (a->pending) { CU(cudaStreamWaitEvent(G.stream, a->ready, 0)); a->pending = false; }
     CU(cudaMemcpyAsync(host, a->p + off, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, G.stream));
     CU(cudaStreamSynchronize(G.stream));
     return 0;
@@ -393,6 +447,8 @@ extern "C" int qcm_array_zero(qcm_array_t a)
 {
     CHECK_INIT();
     if (!a) return fail("null array");
+    if (!a->resident) return fail("qcm_array_zero: the array has been evicted");
+    if (a->pending) { CU(cudaStreamWaitEvent(G.stream, a->ready, 0)); a->pending = false; }
     if (a->n) CU(cudaMemsetAsync(a->p, 0, (size_t)a->n * sizeof(double), G.stream));
     return 0;
 }
@@ -842,6 +898,8 @@ static int check_arr(qcm_array_t a, int64_t need, const char* what)
 {
     if (!a) return fail(std::string(what) + ": null array");
     if (a->n < need) return fail(std::string(what) + ": array holds " + std::to_string(a->n) + " elements, plan needs " + std::to_string(need));
+    if (!a->resident) return fail(std::string(what) + ": the array has been evicted to host memory (qcm_array_prefetch brings it back)");
+    if (a->pending) { CU(cudaStreamWaitEvent(G.stream, a->ready, 0)); a->pending = false; }     // a prefetch is in flight: later work waits for it
     return 0;
 }
 

@@ -227,3 +227,48 @@ def test_sharded_plan_needs_a_matching_communicator(built):
     assert host.qcmd_sigma_dev(h, 1, err, 1024) != 0
     assert b"communicator" in err.value
     host.qcmd_destroy(h)
+
+
+def test_spill_tier_keeps_the_sweep_unchanged(built, monkeypatch):
+    """Boundaries the sweep leaves behind are evicted to pinned host memory and prefetched before they are needed again
+    (qcm_array_evict / qcm_array_prefetch, the storage::disk protocol of utils/storage.h:113-185 around every site): same
+    energies as with everything resident, and the tier is really used."""
+    from qcmaquis_b200.fcidump import make_fcidump
+    cu = ctypes.CDLL(built["cuda"], mode=ctypes.RTLD_GLOBAL)
+    cu.qcm_last_error.restype = ctypes.c_char_p
+    assert cu.qcm_init(0) == 0, cu.qcm_last_error()
+    host = ctypes.CDLL(built["host"]); host.qcmd_create.restype = ctypes.c_void_p
+    host.qcmd_ts_sweeps_synth.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_double, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]
+    path = os.path.join(tempfile.mkdtemp(prefix="qcm_test_"), "s.fcidump")
+    make_fcidump(path, 10, 10)
+    err = ctypes.create_string_buffer(1024)
+    runs = []
+    for spill in (False, True):
+        if spill:
+            monkeypatch.setenv("QCM_SPILL", "1")
+        else:
+            monkeypatch.delenv("QCM_SPILL", raising=False)
+        h = ctypes.c_void_p(host.qcmd_create(path.encode(), b"su2u1", 10, 10, err, 1024)); assert h.value, err.value
+        e = (ctypes.c_double * 4096)(); n = ctypes.c_int(); info = (ctypes.c_double * 32)()
+        assert host.qcmd_ts_sweeps_synth(h, 120, 2, 3, 0, 0, 1, 0, 0.0, e, 4096, ctypes.byref(n), info, err, 1024) == 0, err.value
+        runs.append(([e[i] for i in range(n.value)], info[21], info[22]))
+        host.qcmd_destroy(h)
+    (e0, ev0, pf0), (e1, ev1, pf1) = runs
+    assert len(e0) == len(e1) == 2 * 18
+    assert max(abs(a - b) for a, b in zip(e0, e1)) < 1e-10
+    assert ev0 == 0 and ev1 > 10 and pf1 > 10, (ev0, ev1, pf1)
+
+    # the C entry points themselves: evict -> not usable -> prefetch -> same contents
+    n_el = 1 << 20
+    x = torch.randn(n_el, dtype=torch.float64)
+    a = ctypes.c_void_p(); assert cu.qcm_array_alloc(ctypes.c_int64(n_el), ctypes.byref(a)) == 0
+    assert cu.qcm_array_upload(a, ctypes.c_int64(0), ctypes.c_void_p(x.data_ptr()), ctypes.c_int64(n_el)) == 0
+    pin = ctypes.c_void_p(); assert cu.qcm_pinned_alloc(ctypes.c_int64(n_el), ctypes.byref(pin)) == 0
+    assert cu.qcm_array_evict(a, pin) == 0
+    r = ctypes.c_double()
+    assert cu.qcm_vec_dot(a, a, ctypes.c_int64(n_el), ctypes.byref(r)) != 0 and b"evicted" in cu.qcm_last_error()
+    assert cu.qcm_array_prefetch(a, pin) == 0
+    assert cu.qcm_vec_dot(a, a, ctypes.c_int64(n_el), ctypes.byref(r)) == 0
+    assert r.value == pytest.approx(float(x @ x), rel=1e-12)
+    cu.qcm_array_free(a); cu.qcm_pinned_free(pin)
