@@ -1486,7 +1486,7 @@ private:
         // groups get their places in the source / destination / coefficient arrays by a prefix sum, and are written
         // out in parallel.  The result does not depend on the number of threads.
         typedef std::vector<std::pair<int64_t, int32_t>> UniVec;   // (packed src ref, leading dimension) of a group's sources
-        struct GInfo { size_t q; int32_t g; bool stream; UniVec uni; };
+        struct GInfo { size_t q; int32_t g; bool stream; UniVec uni; std::vector<uint32_t> extra; bool absorbed; };    // extra: destinations taken over from absorbed groups
         std::vector<size_t> run_begin;
         for (size_t q = 0; q < nd; ++q)
             if (q == 0 || keys[q].rows != keys[q - 1].rows || keys[q].cols != keys[q - 1].cols || keys[q].h1 != keys[q - 1].h1) run_begin.push_back(q);
@@ -1523,18 +1523,63 @@ private:
                     }
                     uni.swap(tmp);
                 }
-                per_run[(size_t)r].push_back(GInfo{q, g, stream, uni});
+                per_run[(size_t)r].push_back(GInfo{q, g, stream, uni, std::vector<uint32_t>(), false});
                 q = q2;
             }
         }
         std::vector<GInfo*> flat;
         for (auto& v : per_run) for (auto& gi : v) flat.push_back(&gi);
+        // Piggy-back pass.  The DMMA product of a group always computes ng = 8/16/32/64 destination columns; a group of 55
+        // destinations leaves 9 columns idle.  Small groups with many sources (a single column of the MPO with its own row
+        // set: 1-2 destinations, hundreds of sources -- a pure streaming read) whose sources are (mostly) read by a large
+        // group of the same panel shape anyway move into those idle columns: their sources are then read once instead of
+        // twice.  At cfg3 this removes a quarter of the W pass's HBM traffic.  Serial, deterministic, cheap (a few thousand
+        // candidate pairs).
+        if (!getenv("QCM_NO_PIGGYBACK")) {
+            auto ng_of = [](int32_t g) { return g <= 8 ? 8 : g <= 16 ? 16 : g <= 32 ? 32 : 64; };
+            std::map<std::pair<int32_t, int32_t>, std::vector<size_t>> big;       // panel shape -> groups of the 32 / 64 classes
+            for (size_t f = 0; f < flat.size(); ++f) if (!flat[f]->stream && flat[f]->g > 16) big[std::make_pair(keys[flat[f]->q].rows, keys[flat[f]->q].cols)].push_back(f);
+            std::vector<size_t> small;
+            for (size_t f = 0; f < flat.size(); ++f) if (!flat[f]->stream && flat[f]->g <= 16 && flat[f]->uni.size() >= 32) small.push_back(f);
+            std::stable_sort(small.begin(), small.end(), [&](size_t a, size_t b) { return flat[a]->uni.size() > flat[b]->uni.size(); });
+            UniVec tmp;
+            for (size_t sf : small) {
+                GInfo& sm = *flat[sf];
+                auto it = big.find(std::make_pair(keys[sm.q].rows, keys[sm.q].cols));
+                if (it == big.end()) continue;
+                size_t best = (size_t)-1, best_c = 0;
+                for (size_t bf : it->second) {
+                    GInfo const& bg = *flat[bf];
+                    const int32_t have = bg.g + (int32_t)bg.extra.size();
+                    if (have + sm.g > ng_of(bg.g)) continue;                  // idle columns only: the product does not grow
+                    size_t i = 0, j = 0, c = 0;
+                    while (i < sm.uni.size() && j < bg.uni.size()) { if (sm.uni[i].first == bg.uni[j].first) { ++c; ++i; ++j; } else if (sm.uni[i].first < bg.uni[j].first) ++i; else ++j; }
+                    if (c > best_c) { best_c = c; best = bf; }
+                }
+                if (best == (size_t)-1 || 4 * best_c < 3 * sm.uni.size()) continue;     // at least three quarters of the sources are shared
+                GInfo& bg = *flat[best];
+                for (int32_t d = 0; d < sm.g; ++d) bg.extra.push_back((uint32_t)keys[sm.q + d].idx);
+                tmp.clear();
+                size_t i = 0, j = 0;
+                while (i < bg.uni.size() || j < sm.uni.size()) {
+                    if (j == sm.uni.size() || (i < bg.uni.size() && bg.uni[i].first < sm.uni[j].first)) tmp.push_back(bg.uni[i++]);
+                    else if (i == bg.uni.size() || sm.uni[j].first < bg.uni[i].first) tmp.push_back(sm.uni[j++]);
+                    else { tmp.push_back(bg.uni[i]); ++i; ++j; }
+                }
+                bg.uni.swap(tmp);
+                sm.absorbed = true;
+            }
+            std::vector<GInfo*> kept;
+            for (GInfo* gi : flat) if (!gi->absorbed) kept.push_back(gi);
+            flat.swap(kept);
+        }
+        auto member = [&](GInfo const& gi, int32_t d) -> size_t { return d < gi.g ? keys[gi.q + d].idx : (size_t)gi.extra[(size_t)(d - gi.g)]; };
         const size_t g_base = wl.groups.size();
         size_t n_srcs = wl.srcs.size(), n_dsts = wl.dsts.size(), n_coefs = wl.coefs.size();
         wl.groups.resize(g_base + flat.size());
         for (size_t f = 0; f < flat.size(); ++f) {
             GInfo const& gi = *flat[f];
-            int32_t ns = (int32_t)gi.uni.size(), g = gi.g;
+            int32_t ns = (int32_t)gi.uni.size(), g = gi.g + (int32_t)gi.extra.size();
             WGroup G; G.rows = keys[gi.q].rows; G.cols = keys[gi.q].cols; G.n_src = ns; G.n_dst = g; G.cls = gi.stream ? 1 : 0;
             G.ng = gi.stream ? 4 : (g <= 8 ? 8 : g <= 16 ? 16 : g <= 32 ? 32 : 64);
             G.src_begin = (int32_t)n_srcs; G.dst_begin = (int32_t)n_dsts; G.coef_begin = (int64_t)n_coefs;
@@ -1553,8 +1598,8 @@ private:
             std::fill(wl.coefs.begin() + G.coef_begin, wl.coefs.begin() + G.coef_begin + (int64_t)(ns_pad * (size_t)G.ng), 0.);
             for (size_t u = 0; u < gi.uni.size(); ++u)
                 wl.srcs[(size_t)G.src_begin + u] = WSrc{Ref{(int32_t)(gi.uni[u].first >> 56), gi.uni[u].first & (((int64_t)1 << 56) - 1)}, gi.uni[u].second};
-            for (int32_t d = 0; d < gi.g; ++d) {
-                size_t di = keys[gi.q + d].idx;
+            for (int32_t d = 0; d < G.n_dst; ++d) {
+                size_t di = member(gi, d);
                 wl.dsts[(size_t)G.dst_begin + d] = WDst{al.dsts[di].dst, al.dsts[di].ldd};
                 SrcVec const& m = sorted[di];
                 size_t u = 0;

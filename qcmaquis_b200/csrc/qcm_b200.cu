@@ -563,7 +563,14 @@ static int flush_uploads(qcm_plan_s* P)
 {
     if (g_pin.used == 0) return 0;
     char* base = nullptr;
-    CU(cudaMalloc((void**)&base, g_pin.used));
+    // stream-ordered like the arrays: a sweep creates and destroys two plans per site
+    cudaError_t em = cudaMallocAsync((void**)&base, g_pin.used, G.stream);
+    if (em != cudaSuccess) {
+        cudaGetLastError();
+        cudaStreamSynchronize(G.stream);
+        cudaMemPool_t pool; if (cudaDeviceGetDefaultMemPool(&pool, G.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+        CU(cudaMallocAsync((void**)&base, g_pin.used, G.stream));
+    }
     P->allocs.push_back(base);
     P->task_bytes = (int64_t)g_pin.used;
     CU(cudaMemcpyAsync(base, g_pin.p, g_pin.used, cudaMemcpyHostToDevice, G.stream));
@@ -742,7 +749,7 @@ extern "C" int qcm_plan_create(const qcm_plan_desc* d, qcm_plan_t* out)
     P->world = d->world > 1 ? d->world : 1; P->rank = d->world > 1 ? d->rank : 0;
     if (P->rank < 0 || P->rank >= P->world) { delete P; return fail("qcm_plan_create: rank outside [0, world)"); }
     for (int i = 0; i < QCM_BUF_COUNT; ++i) P->elems[i] = d->elems[i];
-    auto bail = [&]() { for (void* p : P->allocs) cudaFree(p); delete P; return 1; };
+    auto bail = [&]() { for (void* p : P->allocs) cudaFreeAsync(p, G.stream); delete P; return 1; };
     {
         std::vector<DCopy> hc((size_t)d->n_pre_copies);
         for (int64_t i = 0; i < d->n_pre_copies; ++i) {
@@ -774,8 +781,8 @@ extern "C" int qcm_plan_destroy(qcm_plan_t P)
 {
     if (!P) return 0;
     qcm_internal_forget_plan(P);
-    if (G.ready) cudaStreamSynchronize(G.stream);
-    for (void* p : P->allocs) cudaFree(p);
+    // the task arrays are released in stream order: kernels of this plan that are still queued finish first
+    for (void* p : P->allocs) { if (G.ready) cudaFreeAsync(p, G.stream); else cudaFree(p); }
     delete P;
     return 0;
 }

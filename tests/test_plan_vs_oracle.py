@@ -76,3 +76,19 @@ def test_edge_sharding_computes_no_step1_product_twice(harness_cpu, world):
     assert 1.0 - 1e-12 <= out[3] < 1.03                   # no closing product is repeated: partial W sums are exchanged (reduce-scatter); the
                                                          # excess is row units of exchanged blocks that no bond feeds (closed as zeros)
     assert out[1] < 1.25                                 # the heaviest rank stays close to its fair share
+
+
+@pytest.mark.parametrize("symm,M", [("su2u1", 100), ("2u1", 60)])
+@pytest.mark.parametrize("world", [1, 3])
+def test_twelve_orbital_two_site_plan(harness_cpu, symm, M, world):
+    """A problem large enough for the W pass to form its 32/64-destination classes: exercises the piggy-back pass of the
+    grouping (small high fan-in groups moved into idle columns of large ones) and, for world > 1, an exchange region of
+    several hundred thousand elements."""
+    import os, tempfile
+    from qcmaquis_b200.fcidump import make_fcidump
+    path = os.path.join(tempfile.mkdtemp(prefix="qcm_test_"), "synth_12o12e.fcidump")
+    make_fcidump(path, 12, 12)
+    out = harness_cpu.synth_parity(path.encode(), symm, 12, 12, 5, True, M, engine=0, world=world)
+    assert out[0] == 1 and out[1] < TOL, out[:4]
+    if world > 1:
+        assert out[10] > 1e5
