@@ -254,6 +254,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true", help="skip the sweep-level measurement (single-site DMRG sweeps of the 8e/8o system)")
     ap.add_argument("--parity", action="store_true", help="(kept for compatibility: the oracle parity of the sigma vector is reported at every N unless --no-cpu-baseline)")
+    ap.add_argument("--slices", type=int, default=0, help="N=1: run the site problem as this many time-sliced shards on the one GPU (0: automatic -- 2 for cfg4, whose resident step-1 products are 145 GB; 1 otherwise)")
     ap.add_argument("--no-config-sweep", action="store_true", help="skip the two-site DMRG sweep of the benchmarked configuration itself")
     ap.add_argument("--sweep-budget", type=float, default=300.0, help="wall-clock budget (s) of the configuration sweep; it stops at a site boundary when exceeded")
     args = ap.parse_args()
@@ -263,6 +264,9 @@ def main():
     if args.M:
         M = args.M
     site = args.site if args.site >= 0 else norb // 2 - 1
+    slices = args.slices if args.slices > 0 else (2 if args.config.startswith("cfg4") and int(os.environ.get("WORLD_SIZE", "1")) == 1 else 1)
+    if slices > 1:
+        os.environ["QCM_SLICES"] = str(slices)
     if args.impl == "reference":
         run_reference(args, args.config, norb, nelec, symm, M, site)
         return
@@ -404,7 +408,7 @@ def main():
     # W application (k_wgemm_ws + k_wstream).  The GEMM is bound by the FP64 tensor pipe: achieved = FLOPs the schedule
     # hands to it (step-1 products + closing products after panel routing) / its device time; the W application is
     # bound by HBM on all but its 64-destination class: achieved = panel bytes read + written / its device time.
-    t_gemm, t_w = phases[1] + phases[3], phases[2]
+    t_gemm, t_w = max(phases[1] + phases[3], 1e-9), phases[2]
     if t_w > t_gemm:
         b = 8.0 * (info[21] + info[22])
         roof = {"bound": "hbm", "kernel": "k_wgemm_ws + k_wstream (W application)", "achieved": b / (t_w * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
@@ -435,7 +439,7 @@ def main():
     line = {"metric": "sigma_vector_fp64_tflops", "value": flops / (ms_dev * 1e-3) / 1e12, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": args.config, "site": site, "twosite": True, "M": M, "symmetry": symm, "parallelism": "mpo-bond-sharded x%d" % world,
+            "config": {"workload": args.config, "site": site, "twosite": True, "M": M, "symmetry": symm, "parallelism": "mpo-bond-sharded x%d" % world if slices <= 1 else "one GPU, %d time-sliced shards of the MPO bond graph" % slices,
                        "l2": "inputs (boundaries %.2f GB + workspaces %.2f GB) exceed L2" % ((info[7] + info[8]) * 8 / 1e9, info[12] / 1e9),
                        "mpo": "%dx%d nnz %d" % (info[16], info[17], info[18]), "sectors": int(info[14]), "largest_sector": int(info[15]),
                        "flops_per_step": flops, "flops_split": {"step1": f_t, "w_apply": f_w, "step3": f_c},

@@ -147,6 +147,12 @@ int qcm_plan_stats(qcm_plan_t p, double* flops, int64_t* bytes, int64_t* n_launc
 int qcm_site_hamil2(qcm_plan_t p, qcm_array_t left, qcm_array_t right, const double* psi, double* sigma);
 int qcm_site_hamil2_dev(qcm_plan_t p, qcm_array_t left, qcm_array_t right, qcm_array_t psi, qcm_array_t sigma);
 int qcm_boundary_step(qcm_plan_t p, qcm_array_t in, const double* bra, const double* ket, qcm_array_t out);
+/* Time-sliced shards: plans[v] = shard v of n of ONE sigma contraction (qcm_plan_sigma(..., rank = v, world = n, ...)), executed
+ * one after another on this device, so that only one shard's resident step-1 products (QCM_BUF_TP) occupy HBM at a time -- the
+ * single-GPU mode for site problems whose products exceed one device (24e/30o TwoU1 M=4000: 145 GB).  No communicator is
+ * involved: the exchange of partial W sums is a local accumulation, sigma accumulates over the shards. */
+int qcm_site_hamil2_sliced(const qcm_plan_t* plans, int n, qcm_array_t left, qcm_array_t right, const double* psi, double* sigma);
+int qcm_site_hamil2_sliced_dev(const qcm_plan_t* plans, int n, qcm_array_t left, qcm_array_t right, qcm_array_t psi, qcm_array_t sigma);
 /* qcm_hdiag              replaces Engine::diagonal_hamiltonian (abelian/engine.hpp:222-227; bodies abelian/h_diag.hpp:41-168,
  *                        non-abelian/h_diag.hpp:19-155): the diagonal of the effective Hamiltonian in the left-paired
  *                        layout of the site tensor (plan kind 3), written to the HOST buffer `diag` (blocks back to back). */

@@ -113,7 +113,7 @@ extern "C" int qcmd_get_psi(void* h, double* psi)
 extern "C" int qcmd_sigma_host(void* h, const double* psi, double* sigma, char* err, int errlen)
 {
     Driver* D = static_cast<Driver*>(h);
-    if (qcm_site_hamil2(D->plan->handle, D->dl->arr, D->dr->arr, psi, sigma) != 0) { set_err(err, errlen, qcm_last_error()); return 1; }
+    try { D->eng->run_sigma_host(*D->plan, *D->dl, *D->dr, psi, sigma); } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
     return 0;
 }
 
@@ -121,8 +121,7 @@ extern "C" int qcmd_sigma_host(void* h, const double* psi, double* sigma, char* 
 extern "C" int qcmd_sigma_dev(void* h, int n, char* err, int errlen)
 {
     Driver* D = static_cast<Driver*>(h);
-    for (int i = 0; i < n; ++i)
-        if (qcm_site_hamil2_dev(D->plan->handle, D->dl->arr, D->dr->arr, D->d_psi, D->d_sigma) != 0) { set_err(err, errlen, qcm_last_error()); return 1; }
+    try { for (int i = 0; i < n; ++i) D->eng->run_sigma_dev(*D->plan, *D->dl, *D->dr, D->d_psi, D->d_sigma); } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
     return 0;
 }
 extern "C" int qcmd_get_sigma_dev(void* h, double* sigma)

@@ -82,6 +82,7 @@ private:
 struct CompiledPlan
 {
     qcm_plan_t handle = nullptr;
+    std::vector<qcm_plan_t> slices;      // time-sliced shards of one sigma contraction (GpuEngine::slices > 1); handle == slices[0]
     plan::Layout out_tensor;
     plan::BoundaryLayout out_boundary;
     int64_t ket_elems = 0, bra_elems = 0, out_elems = 0;
@@ -92,7 +93,7 @@ struct CompiledPlan
     double exec_w = 0, exec_close = 0;
     int64_t direct_panel_elems = 0, w_panel_elems = 0, skipped_panel_elems = 0;
     int64_t workspace_elems = 0;
-    ~CompiledPlan() { if (handle) qcm_plan_destroy(handle); }
+    ~CompiledPlan() { if (slices.empty()) { if (handle) qcm_plan_destroy(handle); } else for (qcm_plan_t p : slices) qcm_plan_destroy(p); }
 };
 
 class GpuEngine : public EngineIface
@@ -102,6 +103,7 @@ public:
         : symm(s), rank(rank_), world(world_), budget(ws_budget_elems)
     {
         qcm_check(qcm_init(device), "qcm_init");
+        if (const char* e = getenv("QCM_SLICES")) slices = std::max(1, atoi(e));
     }
     ~GpuEngine() { for (auto a : vec_pool) qcm_array_free(a); if (host_xfer) qcm_array_free(host_xfer); }
 
@@ -115,8 +117,7 @@ public:
         Clock c0;
         std::vector<double> psi = flatten(ket_tensor.data(), cp->ket_elems), sigma((size_t)cp->out_elems);
         seconds[4] += c0.lap();
-        qcm_check(qcm_site_hamil2(cp->handle, dl->arr, dr->arr, psi.data(), sigma.data()), "qcm_site_hamil2");
-        sigma_flops += cp->flops; ++n_sigma_calls;
+        run_sigma_host(*cp, *dl, *dr, psi.data(), sigma.data());
         seconds[2] += c0.lap();
         MPSTensor r(ket_tensor.site_dim(), ket_tensor.row_dim(), ket_tensor.col_dim(), unflatten(cp->out_tensor, sigma), LeftPaired, true);
         seconds[4] += c0.lap();
@@ -131,14 +132,54 @@ public:
         if (std::shared_ptr<CompiledPlan> hit = lookup(key, [&](Witness const& w) { return w.matches(dl->layout, dr->layout, ket_tensor, ket_tensor); })) { ++cache_hits; return hit; }
         ++cache_misses;
         Clock c0;
-        plan::Planner planner(symm, mpo, isHermitian, rank, world, budget);
-        plan::Plan P = planner.plan_sigma(desc_of(ket_tensor), dl->layout, dr->layout);
-        seconds[0] += c0.lap();
-        std::shared_ptr<CompiledPlan> cp = compile(P, dl->layout.total, dr->layout.total);
-        seconds[1] += c0.lap();
+        std::shared_ptr<CompiledPlan> cp;
+        if (slices > 1 && world == 1) {
+            // the site problem as `slices` shards, run one after another on this device (qcm_site_hamil2_sliced)
+            for (int v = 0; v < slices; ++v) {
+                plan::Planner planner(symm, mpo, isHermitian, v, slices, budget);
+                plan::Plan P = planner.plan_sigma(desc_of(ket_tensor), dl->layout, dr->layout);
+                seconds[0] += c0.lap();
+                std::shared_ptr<CompiledPlan> part = compile(P, dl->layout.total, dr->layout.total);
+                seconds[1] += c0.lap();
+                if (v == 0) cp = part;
+                else {
+                    cp->flops += part->flops; cp->flops_t += part->flops_t; cp->flops_w += part->flops_w; cp->flops_close += part->flops_close;
+                    cp->exec_w += part->exec_w; cp->exec_close += part->exec_close; cp->n_gemm_tasks += part->n_gemm_tasks; cp->n_axpy_tasks += part->n_axpy_tasks;
+                    cp->w_elems_read += part->w_elems_read; cp->w_elems_written += part->w_elems_written; cp->w_groups += part->w_groups;
+                    cp->direct_panel_elems += part->direct_panel_elems; cp->w_panel_elems += part->w_panel_elems; cp->skipped_panel_elems += part->skipped_panel_elems;
+                    cp->workspace_elems = std::max(cp->workspace_elems, part->workspace_elems);
+                }
+                cp->slices.push_back(part->handle);
+                if (v > 0) part->handle = nullptr;       // owned by cp->slices now
+            }
+            last = cp;
+        } else {
+            plan::Planner planner(symm, mpo, isHermitian, rank, world, budget);
+            plan::Plan P = planner.plan_sigma(desc_of(ket_tensor), dl->layout, dr->layout);
+            seconds[0] += c0.lap();
+            cp = compile(P, dl->layout.total, dr->layout.total);
+            seconds[1] += c0.lap();
+        }
         remember(key, Witness(dl->layout, dr->layout, ket_tensor, ket_tensor), cp);
         return cp;
     }
+
+    // one sigma evaluation of a compiled plan (single plan or time-sliced shards)
+    void run_sigma_dev(CompiledPlan const& cp, DeviceBoundary const& dl, DeviceBoundary const& dr, qcm_array_t psi, qcm_array_t sigma)
+    {
+        if (cp.slices.empty()) qcm_check(qcm_site_hamil2_dev(cp.handle, dl.arr, dr.arr, psi, sigma), "qcm_site_hamil2_dev");
+        else qcm_check(qcm_site_hamil2_sliced_dev(cp.slices.data(), (int)cp.slices.size(), dl.arr, dr.arr, psi, sigma), "qcm_site_hamil2_sliced_dev");
+        sigma_flops += cp.flops; ++n_sigma_calls;
+    }
+    void run_sigma_host(CompiledPlan const& cp, DeviceBoundary const& dl, DeviceBoundary const& dr, const double* psi, double* sigma)
+    {
+        if (cp.slices.empty()) qcm_check(qcm_site_hamil2(cp.handle, dl.arr, dr.arr, psi, sigma), "qcm_site_hamil2");
+        else qcm_check(qcm_site_hamil2_sliced(cp.slices.data(), (int)cp.slices.size(), dl.arr, dr.arr, psi, sigma), "qcm_site_hamil2_sliced");
+        sigma_flops += cp.flops; ++n_sigma_calls;
+    }
+    // > 1: every sigma plan is built as that many shards executed one after another (for site problems whose resident step-1
+    // products exceed the device: per-shard TP is 1/slices); ignored when the engine is one rank of several
+    int slices = 1;
 
     // ---- Jacobi-Davidson with device-resident vectors (ietl/jacobi.h:361-451, ietl_jcd_gmres = 0) ---------------------
     // Same recurrence as the host solver (qcm/sweep.hpp) on flat device arrays: one qcm_site_hamil2_dev per iteration, the small
@@ -188,8 +229,8 @@ public:
         res = EigenResult();
         int it = 0;
         for (;;) {
-            qcm_check(qcm_site_hamil2_dev(cp->handle, dl->arr, dr->arr, V[it], VA[it]), "qcm_site_hamil2_dev");
-            res.n_sigma++; sigma_flops += cp->flops; ++n_sigma_calls;
+            run_sigma_dev(*cp, *dl, *dr, V[it], VA[it]);
+            res.n_sigma++;
             xs.assign(V.begin(), V.begin() + it + 1); ys.assign((size_t)it + 1, VA[it]); dots();                            // (1)
             for (int i = 0; i <= it; ++i) M[(size_t)i + (size_t)it * max_iter] = d[(size_t)i];
             const int dim = it + 1;

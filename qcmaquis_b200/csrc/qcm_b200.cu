@@ -235,6 +235,7 @@ static struct Global
     int64_t ws_elems[QCM_BUF_COUNT] = {0};
     double* scratch = nullptr;          // small device scalar area
     double* dot_partial = nullptr;      // per-block partial sums of qcm_vec_dots + the results
+    double* xacc = nullptr; int64_t xacc_elems = 0;   // accumulator of the exchange region (time-sliced shards)
     static constexpr int kLcSlots = 64;
     char* lc_args = nullptr; unsigned lc_next = 0;   // argument slots of qcm_vec_lincomb
     bool timing = false;
@@ -311,6 +312,8 @@ extern "C" int qcm_finalize(void)
     G.scratch = nullptr;
     if (G.dot_partial) cudaFree(G.dot_partial);
     G.dot_partial = nullptr;
+    if (G.xacc) cudaFree(G.xacc);
+    G.xacc = nullptr; G.xacc_elems = 0;
     if (G.lc_args) cudaFree(G.lc_args);
     G.lc_args = nullptr;
     for (auto& ev : G.ev) cudaEventDestroy(ev);
@@ -901,6 +904,74 @@ static int execute(qcm_plan_s* P, BufTable bufs)
     return 0;
 }
 
+// Time-sliced shards.  A site problem whose resident step-1 products do not fit one device (cfg4: 145 GB) is planned as V
+// shards -- exactly the plans V ranks would run (edges of the MPO bond graph sharded by their step-1 index) -- and the shards are
+// executed one after another on this device: only one shard's step-1 products are resident at a time.  The exchange of
+// partial W sums becomes a local accumulation (the region of every shard is added into an accumulator; the closing products
+// of all chunks then read the complete sums), the allreduce of sigma becomes accumulation into the same output.
+static int execute_sliced(qcm_plan_s* const* Ps, int V, BufTable bufs)
+{
+    for (int slot : {QCM_BUF_KET_RP, QCM_BUF_T, QCM_BUF_TP, QCM_BUF_Y, QCM_BUF_BRA_RP}) {
+        int64_t need = 0;
+        for (int v = 0; v < V; ++v) need = std::max(need, Ps[v]->elems[slot]);
+        if (ensure_ws(slot, need)) return 1;
+        bufs.p[slot] = G.ws[slot];
+    }
+    int64_t x_elems = 0;
+    for (int v = 0; v < V; ++v) {
+        qcm_plan_s* P = Ps[v];
+        const int64_t xe = (!P->waves.empty() && P->waves[0].x_chunk > 0) ? P->waves[0].x_chunk * P->world : 0;
+        if (v == 0) x_elems = xe; else if (xe != x_elems) return fail("qcm_site_hamil2_sliced: the shards disagree on the exchange region");
+    }
+    if (x_elems > G.xacc_elems) {
+        if (G.xacc) { CU(cudaStreamSynchronize(G.stream)); CU(cudaFree(G.xacc)); G.xacc = nullptr; G.xacc_elems = 0; }
+        CU(cudaMalloc((void**)&G.xacc, (size_t)x_elems * 8));
+        G.xacc_elems = x_elems;
+    }
+    const bool tm = G.timing;
+    float acc[4] = {0, 0, 0, 0};
+    auto mark = [&](int i) { if (tm) cudaEventRecord(G.ev[i], G.stream); };
+    auto lap = [&](int phase, int i0, int i1) { if (tm) { cudaEventSynchronize(G.ev[i1]); float ms = 0; cudaEventElapsedTime(&ms, G.ev[i0], G.ev[i1]); acc[phase] += ms; } };
+    for (int v = 0; v < V; ++v) {
+        qcm_plan_s* P = Ps[v];
+        mark(0);
+        if (v == 0 && P->n_copies) {
+            if (P->elems[QCM_BUF_KET_RP]) CU(cudaMemsetAsync(bufs.p[QCM_BUF_KET_RP], 0, (size_t)P->elems[QCM_BUF_KET_RP] * 8, G.stream));
+            k_copy_panels<<<(unsigned)P->n_copies, 128, 0, G.stream>>>(P->d_copies, bufs);
+            G.launches++;
+        }
+        mark(1); lap(0, 0, 1);
+        if (run_gemm_group(P->p, bufs)) return 1;
+        mark(2); lap(1, 1, 2);
+        for (auto const& W : P->waves) {
+            mark(3);
+            if (W.x_chunk > 0) {
+                if (W.x_zero) CU(cudaMemsetAsync(bufs.p[QCM_BUF_Y], 0, (size_t)x_elems * 8, G.stream));
+                if (run_w_group(W.w, bufs)) return 1;
+                if (v == 0) CU(cudaMemcpyAsync(G.xacc, bufs.p[QCM_BUF_Y], (size_t)x_elems * 8, cudaMemcpyDeviceToDevice, G.stream));
+                else { k_vec_axpy<<<G.sm_count * 8, 256, 0, G.stream>>>(1.0, bufs.p[QCM_BUF_Y], G.xacc, x_elems); G.launches++; }
+                mark(4); lap(2, 3, 4);
+                continue;
+            }
+            if (run_gemm_group(W.t, bufs)) return 1;
+            mark(4); lap(1, 3, 4);
+            if (run_w_group(W.w, bufs)) return 1;
+            mark(5); lap(2, 4, 5);
+            if (run_gemm_group(W.c, bufs)) return 1;
+            mark(6); lap(3, 5, 6);
+        }
+    }
+    if (x_elems > 0) {
+        mark(3);
+        CU(cudaMemcpyAsync(bufs.p[QCM_BUF_Y], G.xacc, (size_t)x_elems * 8, cudaMemcpyDeviceToDevice, G.stream));
+        for (int v = 0; v < V; ++v) if (run_gemm_group(Ps[v]->waves[0].c, bufs)) return 1;
+        mark(4); lap(3, 3, 4);
+    }
+    if (tm) { for (int i = 0; i < 4; ++i) G.last_ms[i] = acc[i]; G.last_ms[4] = 0; G.last_ms[5] = acc[0] + acc[1] + acc[2] + acc[3]; }
+    CU(cudaGetLastError());
+    return 0;
+}
+
 static int check_arr(qcm_array_t a, int64_t need, const char* what)
 {
     if (!a) return fail(std::string(what) + ": null array");
@@ -936,12 +1007,44 @@ extern "C" int qcm_site_hamil2_dev(qcm_plan_t P, qcm_array_t left, qcm_array_t r
     return 0;
 }
 
+extern "C" int qcm_site_hamil2_sliced_dev(const qcm_plan_t* plans, int n, qcm_array_t left, qcm_array_t right, qcm_array_t psi, qcm_array_t sigma)
+{
+    CHECK_INIT();
+    if (!plans || n < 1) return fail("qcm_site_hamil2_sliced: no plans");
+    for (int v = 0; v < n; ++v) {
+        qcm_plan_s* P = plans[v];
+        if (!P || P->kind != 0) return fail("qcm_site_hamil2_sliced: plan is not a sigma plan");
+        if ((n > 1 && (P->world != n || P->rank != v)) || (n == 1 && P->world != 1)) return fail("qcm_site_hamil2_sliced: plans[v] must be shard v of n");
+        if (check_arr(left, P->elems[QCM_BUF_LEFT], "left boundary") || check_arr(right, P->elems[QCM_BUF_RIGHT], "right boundary") ||
+            check_arr(psi, P->elems[QCM_BUF_KET_LP], "psi") || check_arr(sigma, P->elems[QCM_BUF_OUT], "sigma")) return 1;
+    }
+    BufTable b; memset(&b, 0, sizeof(b));
+    b.p[QCM_BUF_LEFT] = left->p; b.p[QCM_BUF_RIGHT] = right->p; b.p[QCM_BUF_KET_LP] = psi->p; b.p[QCM_BUF_OUT] = sigma->p;
+    if (plans[0]->elems[QCM_BUF_OUT]) CU(cudaMemsetAsync(sigma->p, 0, (size_t)plans[0]->elems[QCM_BUF_OUT] * 8, G.stream));
+    return execute_sliced(plans, n, b);
+}
+extern "C" int qcm_site_hamil2_sliced(const qcm_plan_t* plans, int n, qcm_array_t left, qcm_array_t right, const double* psi, double* sigma)
+{
+    CHECK_INIT();
+    if (!plans || n < 1 || !plans[0]) return fail("qcm_site_hamil2_sliced: no plans");
+    qcm_plan_s* P = plans[0];
+    if (ensure_ws(QCM_BUF_KET_LP, P->elems[QCM_BUF_KET_LP]) || ensure_ws(QCM_BUF_OUT, P->elems[QCM_BUF_OUT])) return 1;
+    qcm_array_s a_psi, a_sig;
+    a_psi.p = G.ws[QCM_BUF_KET_LP]; a_psi.n = G.ws_elems[QCM_BUF_KET_LP]; a_sig.p = G.ws[QCM_BUF_OUT]; a_sig.n = G.ws_elems[QCM_BUF_OUT];
+    if (P->elems[QCM_BUF_KET_LP]) CU(cudaMemcpyAsync(a_psi.p, psi, (size_t)P->elems[QCM_BUF_KET_LP] * 8, cudaMemcpyHostToDevice, G.stream));
+    if (qcm_site_hamil2_sliced_dev(plans, n, left, right, &a_psi, &a_sig)) return 1;
+    if (P->elems[QCM_BUF_OUT]) CU(cudaMemcpyAsync(sigma, a_sig.p, (size_t)P->elems[QCM_BUF_OUT] * 8, cudaMemcpyDeviceToHost, G.stream));
+    CU(cudaStreamSynchronize(G.stream));
+    return 0;
+}
+
 extern "C" int qcm_site_hamil2(qcm_plan_t P, qcm_array_t left, qcm_array_t right, const double* psi, double* sigma)
 {
     CHECK_INIT();
     if (!P || P->kind != 0) return fail("qcm_site_hamil2: plan is not a sigma plan");
     if (ensure_ws(QCM_BUF_KET_LP, P->elems[QCM_BUF_KET_LP]) || ensure_ws(QCM_BUF_OUT, P->elems[QCM_BUF_OUT])) return 1;
-    qcm_array_s a_psi{G.ws[QCM_BUF_KET_LP], G.ws_elems[QCM_BUF_KET_LP]}, a_sig{G.ws[QCM_BUF_OUT], G.ws_elems[QCM_BUF_OUT]};
+    qcm_array_s a_psi, a_sig;
+    a_psi.p = G.ws[QCM_BUF_KET_LP]; a_psi.n = G.ws_elems[QCM_BUF_KET_LP]; a_sig.p = G.ws[QCM_BUF_OUT]; a_sig.n = G.ws_elems[QCM_BUF_OUT];
     if (P->elems[QCM_BUF_KET_LP]) CU(cudaMemcpyAsync(a_psi.p, psi, (size_t)P->elems[QCM_BUF_KET_LP] * 8, cudaMemcpyHostToDevice, G.stream));
     if (qcm_site_hamil2_dev(P, left, right, &a_psi, &a_sig)) return 1;
     if (P->elems[QCM_BUF_OUT]) CU(cudaMemcpyAsync(sigma, a_sig.p, (size_t)P->elems[QCM_BUF_OUT] * 8, cudaMemcpyDeviceToHost, G.stream));

@@ -272,3 +272,17 @@ def test_spill_tier_keeps_the_sweep_unchanged(built, monkeypatch):
     assert cu.qcm_vec_dot(a, a, ctypes.c_int64(n_el), ctypes.byref(r)) == 0
     assert r.value == pytest.approx(float(x @ x), rel=1e-12)
     cu.qcm_array_free(a); cu.qcm_pinned_free(pin)
+
+
+@pytest.mark.parametrize("symm,M", [("su2u1", 120), ("2u1", 60)])
+@pytest.mark.parametrize("slices", [2, 3])
+def test_time_sliced_shards_match_the_oracle(harness_gpu, monkeypatch, symm, M, slices):
+    """qcm_site_hamil2_sliced: the site problem planned as `slices` shards (the plans that many ranks would run) and executed one
+    after another on ONE device -- the single-GPU mode for problems whose resident step-1 products exceed the device (cfg4).
+    Same sigma as the oracle, structure included."""
+    from qcmaquis_b200.fcidump import make_fcidump
+    path = os.path.join(tempfile.mkdtemp(prefix="qcm_test_"), "synth_12o12e.fcidump")
+    make_fcidump(path, 12, 12)
+    monkeypatch.setenv("QCM_SLICES", str(slices))
+    out = harness_gpu.synth_parity(path.encode(), symm, 12, 12, 5, True, M, engine=GPU)
+    assert out[0] == 1 and out[1] < TOL, out[:4]
