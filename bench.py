@@ -133,6 +133,7 @@ def run_reference(args, cfg_name, norb, nelec, symm, M, site):
     line = {"impl": "reference", "metric": "sigma_vector_fp64_tflops", "value": val, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": done,
             "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": {"workload": cfg_name, "site": site, "twosite": True, "M": M, "symmetry": symm},
+            "steps_note": "one step of this arm is one full sigma of the same instance (25-35 s on the host cores): steps and warm-up are capped so that the run ends within minutes",
             "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -393,10 +394,23 @@ def main():
         host.qcmd_sigma_host(h, ctypes.c_void_p(psi.data_ptr()), ctypes.c_void_p(sig.data_ptr()), e, 1024)
     barrier()
     ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+    # the same call one level up: qcm::GpuEngine::site_hamil2 on host MPSTensor objects (block flatten / unflatten included),
+    # i.e. what a sweep driver that keeps its solver vectors on the host pays per sigma
+    ov = ctypes.c_double()
+    n_eng = min(3, args.steps)
+    host.qcmd_sigma_engine(h, ctypes.byref(ov), e, 1024)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_eng):
+        if host.qcmd_sigma_engine(h, ctypes.byref(ov), e, 1024):
+            raise RuntimeError(e.value.decode())
+    barrier()
+    ms_eng = max_over_ranks((time.perf_counter() - t0) * 1e3 / n_eng)
     progress("phases + e2e done")
 
-    peak = ctypes.c_double()
+    peak = ctypes.c_double(); peak_fma = ctypes.c_double()
     cu.qcm_measure_fp64_dmma_peak(ctypes.byref(peak))
+    cu.qcm_measure_fp64_fma_peak(ctypes.byref(peak_fma))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -439,16 +453,19 @@ def main():
     line = {"metric": "sigma_vector_fp64_tflops", "value": flops / (ms_dev * 1e-3) / 1e12, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": args.config, "site": site, "twosite": True, "M": M, "symmetry": symm, "parallelism": "mpo-bond-sharded x%d" % world if slices <= 1 else "one GPU, %d time-sliced shards of the MPO bond graph" % slices,
+            "config": {"workload": args.config, "site": site, "twosite": True, "M": M, "symmetry": symm},
+            "details": {"parallelism": "mpo-bond-sharded x%d" % world if slices <= 1 else "one GPU, %d time-sliced shards of the MPO bond graph" % slices,
                        "l2": "inputs (boundaries %.2f GB + workspaces %.2f GB) exceed L2" % ((info[7] + info[8]) * 8 / 1e9, info[12] / 1e9),
                        "mpo": "%dx%d nnz %d" % (info[16], info[17], info[18]), "sectors": int(info[14]), "largest_sector": int(info[15]),
                        "flops_per_step": flops, "flops_split": {"step1": f_t, "w_apply": f_w, "step3": f_c},
                        "executed_flops": {"step1": f_t, "w_apply": x_w, "step3": x_c},
                        "algorithmic_bytes": bytes_alg, "plan_seconds": info[13],
                        "w_apply_bytes": 8.0 * (info[21] + info[22]), "w_groups": int(info[23])},
-            "fp64_peak_tflops": peak.value, "frac_of_fp64_peak": flops / (ms_dev * 1e-3) / 1e12 / (peak.value * world) if peak.value else None,
+            "fp64_peak_tflops": peak.value, "fp64_fma_peak_tflops": peak_fma.value, "frac_of_fp64_peak": flops / (ms_dev * 1e-3) / 1e12 / (peak.value * world) if peak.value else None,
             "roofline": roof, "clocks": clocks,
-            "e2e": {"value": flops / (ms_e2e * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": psi_n * 8, "d2h_bytes_per_step": sig_n * 8},
+            "e2e": {"value": flops / (ms_e2e * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": psi_n * 8, "d2h_bytes_per_step": sig_n * 8,
+                    "through": "qcm_site_hamil2 (C ABI, pinned host psi / sigma)",
+                    "engine_mirror": {"value": flops / (ms_eng * 1e-3) / 1e12, "ms_per_step": ms_eng, "through": "qcm::GpuEngine::site_hamil2 (host MPSTensor in, host MPSTensor out: block flatten / unflatten included)"}},
             "gpu_launches": int(launches)}
 
     # ---- CPU baseline + full-size parity on the same instance (rank 0, N=1 only) -------------------------

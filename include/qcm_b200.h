@@ -238,7 +238,7 @@ typedef struct {                               /* block structure of a Boundary:
 typedef struct qcm_mpo_s* qcm_mpo_t;
 int qcm_mpo_upload(const qcm_mpo_desc* d, qcm_mpo_t* out);      /* once per MPO site tensor (or fused two-site tensor) */
 int qcm_mpo_free(qcm_mpo_t m);
-/* rank/world: the shard to plan (0, 1: the whole contraction); ws_budget_elems: workspace budget in elements (0: default) */
+/* rank/world: the shard to plan (0, 1: the whole contraction); ws_budget_elems: workspace budget in elements (0: default, 2^32) */
 int qcm_plan_sigma(qcm_mpo_t m, const qcm_tensor_desc* ket, const qcm_boundary_desc* left, const qcm_boundary_desc* right,
                    int rank, int world, int64_t ws_budget_elems, qcm_plan_t* out);
 int qcm_plan_left_step(qcm_mpo_t m, const qcm_tensor_desc* bra, const qcm_tensor_desc* ket, const qcm_boundary_desc* left,

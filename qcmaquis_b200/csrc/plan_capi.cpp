@@ -142,7 +142,7 @@ extern "C" int qcm_plan_sigma(qcm_mpo_t m, const qcm_tensor_desc* ket, const qcm
     try {
         if (!m || !out) return fail("qcm_plan_sigma: null argument");
         plan::BoundaryLayout ll = boundary_of(left), rl = boundary_of(right);
-        plan::Planner pl(m->symm, m->mpo, true, world > 1 ? rank : 0, world > 1 ? world : 1, budget > 0 ? budget : (int64_t)1 << 31);
+        plan::Planner pl(m->symm, m->mpo, true, world > 1 ? rank : 0, world > 1 ? world : 1, budget > 0 ? budget : (int64_t)1 << 32);
         plan::Plan P = pl.plan_sigma(tensor_of(ket), ll, rl);
         return finish(P, ll.total, rl.total, out);
     } catch (std::exception const& e) { return fail(std::string("qcm_plan_sigma: ") + e.what()); }
@@ -153,7 +153,7 @@ extern "C" int qcm_plan_left_step(qcm_mpo_t m, const qcm_tensor_desc* bra, const
     try {
         if (!m || !out) return fail("qcm_plan_left_step: null argument");
         plan::BoundaryLayout ll = boundary_of(left);
-        plan::Planner pl(m->symm, m->mpo, true, world > 1 ? rank : 0, world > 1 ? world : 1, budget > 0 ? budget : (int64_t)1 << 31);
+        plan::Planner pl(m->symm, m->mpo, true, world > 1 ? rank : 0, world > 1 ? world : 1, budget > 0 ? budget : (int64_t)1 << 32);
         plan::Plan P = pl.plan_left_step(tensor_of(bra), tensor_of(ket), ll);
         return finish(P, ll.total, 0, out);
     } catch (std::exception const& e) { return fail(std::string("qcm_plan_left_step: ") + e.what()); }
@@ -164,7 +164,7 @@ extern "C" int qcm_plan_right_step(qcm_mpo_t m, const qcm_tensor_desc* bra, cons
     try {
         if (!m || !out) return fail("qcm_plan_right_step: null argument");
         plan::BoundaryLayout rl = boundary_of(right);
-        plan::Planner pl(m->symm, m->mpo, true, world > 1 ? rank : 0, world > 1 ? world : 1, budget > 0 ? budget : (int64_t)1 << 31);
+        plan::Planner pl(m->symm, m->mpo, true, world > 1 ? rank : 0, world > 1 ? world : 1, budget > 0 ? budget : (int64_t)1 << 32);
         plan::Plan P = pl.plan_right_step(tensor_of(bra), tensor_of(ket), rl);
         return finish(P, 0, rl.total, out);
     } catch (std::exception const& e) { return fail(std::string("qcm_plan_right_step: ") + e.what()); }

@@ -99,11 +99,16 @@ struct CompiledPlan
 class GpuEngine : public EngineIface
 {
 public:
-    explicit GpuEngine(SymmKind s, int device = 0, int rank_ = 0, int world_ = 1, int64_t ws_budget_elems = (int64_t)1 << 31)
+    // Workspace budget (elements of T + Y per wave).  An output index whose step-1 products and W panels do not fit is pushed into
+    // the next wave -- but destinations in different waves cannot share one read of their sources, so a tight budget inflates the
+    // W pass's HBM traffic (cfg3: 163 GB per sigma in two waves at 2^31 elements, 109 GB in one wave).  2^32 elements = 34 GB.
+    static constexpr int64_t kDefaultBudget = (int64_t)1 << 32;
+    explicit GpuEngine(SymmKind s, int device = 0, int rank_ = 0, int world_ = 1, int64_t ws_budget_elems = kDefaultBudget)
         : symm(s), rank(rank_), world(world_), budget(ws_budget_elems)
     {
         qcm_check(qcm_init(device), "qcm_init");
         if (const char* e = getenv("QCM_SLICES")) slices = std::max(1, atoi(e));
+        if (const char* e = getenv("QCM_WS_BUDGET_GB")) budget = std::max<int64_t>(1, (int64_t)(atof(e) * 1e9 / 8));
     }
     ~GpuEngine() { for (auto a : vec_pool) qcm_array_free(a); if (host_xfer) qcm_array_free(host_xfer); }
 

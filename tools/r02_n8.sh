@@ -10,7 +10,7 @@ import json
 try:
     d = json.load(open("gpurun_out/r02d_bench_cfg3_n$N.json"))
     print("N=$N value %.2f TF/s  %.2f ms  e2e %.2f TF/s  phases %s parity %s" % (d["value"], d["ms_per_step"], d["e2e"]["value"], {k: round(v, 2) for k, v in d["roofline"]["phase_ms"].items()}, d.get("parity_rel_err_vs_oracle")))
-    print("   exec", d["config"]["executed_flops"], "frac", d["frac_of_fp64_peak"])
+    print("   exec", d["details"]["executed_flops"], "frac", d["frac_of_fp64_peak"])
     s = d.get("config_sweep", {})
     print("   sweep", {k: v for k, v in s.items() if k != "energies"})
 except Exception as e:

@@ -12,7 +12,7 @@ for f in ("r02b_bench_cfg2_n2", "r02b_bench_cfg3_n2"):
     try:
         d = json.load(open("gpurun_out/%s.json" % f))
         print(f, "value %.2f TF/s  %.2f ms  e2e %.2f TF/s  phases %s  parity %s" % (d["value"], d["ms_per_step"], d["e2e"]["value"], {k: round(v, 2) for k, v in d["roofline"]["phase_ms"].items()}, d.get("parity_rel_err_vs_oracle")))
-        print("   exec", d["config"]["executed_flops"])
+        print("   exec", d["details"]["executed_flops"])
         s = d.get("config_sweep", {})
         print("   sweep", {k: v for k, v in s.items() if k != "energies"})
     except Exception as e:
