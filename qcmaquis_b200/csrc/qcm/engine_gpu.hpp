@@ -136,6 +136,7 @@ public:
         PlanKey key{mpo.uid(), dl->structure_hash(), dr->structure_hash(), structure_hash(ket_tensor), isHermitian ? 0 : 3};
         if (std::shared_ptr<CompiledPlan> hit = lookup(key, [&](Witness const& w) { return w.matches(dl->layout, dr->layout, ket_tensor, ket_tensor); })) { ++cache_hits; return hit; }
         ++cache_misses;
+        make_room();
         Clock c0;
         std::shared_ptr<CompiledPlan> cp;
         if (slices > 1 && world == 1) {
@@ -473,6 +474,7 @@ private:
         static const plan::BoundaryLayout no_boundary;
         std::shared_ptr<CompiledPlan> cp = lookup(key, [&](Witness const& w) { return w.matches(din->layout, no_boundary, bra_tensor, ket_tensor); });
         if (!cp) {
+            make_room();
             plan::Planner planner(symm, mpo, isHermitian, rank, world, budget);
             plan::Plan P = kind == 1 ? planner.plan_left_step(desc_of(bra_tensor), desc_of(ket_tensor), din->layout)
                                      : planner.plan_right_step(desc_of(bra_tensor), desc_of(ket_tensor), din->layout);
@@ -535,6 +537,9 @@ private:
         for (auto& e : cache) if (e.key == k && confirm(e.witness)) return e.plan;
         return std::shared_ptr<CompiledPlan>();
     }
+    // the oldest plan leaves the cache before a new one is built: its task arrays (0.5 GB at cfg3) go back to the device
+    // pool and the new plan's arrays take their place instead of growing the pool
+    void make_room() { while (cache.size() + 1 > cache_capacity && !cache.empty()) cache.pop_back(); }
     void remember(PlanKey const& k, Witness w, std::shared_ptr<CompiledPlan> const& cp)
     {
         cache.push_front(CacheEntry{k, std::move(w), cp});

@@ -485,8 +485,9 @@ inline sweep::SweepLog ts_sweeps(SymmKind symm, EngineIface& eng, MPO const& mpo
                 if (site2 < L - 1) sweep::multiply_from_left(mps[site2 + 1], t);
                 sclk.lap(4);
                 log.phase_seconds[3] += lap();
-                left[site2] = eng.overlap_mpo_left_step(mps[site1], mps[site1], left[site1], mpo[site1]);
+                // the stale boundary at this bond goes first: the new one has the same size and takes over its memory
                 if (prm.drop_stale && site2 < L - 1) right[site2] = Boundary();
+                left[site2] = eng.overlap_mpo_left_step(mps[site1], mps[site1], left[site1], mpo[site1]);
                 if (prm.spill && site1 > 0) eng.evict(left[site1]);
             } else {
                 tst.split_mps_r2l(prm.Mmax, prm.cutoff, mps[site1], mps[site2], trunc, &eng);
@@ -495,8 +496,8 @@ inline sweep::SweepLog ts_sweeps(SymmKind symm, EngineIface& eng, MPO const& mpo
                 if (site1 > 0) sweep::multiply_from_right(mps[site1 - 1], t);
                 sclk.lap(4);
                 log.phase_seconds[3] += lap();
-                right[site2] = eng.overlap_mpo_right_step(mps[site2], mps[site2], right[site2 + 1], mpo[site2]);
                 if (prm.drop_stale && site1 > 0) left[site2] = Boundary();
+                right[site2] = eng.overlap_mpo_right_step(mps[site2], mps[site2], right[site2 + 1], mpo[site2]);
                 if (prm.spill && site2 + 1 < L) eng.evict(right[site2 + 1]);
             }
             log.phase_seconds[4] += lap();
