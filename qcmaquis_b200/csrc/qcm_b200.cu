@@ -19,6 +19,7 @@
 
 #include <dlfcn.h>
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -643,9 +644,20 @@ static int build_gemm_group(qcm_plan_s* P, GemmGroup& g, const qcm_gemm_out* out
     std::sort(order.begin(), order.end());
     for (auto const& ov : order) {
         const int v = ov.second;
-        std::stable_sort(per_variant[v].begin(), per_variant[v].end(), [](std::pair<double, DWork> const& a, std::pair<double, DWork> const& b) { return a.first > b.first; });
-        g.launches.push_back(GemmLaunch{v, (int64_t)hw.size(), (int64_t)per_variant[v].size()});
-        for (auto const& x : per_variant[v]) hw.push_back(x.second);
+        // heaviest first -- to the resolution that matters for load balance: a stable counting sort over 1/8-octave cost classes
+        // (a comparison sort of the 10^6 work items of a cfg3 closing group took longer than planning the boundary step)
+        {
+            auto const& items = per_variant[v];
+            constexpr int kBins = 8 * 64;
+            auto bin_of = [](double c) { int e = 0; double m = std::frexp(c > 1. ? c : 1., &e); int b = e * 8 + (int)((m - 0.5) * 16.); return kBins - 1 - std::min(kBins - 1, std::max(0, b)); };
+            std::vector<uint32_t> start(kBins + 1, 0);
+            for (auto const& x : items) start[(size_t)bin_of(x.first) + 1]++;
+            for (int b = 0; b < kBins; ++b) start[(size_t)b + 1] += start[(size_t)b];
+            const size_t base = hw.size();
+            hw.resize(base + items.size());
+            for (auto const& x : items) hw[base + start[(size_t)bin_of(x.first)]++] = x.second;
+            g.launches.push_back(GemmLaunch{v, (int64_t)base, (int64_t)items.size()});
+        }
         if (getenv("QCM_DEBUG")) {      // useful vs issued FLOPs of this launch (issued = whole warp tiles, K padded to 4)
             const GemmWsVariant var = gemm_ws_variant(v);
             double useful = 0, chunks_n = 0;
