@@ -897,6 +897,55 @@ public:
         return ret;
     }
 
+    // common/move_boundary.hpp:68-95 (left_boundary_tensor_mpo) followed by the accumulation loop of prediction.hpp:34-47 /
+    // twositetensor.hpp:196-219 without alpha and without the restriction to the density matrix's blocks
+    block_matrix noise_left(MPSTensor const& mps_in, Boundary const& left, MPOTensor const& mpo) override
+    {
+        MPSTensor mps = mps_in;
+        Index physical_i = mps.site_dim(), left_i = mps.row_dim(), right_i = mps.col_dim(), out_left_i = physical_i * left_i;
+        BoundaryMPSProduct t(su2_, mps, left, mpo, left_i, true);
+        ProductBasis out_left_pb(physical_i, left_i);
+        ProductBasis in_right_pb(physical_i, right_i, true);
+        mps.make_right_paired();
+        DualIndex ket_basis = mps.data().basis();
+        DualIndex ket_basis_transpose = swapped(ket_basis);
+        const int loop_max = (int)mpo.col_dim();
+        std::vector<block_matrix> parts((size_t)loop_max);
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int b2 = 0; b2 < loop_max; ++b2) {
+            block_matrix grid;
+            if (su2_) nonabelian::lbtm_kernel(b2, grid, t, mpo, ket_basis_transpose, right_i, out_left_i, in_right_pb, out_left_pb);
+            else abelian::lbtm_kernel(b2, grid, t, mpo, ket_basis, ket_basis, right_i, out_left_i, in_right_pb, out_left_pb);
+            gemm(plain(grid), transpose(grid), parts[(size_t)b2], -1);
+        }
+        block_matrix ret;
+        for (auto const& tdm : parts) for (size_t k = 0; k < tdm.n_blocks(); ++k) ret.match_and_add_block(tdm[k], tdm.basis().left_charge(k), tdm.basis().right_charge(k));
+        return ret;
+    }
+    // common/move_boundary.hpp:97-126 (right_boundary_tensor_mpo) + prediction.hpp:101-114 / twositetensor.hpp:264-287
+    block_matrix noise_right(MPSTensor const& mps_in, Boundary const& right, MPOTensor const& mpo) override
+    {
+        MPSTensor mps = mps_in;
+        Index physical_i = mps.site_dim(), left_i = mps.row_dim(), right_i = mps.col_dim(), out_right_i = adjoin(physical_i) * right_i;
+        MPSBoundaryProduct t(su2_, mps, right, mpo, mps.row_dim(), true);       // "constructor without index": boundary_times_mps.hpp:258-261
+        ProductBasis in_left_pb(physical_i, left_i);
+        ProductBasis out_right_pb(physical_i, right_i, true);
+        mps.make_left_paired();
+        DualIndex ket_basis = mps.data().basis();
+        const int loop_max = (int)mpo.row_dim();
+        std::vector<block_matrix> parts((size_t)loop_max);
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int b1 = 0; b1 < loop_max; ++b1) {
+            block_matrix y;
+            if (su2_) nonabelian::rbtm_kernel(b1, y, t, mpo, ket_basis, left_i, out_right_i, in_left_pb, out_right_pb);
+            else abelian::rbtm_kernel(b1, y, t, mpo, left_i, out_right_i, in_left_pb, out_right_pb);
+            gemm(transpose(y), plain(y), parts[(size_t)b1], -1);
+        }
+        block_matrix ret;
+        for (auto const& tdm : parts) for (size_t k = 0; k < tdm.n_blocks(); ++k) ret.match_and_add_block(tdm[k], tdm.basis().left_charge(k), tdm.basis().right_charge(k));
+        return ret;
+    }
+
 private:
     static DualIndex swapped(DualIndex const& b)
     {

@@ -54,6 +54,12 @@ inline void dgemm(MatRef const& A, MatRef const& B, double alpha, double beta, d
     if (m == 0 || n == 0) return;
     char ta = A.trans ? 'T' : 'N', tb = B.trans ? 'T' : 'N';
     if (lda < 1) lda = 1; if (ldb < 1) ldb = 1;
+#ifdef QCM_DGEMM_CHECK
+    if (ldb < std::max(1, B.trans ? n : k) || lda < std::max(1, A.trans ? k : m)) {
+        fprintf(stderr, "dgemm check: m %d n %d k %d lda %d ldb %d ta %c tb %c\n", m, n, k, lda, ldb, ta, tb);
+        void* bt[64]; int nb = backtrace(bt, 64); backtrace_symbols_fd(bt, nb, 2); abort();
+    }
+#endif
     scipy_dgemm_(&ta, &tb, &m, &n, &k, &alpha, A.p, &lda, B.p, &ldb, &beta, C, &ldc_);
 }
 

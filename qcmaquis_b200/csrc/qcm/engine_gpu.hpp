@@ -344,6 +344,36 @@ public:
         return boundary_step(2, bra_tensor, ket_tensor, right, mpo, isHermitian);
     }
 
+    // ---- noise term of the perturbed density matrix (EngineIface::noise_left / noise_right) ----------------------------
+    // Planned like a boundary step whose closing products are panel x panel^T tiles (plan_noise_left / plan_noise_right) and
+    // executed by qcm_boundary_step into a one-entry "boundary" = the density-matrix blocks.  Quadratic in the W-applied
+    // product, hence never sharded: with several ranks every rank computes the whole (cheap: two boundary steps' worth) term.
+    block_matrix noise_left(MPSTensor const& mps, Boundary const& left, MPOTensor const& mpo) override { return noise(true, mps, left, mpo); }
+    block_matrix noise_right(MPSTensor const& mps, Boundary const& right, MPOTensor const& mpo) override { return noise(false, mps, right, mpo); }
+    block_matrix noise(bool left_side, MPSTensor const& mps, Boundary const& in, MPOTensor const& mpo)
+    {
+        mps.make_left_paired();
+        std::shared_ptr<DeviceBoundary> din = mirror(in);
+        Clock c0;
+        make_room();
+        plan::Planner planner(symm, mpo, true, 0, 1, budget);
+        plan::Plan P = left_side ? planner.plan_noise_left(desc_of(mps), din->layout) : planner.plan_noise_right(desc_of(mps), din->layout);
+        seconds[0] += c0.lap();
+        std::shared_ptr<CompiledPlan> cp = compile(P, left_side ? din->layout.total : 0, left_side ? 0 : din->layout.total);
+        seconds[1] += c0.lap();
+        qcm_array_t out = nullptr;
+        qcm_check(qcm_array_alloc(cp->out_boundary.total, &out), "qcm_array_alloc");
+        std::vector<double> ket = flatten(mps.data(), cp->ket_elems);
+        int rc = qcm_boundary_step(cp->handle, din->arr, ket.data(), ket.data(), out);
+        std::vector<double> flat((size_t)cp->out_boundary.total);
+        if (rc == 0) rc = qcm_array_download(out, 0, flat.data(), cp->out_boundary.total);
+        qcm_array_free(out);
+        qcm_check(rc, "noise term (qcm_boundary_step)");
+        boundary_flops += cp->flops; ++n_boundary_calls;
+        seconds[3] += c0.lap();
+        return unflatten(cp->out_boundary.b[0], flat);
+    }
+
     // ---- Engine::diagonal_hamiltonian (abelian/engine.hpp:222-227) --------------------------------------------
     block_matrix diagonal_hamiltonian(Boundary const& left, Boundary const& right, MPOTensor const& mpo, MPSTensor const& x)
     {

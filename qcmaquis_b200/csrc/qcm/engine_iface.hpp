@@ -26,6 +26,13 @@ struct EngineIface
                                            MPOTensor const& mpo, bool isHermitian = true) = 0;
     virtual Boundary overlap_mpo_right_step(MPSTensor const& bra_tensor, MPSTensor const& ket_tensor, Boundary const& right,
                                             MPOTensor const& mpo, bool isHermitian = true) = 0;
+    // ---- noise term of the perturbed density matrix (the "remaining" contractions of SURVEY 8(a9)):
+    //   noise_left:  sum over b2 of Y[b2] Y[b2]^T,  Y = Engine::left_boundary_tensor_mpo(mps, left, mpo)   (move_boundary.hpp:68-95)
+    //   noise_right: sum over b1 of Y'[b1]^T Y'[b1], Y' = Engine::right_boundary_tensor_mpo(mps, right, mpo) (move_boundary.hpp:97-126)
+    // i.e. what prediction.hpp:34-47,101-114 and twositetensor.hpp:192-219,260-287 add, times alpha, to the reduced density matrix
+    // before heev_truncate.  All blocks are returned; the caller keeps those its density matrix has.
+    virtual block_matrix noise_left(MPSTensor const& /*mps*/, Boundary const& /*left*/, MPOTensor const& /*mpo*/) { throw std::runtime_error("this engine does not provide the noise term"); }
+    virtual block_matrix noise_right(MPSTensor const& /*mps*/, Boundary const& /*right*/, MPOTensor const& /*mpo*/) { throw std::runtime_error("this engine does not provide the noise term"); }
     // ---- boundary storage protocol of the sweep drivers (utils/storage.h:113-185: storage::disk::prefetch / evict; drop is the
     // destruction of the Boundary).  Engines that keep boundaries in a fast tier move them here; the default does nothing.
     virtual void prefetch(Boundary const& /*b*/) {}

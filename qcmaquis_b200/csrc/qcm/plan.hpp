@@ -733,6 +733,81 @@ public:
         return P;
     }
 
+
+    // -----------------------------------------------------------------------------------------------------
+    // Noise term of the perturbed density matrix (C/common/prediction.hpp:34-47, twositetensor.hpp:192-219):
+    //   left:  sum over b2 of Y[b2] Y[b2]^T   with Y = left_boundary_tensor_mpo  (C/common/move_boundary.hpp:68-95): blocks (lc, lc)
+    //   right: sum over b1 of Y'[b1]^T Y'[b1] with Y' = right_boundary_tensor_mpo (:97-126):                          blocks (rc, rc)
+    // Y is the W-applied product of the boundary steps WITHOUT the closing bra: same step-1 products, same W passes; the closing
+    // products become panel x panel^T tiles of the density-matrix blocks.  The result is quadratic in Y, so the plan is never
+    // sharded (every rank computes the whole term); it runs through qcm_boundary_step as a boundary with a single entry.
+    Plan plan_noise_left(TensorDesc const& ket, BoundaryLayout const& left)
+    {
+        if (world > 1) throw std::runtime_error("plan_noise_left: the noise term is not sharded; plan it with world = 1");
+        Plan P; P.kind = 1; P.accumulate_out = true;
+        Layout ket_lp; ket_lp.assign(ket.lp_basis);
+        Layout ket_rp = plan_left_to_right(ket, ket_lp, BUF_KET_LP, BUF_KET_RP, P.pre_copies);
+        P.ket_lp_elems = ket_lp.total; P.ket_rp_elems = ket_rp.total; P.bra_lp_elems = 0;
+        Index const& physical_i = ket.phys_i;
+        Index const& left_i = ket.left_i;
+        Index right_i = ket.right_i;
+        Index out_left_i = physical_i * left_i;                         // not trimmed (move_boundary.hpp:82-83)
+        ProductBasis out_left_pb(physical_i, left_i);
+        ProductBasis in_right_pb(physical_i, right_i, true);
+        setup_t_left(P, left, ket_rp, left_i);
+        if (su2_) build_lbtm_tables(ket_rp, physical_i, right_i, out_left_i, in_right_pb, out_left_pb);
+        const size_t loop_max = mpo.col_dim();
+        struct Pending { DualIndex y; std::vector<YTask> ytasks; std::vector<size_t> t_rows; };
+        std::vector<Pending> pend(loop_max);
+#pragma omp parallel for schedule(dynamic, 4)
+        for (long b2l = 0; b2l < (long)loop_max; ++b2l) {
+            Pending& pd = pend[(size_t)b2l];
+            if (su2_) y_struct_su2_lbtm((size_t)b2l, ket_rp, right_i, out_left_i, in_right_pb, out_left_pb, pd.y, pd.ytasks, pd.t_rows);
+            else y_struct_abelian_lbtm((size_t)b2l, ket_rp.basis, ket_rp.basis, right_i, out_left_i, in_right_pb, out_left_pb, pd.y, pd.ytasks, pd.t_rows);
+        }
+        block_struct os;
+        for (size_t b2 = 0; b2 < loop_max; ++b2) for (size_t k = 0; k < pend[b2].y.size(); ++k) os.add(pend[b2].y[k].lc, pend[b2].y[k].lc, pend[b2].y[k].ls, pend[b2].y[k].ls);
+        P.out_boundary.assign(std::vector<DualIndex>(1, os.basis));
+        if (structure_only) return P;
+        noise_emit(P, pend.size(), [&](size_t i) -> std::vector<size_t> const& { return pend[i].t_rows; },
+                   [&](size_t i) -> std::vector<YTask> const& { return pend[i].ytasks; }, [&](size_t i) -> DualIndex const& { return pend[i].y; },
+                   [&](Plan& PP, GemmList& gl, size_t b, Layout const& tl, int buf) { emit_t_gemm(PP, gl, b, tl, buf, ket_rp); }, true);
+        P.bytes_algorithmic = 8 * (left.total + ket_lp.total + P.out_boundary.total);
+        return P;
+    }
+    Plan plan_noise_right(TensorDesc const& ket, BoundaryLayout const& right)
+    {
+        if (world > 1) throw std::runtime_error("plan_noise_right: the noise term is not sharded; plan it with world = 1");
+        Plan P; P.kind = 2; P.accumulate_out = true;
+        Layout ket_lp; ket_lp.assign(ket.lp_basis);
+        P.ket_lp_elems = ket_lp.total; P.bra_lp_elems = 0; P.bra_rp_elems = 0;
+        Index const& physical_i = ket.phys_i;
+        Index right_i = ket.right_i;
+        Index left_i = ket.left_i, out_right_i = adjoin(physical_i) * right_i;     // not trimmed (move_boundary.hpp:110-111)
+        ProductBasis in_left_pb(physical_i, left_i);
+        ProductBasis out_right_pb(physical_i, right_i, true);
+        // MPSBoundaryProduct(mps, right, mpo) "without index" trims by the tensor's ROW index (boundary_times_mps.hpp:258-261)
+        setup_t_right(P, right, ket_lp, left_i);
+        const size_t loop_max = mpo.row_dim();
+        struct Pending { DualIndex y; std::vector<YTask> ytasks; std::vector<size_t> t_cols; };
+        std::vector<Pending> pend(loop_max);
+#pragma omp parallel for schedule(dynamic, 4)
+        for (long b1l = 0; b1l < (long)loop_max; ++b1l) {
+            Pending& pd = pend[(size_t)b1l];
+            if (su2_) y_struct_su2_rbtm((size_t)b1l, ket_lp.basis, left_i, out_right_i, in_left_pb, out_right_pb, pd.y, pd.ytasks, pd.t_cols);
+            else y_struct_abelian_rbtm((size_t)b1l, left_i, out_right_i, in_left_pb, out_right_pb, pd.y, pd.ytasks, pd.t_cols);
+        }
+        block_struct os;
+        for (size_t b1 = 0; b1 < loop_max; ++b1) for (size_t k = 0; k < pend[b1].y.size(); ++k) os.add(pend[b1].y[k].rc, pend[b1].y[k].rc, pend[b1].y[k].rs, pend[b1].y[k].rs);
+        P.out_boundary.assign(std::vector<DualIndex>(1, os.basis));
+        if (structure_only) return P;
+        noise_emit(P, pend.size(), [&](size_t i) -> std::vector<size_t> const& { return pend[i].t_cols; },
+                   [&](size_t i) -> std::vector<YTask> const& { return pend[i].ytasks; }, [&](size_t i) -> DualIndex const& { return pend[i].y; },
+                   [&](Plan& PP, GemmList& gl, size_t b, Layout const& tl, int buf) { emit_t_gemm_right(PP, gl, b, tl, buf, ket_lp); }, false);
+        P.bytes_algorithmic = 8 * (right.total + ket_lp.total + P.out_boundary.total);
+        return P;
+    }
+
 private:
     struct block_struct   // accumulates an output block structure with match_and_add_block growth semantics
     {
@@ -1613,14 +1688,85 @@ private:
         AxpyList().dsts.swap(al.dsts); AxpyList().lists.swap(al.lists);
     }
 
+
+    // waves, panels and closing tiles of a noise plan.  left: a Y block (lc, rc) is made of row units (panels p, q) and adds
+    // p q^T to tile (row of p, row of q) of density-matrix block (lc, lc); right: column units, p^T q into block (rc, rc).
+    template <class RowsOf, class TasksOf, class BasisOf, class EmitT>
+    void noise_emit(Plan& P, size_t n_out, RowsOf rows_of, TasksOf tasks_of, BasisOf basis_of, EmitT emit_t, bool left_side)
+    {
+        std::vector<char> own = shard_sources(P, n_out, [&](size_t) { return 1.0; }, rows_of);
+        (void)own;
+        Layout const& ol = P.out_boundary.b[0];
+        PanelCache pcache;
+        Wave cur; int64_t cur_y = 0, cur_t = 0;
+        auto flush = [&]() {
+            if (cur.w_apply.dsts.empty() && cur.close_gemm.outs.empty() && cur.t_gemm.outs.empty()) return;
+            cur.y_elems = cur_y; cur.t_elems = cur_t;
+            P.y_elems_max = std::max(P.y_elems_max, cur_y); P.t_elems_max = std::max(P.t_elems_max, cur_t);
+            merge_outputs(cur.close_gemm); merge_outputs(cur.t_gemm);
+            group_axpy(P, cur.w_apply, cur.w_groups);
+            P.waves.push_back(std::move(cur));
+            cur = Wave(); cur_y = 0; cur_t = 0;
+        };
+        for (size_t i = 0; i < n_out; ++i) {
+            DualIndex const& ybasis = basis_of(i);
+            if (ybasis.size() == 0) continue;
+            Layout ytmp; ytmp.assign(ybasis);
+            int64_t need_t = 0;
+            for (size_t b : rows_of(i)) if (!t_persistent[b]) need_t += t_layout_size(b);
+            if ((cur_y + cur_t) > 0 && cur_y + cur_t + ytmp.total + need_t > budget) flush();
+            const int64_t t_begin = cur_t;
+            std::map<size_t, Layout> tl;
+            for (size_t b : rows_of(i)) {
+                if (t_persistent[b]) { tl[b] = tp_layout[b]; continue; }
+                Layout L; L.assign(t_basis[b], cur_t);
+                emit_t(P, cur.t_gemm, b, L, BUF_T);
+                cur_t += L.total; tl[b] = L;
+            }
+            for (size_t k = 0; k < ybasis.size(); ++k) {
+                QnBlock const& yb = ybasis[k];
+                P.flops_close += left_side ? 2.0 * yb.ls * yb.ls * yb.rs : 2.0 * yb.rs * yb.rs * yb.ls; P.n_gemm_tasks++;
+            }
+            PanelCounts pcnt;
+            std::vector<Panel> panels = cached_panels(pcache, n_out, i, t_begin, rows_of,
+                [&](size_t j, std::vector<YTask>&) -> std::vector<YTask> const& { return tasks_of(j); }, [&](size_t j) { return basis_of(j).size() == 0; }, tl, pcnt);
+            P.flops_w += pcnt.flops_w; P.n_axpy_tasks += pcnt.n_axpy;
+            struct Placed { PanelRef pr; Panel const* pn; };
+            std::vector<std::vector<Placed>> per_block(ybasis.size());
+            for (Panel& pn : panels) {
+                PanelRef pr;
+                if (!place_panel(P, cur.w_apply, pn, cur_y, pr)) continue;
+                per_block[pn.o].push_back(Placed{pr, &pn});
+            }
+            for (size_t k = 0; k < ybasis.size(); ++k) {
+                QnBlock const& yb = ybasis[k];
+                Charge const& c = left_side ? yb.lc : yb.rc;
+                for (Placed const& p : per_block[k])
+                    for (Placed const& q : per_block[k]) {
+                        if (left_side) {
+                            // tile (p rows, q rows) += (alpha_p P)(rows_p x cols) * (alpha_q Q)^T (cols x rows_q)
+                            VBlock bq{c, c, p.pn->cols, q.pn->rows, q.pr.A.off, q.pr.lda, 1, q.pr.alpha};
+                            emit_close(P, cur.close_gemm, ol, c, c, p.pr.A, p.pr.lda, 0, p.pn->rows, p.pn->cols, p.pr.alpha, bq, q.pr.A.buf, p.pn->dst_row, 0, q.pn->dst_row);
+                        } else {
+                            // tile (p cols, q cols) += (alpha_p P)^T (cols_p x rows) * (alpha_q Q)(rows x cols_q)
+                            VBlock bq{c, c, p.pn->rows, q.pn->cols, q.pr.A.off, q.pr.lda, 0, q.pr.alpha};
+                            emit_close(P, cur.close_gemm, ol, c, c, p.pr.A, p.pr.lda, 1, p.pn->cols, p.pn->rows, p.pr.alpha, bq, q.pr.A.buf, p.pn->dst_col, 0, q.pn->dst_col);
+                        }
+                    }
+            }
+        }
+        flush();
+        merge_outputs(P.persistent_t);
+    }
+
     // step 3: one K-segment alpha * op(A)(m x k) * op(B)(k x n) into rows [c_row, c_row + m) of output block (lc, rc);
     // op(B) starts at row b_k of the stored operand (a panel covers a K sub-range of the reference's product)
     void emit_close(Plan& P, GemmList& gl, Layout const& ol, Charge const& lc, Charge const& rc, Ref A, int32_t lda, int32_t ta, int32_t m, int32_t k,
-                    double alpha, VBlock const& b, int bbuf, int32_t c_row, int32_t b_k)
+                    double alpha, VBlock const& b, int bbuf, int32_t c_row, int32_t b_k, int32_t c_col = 0)
     {
         size_t cb = ol.basis.position(lc, rc);
         if (cb == ol.basis.size()) return;
-        Out o; o.C = Ref{BUF_OUT, ol.off[cb] + c_row}; o.ldc = (int32_t)ol.basis[cb].ls; o.m = m; o.n = b.rs;
+        Out o; o.C = Ref{BUF_OUT, ol.off[cb] + c_row + (int64_t)c_col * (int64_t)ol.basis[cb].ls}; o.ldc = (int32_t)ol.basis[cb].ls; o.m = m; o.n = b.rs;
         o.seg_begin = (int32_t)gl.segs.size();
         int64_t boff = b.off + (b.trans ? (int64_t)b_k * b.ld : (int64_t)b_k);
         gl.segs.push_back(Seg{A, Ref{bbuf, boff}, lda, b.ld, m, o.n, k, ta, b.trans, alpha * b.scale});

@@ -258,7 +258,16 @@ struct SweepLog
     double phase_seconds[5] = {0, 0, 0, 0, 0};
 };
 
-inline SweepLog ss_sweeps(EngineIface& eng, MPO const& mpo, MPS& mps, int nsweeps, int jcd_maxiter = 10, double jcd_tol = 1e-8)
+// Grow hook of the single-site loop (ss_optimize.hpp:168-195: mps.grow_l2r_sweep / grow_r2l_sweep replace the plain
+// normalisation when the site has a neighbour in the sweep direction).  Returns false when it did nothing (alpha = 0 runs:
+// the site tensor is re-orthogonalised by QR instead).  ts::NoiseGrow (twosite.hpp) is the noise-perturbed one.
+struct NoGrow
+{
+    bool operator()(int /*lr*/, int /*site*/, MPS& /*mps*/, MPOTensor const& /*mpo*/, Boundary const& /*left*/, Boundary const& /*right*/) const { return false; }
+};
+
+template <class Grow = NoGrow>
+inline SweepLog ss_sweeps(EngineIface& eng, MPO const& mpo, MPS& mps, int nsweeps, int jcd_maxiter = 10, double jcd_tol = 1e-8, Grow grow = Grow())
 {
     const int L = (int)mps.size();
     SweepLog log;
@@ -277,12 +286,16 @@ inline SweepLog ss_sweeps(EngineIface& eng, MPO const& mpo, MPS& mps, int nsweep
             log.energies.push_back(r.theta + mpo.core_energy);
             log.n_sigma.push_back(r.n_sigma); log.total_sigma += r.n_sigma;
             if (lr == +1) {
-                block_matrix t = normalize_left(mps[site]);
-                if (site < L - 1) multiply_from_left(mps[site + 1], t);
+                if (!(site < L - 1 && grow(+1, site, mps, mpo[site], left[site], right[site + 1]))) {
+                    block_matrix t = normalize_left(mps[site]);
+                    if (site < L - 1) multiply_from_left(mps[site + 1], t);
+                }
                 left[site + 1] = eng.overlap_mpo_left_step(mps[site], mps[site], left[site], mpo[site]);
             } else {
-                block_matrix t = normalize_right(mps[site]);
-                if (site > 0) multiply_from_right(mps[site - 1], t);
+                if (!(site > 0 && grow(-1, site, mps, mpo[site], left[site], right[site + 1]))) {
+                    block_matrix t = normalize_right(mps[site]);
+                    if (site > 0) multiply_from_right(mps[site - 1], t);
+                }
                 right[site] = eng.overlap_mpo_right_step(mps[site], mps[site], right[site + 1], mpo[site]);
             }
         }

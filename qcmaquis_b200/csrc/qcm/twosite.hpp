@@ -319,6 +319,135 @@ inline Truncation svd_truncate(block_matrix const& M, block_matrix& U, block_mat
     clk.lap(2);
     return tr;
 }
+// ---- heev_truncate (block_matrix_algorithms.h:187-200,211-262,387-440): eigen-decomposition of the (perturbed) reduced density
+// matrix per block, eigenvalues descending; eigenvalues below max(cutoff * largest, the (Mmax+1)-th largest) are dropped.
+// Eigenvector signs: largest-magnitude component positive (adjustPhase).
+inline Truncation heev_truncate(block_matrix const& M, block_matrix& evecs, std::vector<std::vector<double>>& evals, double cutoff, size_t Mmax)
+{
+    const size_t nb = M.n_blocks();
+    std::vector<Matrix> vs(nb);
+    evals.assign(nb, std::vector<double>());
+    sweep::run_blocks(nb, [&](size_t b) { double n = (double)M[b].rows; return 10.0 * n * n * n; }, [&](size_t b) {
+        Matrix a = M[b];
+        const int n = (int)a.rows;
+        if (a.rows != a.cols) throw std::runtime_error("heev_truncate: density-matrix block is not square");
+        std::vector<double> w((size_t)n), work(1);
+        int lwork = -1, info = 0;
+        scipy_dsyev_("V", "U", &n, a.data(), &n, w.data(), work.data(), &lwork, &info);
+        lwork = (int)work[0]; work.resize(std::max(1, lwork));
+        scipy_dsyev_("V", "U", &n, a.data(), &n, w.data(), work.data(), &lwork, &info);
+        if (info) throw std::runtime_error("dsyev failed");
+        Matrix v((size_t)n, (size_t)n);
+        evals[b].resize((size_t)n);
+        for (int j = 0; j < n; ++j) {          // descending
+            evals[b][(size_t)j] = w[(size_t)(n - 1 - j)];
+            size_t imax = 0;
+            for (int i = 0; i < n; ++i) { v((size_t)i, (size_t)j) = a((size_t)i, (size_t)(n - 1 - j)); if (std::abs(v((size_t)i, (size_t)j)) > std::abs(v(imax, (size_t)j))) imax = (size_t)i; }
+            if (v(imax, (size_t)j) < 0) for (int i = 0; i < n; ++i) v((size_t)i, (size_t)j) = -v((size_t)i, (size_t)j);
+        }
+        vs[b] = std::move(v);
+    });
+    std::vector<double> all;
+    for (auto const& e : evals) all.insert(all.end(), e.begin(), e.end());
+    if (all.empty()) throw std::runtime_error("heev_truncate: empty matrix");
+    std::sort(all.begin(), all.end(), std::greater<double>());
+    double cut = cutoff * all[0];
+    if (all.size() > Mmax) cut = std::max(cut, all[Mmax]);
+    Truncation tr;
+    tr.smallest_ev = cut / all[0];
+    double sum1 = 0;
+    for (double x : all) { sum1 += x; if (x < cut) tr.truncated_fraction += x; }
+    tr.truncated_fraction /= sum1; tr.truncated_weight = tr.truncated_fraction;
+    evecs.clear();
+    std::vector<std::vector<double>> kept;
+    for (size_t b = 0; b < nb; ++b) {
+        size_t keep = std::find_if(evals[b].begin(), evals[b].end(), [cut](double x) { return x < cut; }) - evals[b].begin();
+        if (keep == 0) continue;
+        Matrix v = vs[b];
+        v.resize(v.rows, keep);
+        size_t iu = evecs.insert_block(v, M.basis()[b].lc, M.basis()[b].rc);
+        kept.insert(kept.begin() + iu, std::vector<double>(evals[b].begin(), evals[b].begin() + keep));
+        tr.bond_dimension += keep;
+    }
+    evals.swap(kept);
+    return tr;
+}
+inline block_matrix transposed(block_matrix const& A)
+{
+    block_matrix r;
+    for (size_t k = 0; k < A.n_blocks(); ++k) {
+        Matrix const& m = A[k]; Matrix t(m.cols, m.rows);
+        for (size_t j = 0; j < m.cols; ++j) for (size_t i = 0; i < m.rows; ++i) t(j, i) = m(i, j);
+        r.insert_block(t, A.basis()[k].rc, A.basis()[k].lc);
+    }
+    return r;
+}
+// the blocks of a noise term its consumer keeps: those the tensor's own block structure has (SU2: Y Y^T also couples
+// different spin sectors through a common column sector; these never enter the density matrix)
+inline block_matrix noise_kept(block_matrix const& noise, DualIndex const& keep_basis)
+{
+    block_matrix r;
+    for (size_t k = 0; k < noise.n_blocks(); ++k)
+        if (keep_basis.has(noise.basis()[k].lc, noise.basis()[k].rc)) r.insert_block(noise[k], noise.basis()[k].lc, noise.basis()[k].rc);
+    return r;
+}
+// dm += alpha * noise, only where dm has a block (twositetensor.hpp:204-219; prediction.hpp:38-46)
+inline void add_noise(block_matrix& dm, block_matrix const& noise, double alpha, DualIndex const& keep_basis)
+{
+    for (size_t k = 0; k < noise.n_blocks(); ++k) {
+        Charge lc = noise.basis()[k].lc, rc = noise.basis()[k].rc;
+        if (!keep_basis.has(lc, rc)) continue;
+        Matrix t = noise[k];
+        for (double& x : t.v) x *= alpha;
+        dm.match_and_add_block(t, lc, rc);
+    }
+}
+
+// ---- single-site subspace expansion: MPS::grow_l2r_sweep / grow_r2l_sweep (mps.hpp:213-240) =
+// predict_new_state_*_sweep (prediction.hpp:19-57, 84-130; doPerturbDM) followed by predict_lanczos_*_sweep (:59-82, 132-156).
+// The reduced density matrix of the optimised site tensor is perturbed by alpha times the engine's noise term, its leading
+// eigenvectors become the new site tensor U, and U^T M (M U^T) is pushed into the neighbour, whose bond grows accordingly.
+struct NoiseGrow
+{
+    EngineIface& eng;
+    double alpha, cutoff;
+    size_t Mmax;
+    std::vector<Truncation>* log = nullptr;
+    bool operator()(int lr, int site, MPS& mps, MPOTensor const& mpo, Boundary const& left, Boundary const& right) const
+    {
+        MPSTensor& cur = mps[(size_t)site];
+        block_matrix dm, U; std::vector<std::vector<double>> S;
+        Truncation tr;
+        if (lr == +1) {
+            cur.make_left_paired();
+            sweep::gemm(cur.data(), transposed(cur.data()), dm);
+            block_matrix nz = eng.noise_left(cur, left, mpo);
+            cur.make_left_paired();
+            add_noise(dm, nz, alpha, cur.data().basis());
+            tr = heev_truncate(dm, U, S, cutoff, Mmax);
+            block_matrix rest;
+            sweep::gemm(transposed(U), cur.data(), rest);            // getZeroSiteTensorL2R: U^T M
+            MPSTensor& next = mps[(size_t)site + 1];
+            sweep::multiply_from_left(next, rest);
+            cur.replace_left_paired(U);
+        } else {
+            cur.make_right_paired();
+            sweep::gemm(transposed(cur.data()), cur.data(), dm);
+            block_matrix nz = eng.noise_right(cur, right, mpo);
+            cur.make_right_paired();                                 // engines may re-pair their operand (prediction.hpp:115)
+            add_noise(dm, nz, alpha, cur.data().basis());
+            tr = heev_truncate(dm, U, S, cutoff, Mmax);
+            block_matrix rest;
+            sweep::gemm(cur.data(), U, rest);                        // getZeroSiteTensorR2L: M U  (U holds adjoint(U^T)'s columns)
+            MPSTensor& prev = mps[(size_t)site - 1];
+            sweep::multiply_from_right(prev, rest);
+            cur.replace_right_paired(transposed(U));
+        }
+        if (log) log->push_back(tr);
+        return true;
+    }
+};
+
 // diag(S) * V and U * diag(S), block by block (U, V, S in the same block order)
 inline block_matrix scale_rows(block_matrix const& V, std::vector<std::vector<double>> const& S)
 {
@@ -389,6 +518,56 @@ public:
         t1 = MPSTensor(phys_i_left, left_i, us.right_basis(), us, LeftPaired);
     }
 
+    // the both-paired two-site data seen as a tensor of site 1 with a fat right index / of site 2 with a fat left index: the
+    // operands predict_split_l2r / r2l hand to left / right_boundary_tensor_mpo (:195-196, :247-248)
+    MPSTensor fat_right_tensor()
+    {
+        make_both_paired();
+        return MPSTensor(phys_i_left, left_i, adjoin(phys_i_right) * right_i, data_, LeftPaired);
+    }
+    DualIndex both_paired_basis() { make_both_paired(); return data_.basis(); }
+    MPSTensor fat_left_tensor()
+    {
+        make_both_paired();
+        return MPSTensor(phys_i_right, phys_i_left * left_i, right_i, data_, RightPaired);
+    }
+    // :184-233 -- split with the noise-perturbed reduced density matrix (left index open): dm = T T^T + alpha * sum_b Y_b Y_b^T with
+    // Y = left_boundary_tensor_mpo of the two-site tensor seen as a site-1 tensor with a fat right index; heev_truncate
+    void predict_split_l2r(size_t Mmax, double cutoff, double alpha, Boundary const& left, MPOTensor const& mpo_site1, EngineIface& eng,
+                           MPSTensor& t1, MPSTensor& t2, Truncation& trunc)
+    {
+        make_both_paired();
+        block_matrix dm;
+        sweep::gemm(data_, transposed(data_), dm);
+        if (alpha != 0.) {
+            add_noise(dm, eng.noise_left(fat_right_tensor(), left, mpo_site1), alpha, data_.basis());
+        }
+        block_matrix U; std::vector<std::vector<double>> S;
+        trunc = heev_truncate(dm, U, S, cutoff, Mmax);
+        t1 = MPSTensor(phys_i_left, left_i, U.right_basis(), U, LeftPaired);
+        block_matrix V;
+        sweep::gemm(transposed(U), data_, V);
+        t2 = MPSTensor(phys_i_right, V.left_basis(), right_i, V, RightPaired);
+    }
+    // :236-300 -- right index open
+    void predict_split_r2l(size_t Mmax, double cutoff, double alpha, Boundary const& right, MPOTensor const& mpo_site2, EngineIface& eng,
+                           MPSTensor& t1, MPSTensor& t2, Truncation& trunc)
+    {
+        make_both_paired();
+        block_matrix dm;
+        sweep::gemm(transposed(data_), data_, dm);
+        if (alpha != 0.) {
+            add_noise(dm, eng.noise_right(fat_left_tensor(), right, mpo_site2), alpha, data_.basis());
+        }
+        block_matrix U; std::vector<std::vector<double>> S;
+        trunc = heev_truncate(dm, U, S, cutoff, Mmax);
+        block_matrix Ut = transposed(U);
+        t2 = MPSTensor(phys_i_right, Ut.left_basis(), right_i, Ut, RightPaired);
+        block_matrix V;
+        sweep::gemm(data_, U, V);
+        t1 = MPSTensor(phys_i_left, left_i, V.right_basis(), V, LeftPaired);
+    }
+
 private:
     enum Storage { Both, Left };
     void make_both_paired()
@@ -412,6 +591,9 @@ struct TsParams
     // (optimize.h:150-165): with drop_stale its storage is released right away, so that at most L + 1 boundaries are
     // resident at any time (the reference's storage::drop on the disk tier, utils/storage.h:176-181).
     bool drop_stale = false;
+    // noise parameter of the perturbed truncation (ts_optimize.hpp:198-215 predict_split_l2r / predict_split_r2l; the
+    // reference's default schedule starts at alpha_initial = 1e-2, DmrgParameters.h:47-49).  0: plain SVD split
+    double alpha = 0.;
     // storage protocol of ts_optimize.hpp:92-118: the boundaries of the next site are prefetched while this site is solved,
     // the one the sweep leaves behind is evicted (it is needed again only on the way back); with spill the engine keeps
     // three to four boundaries in its fast tier instead of L + 1
@@ -439,7 +621,7 @@ inline sweep::SweepLog ts_sweeps(SymmKind symm, EngineIface& eng, MPO const& mpo
         if (prm.spill && i + 1 < L) eng.evict(right[i + 1]);
     }
     if (init_seconds) *init_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_init).count();
-    auto to_site = [L](int i) { return i < L ? i : 2 * L - 1 - i; };
+    auto to_site = [L](int i) { return i < L - 1 ? i : 2 * L - 2 - i; };      // ts_optimize.hpp:47-52: the last bond is visited twice, the first once
     bool stopped = false;
     for (int sw = 0; sw < nsweeps && !stopped; ++sw) {
         auto t0 = std::chrono::steady_clock::now();
@@ -479,7 +661,8 @@ inline sweep::SweepLog ts_sweeps(SymmKind symm, EngineIface& eng, MPO const& mpo
                 eng.assert_consistent(fp, "eigensolver result");
             }
             if (lr == +1) {
-                tst.split_mps_l2r(prm.Mmax, prm.cutoff, mps[site1], mps[site2], trunc, &eng);
+                if (prm.alpha != 0.) tst.predict_split_l2r(prm.Mmax, prm.cutoff, prm.alpha, left[site1], mpo[site1], eng, mps[site1], mps[site2], trunc);
+                else tst.split_mps_l2r(prm.Mmax, prm.cutoff, mps[site1], mps[site2], trunc, &eng);
                 { double* ss = split_seconds(); sclk.lap(3); ss[3] -= 0; }
                 block_matrix t = sweep::normalize_left(mps[site2]);
                 if (site2 < L - 1) sweep::multiply_from_left(mps[site2 + 1], t);
@@ -490,7 +673,8 @@ inline sweep::SweepLog ts_sweeps(SymmKind symm, EngineIface& eng, MPO const& mpo
                 left[site2] = eng.overlap_mpo_left_step(mps[site1], mps[site1], left[site1], mpo[site1]);
                 if (prm.spill && site1 > 0) eng.evict(left[site1]);
             } else {
-                tst.split_mps_r2l(prm.Mmax, prm.cutoff, mps[site1], mps[site2], trunc, &eng);
+                if (prm.alpha != 0.) tst.predict_split_r2l(prm.Mmax, prm.cutoff, prm.alpha, right[site2 + 1], mpo[site2], eng, mps[site1], mps[site2], trunc);
+                else tst.split_mps_r2l(prm.Mmax, prm.cutoff, mps[site1], mps[site2], trunc, &eng);
                 sclk.lap(3);
                 block_matrix t = sweep::normalize_right(mps[site1]);
                 if (site1 > 0) sweep::multiply_from_right(mps[site1 - 1], t);

@@ -644,3 +644,104 @@ extern "C" int qcmt_ss_dmrg_const(const char* fcidump, const char* symm, int L, 
         return 0;
     } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
 }
+
+static std::unique_ptr<EngineIface> make_engine(SymmKind symm, int engine_kind, long long budget = (long long)1 << 40)
+{
+    std::unique_ptr<EngineIface> eng;
+    if (engine_kind < 0) eng.reset(new oracle::OracleEngine(symm));
+    else if (engine_kind == 0) eng.reset(new qcmtest::InterpEngine(symm, 1, budget));
+    else {
+#ifdef QCMT_WITH_GPU
+        eng.reset(new GpuEngine(symm, 0, 0, 1, budget));
+#else
+        throw std::runtime_error("harness built without GPU support");
+#endif
+    }
+    return eng;
+}
+
+// Noise term of the perturbed density matrix (EngineIface::noise_left / noise_right; prediction.hpp:34-47,101-114,
+// twositetensor.hpp:192-219,260-287) on every site of a random MPS and on every bond with a random two-site tensor seen as
+// a fat single-site tensor: engine under test against the oracle's restatement of left/right_boundary_tensor_mpo.
+// out[0] cases  out[1] all structures equal  out[2] max rel diff  out[3] max |noise| (non-trivial check)
+extern "C" int qcmt_noise_parity(const char* fcidump, const char* symm, int L, int nelec, int Mmax, unsigned seed, int engine_kind, long long budget,
+                                 double* out, char* err, int errlen)
+{
+    try {
+        Problem P = make_problem(fcidump, symm, L, nelec);
+        P.init_mps((size_t)Mmax, true, 0., seed);
+        oracle::OracleEngine orc(P.params.symm);
+        P.build_boundaries(orc);
+        std::unique_ptr<EngineIface> eng = make_engine(P.params.symm, engine_kind, budget);
+        double dmax = 0, nmax = 0; int st = 1, n = 0;
+        auto check = [&](block_matrix const& a_all, block_matrix const& b_all, DualIndex const& keep) {
+            block_matrix a = ts::noise_kept(a_all, keep), b = ts::noise_kept(b_all, keep);
+            DiffReport d = compare(a, b);
+            dmax = std::max(dmax, rel_diff(d)); st &= d.structure_equal; nmax = std::max(nmax, std::sqrt(d.ref_norm)); ++n;
+        };
+        for (int p = 0; p < L; ++p) {
+            P.mps[p].make_left_paired(); DualIndex lb = P.mps[p].data().basis();
+            P.mps[p].make_right_paired(); DualIndex rb = P.mps[p].data().basis();
+            check(eng->noise_left(P.mps[p], P.left[p], P.mpo[p]), orc.noise_left(P.mps[p], P.left[p], P.mpo[p]), lb);
+            check(eng->noise_right(P.mps[p], P.right[p + 1], P.mpo[p]), orc.noise_right(P.mps[p], P.right[p + 1], P.mpo[p]), rb);
+        }
+        for (int p = 0; p + 1 < L; ++p) {
+            // the operands of TwoSiteTensor::predict_split_l2r / r2l: both-paired two-site data as a site tensor with a fat index
+            ts::TwoSiteTensor tst(P.params.symm, P.mps[p], P.mps[p + 1]);
+            MPSTensor fl = tst.fat_right_tensor(), fr = tst.fat_left_tensor();
+            DualIndex both = tst.both_paired_basis();
+            check(eng->noise_left(fl, P.left[p], P.mpo[p]), orc.noise_left(fl, P.left[p], P.mpo[p]), both);
+            check(eng->noise_right(fr, P.right[p + 2], P.mpo[p + 1]), orc.noise_right(fr, P.right[p + 2], P.mpo[p + 1]), both);
+        }
+        out[0] = n; out[1] = st; out[2] = dmax; out[3] = nmax;
+        return 0;
+    } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
+}
+
+// The reference's own run H2_2e4o.TI.SS (single-site, init_type = const, alpha_initial = 1e-10, truncation 1e-50, M = 100):
+// single-site sweeps with the noise-perturbed subspace expansion (ts::NoiseGrow = MPS::grow_l2r_sweep / grow_r2l_sweep).
+// bond_before/after[i]: "Bond dimension before / after truncation" of micro-iteration i (0 where the sweep turns).
+extern "C" int qcmt_ss_dmrg_const_noise(const char* fcidump, const char* symm, int L, int nelec, int init_bond_dimension, int nsweeps, int engine_kind,
+                                        double alpha, double cutoff, int Mmax, double* energies, int* n_sigma, int* bond_after, int n_max, int* n_out,
+                                        char* err, int errlen)
+{
+    try {
+        Problem P = make_problem(fcidump, symm, L, nelec);
+        P.init_mps((size_t)init_bond_dimension, false, 1., 0);
+        std::unique_ptr<EngineIface> eng = make_engine(P.params.symm, engine_kind);
+        std::vector<ts::Truncation> trs;
+        sweep::SweepLog log = sweep::ss_sweeps(*eng, P.mpo, P.mps, nsweeps, 10, 1e-8, ts::NoiseGrow{*eng, alpha, cutoff, (size_t)Mmax, &trs});
+        int n = (int)std::min<size_t>(log.energies.size(), (size_t)n_max);
+        // grow is skipped at the turning points (site L-1 forward, site 0 backward): map the truncation log onto micro-iterations
+        size_t q = 0;
+        for (int i = 0; i < n; ++i) {
+            energies[i] = log.energies[i]; n_sigma[i] = log.n_sigma[i];
+            const int w = i % (2 * L);
+            const bool turning = (w == L - 1) || (w == 2 * L - 1);
+            bond_after[i] = turning || q >= trs.size() ? 0 : (int)trs[q++].bond_dimension;
+        }
+        *n_out = n;
+        return 0;
+    } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
+}
+
+// two-site sweeps with the noise-perturbed split (ts_optimize.hpp:198-215 predict_split_l2r / r2l), the reference's default path
+extern "C" int qcmt_ts_dmrg_noise(const char* fcidump, const char* symm, int L, int nelec, int M0, int Mmax, int nsweeps, unsigned seed, int engine_kind,
+                                  double alpha, double cutoff, double* energies, int n_max, int* n_out, double* info, char* err, int errlen)
+{
+    try {
+        Problem P = make_problem(fcidump, symm, L, nelec);
+        P.init_mps((size_t)M0, true, 0., seed);
+        std::unique_ptr<EngineIface> eng = make_engine(P.params.symm, engine_kind);
+        ts::TsParams prm; prm.Mmax = (size_t)Mmax; prm.alpha = alpha; prm.cutoff = cutoff;
+        std::vector<size_t> dims;
+        sweep::SweepLog log = ts::ts_sweeps(P.params.symm, *eng, P.mpo, [&](int p) -> MPOTensor const& { return P.twosite_mpo(p); }, P.mps, nsweeps, prm, &dims);
+        int n = (int)std::min<size_t>(log.energies.size(), (size_t)n_max);
+        for (int i = 0; i < n; ++i) energies[i] = log.energies[i];
+        *n_out = n;
+        double secs = 0; for (double s : log.sweep_seconds) secs += s;
+        info[0] = (double)log.total_sigma; info[1] = secs; info[2] = log.energies.back();
+        info[3] = dims.empty() ? 0. : (double)*std::max_element(dims.begin(), dims.end());
+        return 0;
+    } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
+}

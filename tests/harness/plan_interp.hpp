@@ -201,6 +201,21 @@ public:
         run_plan(P, B);
         return unflat(P.out_tensor, B.b[plan::BUF_OUT], 0);
     }
+    block_matrix noise(bool left_side, MPSTensor const& mps, Boundary const& in, MPOTensor const& mpo)
+    {
+        mps.make_left_paired();
+        plan::BoundaryLayout il = layout_of(in);
+        plan::Planner pl(symm, mpo, true, 0, 1, budget);
+        plan::Plan P = left_side ? pl.plan_noise_left(desc_of(mps), il) : pl.plan_noise_right(desc_of(mps), il);
+        Bufs B;
+        B.b[plan::BUF_KET_LP] = flat(mps.data());
+        B.b[left_side ? plan::BUF_LEFT : plan::BUF_RIGHT] = flat(in);
+        B.b[plan::BUF_OUT].assign((size_t)P.out_boundary.total, 0.);
+        run_plan(P, B);
+        return unflat(P.out_boundary.b[0], B.b[plan::BUF_OUT], 0);
+    }
+    block_matrix noise_left(MPSTensor const& mps, Boundary const& left, MPOTensor const& mpo) override { return noise(true, mps, left, mpo); }
+    block_matrix noise_right(MPSTensor const& mps, Boundary const& right, MPOTensor const& mpo) override { return noise(false, mps, right, mpo); }
     Boundary overlap_mpo_left_step(MPSTensor const& bra, MPSTensor const& ket, Boundary const& left, MPOTensor const& mpo, bool h = true) override { return step(1, bra, ket, left, mpo, h); }
     Boundary overlap_mpo_right_step(MPSTensor const& bra, MPSTensor const& ket, Boundary const& right, MPOTensor const& mpo, bool h = true) override { return step(2, bra, ket, right, mpo, h); }
     double last_flops = 0, last_exec_close = 0; size_t last_waves = 0; int64_t last_exchange_elems = 0;

@@ -150,8 +150,8 @@ def _check_const_init(energies, n_sigma):
     micro-iteration 2 on (:61, :70) the reference's numbers need its noise-perturbed subspace expansion
     (alpha_initial = 1e-10, prediction.hpp:34): canonising the rank-one constant tensors shrinks the bond between sites 1
     and 2 (sector (1,1): 4 -> 1 state) and only the noise term grows it back ("Bond dimension before truncation: 9").
-    The drivers here run with alpha = 0, where the bond stays small; the exact energy of :70 is pinned
-    through the two-site sweeps instead."""
+    This test runs the alpha = 0 driver, where the bond stays small; the full run with the noise term -- all printed energies
+    and the iteration counts 4, 10, 8, 1, 1 -- is tests/test_noise.py."""
     ref = json.load(open(os.path.join(GOLDEN, "reference_values.json")))["h2_4o_microiteration_energies_2u1pg_singlesite_const_init"]
     for i in range(2):
         assert abs(energies[i] - ref[i]) < 1e-8, (i, energies[i], ref[i])
