@@ -897,6 +897,30 @@ public:
         return ret;
     }
 
+    // common/move_boundary.hpp:21-45 (overlap_left_step): t1 = left * ket (right-paired), reshaped to left-paired with the bra's
+    // row index, closed with bra^T.  Gemm::gemm is the plain block product for both symmetry kinds (SU2::gemm with spin = -1)
+    block_matrix overlap_left_step(MPSTensor const& bra_tensor, MPSTensor const& ket_tensor, block_matrix const& left)
+    {
+        block_matrix t1, t3;
+        ket_tensor.make_right_paired();
+        gemm(plain(left), plain(ket_tensor.data()), t1);
+        reshape_right_to_left_new(ket_tensor.site_dim(), bra_tensor.row_dim(), ket_tensor.col_dim(), t1, t3);
+        bra_tensor.make_left_paired();
+        gemm(transpose(bra_tensor.data()), plain(t3), t1);
+        return t1;
+    }
+    // common/move_boundary.hpp:47-63 (overlap_right_step)
+    block_matrix overlap_right_step(MPSTensor const& bra_tensor, MPSTensor const& ket_tensor, block_matrix const& right)
+    {
+        block_matrix t1, t3;
+        ket_tensor.make_left_paired();
+        gemm(plain(ket_tensor.data()), transpose(right), t1);
+        reshape_left_to_right_new(ket_tensor.site_dim(), ket_tensor.row_dim(), bra_tensor.col_dim(), t1, t3);
+        bra_tensor.make_right_paired();
+        gemm(plain(bra_tensor.data()), transpose(t3), t1);
+        return t1;
+    }
+
     // common/move_boundary.hpp:68-95 (left_boundary_tensor_mpo) followed by the accumulation loop of prediction.hpp:34-47 /
     // twositetensor.hpp:196-219 without alpha and without the restriction to the density matrix's blocks
     block_matrix noise_left(MPSTensor const& mps_in, Boundary const& left, MPOTensor const& mpo) override

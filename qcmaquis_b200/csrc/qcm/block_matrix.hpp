@@ -54,12 +54,6 @@ inline void dgemm(MatRef const& A, MatRef const& B, double alpha, double beta, d
     if (m == 0 || n == 0) return;
     char ta = A.trans ? 'T' : 'N', tb = B.trans ? 'T' : 'N';
     if (lda < 1) lda = 1; if (ldb < 1) ldb = 1;
-#ifdef QCM_DGEMM_CHECK
-    if (ldb < std::max(1, B.trans ? n : k) || lda < std::max(1, A.trans ? k : m)) {
-        fprintf(stderr, "dgemm check: m %d n %d k %d lda %d ldb %d ta %c tb %c\n", m, n, k, lda, ldb, ta, tb);
-        void* bt[64]; int nb = backtrace(bt, 64); backtrace_symbols_fd(bt, nb, 2); abort();
-    }
-#endif
     scipy_dgemm_(&ta, &tb, &m, &n, &k, &alpha, A.p, &lda, B.p, &ldb, &beta, C, &ldc_);
 }
 
@@ -210,5 +204,16 @@ inline block_view transpose(block_matrix const& m) { return block_view(m, true);
 inline block_view adjoint(block_matrix const& m) { return block_view(m, true); }
 inline block_view conjugate(block_matrix const& m) { return block_view(m, false); }
 inline block_view plain(block_matrix const& m) { return block_view(m, false); }
+// a transposed COPY (block (lc, rc) of size m x n becomes block (rc, lc) of size n x m)
+inline block_matrix transposed(block_matrix const& A)
+{
+    block_matrix r;
+    for (size_t k = 0; k < A.n_blocks(); ++k) {
+        Matrix const& m = A[k]; Matrix t(m.cols, m.rows);
+        for (size_t j = 0; j < m.cols; ++j) for (size_t i = 0; i < m.rows; ++i) t(j, i) = m(i, j);
+        r.insert_block(t, A.basis()[k].rc, A.basis()[k].lc);
+    }
+    return r;
+}
 
 } // namespace qcm

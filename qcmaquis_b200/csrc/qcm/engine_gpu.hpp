@@ -421,6 +421,7 @@ public:
             }
         b.host_valid = true;
     }
+    void fetch(Boundary& b) override { download(b); }
     void clear_cache() { cache.clear(); }
     // plans kept (least recently created dropped first).  A sweep driver sets this to a few times the chain length: once
     // the bond dimensions have settled every (site, direction) finds its plan from the previous sweep.

@@ -35,6 +35,8 @@ struct EngineIface
     virtual block_matrix noise_right(MPSTensor const& /*mps*/, Boundary const& /*right*/, MPOTensor const& /*mpo*/) { throw std::runtime_error("this engine does not provide the noise term"); }
     // ---- boundary storage protocol of the sweep drivers (utils/storage.h:113-185: storage::disk::prefetch / evict; drop is the
     // destruction of the Boundary).  Engines that keep boundaries in a fast tier move them here; the default does nothing.
+    // make the dense blocks of a boundary this engine returned readable on the host (engines that keep results in a fast tier)
+    virtual void fetch(Boundary& /*b*/) {}
     virtual void prefetch(Boundary const& /*b*/) {}
     virtual void evict(Boundary const& /*b*/) {}
     // ---- one process per GPU: the host side of a sweep runs on every rank.  Work that is the same on all ranks (the block

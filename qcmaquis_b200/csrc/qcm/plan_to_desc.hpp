@@ -19,10 +19,13 @@ struct PlanDescHolder
     static void cvt(plan::GemmList const& g, std::vector<qcm_gemm_out>& outs, std::vector<qcm_gemm_seg>& segs)
     {
         outs.resize(g.outs.size()); segs.resize(g.segs.size());
+        // 10^6 records per list at cfg3: converted on all cores (the caller sits between two device phases of a sweep)
+#pragma omp parallel for schedule(static) if (g.outs.size() > 65536)
         for (size_t i = 0; i < g.outs.size(); ++i) {
             plan::Out const& o = g.outs[i];
             outs[i] = qcm_gemm_out{qcm_ref{o.C.buf, 0, o.C.off}, o.ldc, o.m, o.n, o.seg_begin, o.seg_end, 0};
         }
+#pragma omp parallel for schedule(static) if (g.segs.size() > 65536)
         for (size_t i = 0; i < g.segs.size(); ++i) {
             plan::Seg const& s = g.segs[i];
             segs[i] = qcm_gemm_seg{qcm_ref{s.A.buf, 0, s.A.off}, qcm_ref{s.B.buf, 0, s.B.off}, s.lda, s.ldb, s.m, s.n, s.k, s.ta, s.tb, 0, s.alpha};
@@ -43,7 +46,9 @@ struct PlanDescHolder
                 plan::WGroup const& g = wl.groups[i];
                 S.wg[i] = qcm_w_group{g.rows, g.cols, g.n_src, g.n_dst, g.ng, g.src_begin, g.dst_begin, g.cls, g.coef_begin};
             }
+#pragma omp parallel for schedule(static) if (S.wd.size() > 65536)
             for (size_t i = 0; i < S.wd.size(); ++i) S.wd[i] = qcm_w_dst{qcm_ref{wl.dsts[i].dst.buf, 0, wl.dsts[i].dst.off}, wl.dsts[i].ldd, 0};
+#pragma omp parallel for schedule(static) if (S.wsrc.size() > 65536)
             for (size_t i = 0; i < S.wsrc.size(); ++i) S.wsrc[i] = qcm_w_src{qcm_ref{wl.srcs[i].src.buf, 0, wl.srcs[i].src.off}, wl.srcs[i].lds, 0};
             waves[w] = qcm_wave_desc{S.to.data(), (int64_t)S.to.size(), S.ts.data(), (int64_t)S.ts.size(),
                                      S.wg.data(), (int64_t)S.wg.size(), S.wsrc.data(), (int64_t)S.wsrc.size(), S.wd.data(), (int64_t)S.wd.size(),

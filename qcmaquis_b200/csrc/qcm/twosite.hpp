@@ -372,16 +372,7 @@ inline Truncation heev_truncate(block_matrix const& M, block_matrix& evecs, std:
     evals.swap(kept);
     return tr;
 }
-inline block_matrix transposed(block_matrix const& A)
-{
-    block_matrix r;
-    for (size_t k = 0; k < A.n_blocks(); ++k) {
-        Matrix const& m = A[k]; Matrix t(m.cols, m.rows);
-        for (size_t j = 0; j < m.cols; ++j) for (size_t i = 0; i < m.rows; ++i) t(j, i) = m(i, j);
-        r.insert_block(t, A.basis()[k].rc, A.basis()[k].lc);
-    }
-    return r;
-}
+using qcm::transposed;
 // the blocks of a noise term its consumer keeps: those the tensor's own block structure has (SU2: Y Y^T also couples
 // different spin sectors through a common column sector; these never enter the density matrix)
 inline block_matrix noise_kept(block_matrix const& noise, DualIndex const& keep_basis)

@@ -585,52 +585,92 @@ static int flush_uploads(qcm_plan_s* P)
     return 0;
 }
 
+// Host threads of plan creation.  qcm_plan_create sits between two device phases of a sweep (the solver of one site and the
+// next), so its loops over 10^6 outputs / segments run on several threads; ranges are contiguous and their results are
+// concatenated in range order, so the task arrays do not depend on the number of threads.
+static int plan_threads()
+{
+    static const int n = []() {
+        if (const char* e = getenv("QCM_PLAN_THREADS")) return std::max(1, atoi(e));
+        unsigned hc = std::thread::hardware_concurrency();
+        return (int)std::min<unsigned>(16u, std::max<unsigned>(1u, hc));
+    }();
+    return n;
+}
+template <class F> static void parallel_ranges(int64_t n, int64_t min_per_thread, F f /* (int t, int64_t begin, int64_t end) */, int* n_ranges = nullptr)
+{
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(plan_threads(), n / std::max<int64_t>(1, min_per_thread)));
+    if (n_ranges) *n_ranges = nt;
+    if (nt == 1) { f(0, (int64_t)0, n); return; }
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back([=]() { f(t, n * t / nt, n * (t + 1) / nt); });
+    f(0, (int64_t)0, n / nt);
+    for (auto& x : th) x.join();
+}
+
 // output blocks -> tile work items; long segment lists are split (split-K over the MPO bond index) and
 // combined with FP64 atomics
 static int build_gemm_group(qcm_plan_s* P, GemmGroup& g, const qcm_gemm_out* outs, int64_t n_outs, const qcm_gemm_seg* segs, int64_t n_segs,
                             int base_mode /*0 store, 1 add*/)
 {
     std::vector<DSeg> hs((size_t)n_segs);
-    for (int64_t i = 0; i < n_segs; ++i) {
-        qcm_gemm_seg const& s = segs[i];
-        hs[i] = DSeg{s.A.off, s.B.off, s.A.buf, s.B.buf, s.lda, s.ldb, s.m, s.n, s.k, s.ta, s.tb, 0, s.alpha};
-    }
+    parallel_ranges(n_segs, 1 << 16, [&](int, int64_t b, int64_t e) {
+        for (int64_t i = b; i < e; ++i) {
+            qcm_gemm_seg const& s = segs[i];
+            hs[i] = DSeg{s.A.off, s.B.off, s.A.buf, s.B.buf, s.lda, s.ldb, s.m, s.n, s.k, s.ta, s.tb, 0, s.alpha};
+        }
+    });
     const int kNumVariants = gemm_ws_num_variants();
-    std::vector<std::vector<std::pair<double, DWork>>> per_variant(kNumVariants);
+    typedef std::vector<std::vector<std::pair<double, DWork>>> PerVariant;
     const int max_chunks = 96;       // K chunks (of KC) per work item before the segment list is split
-    for (int64_t o = 0; o < n_outs; ++o) {
-        qcm_gemm_out const& out = outs[o];
-        if (out.m <= 0 || out.n <= 0) continue;
-        std::vector<std::pair<int, int>> chunks;
-        {
-            int csum = 0, cb = out.seg_begin;
-            for (int s = out.seg_begin; s < out.seg_end; ++s) {
-                csum += (segs[s].k + KC - 1) / KC;
-                // only accumulating outputs are split: a store-mode output (step-1 products) runs its whole K list in one work item
-                if (base_mode == 1 && csum >= max_chunks && s + 1 < out.seg_end) { chunks.push_back(std::make_pair(cb, s + 1)); cb = s + 1; csum = 0; }
-            }
-            chunks.push_back(std::make_pair(cb, out.seg_end));
-        }
-        int total_chunks = 0;
-        for (int s = out.seg_begin; s < out.seg_end; ++s) total_chunks += (segs[s].k + KC - 1) / KC;
-        const int avg_chunks = std::max(1, total_chunks / (int)chunks.size());
-        int mode = chunks.size() > 1 ? 2 : base_mode;
-        std::vector<std::pair<int, int>> rows, cols;
-        cut_dimension(out.m, avg_chunks, rows);
-        cut_dimension(out.n, avg_chunks, cols);
-        for (auto const& ch : chunks) {
-            int nch = 0;
-            for (int s = ch.first; s < ch.second; ++s) nch += (segs[s].k + KC - 1) / KC;
-            for (auto const& cs : cols)
-                for (auto const& rs : rows) {
-                    const int v = variant_for(rs.second, cs.second);
-                    const GemmWsVariant var = gemm_ws_variant(v);
-                    // a variant tile may be larger than the strip pair (corner pieces): it is clipped by the block edge
-                    per_variant[v].push_back(std::make_pair(tile_cost(std::min(var.tm, out.m - rs.first), std::min(var.tn, out.n - cs.first), nch),
-                                                            DWork{out.C.off, out.C.buf, out.ldc, rs.first, cs.first, out.m, out.n, ch.first, ch.second, mode, 0}));
+    std::vector<PerVariant> parts((size_t)plan_threads(), PerVariant((size_t)kNumVariants));
+    int n_parts = 1;
+    parallel_ranges(n_outs, 1 << 12, [&](int t, int64_t ob, int64_t oe) {
+        PerVariant& per_variant = parts[(size_t)t];
+        std::vector<std::pair<int, int>> chunks, rows, cols;
+        for (int64_t o = ob; o < oe; ++o) {
+            qcm_gemm_out const& out = outs[o];
+            if (out.m <= 0 || out.n <= 0) continue;
+            chunks.clear();
+            {
+                int csum = 0, cb = out.seg_begin;
+                for (int s = out.seg_begin; s < out.seg_end; ++s) {
+                    csum += (segs[s].k + KC - 1) / KC;
+                    // only accumulating outputs are split: a store-mode output (step-1 products) runs its whole K list in one work item
+                    if (base_mode == 1 && csum >= max_chunks && s + 1 < out.seg_end) { chunks.push_back(std::make_pair(cb, s + 1)); cb = s + 1; csum = 0; }
                 }
+                chunks.push_back(std::make_pair(cb, out.seg_end));
+            }
+            int total_chunks = 0;
+            for (int s = out.seg_begin; s < out.seg_end; ++s) total_chunks += (segs[s].k + KC - 1) / KC;
+            const int avg_chunks = std::max(1, total_chunks / (int)chunks.size());
+            int mode = chunks.size() > 1 ? 2 : base_mode;
+            cut_dimension(out.m, avg_chunks, rows);
+            cut_dimension(out.n, avg_chunks, cols);
+            for (auto const& ch : chunks) {
+                int nch = 0;
+                for (int s = ch.first; s < ch.second; ++s) nch += (segs[s].k + KC - 1) / KC;
+                for (auto const& cs : cols)
+                    for (auto const& rs : rows) {
+                        const int v = variant_for(rs.second, cs.second);
+                        const GemmWsVariant var = gemm_ws_variant(v);
+                        // a variant tile may be larger than the strip pair (corner pieces): it is clipped by the block edge
+                        per_variant[v].push_back(std::make_pair(tile_cost(std::min(var.tm, out.m - rs.first), std::min(var.tn, out.n - cs.first), nch),
+                                                                DWork{out.C.off, out.C.buf, out.ldc, rs.first, cs.first, out.m, out.n, ch.first, ch.second, mode, 0}));
+                    }
+            }
         }
+    }, &n_parts);
+    // ranges in order: the same sequence per variant as a single pass over the outputs
+    PerVariant per_variant((size_t)kNumVariants);
+    for (int v = 0; v < kNumVariants; ++v) {
+        size_t tot = 0;
+        for (int t = 0; t < n_parts; ++t) tot += parts[(size_t)t][(size_t)v].size();
+        if (n_parts == 1) { per_variant[(size_t)v].swap(parts[0][(size_t)v]); continue; }
+        per_variant[(size_t)v].reserve(tot);
+        for (int t = 0; t < n_parts; ++t) per_variant[(size_t)v].insert(per_variant[(size_t)v].end(), parts[(size_t)t][(size_t)v].begin(), parts[(size_t)t][(size_t)v].end());
     }
+    parts.clear();
     // the persistent CTAs take work items round-robin: heaviest first, so that every CTA gets a similar mix and the
     // launch ends on light items; the launches of a group are ordered by total cost
     std::vector<DWork> hw;
@@ -683,9 +723,9 @@ static int build_gemm_group(qcm_plan_s* P, GemmGroup& g, const qcm_gemm_out* out
 static int build_axpy_group(qcm_plan_s* P, AxpyGroup& g, qcm_wave_desc const& wd)
 {
     std::vector<DWSrc> hs((size_t)wd.n_w_srcs);
-    for (int64_t i = 0; i < wd.n_w_srcs; ++i) hs[i] = DWSrc{wd.w_srcs[i].src.off, wd.w_srcs[i].src.buf, wd.w_srcs[i].lds};
+    parallel_ranges(wd.n_w_srcs, 1 << 17, [&](int, int64_t b, int64_t e) { for (int64_t i = b; i < e; ++i) hs[i] = DWSrc{wd.w_srcs[i].src.off, wd.w_srcs[i].src.buf, wd.w_srcs[i].lds}; });
     std::vector<DWDst> hd((size_t)wd.n_w_dsts);
-    for (int64_t i = 0; i < wd.n_w_dsts; ++i) hd[i] = DWDst{wd.w_dsts[i].dst.off, wd.w_dsts[i].dst.buf, wd.w_dsts[i].ldd};
+    parallel_ranges(wd.n_w_dsts, 1 << 17, [&](int, int64_t b, int64_t e) { for (int64_t i = b; i < e; ++i) hd[i] = DWDst{wd.w_dsts[i].dst.off, wd.w_dsts[i].dst.buf, wd.w_dsts[i].ldd}; });
     std::vector<DWGroup> hg((size_t)wd.n_w_groups);
     std::vector<DWWork> cls[5];
     for (int64_t i = 0; i < wd.n_w_groups; ++i) {

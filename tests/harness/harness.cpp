@@ -8,6 +8,7 @@
 #include "qcm/scenarios.hpp"
 #include "qcm/sweep.hpp"
 #include "qcm/twosite.hpp"
+#include "qcm/overlap.hpp"
 #include "plan_interp.hpp"
 #include "flatten_desc.hpp"
 #ifdef QCMT_WITH_GPU
@@ -742,6 +743,43 @@ extern "C" int qcmt_ts_dmrg_noise(const char* fcidump, const char* symm, int L, 
         double secs = 0; for (double s : log.sweep_seconds) secs += s;
         info[0] = (double)log.total_sigma; info[1] = secs; info[2] = log.energies.back();
         info[3] = dims.empty() ? 0. : (double)*std::max_element(dims.begin(), dims.end());
+        return 0;
+    } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
+}
+
+// MPS-MPS overlap steps (contraction::Engine::overlap_left_step / overlap_right_step, move_boundary.hpp:21-64) along the whole
+// chain for two different random states: the engine under test (boundary step with the identity MPO tensor, qcm/overlap.hpp)
+// against the oracle's literal restatement.
+// out[0] steps compared  out[1] structures equal  out[2] max rel diff  out[3] <bra|ket> from the left chain (engine)
+// out[4] the same from the right chain (engine)  out[5] <bra|ket> oracle  out[6] norm^2 of the canonised ket through the engine
+extern "C" int qcmt_overlap_parity(const char* fcidump, const char* symm, int L, int nelec, int Mbra, int Mket, unsigned seed, int engine_kind,
+                                   double* out, char* err, int errlen)
+{
+    try {
+        Problem P = make_problem(fcidump, symm, L, nelec);
+        Problem Q = P;
+        P.init_mps((size_t)Mket, true, 0., seed);
+        Q.init_mps((size_t)Mbra, true, 0., seed + 101);
+        const bool su2 = is_su2(P.params.symm);
+        oracle::OracleEngine orc(P.params.symm);
+        std::unique_ptr<EngineIface> eng = make_engine(P.params.symm, engine_kind);
+        double dmax = 0; int st = 1, n = 0;
+        auto check = [&](block_matrix const& a, block_matrix const& b) { DiffReport d = compare(a, b); dmax = std::max(dmax, rel_diff(d)); st &= d.structure_equal; ++n; };
+        block_matrix le = Q.mps.left_boundary()[0], lo = le;
+        for (int p = 0; p < L; ++p) {
+            le = overlap_left_step(*eng, su2, Q.mps[p], P.mps[p], le);
+            lo = orc.overlap_left_step(Q.mps[p], P.mps[p], lo);
+            check(le, lo);
+        }
+        block_matrix re = Q.mps.right_boundary()[0], ro = re;
+        for (int p = L - 1; p >= 0; --p) {
+            re = overlap_right_step(*eng, su2, Q.mps[p], P.mps[p], re);
+            ro = orc.overlap_right_step(Q.mps[p], P.mps[p], ro);
+            check(re, ro);
+        }
+        out[0] = n; out[1] = st; out[2] = dmax; out[3] = le.trace(); out[4] = re.trace(); out[5] = lo.trace();
+        sweep::canonize_to_first(P.mps);
+        out[6] = overlap(*eng, su2, P.mps, P.mps);
         return 0;
     } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
 }
