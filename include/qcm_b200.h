@@ -245,7 +245,15 @@ int qcm_plan_left_step(qcm_mpo_t m, const qcm_tensor_desc* bra, const qcm_tensor
                        int rank, int world, int64_t ws_budget_elems, qcm_plan_t* out);
 int qcm_plan_right_step(qcm_mpo_t m, const qcm_tensor_desc* bra, const qcm_tensor_desc* ket, const qcm_boundary_desc* right,
                         int rank, int world, int64_t ws_budget_elems, qcm_plan_t* out);
-/* block structure of the result of a plan made by the three calls above: sigma (aux_dim 1) or the new boundary.
+/* Noise term of the perturbed density matrix -- replaces Engine::left_boundary_tensor_mpo / right_boundary_tensor_mpo
+ * (dmrg/framework/dmrg/mp_tensors/contractions/common/move_boundary.hpp:68-126) TOGETHER WITH the accumulation loops of their only
+ * callers (contractions/common/prediction.hpp:34-47,101-114; mp_tensors/twositetensor.hpp:192-219,260-287):
+ *   left:  sum over b2 of Y[b2] Y[b2]^T,   right: sum over b1 of Y'[b1]^T Y'[b1]   (all blocks; the caller keeps those its dm has).
+ * Execute with qcm_boundary_step(plan, boundary, ket, ket, out); out holds ONE bond entry (the density-matrix blocks), described
+ * by qcm_plan_out_size / qcm_plan_out_blocks.  The term is quadratic in the half-contracted boundary and is not sharded. */
+int qcm_plan_noise_left(qcm_mpo_t m, const qcm_tensor_desc* ket, const qcm_boundary_desc* left, int64_t ws_budget_elems, qcm_plan_t* out);
+int qcm_plan_noise_right(qcm_mpo_t m, const qcm_tensor_desc* ket, const qcm_boundary_desc* right, int64_t ws_budget_elems, qcm_plan_t* out);
+/* block structure of the result of a plan made by the calls above: sigma (aux_dim 1) or the new boundary.
  * qcm_plan_out_size: number of bond entries, blocks and elements; qcm_plan_out_blocks: block_ptr (aux_dim + 1), the blocks in
  * DualIndex order and the element offset of every block inside the output array. */
 int qcm_plan_out_size(qcm_plan_t p, int64_t* aux_dim, int64_t* n_blocks, int64_t* n_elems);

@@ -170,6 +170,29 @@ extern "C" int qcm_plan_right_step(qcm_mpo_t m, const qcm_tensor_desc* bra, cons
     } catch (std::exception const& e) { return fail(std::string("qcm_plan_right_step: ") + e.what()); }
 }
 
+// noise term of the perturbed density matrix (C/common/move_boundary.hpp:68-126 + prediction.hpp:34-47,101-114): the plan runs
+// through qcm_boundary_step(plan, boundary, ket, ket, out); out = the density-matrix blocks (one bond entry).  Never sharded.
+extern "C" int qcm_plan_noise_left(qcm_mpo_t m, const qcm_tensor_desc* ket, const qcm_boundary_desc* left, int64_t budget, qcm_plan_t* out)
+{
+    try {
+        if (!m || !out) return fail("qcm_plan_noise_left: null argument");
+        plan::BoundaryLayout ll = boundary_of(left);
+        plan::Planner pl(m->symm, m->mpo, true, 0, 1, budget > 0 ? budget : (int64_t)1 << 32);
+        plan::Plan P = pl.plan_noise_left(tensor_of(ket), ll);
+        return finish(P, ll.total, 0, out);
+    } catch (std::exception const& e) { return fail(std::string("qcm_plan_noise_left: ") + e.what()); }
+}
+extern "C" int qcm_plan_noise_right(qcm_mpo_t m, const qcm_tensor_desc* ket, const qcm_boundary_desc* right, int64_t budget, qcm_plan_t* out)
+{
+    try {
+        if (!m || !out) return fail("qcm_plan_noise_right: null argument");
+        plan::BoundaryLayout rl = boundary_of(right);
+        plan::Planner pl(m->symm, m->mpo, true, 0, 1, budget > 0 ? budget : (int64_t)1 << 32);
+        plan::Plan P = pl.plan_noise_right(tensor_of(ket), rl);
+        return finish(P, 0, rl.total, out);
+    } catch (std::exception const& e) { return fail(std::string("qcm_plan_noise_right: ") + e.what()); }
+}
+
 extern "C" int qcm_plan_out_size(qcm_plan_t p, int64_t* aux_dim, int64_t* n_blocks, int64_t* n_elems)
 {
     std::lock_guard<std::mutex> lock(g_mutex);

@@ -558,12 +558,12 @@ extern "C" int qcmt_sharded_split(const char* fcidump, const char* symm, int L, 
 // The descriptor entry points of the C ABI (qcm_mpo_upload, qcm_plan_sigma / left_step / right_step, qcm_plan_out_*): the
 // problem is flattened into plain arrays (tests/harness/flatten_desc.hpp -- the binding a QCMaquis maintainer would write),
 // planned INSIDE the library and executed; no C++ object of this repository crosses the boundary.  Compared with the oracle.
-// out[0] sigma structure equal, [1] sigma rel. error, [2..3] left step, [4..5] right step (single-site problems)
+// out[0] sigma structure equal, [1] sigma rel. error, [2..3] left step, [4..5] right step, [6] noise plans with equal structure (of 2), [7] noise rel. error (single-site problems)
 extern "C" int qcmt_desc_parity(const char* fcidump, const char* symm, int L, int nelec, int site, int twosite, int M, unsigned seed, double* out, char* err, int errlen)
 {
     try {
 #ifdef QCMT_WITH_GPU
-        for (int i = 0; i < 6; ++i) out[i] = 0;
+        for (int i = 0; i < 8; ++i) out[i] = 0;
         Problem P = make_problem(fcidump, symm, L, nelec);
         SyntheticSite S = make_synthetic_site(P, site, twosite != 0, (size_t)M, seed);
         oracle::OracleEngine orc(P.params.symm);
@@ -608,6 +608,25 @@ extern "C" int qcmt_desc_parity(const char* fcidump, const char* symm, int L, in
                 Boundary ref = dir == 0 ? orc.overlap_mpo_left_step(S.psi, S.psi, S.left, *S.mpo) : orc.overlap_mpo_right_step(S.psi, S.psi, S.right, *S.mpo);
                 DiffReport d = compare(got, ref);
                 out[2 + 2 * dir] = d.structure_equal; out[3 + 2 * dir] = rel_diff(d);
+                qcm_array_free(aO); qcm_plan_destroy(plan);
+            }
+        if (!twosite)      // noise term through the descriptor entry points (kept blocks = those of the tensor's own structure)
+            for (int dir = 0; dir < 2; ++dir) {
+                qcm_plan_t plan = nullptr;
+                if (dir == 0) ck(qcm_plan_noise_left(m, &ft.d, &fl.d, 0, &plan), "qcm_plan_noise_left");
+                else ck(qcm_plan_noise_right(m, &ft.d, &fr.d, 0, &plan), "qcm_plan_noise_right");
+                std::vector<int64_t> ptr, off; std::vector<qcm_block> blocks; int64_t n = 0;
+                fetch(plan, ptr, blocks, off, n);
+                if (ptr.size() != 2) throw std::runtime_error("noise plan: expected one bond entry");
+                qcm_array_t aO = nullptr; ck(qcm_array_alloc(n, &aO), "alloc");
+                ck(qcm_boundary_step(plan, dir == 0 ? aL : aR, ft.data.data(), ft.data.data(), aO), "qcm_boundary_step (noise)");
+                std::vector<double> flat((size_t)n); ck(qcm_array_download(aO, 0, flat.data(), n), "download");
+                block_matrix got = qcmflat::unflatten(blocks, off, ptr[0], ptr[1], flat.data());
+                block_matrix ref = dir == 0 ? orc.noise_left(S.psi, S.left, *S.mpo) : orc.noise_right(S.psi, S.right, *S.mpo);
+                if (dir == 0) S.psi.make_left_paired(); else S.psi.make_right_paired();
+                DualIndex keep = S.psi.data().basis();
+                DiffReport d = compare(ts::noise_kept(got, keep), ts::noise_kept(ref, keep));
+                out[6] += d.structure_equal; out[7] = std::max(out[7], rel_diff(d));
                 qcm_array_free(aO); qcm_plan_destroy(plan);
             }
         qcm_array_free(aL); qcm_array_free(aR); qcm_mpo_free(m);

@@ -20,6 +20,7 @@ def test_plans_built_from_descriptors_match_the_oracle(harness_gpu, symm, site, 
     assert out[0] == 1 and out[1] < TOL, list(out)
     if not twosite:
         assert out[2] == 1 and out[3] < TOL and out[4] == 1 and out[5] < TOL, list(out)
+        assert out[6] == 2 and out[7] < TOL, list(out)        # qcm_plan_noise_left / qcm_plan_noise_right
 
 
 def test_descriptor_plan_at_config1_size(harness_gpu, fcidump_8o8e):
