@@ -285,7 +285,8 @@ extern "C" int qcmd_ts_sweeps_synth(void* h, int M, int nsweeps, unsigned seed, 
         if (getenv("QCM_DEBUG")) {
             double* ss = ts::split_seconds();
             fprintf(stderr, "[rank %d] split seconds: block SVDs %.2f | combination across ranks %.2f | truncation %.2f | whole split incl. the former (reshapes, recoupling) %.2f | "
-                            "normalisation + shift %.2f ; device solver host syncs %zu\n", rank, ss[0], ss[1], ss[2], ss[3], ss[4], eng.host_syncs);
+                            "normalisation + shift %.2f ; device solver host syncs %zu ; boundary steps: allocation %.2f flatten %.2f\n", rank, ss[0], ss[1], ss[2], ss[3], ss[4], eng.host_syncs,
+                    eng.detail_seconds[0], eng.detail_seconds[1]);
         }
         return 0;
     } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }

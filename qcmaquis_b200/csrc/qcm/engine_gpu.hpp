@@ -430,6 +430,8 @@ public:
     // host-side time spent in this engine, by kind (seconds): [0] planning (Planner) [1] plan upload (qcm_plan_create)
     // [2] sigma calls (H2D + kernels + D2H) [3] boundary-step calls [4] flatten / unflatten
     double seconds[5] = {0, 0, 0, 0, 0};
+    // development aid (printed by the drivers under QCM_DEBUG): [0] allocation of the new boundary [1] flattening of bra / ket in the boundary steps
+    double detail_seconds[4] = {0, 0, 0, 0};
     // algorithmic FLOPs (schedule-derived, this rank's share) of the sigma evaluations / boundary steps executed so far
     double sigma_flops = 0, boundary_flops = 0;
     size_t n_sigma_calls = 0, n_boundary_calls = 0;
@@ -518,8 +520,9 @@ private:
         std::shared_ptr<DeviceBoundary> dout(new DeviceBoundary());
         dout->layout = cp->out_boundary;
         qcm_check(qcm_array_alloc(dout->layout.total, &dout->arr), "qcm_array_alloc");
+        { double s = c0.lap(); seconds[4] += s; detail_seconds[0] += s; }
         std::vector<double> bra = flatten(bra_tensor.data(), cp->bra_elems), ket = flatten(ket_tensor.data(), cp->ket_elems);
-        seconds[4] += c0.lap();
+        { double s = c0.lap(); seconds[4] += s; detail_seconds[1] += s; }
         qcm_check(qcm_boundary_step(cp->handle, din->arr, bra.data(), ket.data(), dout->arr), "qcm_boundary_step");
         boundary_flops += cp->flops; ++n_boundary_calls;
         seconds[3] += c0.lap();

@@ -802,3 +802,23 @@ extern "C" int qcmt_overlap_parity(const char* fcidump, const char* symm, int L,
         return 0;
     } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
 }
+
+// single-site sweeps from a random MPS of bond dimension M0 with the noise-perturbed subspace expansion (alpha > 0) or the plain
+// QR normalisation (alpha = 0); info as qcmt_ss_dmrg
+extern "C" int qcmt_ss_dmrg_noise(const char* fcidump, const char* symm, int L, int nelec, int M0, int Mmax, int nsweeps, unsigned seed, int engine_kind,
+                                  double alpha, double cutoff, double* energies, int n_max, int* n_out, double* info, char* err, int errlen)
+{
+    try {
+        Problem P = make_problem(fcidump, symm, L, nelec);
+        P.init_mps((size_t)M0, true, 0., seed);
+        std::unique_ptr<EngineIface> eng = make_engine(P.params.symm, engine_kind);
+        sweep::SweepLog log = alpha != 0. ? sweep::ss_sweeps(*eng, P.mpo, P.mps, nsweeps, 10, 1e-8, ts::NoiseGrow{*eng, alpha, cutoff, (size_t)Mmax, nullptr})
+                                          : sweep::ss_sweeps(*eng, P.mpo, P.mps, nsweeps);
+        int n = (int)std::min<size_t>(log.energies.size(), (size_t)n_max);
+        for (int i = 0; i < n; ++i) energies[i] = log.energies[i];
+        *n_out = n;
+        double secs = 0; for (double s : log.sweep_seconds) secs += s;
+        info[0] = (double)log.total_sigma; info[1] = secs; info[2] = log.energies.back(); info[3] = 2.0 * L;
+        return 0;
+    } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
+}
