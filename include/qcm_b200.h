@@ -143,7 +143,9 @@ int qcm_plan_stats(qcm_plan_t p, double* flops, int64_t* bytes, int64_t* n_launc
  * qcm_boundary_step      replaces Engine::overlap_mpo_left_step / overlap_mpo_right_step
  *                        (abelian/engine.hpp:102-122; common/move_boundary.hpp:128-229); `in` is the old
  *                        boundary, `out` the new one (device resident, zeroed and filled by the call);
- *                        bra/ket are host buffers (left-paired blocks). */
+ *                        bra/ket are host buffers (left-paired blocks), consumed before the call returns.  The
+ *                        step itself is queued: `out` is complete for every later call of this library and for
+ *                        qcm_array_download (stream order); call qcm_sync() to wait for it explicitly. */
 int qcm_site_hamil2(qcm_plan_t p, qcm_array_t left, qcm_array_t right, const double* psi, double* sigma);
 int qcm_site_hamil2_dev(qcm_plan_t p, qcm_array_t left, qcm_array_t right, qcm_array_t psi, qcm_array_t sigma);
 int qcm_boundary_step(qcm_plan_t p, qcm_array_t in, const double* bra, const double* ket, qcm_array_t out);

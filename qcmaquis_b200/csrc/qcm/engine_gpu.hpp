@@ -47,16 +47,65 @@ struct SpillPool
     ~SpillPool() { for (auto& e : free_list) qcm_pinned_free(e.second); }
 };
 
+// Device arrays of boundaries the sweep has dropped, kept for the boundaries it creates next.  A sweep frees one boundary and
+// allocates one of nearly the same size at every site (the stale one at a bond makes room for the new one at the same bond);
+// asking the device pool for gigabytes of a slightly different size each time cost 50-100 ms per site
+// (profiles/r02n: 15 s of a 128 s cfg3 sweep).  Arrays are requested in size classes of 1/8 octave so that the one just given
+// back fits; all device work is ordered on the library's stream, so a recycled array can be handed out at once.
+struct ArrayRecycler
+{
+    std::vector<std::pair<int64_t, qcm_array_t>> kept;     // (capacity in elements, array)
+    size_t max_kept = 3;
+    static int64_t size_class(int64_t n)
+    {
+        if (n < ((int64_t)1 << 23)) return n;               // below 64 MB: exact
+        int64_t gran = (int64_t)1 << 20;
+        while ((gran << 4) <= n) gran <<= 1;                // 1/8 .. 1/16 of the size
+        return (n + gran - 1) / gran * gran;
+    }
+    qcm_array_t take(int64_t n)
+    {
+        size_t best = kept.size();
+        for (size_t i = 0; i < kept.size(); ++i)
+            if (kept[i].first >= n && kept[i].first <= n + n / 4 + 1024 && (best == kept.size() || kept[i].first < kept[best].first)) best = i;
+        if (best != kept.size()) { qcm_array_t a = kept[best].second; kept.erase(kept.begin() + (long)best); ++hits; return a; }
+        ++misses;
+        qcm_array_t a = nullptr;
+        if (qcm_array_alloc(size_class(n), &a) != 0) {
+            clear();                                        // memory is short: give everything back and ask for the exact size
+            if (qcm_array_alloc(n, &a) != 0) throw std::runtime_error(std::string("qcm_array_alloc: ") + qcm_last_error());
+        }
+        return a;
+    }
+    void give(qcm_array_t a)
+    {
+        int64_t cap = 0;
+        int resident = 0;
+        if (!a) return;
+        if (qcm_array_size(a, &cap) != 0 || qcm_array_resident(a, &resident) != 0 || !resident || cap < ((int64_t)1 << 23)) { qcm_array_free(a); return; }
+        kept.push_back(std::make_pair(cap, a));
+        while (kept.size() > max_kept) {                    // the smallest goes
+            size_t m = 0;
+            for (size_t i = 1; i < kept.size(); ++i) if (kept[i].first < kept[m].first) m = i;
+            qcm_array_free(kept[m].second); kept.erase(kept.begin() + (long)m);
+        }
+    }
+    void clear() { for (auto& e : kept) qcm_array_free(e.second); kept.clear(); }
+    size_t hits = 0, misses = 0;
+    ~ArrayRecycler() { clear(); }
+};
+
 struct DeviceBoundary
 {
     qcm_array_t arr = nullptr;
     plan::BoundaryLayout layout;
     double* spill = nullptr; int64_t spill_cap = 0;     // pinned host copy while the boundary is evicted from HBM
     std::shared_ptr<SpillPool> pool;
+    std::shared_ptr<ArrayRecycler> recycler;            // set for boundaries a GpuEngine produced: the array goes back there
     bool evicted = false;
     ~DeviceBoundary()
     {
-        if (arr) qcm_array_free(arr);
+        if (arr) { if (recycler && !evicted) recycler->give(arr); else qcm_array_free(arr); }
         if (spill) { if (evicted) qcm_sync(); if (pool) pool->give(spill, spill_cap); else qcm_pinned_free(spill); }
     }
     // 64-bit hash of the block structure (charges and sizes of every block of every bond entry): a plan depends on the
@@ -292,7 +341,9 @@ public:
     {
         std::shared_ptr<DeviceBoundary> d = std::static_pointer_cast<DeviceBoundary>(b.device_mirror);
         if (!d || d->evicted || d->layout.total == 0) return;
-        if (!d->spill) { d->pool = spill_pool; d->spill = spill_pool->take(d->layout.total, d->spill_cap); }
+        int64_t held = 0;                       // a recycled array may be larger than the boundary: the copy moves all of it
+        qcm_check(qcm_array_size(d->arr, &held), "qcm_array_size");
+        if (!d->spill) { d->pool = spill_pool; d->spill = spill_pool->take(std::max(held, d->layout.total), d->spill_cap); }
         qcm_check(qcm_array_evict(d->arr, d->spill), "qcm_array_evict");
         d->evicted = true; ++n_evicted;
     }
@@ -305,6 +356,7 @@ public:
     }
     size_t n_evicted = 0, n_prefetched = 0;
     std::shared_ptr<SpillPool> spill_pool{new SpillPool()};
+    std::shared_ptr<ArrayRecycler> recycler{new ArrayRecycler()};
 
     // ---- host-side collectives of a sharded sweep (EngineIface) --------------------------------------------------------
     int comm_rank() const override { return rank; }
@@ -437,21 +489,30 @@ public:
     size_t n_sigma_calls = 0, n_boundary_calls = 0;
     std::shared_ptr<CompiledPlan> last_plan() const { return last; }
 
+    // blocks <-> one flat array (blocks back to back in DualIndex order); the copies run block-parallel on the host cores
     static std::vector<double> flatten(block_matrix const& m, int64_t expect)
     {
-        std::vector<double> flat; flat.reserve((size_t)expect);
-        for (size_t k = 0; k < m.n_blocks(); ++k) flat.insert(flat.end(), m[k].v.begin(), m[k].v.end());
-        if ((int64_t)flat.size() != expect) throw std::runtime_error("GpuEngine: tensor data does not match the planned structure");
+        std::vector<size_t> off(m.n_blocks() + 1, 0);
+        for (size_t k = 0; k < m.n_blocks(); ++k) off[k + 1] = off[k] + m[k].v.size();
+        if ((int64_t)off.back() != expect) throw std::runtime_error("GpuEngine: tensor data does not match the planned structure");
+        std::vector<double> flat(off.back());
+        double* p = flat.data();
+#pragma omp parallel for schedule(dynamic, 1) if (off.back() > (size_t)1 << 18)
+        for (long k = 0; k < (long)m.n_blocks(); ++k) std::memcpy(p + off[(size_t)k], m[(size_t)k].v.data(), m[(size_t)k].v.size() * sizeof(double));
         return flat;
     }
     static block_matrix unflatten(plan::Layout const& L, std::vector<double> const& flat)
     {
-        block_matrix r;
-        for (size_t k = 0; k < L.basis.size(); ++k) {
-            Matrix m(L.basis[k].ls, L.basis[k].rs);
-            std::copy(flat.begin() + L.off[k], flat.begin() + L.off[k] + m.v.size(), m.v.begin());
-            r.insert_block(std::move(m), L.basis[k].lc, L.basis[k].rc);
+        const size_t nb = L.basis.size();
+        std::vector<Matrix> ms(nb);
+#pragma omp parallel for schedule(dynamic, 1) if (flat.size() > (size_t)1 << 18)
+        for (long k = 0; k < (long)nb; ++k) {
+            Matrix m = Matrix::shell(L.basis[(size_t)k].ls, L.basis[(size_t)k].rs);
+            m.v.assign(flat.begin() + L.off[(size_t)k], flat.begin() + L.off[(size_t)k] + (size_t)m.rows * m.cols);
+            ms[(size_t)k] = std::move(m);
         }
+        block_matrix r;
+        for (size_t k = 0; k < nb; ++k) r.insert_block(std::move(ms[k]), L.basis[k].lc, L.basis[k].rc);
         return r;
     }
     static plan::TensorDesc desc_of(MPSTensor const& t)
@@ -519,11 +580,15 @@ private:
         last = cp;
         std::shared_ptr<DeviceBoundary> dout(new DeviceBoundary());
         dout->layout = cp->out_boundary;
-        qcm_check(qcm_array_alloc(dout->layout.total, &dout->arr), "qcm_array_alloc");
+        dout->recycler = recycler;
+        dout->arr = recycler->take(dout->layout.total);
         { double s = c0.lap(); seconds[4] += s; detail_seconds[0] += s; }
-        std::vector<double> bra = flatten(bra_tensor.data(), cp->bra_elems), ket = flatten(ket_tensor.data(), cp->ket_elems);
+        // the sweep drivers move the boundary with bra == ket (one tensor): flattened once
+        const bool same = &bra_tensor == &ket_tensor;
+        std::vector<double> ket = flatten(ket_tensor.data(), cp->ket_elems), bra;
+        if (!same) bra = flatten(bra_tensor.data(), cp->bra_elems);
         { double s = c0.lap(); seconds[4] += s; detail_seconds[1] += s; }
-        qcm_check(qcm_boundary_step(cp->handle, din->arr, bra.data(), ket.data(), dout->arr), "qcm_boundary_step");
+        qcm_check(qcm_boundary_step(cp->handle, din->arr, same ? ket.data() : bra.data(), ket.data(), dout->arr), "qcm_boundary_step");
         boundary_flops += cp->flops; ++n_boundary_calls;
         seconds[3] += c0.lap();
         Boundary ret; ret.resize(dout->layout.aux_dim());

@@ -206,6 +206,7 @@ struct qcm_plan_s
     double flops = 0; int64_t bytes = 0;
     int64_t n_launches = 0;
     std::vector<void*> allocs;
+    std::vector<size_t> alloc_caps;       // capacity of allocs[i] when it is a recyclable task buffer (flush_uploads)
     // task arrays are staged in the library's pinned buffer while the plan is built and go to the device in ONE allocation and one copy
     int64_t task_bytes = 0;
     struct PendingPtr { void** where; size_t offset; };
@@ -358,7 +359,8 @@ extern "C" int qcm_array_alloc(int64_t n, qcm_array_t* out)
     if (n > 0) {
         // stream-ordered allocation from the device's default pool (its release threshold is raised in qcm_init): boundaries
         // and solver vectors come and go at every site of a sweep without a device-wide synchronisation
-        cudaError_t e = cudaMallocAsync((void**)&a->p, (size_t)n * sizeof(double), G.stream);
+        const size_t bytes = (size_t)n * sizeof(double);
+        cudaError_t e = cudaMallocAsync((void**)&a->p, bytes, G.stream);
         if (e != cudaSuccess) {
             cudaGetLastError();
             cudaStreamSynchronize(G.stream);
@@ -525,6 +527,8 @@ static int variant_for(int hr, int hc)
 // pageable staging, and the large arrays (the W coefficient tables, 0.4 GB for a cfg3 centre site) are copied exactly once
 // on the host, by several threads.
 static struct PinnedStage { char* p = nullptr; size_t cap = 0, used = 0; } g_pin;
+static std::vector<std::pair<char*, size_t>> g_task_bufs;      // device buffers of destroyed plans, kept for the next plans (at most kTaskBufsKept)
+constexpr size_t kTaskBufsKept = 3;
 static int pin_reserve(size_t need)
 {
     if (need <= g_pin.cap) return 0;
@@ -567,15 +571,32 @@ static int flush_uploads(qcm_plan_s* P)
 {
     if (g_pin.used == 0) return 0;
     char* base = nullptr;
-    // stream-ordered like the arrays: a sweep creates and destroys two plans per site
-    cudaError_t em = cudaMallocAsync((void**)&base, g_pin.used, G.stream);
-    if (em != cudaSuccess) {
-        cudaGetLastError();
-        cudaStreamSynchronize(G.stream);
-        cudaMemPool_t pool; if (cudaDeviceGetDefaultMemPool(&pool, G.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
-        CU(cudaMallocAsync((void**)&base, g_pin.used, G.stream));
+    // A sweep creates and destroys two plans per site.  Their task buffers are recycled (g_task_bufs: the buffer of a destroyed plan
+    // serves the next plan that fits; all use is ordered on the library's stream) -- asking the device pool for half a gigabyte of a
+    // new size at every site costs tens of milliseconds each time.
+    size_t cap = 0;
+    {
+        size_t best = g_task_bufs.size();
+        for (size_t i = 0; i < g_task_bufs.size(); ++i)
+            if (g_task_bufs[i].second >= g_pin.used && g_task_bufs[i].second <= 4 * g_pin.used + ((size_t)16 << 20) &&
+                (best == g_task_bufs.size() || g_task_bufs[i].second < g_task_bufs[best].second)) best = i;
+        if (best != g_task_bufs.size()) { base = g_task_bufs[best].first; cap = g_task_bufs[best].second; g_task_bufs.erase(g_task_bufs.begin() + (long)best); }
+    }
+    if (!base) {
+        cap = g_pin.used + g_pin.used / 4;
+        cudaError_t em = cudaMallocAsync((void**)&base, cap, G.stream);
+        if (em != cudaSuccess) {
+            cudaGetLastError();
+            cudaStreamSynchronize(G.stream);
+            for (auto& b : g_task_bufs) cudaFree(b.first);
+            g_task_bufs.clear();
+            cudaMemPool_t pool; if (cudaDeviceGetDefaultMemPool(&pool, G.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+            cap = g_pin.used;
+            CU(cudaMallocAsync((void**)&base, cap, G.stream));
+        }
     }
     P->allocs.push_back(base);
+    P->alloc_caps.push_back(cap);
     P->task_bytes = (int64_t)g_pin.used;
     CU(cudaMemcpyAsync(base, g_pin.p, g_pin.used, cudaMemcpyHostToDevice, G.stream));
     CU(cudaStreamSynchronize(G.stream));
@@ -837,7 +858,19 @@ extern "C" int qcm_plan_destroy(qcm_plan_t P)
     if (!P) return 0;
     qcm_internal_forget_plan(P);
     // the task arrays are released in stream order: kernels of this plan that are still queued finish first
-    for (void* p : P->allocs) { if (G.ready) cudaFreeAsync(p, G.stream); else cudaFree(p); }
+    for (size_t i = 0; i < P->allocs.size(); ++i) {
+        void* p = P->allocs[i];
+        const size_t cap = i < P->alloc_caps.size() ? P->alloc_caps[i] : 0;
+        if (G.ready && cap > 0) {
+            g_task_bufs.push_back(std::make_pair((char*)p, cap));
+            if (g_task_bufs.size() > kTaskBufsKept) {       // drop the smallest
+                size_t m = 0;
+                for (size_t j = 1; j < g_task_bufs.size(); ++j) if (g_task_bufs[j].second < g_task_bufs[m].second) m = j;
+                cudaFreeAsync(g_task_bufs[m].first, G.stream);
+                g_task_bufs.erase(g_task_bufs.begin() + (long)m);
+            }
+        } else if (G.ready) cudaFreeAsync(p, G.stream); else cudaFree(p);
+    }
     delete P;
     return 0;
 }
@@ -1120,7 +1153,10 @@ extern "C" int qcm_boundary_step(qcm_plan_t P, qcm_array_t in, const double* bra
     if (execute(P, b)) return 1;
     // every rank computed its share of the output bond indices into a zeroed array: the sum is the full boundary
     if (P->world > 1 && allreduce_ptr(out->p, P->elems[QCM_BUF_OUT])) return 1;
-    CU(cudaStreamSynchronize(G.stream));
+    // The step is QUEUED, not awaited: `out` stays on the device and every later use of it (the next sigma, the next boundary step,
+    // qcm_array_download) is ordered behind it on the library's stream, so the host goes on to plan the next site while the device
+    // works.  (bra / ket were pageable host memory: cudaMemcpyAsync has staged them before returning.)
+    if (G.timing) CU(cudaStreamSynchronize(G.stream));
     return 0;
 }
 
