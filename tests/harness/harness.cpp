@@ -822,3 +822,55 @@ extern "C" int qcmt_ss_dmrg_noise(const char* fcidump, const char* symm, int L, 
         return 0;
     } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
 }
+
+// A hand-made plan at the task-array level of the C ABI (qcm_plan_create): one STORE-mode step-1 output whose K-segment list is
+// longer than 96 K-chunks (K = 1600 + 300 + 200: the situation of an SU2 site whose leading sector passes ~1.5k rows; store-mode
+// outputs must run their whole K list in one work item) feeding one ACCUMULATING closing output whose list (K = 1000 + 400 + 300) is
+// split and combined with FP64 atomics.  sigma = (A^T psi) R, checked against host dgemm.
+// out[0] max rel error of sigma  out[1] |sigma|_max
+extern "C" int qcmt_long_k_plan(double* out, char* err, int errlen)
+{
+    try {
+#ifdef QCMT_WITH_GPU
+        auto ck = [](int rc, const char* what) { if (rc != 0) throw std::runtime_error(std::string(what) + ": " + qcm_last_error()); };
+        ck(qcm_init(0), "qcm_init");
+        const int m = 96, n = 1700, n2 = 64, ks[3] = {1600, 300, 200}, K = 2100, cs[3] = {1000, 400, 300};
+        UniformGen gen(123);
+        std::vector<double> A((size_t)K * m), psi((size_t)K * n), R((size_t)n * n2);
+        for (double& x : A) x = gen() - 0.5; for (double& x : psi) x = gen() - 0.5; for (double& x : R) x = gen() - 0.5;
+        // step 1 (persistent group, QCM_BUF_TP): T(m x n) = sum over K slices of A[k0:k0+k, :]^T psi[k0:k0+k, :]
+        std::vector<qcm_gemm_seg> ps, cseg; std::vector<qcm_gemm_out> po(1), co(1);
+        int k0 = 0;
+        for (int s = 0; s < 3; ++s) { ps.push_back(qcm_gemm_seg{qcm_ref{QCM_BUF_LEFT, 0, k0}, qcm_ref{QCM_BUF_KET_LP, 0, k0}, K, K, m, n, ks[s], 1, 0, 0, 1.0}); k0 += ks[s]; }
+        po[0] = qcm_gemm_out{qcm_ref{QCM_BUF_TP, 0, 0}, m, m, n, 0, 3, 0};
+        // step 3: sigma(m x n2) += T[:, c0:c0+c] R[c0:c0+c, :]
+        int c0 = 0;
+        for (int s = 0; s < 3; ++s) { cseg.push_back(qcm_gemm_seg{qcm_ref{QCM_BUF_TP, 0, (int64_t)c0 * m}, qcm_ref{QCM_BUF_RIGHT, 0, c0}, m, n, m, n2, cs[s], 0, 0, 0, 1.0}); c0 += cs[s]; }
+        co[0] = qcm_gemm_out{qcm_ref{QCM_BUF_OUT, 0, 0}, m, m, n2, 0, 3, 0};
+        qcm_wave_desc w; std::memset(&w, 0, sizeof(w));
+        w.c_outs = co.data(); w.n_c_outs = 1; w.c_segs = cseg.data(); w.n_c_segs = 3;
+        qcm_plan_desc d; std::memset(&d, 0, sizeof(d));
+        d.kind = 0; d.n_waves = 1; d.waves = &w; d.p_outs = po.data(); d.n_p_outs = 1; d.p_segs = ps.data(); d.n_p_segs = 3;
+        d.elems[QCM_BUF_KET_LP] = (int64_t)K * n; d.elems[QCM_BUF_LEFT] = (int64_t)K * m; d.elems[QCM_BUF_RIGHT] = (int64_t)n * n2;
+        d.elems[QCM_BUF_TP] = (int64_t)m * n; d.elems[QCM_BUF_OUT] = (int64_t)m * n2;
+        d.flops = 2.0 * m * n * K + 2.0 * m * n2 * n; d.world = 1;
+        qcm_plan_t plan = nullptr; ck(qcm_plan_create(&d, &plan), "qcm_plan_create");
+        qcm_array_t aL = nullptr, aR = nullptr;
+        ck(qcm_array_alloc((int64_t)A.size(), &aL), "alloc"); ck(qcm_array_upload(aL, 0, A.data(), (int64_t)A.size()), "upload");
+        ck(qcm_array_alloc((int64_t)R.size(), &aR), "alloc"); ck(qcm_array_upload(aR, 0, R.data(), (int64_t)R.size()), "upload");
+        std::vector<double> sigma((size_t)m * n2, 0.);
+        for (int rep = 0; rep < 2; ++rep) ck(qcm_site_hamil2(plan, aL, aR, psi.data(), sigma.data()), "qcm_site_hamil2");     // twice: the output is re-zeroed per call
+        std::vector<double> T((size_t)m * n), ref((size_t)m * n2);
+        dgemm(MatRef{A.data(), (size_t)m, (size_t)K, (size_t)K, true}, MatRef{psi.data(), (size_t)K, (size_t)n, (size_t)K, false}, 1.0, 0.0, T.data(), (size_t)m);
+        dgemm(MatRef{T.data(), (size_t)m, (size_t)n, (size_t)m, false}, MatRef{R.data(), (size_t)n, (size_t)n2, (size_t)n, false}, 1.0, 0.0, ref.data(), (size_t)m);
+        double dmax = 0, rmax = 0;
+        for (size_t i = 0; i < ref.size(); ++i) { dmax = std::max(dmax, std::abs(sigma[i] - ref[i])); rmax = std::max(rmax, std::abs(ref[i])); }
+        out[0] = dmax / rmax; out[1] = rmax;
+        qcm_plan_destroy(plan); qcm_array_free(aL); qcm_array_free(aR);
+        return 0;
+#else
+        (void)out;
+        throw std::runtime_error("harness built without GPU support");
+#endif
+    } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
+}

@@ -286,3 +286,12 @@ def test_time_sliced_shards_match_the_oracle(harness_gpu, monkeypatch, symm, M, 
     monkeypatch.setenv("QCM_SLICES", str(slices))
     out = harness_gpu.synth_parity(path.encode(), symm, 12, 12, 5, True, M, engine=GPU)
     assert out[0] == 1 and out[1] < TOL, out[:4]
+
+
+def test_store_mode_output_with_a_long_k_list(harness_gpu):
+    """Task-array level of the C ABI: a step-1 (store-mode) output whose K-segment list exceeds 96 K-chunks must run in one work
+    item (an SU2 site whose leading sector passes ~1.5k rows), an accumulating output of the same length is split and combined
+    with FP64 atomics -- both against host dgemm."""
+    out = (ctypes.c_double * 2)(); err = ctypes.create_string_buffer(1024)
+    assert harness_gpu.lib.qcmt_long_k_plan(out, err, 1024) == 0, err.value.decode()
+    assert out[0] < 1e-12 and out[1] > 1.0, list(out)
