@@ -253,6 +253,7 @@ static struct Global
 
 static int gemm_set_attributes();
 static int wgemm_set_attributes();
+static void release_task_bufs();      // recycled task buffers of destroyed plans (plan construction, below)
 static int ensure_ws(int slot, int64_t n)
 {
     if (n <= G.ws_elems[slot]) return 0;
@@ -263,6 +264,7 @@ static int ensure_ws(int slot, int64_t n)
         cudaGetLastError();
         want = n;
         cudaStreamSynchronize(G.stream);
+        release_task_bufs();
         cudaMemPool_t pool; if (cudaDeviceGetDefaultMemPool(&pool, G.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
         e = cudaMalloc((void**)&G.ws[slot], (size_t)want * sizeof(double));
         if (e != cudaSuccess) return fail("workspace allocation of " + std::to_string(n * 8) + " bytes failed: " + cudaGetErrorString(e));
@@ -309,6 +311,7 @@ extern "C" int qcm_finalize(void)
 {
     if (!G.ready) return 0;
     cudaStreamSynchronize(G.stream);
+    release_task_bufs();
     for (int i = 0; i < QCM_BUF_COUNT; ++i) if (G.ws[i]) { cudaFree(G.ws[i]); G.ws[i] = nullptr; G.ws_elems[i] = 0; }
     if (G.scratch) cudaFree(G.scratch);
     G.scratch = nullptr;
@@ -364,6 +367,7 @@ extern "C" int qcm_array_alloc(int64_t n, qcm_array_t* out)
         if (e != cudaSuccess) {
             cudaGetLastError();
             cudaStreamSynchronize(G.stream);
+            release_task_bufs();
             cudaMemPool_t pool; if (cudaDeviceGetDefaultMemPool(&pool, G.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
             e = cudaMallocAsync((void**)&a->p, (size_t)n * sizeof(double), G.stream);
         }
@@ -529,6 +533,11 @@ static int variant_for(int hr, int hc)
 static struct PinnedStage { char* p = nullptr; size_t cap = 0, used = 0; } g_pin;
 static std::vector<std::pair<char*, size_t>> g_task_bufs;      // device buffers of destroyed plans, kept for the next plans (at most kTaskBufsKept)
 constexpr size_t kTaskBufsKept = 3;
+static void release_task_bufs()
+{
+    for (auto& b : g_task_bufs) cudaFree(b.first);
+    g_task_bufs.clear();
+}
 static int pin_reserve(size_t need)
 {
     if (need <= g_pin.cap) return 0;
@@ -588,8 +597,7 @@ static int flush_uploads(qcm_plan_s* P)
         if (em != cudaSuccess) {
             cudaGetLastError();
             cudaStreamSynchronize(G.stream);
-            for (auto& b : g_task_bufs) cudaFree(b.first);
-            g_task_bufs.clear();
+            release_task_bufs();
             cudaMemPool_t pool; if (cudaDeviceGetDefaultMemPool(&pool, G.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
             cap = g_pin.used;
             CU(cudaMallocAsync((void**)&base, cap, G.stream));
