@@ -44,6 +44,34 @@ inline void reshape_left_to_right_new(Index const& physical_i, Index const& left
     }
 }
 
+// left-paired m1 over (in_left_i, in_right_i) copied into the (larger) left-paired structure of m2 over (out_left_i, out_right_i),
+// everything else of m2 zeroed   (reshapes.h:228-281 reshape_and_pad_left; used by site_ortho_boundaries)
+inline void reshape_and_pad_left(Index const& physical_i, Index const& in_left_i, Index const& in_right_i, Index const& out_left_i,
+                                 Index const& /*out_right_i*/, block_matrix const& m1, block_matrix& m2)
+{
+    m2 *= 0.;
+    ProductBasis in_left(physical_i, in_left_i);
+    ProductBasis out_left(physical_i, out_left_i);
+    for (size_t block = 0; block < m1.n_blocks(); ++block)
+        for (size_t s = 0; s < physical_i.size(); ++s) {
+            size_t r = in_right_i.position(m1.basis().right_charge(block));
+            if (r == in_right_i.size()) continue;
+            size_t l = in_left_i.position(fuse(m1.basis().left_charge(block), -physical_i[s].first));
+            if (l == in_left_i.size()) continue;
+            Charge l_charge = fuse(physical_i[s].first, in_left_i[l].first), r_charge = in_right_i[r].first;
+            if (!out_left_i.has(in_left_i[l].first)) continue;
+            if (!m1.has_block(l_charge, r_charge) || !m2.has_block(l_charge, r_charge)) continue;
+            size_t in_left_offset = in_left(physical_i[s].first, in_left_i[l].first);
+            size_t out_left_offset = out_left(physical_i[s].first, in_left_i[l].first);
+            Matrix const& in_block = m1(l_charge, r_charge);
+            Matrix& out_block = m2(l_charge, r_charge);
+            const size_t ldim = in_left_i[l].second;
+            for (size_t ss = 0; ss < physical_i[s].second; ++ss)
+                for (size_t rr = 0; rr < in_right_i[r].second; ++rr)
+                    for (size_t ll = 0; ll < ldim; ++ll) out_block(out_left_offset + ss * ldim + ll, rr) = in_block(in_left_offset + ss * ldim + ll, rr);
+        }
+}
+
 // [left, (-phys, right)] --> [(phys, left), right]   (reshapes.h:289-335)
 inline void reshape_right_to_left_new(Index const& physical_i, Index const& left_i, Index const& right_i,
                                       block_matrix const& m1, block_matrix& m2)

@@ -12,6 +12,7 @@
 // the engine.
 #pragma once
 #include "engine_iface.hpp"
+#include "overlap.hpp"
 #include <chrono>
 #include <exception>
 #ifdef _OPENMP
@@ -197,15 +198,60 @@ inline void axpy(MPSTensor& y, double a, MPSTensor const& x)       // y += a x, 
 }
 typedef EigenResult JDResult;
 
+// contraction::site_ortho_boundaries (contractions/abelian/special.hpp:16-46): the component of an orthogonal state inside the
+// variational space of the site being optimised,  o = ortho_left (x) ortho_mps (x) ortho_right^T, padded to the structure of mps.
+// ortho_left / ortho_right are the MPS-MPS overlap matrices kept by the sweep (optimize.h:105-117).
+inline MPSTensor site_ortho_boundaries(MPSTensor const& mps, MPSTensor const& ortho_mps, block_matrix const& ortho_left, block_matrix const& ortho_right)
+{
+    ortho_mps.make_right_paired();
+    block_matrix t, t2, t3;
+    gemm(ortho_left, ortho_mps.data(), t);
+    reshape_right_to_left_new(mps.site_dim(), ortho_left.left_basis(), ortho_mps.col_dim(), t, t2);
+    gemm(t2, transposed(ortho_right), t3);
+    mps.make_left_paired();
+    t = mps.data();
+    reshape_and_pad_left(mps.site_dim(), ortho_left.left_basis(), ortho_right.left_basis(), mps.row_dim(), mps.col_dim(), t3, t);
+    return MPSTensor(mps.site_dim(), mps.row_dim(), mps.col_dim(), t, LeftPaired);
+}
+// The local components of several orthogonal states are in general NOT orthogonal to each other, and the sequential projection of
+// SingleSiteVS::project is exact only for mutually orthogonal vectors (otherwise the solver's basis loses its orthonormality and the
+// Ritz values stop being variational -- seen here as energies below the full-CI ground state with two orthogonal states).  The
+// drivers therefore hand the solver an orthogonalised set spanning the same space (modified Gram-Schmidt; components that vanish
+// against the largest one are dropped).
+inline std::vector<MPSTensor> orthogonalised(std::vector<MPSTensor> vecs)
+{
+    std::vector<MPSTensor> out;
+    double largest = 0;
+    for (MPSTensor& v : vecs) { v.make_left_paired(); largest = std::max(largest, v.scalar_overlap(v)); }
+    for (MPSTensor& v : vecs) {
+        for (int pass = 0; pass < 2; ++pass)
+            for (MPSTensor const& o : out) axpy(v, -o.scalar_overlap(v) / o.scalar_overlap(o), o);
+        const double nn = v.scalar_overlap(v);
+        if (nn > 1e-20 * largest && nn > 1e-28) out.push_back(v);
+    }
+    return out;
+}
+// SingleSiteVS::project (optimize/ietl_lanczos_solver.h:90-95): t -= (o.t / o.o) o for every orthogonal vector
+inline void project(MPSTensor& t, std::vector<MPSTensor> const& ortho_vecs)
+{
+    for (MPSTensor const& o : ortho_vecs) {
+        const double oo = o.scalar_overlap(o);
+        if (oo > 1e-24) axpy(t, -o.scalar_overlap(t) / oo, o);       // a vanishing component has nothing to project out (and no direction)
+    }
+}
+
+// ortho_vecs: states the solution is kept orthogonal to (excited states: the vector space projects them out at the three points
+// of ietl/jacobi.h:378,393,432); with orthogonal states the recurrence runs on the host vectors, sigma through the engine
 inline JDResult jacobi_davidson(EngineIface& eng, MPSTensor const& x0, Boundary const& left, Boundary const& right, MPOTensor const& mpo,
-                                int max_iter, double tol)
+                                int max_iter, double tol, std::vector<MPSTensor> const& ortho_vecs = std::vector<MPSTensor>())
 {
     JDResult res;
-    if (eng.jacobi_davidson(x0, left, right, mpo, max_iter, tol, res)) return res;      // solver vectors kept on the device
+    if (ortho_vecs.empty() && eng.jacobi_davidson(x0, left, right, mpo, max_iter, tol, res)) return res;      // solver vectors kept on the device
     std::vector<MPSTensor> V(max_iter + 1), VA(max_iter);
     std::vector<double> M((size_t)max_iter * max_iter, 0.);
     const double kappa = 0.25;
     V[0] = x0; V[0].make_left_paired();
+    project(V[0], ortho_vecs);
     int it = 0;
     for (;;) {
         MPSTensor& t = V[it];
@@ -214,6 +260,7 @@ inline JDResult jacobi_davidson(EngineIface& eng, MPSTensor const& x0, Boundary 
         for (int i = 0; i < it; ++i) axpy(t, -V[i].scalar_overlap(t), V[i]);
         if (t.scalar_norm() < kappa * tau)
             for (int i = 0; i < it; ++i) axpy(t, -V[i].scalar_overlap(t), V[i]);
+        project(t, ortho_vecs);
         t.divide_by_scalar(t.scalar_norm());
         VA[it] = eng.site_hamil2(t, left, right, mpo);       // ietl::mult (y = H x; x.make_left_paired())
         VA[it].make_left_paired(); t.make_left_paired();
@@ -232,6 +279,7 @@ inline JDResult jacobi_davidson(EngineIface& eng, MPSTensor const& x0, Boundary 
         for (int j = 1; j <= it; ++j) axpy(u, s[j], V[j]);
         MPSTensor r = VA[0]; r.multiply_by_scalar(s[0]);
         for (int j = 1; j <= it; ++j) axpy(r, s[j], VA[j]);
+        project(r, ortho_vecs);
         axpy(r, -theta, u);
         ++it;
         const double rn = r.scalar_norm();
@@ -266,8 +314,13 @@ struct NoGrow
     bool operator()(int /*lr*/, int /*site*/, MPS& /*mps*/, MPOTensor const& /*mpo*/, Boundary const& /*left*/, Boundary const& /*right*/) const { return false; }
 };
 
+// States the optimised state is kept orthogonal to (excited-state DMRG: optimize.h:44-75 ortho_mps, :105-117 the overlap
+// boundaries ortho_left_ / ortho_right_ moved along with the sweep through Engine::overlap_left_step / overlap_right_step).
+struct OrthoStates { std::vector<MPS> states; bool su2 = false; };
+
 template <class Grow = NoGrow>
-inline SweepLog ss_sweeps(EngineIface& eng, MPO const& mpo, MPS& mps, int nsweeps, int jcd_maxiter = 10, double jcd_tol = 1e-8, Grow grow = Grow())
+inline SweepLog ss_sweeps(EngineIface& eng, MPO const& mpo, MPS& mps, int nsweeps, int jcd_maxiter = 10, double jcd_tol = 1e-8, Grow grow = Grow(),
+                          OrthoStates const* ortho = nullptr)
 {
     const int L = (int)mps.size();
     SweepLog log;
@@ -276,12 +329,25 @@ inline SweepLog ss_sweeps(EngineIface& eng, MPO const& mpo, MPS& mps, int nsweep
     left[0] = mps.left_boundary();
     right[L] = mps.right_boundary();
     for (int i = L - 1; i >= 0; --i) right[i] = eng.overlap_mpo_right_step(mps[i], mps[i], right[i + 1], mpo[i]);
+    const int northo = ortho ? (int)ortho->states.size() : 0;
+    std::vector<std::vector<block_matrix>> oleft((size_t)northo, std::vector<block_matrix>((size_t)L + 1)), oright = oleft;
+    for (int n = 0; n < northo; ++n) {
+        if ((int)ortho->states[(size_t)n].size() != L) throw std::runtime_error("ss_sweeps: orthogonal state of a different length");
+        oleft[(size_t)n][0] = mps.left_boundary()[0];
+        oright[(size_t)n][(size_t)L] = mps.right_boundary()[0];
+        for (int i = L - 1; i >= 0; --i)
+            oright[(size_t)n][(size_t)i] = overlap_right_step(eng, ortho->su2, mps[i], ortho->states[(size_t)n][(size_t)i], oright[(size_t)n][(size_t)i + 1]);
+    }
     for (int sweep = 0; sweep < nsweeps; ++sweep) {
         auto t0 = std::chrono::steady_clock::now();
         for (int _site = 0; _site < 2 * L; ++_site) {
             const int lr = _site < L ? +1 : -1;
             const int site = _site < L ? _site : 2 * L - _site - 1;
-            JDResult r = jacobi_davidson(eng, mps[site], left[site], right[site + 1], mpo[site], jcd_maxiter, jcd_tol);
+            std::vector<MPSTensor> ortho_vecs((size_t)northo);        // ss_optimize.hpp:107-111
+            for (int n = 0; n < northo; ++n)
+                ortho_vecs[(size_t)n] = site_ortho_boundaries(mps[site], ortho->states[(size_t)n][(size_t)site], oleft[(size_t)n][(size_t)site], oright[(size_t)n][(size_t)site + 1]);
+            if (northo > 1) ortho_vecs = orthogonalised(ortho_vecs);
+            JDResult r = jacobi_davidson(eng, mps[site], left[site], right[site + 1], mpo[site], jcd_maxiter, jcd_tol, ortho_vecs);
             mps[site] = r.vec;
             log.energies.push_back(r.theta + mpo.core_energy);
             log.n_sigma.push_back(r.n_sigma); log.total_sigma += r.n_sigma;
@@ -291,12 +357,16 @@ inline SweepLog ss_sweeps(EngineIface& eng, MPO const& mpo, MPS& mps, int nsweep
                     if (site < L - 1) multiply_from_left(mps[site + 1], t);
                 }
                 left[site + 1] = eng.overlap_mpo_left_step(mps[site], mps[site], left[site], mpo[site]);
+                for (int n = 0; n < northo; ++n)
+                    oleft[(size_t)n][(size_t)site + 1] = overlap_left_step(eng, ortho->su2, mps[site], ortho->states[(size_t)n][(size_t)site], oleft[(size_t)n][(size_t)site]);
             } else {
                 if (!(site > 0 && grow(-1, site, mps, mpo[site], left[site], right[site + 1]))) {
                     block_matrix t = normalize_right(mps[site]);
                     if (site > 0) multiply_from_right(mps[site - 1], t);
                 }
                 right[site] = eng.overlap_mpo_right_step(mps[site], mps[site], right[site + 1], mpo[site]);
+                for (int n = 0; n < northo; ++n)
+                    oright[(size_t)n][(size_t)site] = overlap_right_step(eng, ortho->su2, mps[site], ortho->states[(size_t)n][(size_t)site], oright[(size_t)n][(size_t)site + 1]);
             }
         }
         log.sweep_energy.push_back(log.energies.back());

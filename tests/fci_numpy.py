@@ -41,9 +41,9 @@ def _apply(op_list, det):
     return sign, det
 
 
-def fci_ground_state_energy(path, nup=None, ndown=None, total_spin=None):
-    """lowest energy in the (nup, ndown) sector; total_spin = 2S: lowest state of that total spin (what an SU2 run with spin = 2S
-    targets).  H = sum_pq [h_pq - 1/2 sum_r (pr|rq)] E_pq + 1/2 sum_pqrs (pq|rs) E_pq E_rs with the spin-summed excitation
+def fci_ground_state_energy(path, nup=None, ndown=None, total_spin=None, n_states=1):
+    """lowest energy in the (nup, ndown) sector (n_states > 1: the n_states lowest, as a list); total_spin = 2S: lowest state(s) of that
+    total spin (what an SU2 run with spin = 2S targets).  H = sum_pq [h_pq - 1/2 sum_r (pr|rq)] E_pq + 1/2 sum_pqrs (pq|rs) E_pq E_rs with the spin-summed excitation
     operators E_pq = sum_sigma a+_{p sigma} a_{q sigma}, built as sparse matrices over the determinants."""
     import scipy.sparse as sp
     norb, nelec, h, eri, core = read_fcidump(path)
@@ -79,7 +79,8 @@ def fci_ground_state_energy(path, nup=None, ndown=None, total_spin=None):
     H = H.toarray()
     assert np.abs(H - H.T).max() < 1e-10
     if total_spin is None:
-        return float(np.linalg.eigvalsh(H)[0]) + core
+        w = np.linalg.eigvalsh(H)
+        return float(w[0]) + core if n_states == 1 else [float(x) + core for x in w[:n_states]]
     # lowest state of total spin S = total_spin / 2.  S^2 = S- S+ + Sz (Sz + 1) in the same basis; H commutes with it, a small
     # multiple of S^2 added to H lifts accidental degeneracies between multiplets, so the eigenvectors are spin pure
     S2 = np.zeros((n, n))
@@ -93,8 +94,11 @@ def fci_ground_state_energy(path, nup=None, ndown=None, total_spin=None):
     assert np.abs(H @ S2 - S2 @ H).max() < 1e-9
     w, v = np.linalg.eigh(H + 1e-3 * S2)
     target = 0.5 * total_spin * (0.5 * total_spin + 1)
+    found = []
     for k in range(n):
         s2 = float(v[:, k] @ S2 @ v[:, k])
         if abs(s2 - target) < 1e-6:
-            return float(v[:, k] @ H @ v[:, k]) + core
-    raise RuntimeError("no state of the requested spin")
+            found.append(float(v[:, k] @ H @ v[:, k]) + core)
+            if len(found) == n_states:
+                return found[0] if n_states == 1 else sorted(found)
+    raise RuntimeError("not enough states of the requested spin")
