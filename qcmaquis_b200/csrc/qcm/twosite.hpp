@@ -585,6 +585,8 @@ struct TsParams
     // noise parameter of the perturbed truncation (ts_optimize.hpp:198-215 predict_split_l2r / predict_split_r2l; the
     // reference's default schedule starts at alpha_initial = 1e-2, DmrgParameters.h:47-49).  0: plain SVD split
     double alpha = 0.;
+    // states the optimised state is kept orthogonal to (excited states; ts_optimize.hpp:120-128, optimize.h:105-117)
+    sweep::OrthoStates const* ortho = nullptr;
     // storage protocol of ts_optimize.hpp:92-118: the boundaries of the next site are prefetched while this site is solved,
     // the one the sweep leaves behind is evicted (it is needed again only on the way back); with spill the engine keeps
     // three to four boundaries in its fast tier instead of L + 1
@@ -611,6 +613,15 @@ inline sweep::SweepLog ts_sweeps(SymmKind symm, EngineIface& eng, MPO const& mpo
         right[i] = eng.overlap_mpo_right_step(mps[i], mps[i], right[i + 1], mpo[i]);
         if (prm.spill && i + 1 < L) eng.evict(right[i + 1]);
     }
+    const int northo = prm.ortho ? (int)prm.ortho->states.size() : 0;
+    std::vector<std::vector<block_matrix>> oleft((size_t)northo, std::vector<block_matrix>((size_t)L + 1)), oright = oleft;
+    for (int n = 0; n < northo; ++n) {
+        MPS const& om = prm.ortho->states[(size_t)n];
+        if ((int)om.size() != L) throw std::runtime_error("ts_sweeps: orthogonal state of a different length");
+        oleft[(size_t)n][0] = mps.left_boundary()[0];
+        oright[(size_t)n][(size_t)L] = mps.right_boundary()[0];
+        for (int i = L - 1; i >= 0; --i) oright[(size_t)n][(size_t)i] = overlap_right_step(eng, prm.ortho->su2, mps[i], om[(size_t)i], oright[(size_t)n][(size_t)i + 1]);
+    }
     if (init_seconds) *init_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_init).count();
     auto to_site = [L](int i) { return i < L - 1 ? i : 2 * L - 2 - i; };      // ts_optimize.hpp:47-52: the last bond is visited twice, the first once
     bool stopped = false;
@@ -634,7 +645,14 @@ inline sweep::SweepLog ts_sweeps(SymmKind symm, EngineIface& eng, MPO const& mpo
             log.phase_seconds[0] += lap();
             MPOTensor const& tsw = ts_mpo(site1);
             log.phase_seconds[1] += lap();
-            sweep::JDResult r = sweep::jacobi_davidson(eng, twin, left[site1], right[site2 + 1], tsw, prm.jcd_maxiter, prm.jcd_tol);
+            std::vector<MPSTensor> ortho_vecs((size_t)northo);
+            for (int n = 0; n < northo; ++n) {
+                MPS const& om = prm.ortho->states[(size_t)n];
+                TwoSiteTensor ts_ortho(symm, om[(size_t)site1], om[(size_t)site2]);
+                ortho_vecs[(size_t)n] = sweep::site_ortho_boundaries(twin, ts_ortho.make_mps(), oleft[(size_t)n][(size_t)site1], oright[(size_t)n][(size_t)site2 + 1]);
+            }
+            if (northo > 1) ortho_vecs = sweep::orthogonalised(ortho_vecs);
+            sweep::JDResult r = sweep::jacobi_davidson(eng, twin, left[site1], right[site2 + 1], tsw, prm.jcd_maxiter, prm.jcd_tol, ortho_vecs);
             log.phase_seconds[2] += lap();
             tst << r.vec;
             log.energies.push_back(r.theta + mpo.core_energy);
@@ -662,6 +680,8 @@ inline sweep::SweepLog ts_sweeps(SymmKind symm, EngineIface& eng, MPO const& mpo
                 // the stale boundary at this bond goes first: the new one has the same size and takes over its memory
                 if (prm.drop_stale && site2 < L - 1) right[site2] = Boundary();
                 left[site2] = eng.overlap_mpo_left_step(mps[site1], mps[site1], left[site1], mpo[site1]);
+                for (int n = 0; n < northo; ++n)
+                    oleft[(size_t)n][(size_t)site2] = overlap_left_step(eng, prm.ortho->su2, mps[site1], prm.ortho->states[(size_t)n][(size_t)site1], oleft[(size_t)n][(size_t)site1]);
                 if (prm.spill && site1 > 0) eng.evict(left[site1]);
             } else {
                 if (prm.alpha != 0.) tst.predict_split_r2l(prm.Mmax, prm.cutoff, prm.alpha, right[site2 + 1], mpo[site2], eng, mps[site1], mps[site2], trunc);
@@ -673,6 +693,8 @@ inline sweep::SweepLog ts_sweeps(SymmKind symm, EngineIface& eng, MPO const& mpo
                 log.phase_seconds[3] += lap();
                 if (prm.drop_stale && site1 > 0) left[site2] = Boundary();
                 right[site2] = eng.overlap_mpo_right_step(mps[site2], mps[site2], right[site2 + 1], mpo[site2]);
+                for (int n = 0; n < northo; ++n)
+                    oright[(size_t)n][(size_t)site2] = overlap_right_step(eng, prm.ortho->su2, mps[site2], prm.ortho->states[(size_t)n][(size_t)site2], oright[(size_t)n][(size_t)site2 + 1]);
                 if (prm.spill && site2 + 1 < L) eng.evict(right[site2 + 1]);
             }
             log.phase_seconds[4] += lap();

@@ -875,11 +875,19 @@ extern "C" int qcmt_long_k_plan(double* out, char* err, int errlen)
     } catch (std::exception const& e) { set_err(err, errlen, e.what()); return 1; }
 }
 
+extern "C" int qcmt_excited_states_driver(const char* fcidump, const char* symm, int L, int nelec, int Mmax, int nsweeps, int nstates, int engine_kind, int twosite,
+                                          double* energies, double* overlaps, char* err, int errlen);
 // Excited states by orthogonal-state projection (optimize.h ortho_mps; ss_optimize.hpp:107-111; ietl/jacobi.h:378,393,432): state 0 is
 // optimised first, state k is then optimised orthogonal to states 0 .. k-1.  Single-site sweeps from random MPS of the full bond
 // dimension with the noise-perturbed subspace expansion.  energies[k] = last energy of state k; overlaps[k] = |<state k | state 0>|.
 extern "C" int qcmt_excited_states(const char* fcidump, const char* symm, int L, int nelec, int Mmax, int nsweeps, int nstates, int engine_kind,
                                    double* energies, double* overlaps, char* err, int errlen)
+{
+    return qcmt_excited_states_driver(fcidump, symm, L, nelec, Mmax, nsweeps, nstates, engine_kind, 0, energies, overlaps, err, errlen);
+}
+// twosite != 0: two-site sweeps (ts_optimize.hpp:120-128: the orthogonal states enter as two-site tensors) from M0 = 4 random states
+extern "C" int qcmt_excited_states_driver(const char* fcidump, const char* symm, int L, int nelec, int Mmax, int nsweeps, int nstates, int engine_kind, int twosite,
+                                          double* energies, double* overlaps, char* err, int errlen)
 {
     try {
         Problem P = make_problem(fcidump, symm, L, nelec);
@@ -887,8 +895,13 @@ extern "C" int qcmt_excited_states(const char* fcidump, const char* symm, int L,
         const bool su2 = is_su2(P.params.symm);
         sweep::OrthoStates found; found.su2 = su2;
         for (int k = 0; k < nstates; ++k) {
-            P.init_mps((size_t)Mmax, true, 0., 42u + 17u * (unsigned)k);
-            sweep::SweepLog log = sweep::ss_sweeps(*eng, P.mpo, P.mps, nsweeps, 10, 1e-8, ts::NoiseGrow{*eng, 1e-6, 1e-14, (size_t)Mmax, nullptr}, &found);
+            P.init_mps(twosite ? (size_t)4 : (size_t)Mmax, true, 0., 42u + 17u * (unsigned)k);
+            sweep::SweepLog log;
+            if (twosite) {
+                ts::TsParams prm; prm.Mmax = (size_t)Mmax; prm.ortho = &found;
+                log = ts::ts_sweeps(P.params.symm, *eng, P.mpo, [&](int p) -> MPOTensor const& { return P.twosite_mpo(p); }, P.mps, nsweeps, prm);
+            } else
+                log = sweep::ss_sweeps(*eng, P.mpo, P.mps, nsweeps, 10, 1e-8, ts::NoiseGrow{*eng, 1e-6, 1e-14, (size_t)Mmax, nullptr}, &found);
             energies[k] = log.energies.back();
             sweep::canonize_to_first(P.mps);
             overlaps[k] = k == 0 ? 1. : std::abs(overlap(*eng, su2, found.states[0], P.mps));
