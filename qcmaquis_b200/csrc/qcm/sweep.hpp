@@ -213,21 +213,21 @@ inline MPSTensor site_ortho_boundaries(MPSTensor const& mps, MPSTensor const& or
     reshape_and_pad_left(mps.site_dim(), ortho_left.left_basis(), ortho_right.left_basis(), mps.row_dim(), mps.col_dim(), t3, t);
     return MPSTensor(mps.site_dim(), mps.row_dim(), mps.col_dim(), t, LeftPaired);
 }
-// The local components of several orthogonal states are in general NOT orthogonal to each other, and the sequential projection of
-// SingleSiteVS::project is exact only for mutually orthogonal vectors (otherwise the solver's basis loses its orthonormality and the
-// Ritz values stop being variational -- seen here as energies below the full-CI ground state with two orthogonal states).  The
-// drivers therefore hand the solver an orthogonalised set spanning the same space (modified Gram-Schmidt; components that vanish
-// against the largest one are dropped).
-inline std::vector<MPSTensor> orthogonalised(std::vector<MPSTensor> vecs)
+// solve_ietl_jcd, optimize/ietl_jacobi_davidson.h:29-43: the local components of several orthogonal states are in general NOT
+// orthogonal to each other, and the sequential projection of SingleSiteVS::project is exact only for mutually orthogonal vectors
+// (without this step the solver's basis loses its orthonormality and the Ritz values stop being variational -- seen here as
+// energies below the full-CI ground state with two orthogonal states).  Gram-Schmidt over the vectors in order; a vector whose
+// remainder is shorter than thresholdForCompleteness = 1e-10 is neglected ("the corresponding boundary is too small"), the others
+// are normalised.  (Two passes per vector instead of the reference's one: same span, better orthogonality.)
+inline std::vector<MPSTensor> orthogonalised(std::vector<MPSTensor> vecs, double threshold = 1e-10)
 {
     std::vector<MPSTensor> out;
-    double largest = 0;
-    for (MPSTensor& v : vecs) { v.make_left_paired(); largest = std::max(largest, v.scalar_overlap(v)); }
     for (MPSTensor& v : vecs) {
+        v.make_left_paired();
         for (int pass = 0; pass < 2; ++pass)
-            for (MPSTensor const& o : out) axpy(v, -o.scalar_overlap(v) / o.scalar_overlap(o), o);
-        const double nn = v.scalar_overlap(v);
-        if (nn > 1e-20 * largest && nn > 1e-28) out.push_back(v);
+            for (MPSTensor const& o : out) axpy(v, -o.scalar_overlap(v), o);
+        const double nrm = v.scalar_norm();
+        if (nrm > threshold) { v.divide_by_scalar(nrm); out.push_back(v); }
     }
     return out;
 }
@@ -236,17 +236,30 @@ inline void project(MPSTensor& t, std::vector<MPSTensor> const& ortho_vecs)
 {
     for (MPSTensor const& o : ortho_vecs) {
         const double oo = o.scalar_overlap(o);
-        if (oo > 1e-24) axpy(t, -o.scalar_overlap(t) / oo, o);       // a vanishing component has nothing to project out (and no direction)
+        if (oo > 0.) axpy(t, -o.scalar_overlap(t) / oo, o);
     }
 }
 
 // ortho_vecs: states the solution is kept orthogonal to (excited states: the vector space projects them out at the three points
 // of ietl/jacobi.h:378,393,432); with orthogonal states the recurrence runs on the host vectors, sigma through the engine
 inline JDResult jacobi_davidson(EngineIface& eng, MPSTensor const& x0, Boundary const& left, Boundary const& right, MPOTensor const& mpo,
-                                int max_iter, double tol, std::vector<MPSTensor> const& ortho_vecs = std::vector<MPSTensor>())
+                                int max_iter, double tol, std::vector<MPSTensor> const& ortho_vecs_in = std::vector<MPSTensor>())
 {
     JDResult res;
-    if (ortho_vecs.empty() && eng.jacobi_davidson(x0, left, right, mpo, max_iter, tol, res)) return res;      // solver vectors kept on the device
+    if (ortho_vecs_in.empty() && eng.jacobi_davidson(x0, left, right, mpo, max_iter, tol, res)) return res;      // solver vectors kept on the device
+    const std::vector<MPSTensor> ortho_vecs = orthogonalised(ortho_vecs_in);
+    if (!ortho_vecs.empty()) {
+        // ietl_jacobi_davidson.h:44-50,68-74: nothing left of the start vector outside the orthogonal states -- the space is
+        // exhausted, the optimisation is skipped and the energy is the expectation value of the start vector
+        MPSTensor tmp = x0; tmp.make_left_paired();
+        for (MPSTensor const& o : ortho_vecs) axpy(tmp, -o.scalar_overlap(tmp), o);
+        if (tmp.scalar_norm() < 1e-10) {
+            MPSTensor hx = eng.site_hamil2(x0, left, right, mpo);
+            hx.make_left_paired(); x0.make_left_paired();
+            res.theta = x0.scalar_overlap(hx); res.vec = x0; res.n_sigma = 1;
+            return res;
+        }
+    }
     std::vector<MPSTensor> V(max_iter + 1), VA(max_iter);
     std::vector<double> M((size_t)max_iter * max_iter, 0.);
     const double kappa = 0.25;
@@ -346,7 +359,6 @@ inline SweepLog ss_sweeps(EngineIface& eng, MPO const& mpo, MPS& mps, int nsweep
             std::vector<MPSTensor> ortho_vecs((size_t)northo);        // ss_optimize.hpp:107-111
             for (int n = 0; n < northo; ++n)
                 ortho_vecs[(size_t)n] = site_ortho_boundaries(mps[site], ortho->states[(size_t)n][(size_t)site], oleft[(size_t)n][(size_t)site], oright[(size_t)n][(size_t)site + 1]);
-            if (northo > 1) ortho_vecs = orthogonalised(ortho_vecs);
             JDResult r = jacobi_davidson(eng, mps[site], left[site], right[site + 1], mpo[site], jcd_maxiter, jcd_tol, ortho_vecs);
             mps[site] = r.vec;
             log.energies.push_back(r.theta + mpo.core_energy);

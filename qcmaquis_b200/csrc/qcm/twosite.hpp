@@ -651,7 +651,6 @@ inline sweep::SweepLog ts_sweeps(SymmKind symm, EngineIface& eng, MPO const& mpo
                 TwoSiteTensor ts_ortho(symm, om[(size_t)site1], om[(size_t)site2]);
                 ortho_vecs[(size_t)n] = sweep::site_ortho_boundaries(twin, ts_ortho.make_mps(), oleft[(size_t)n][(size_t)site1], oright[(size_t)n][(size_t)site2 + 1]);
             }
-            if (northo > 1) ortho_vecs = sweep::orthogonalised(ortho_vecs);
             sweep::JDResult r = sweep::jacobi_davidson(eng, twin, left[site1], right[site2 + 1], tsw, prm.jcd_maxiter, prm.jcd_tol, ortho_vecs);
             log.phase_seconds[2] += lap();
             tst << r.vec;
