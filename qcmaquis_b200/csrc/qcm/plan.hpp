@@ -1785,20 +1785,33 @@ private:
 #else
         std::stable_sort(order.begin(), order.end(), by_target);
 #endif
+        // runs of equal target -> one output each; the segments are copied run by run at prefix-summed offsets (in parallel)
+        std::vector<size_t> run_begin;
+        for (size_t q = 0; q < order.size(); ++q)
+            if (q == 0 || gl.outs[order[q]].C.off != gl.outs[order[q - 1]].C.off) run_begin.push_back(q);
+        const size_t n_runs = run_begin.size();
+        run_begin.push_back(order.size());
+        std::vector<int64_t> seg_off(n_runs + 1, 0);
+#pragma omp parallel for schedule(static) if (n_runs > 4096)
+        for (long r_ = 0; r_ < (long)n_runs; ++r_) {
+            int64_t c = 0;
+            for (size_t q = run_begin[(size_t)r_]; q < run_begin[(size_t)r_ + 1]; ++q) c += gl.outs[order[q]].seg_end - gl.outs[order[q]].seg_begin;
+            seg_off[(size_t)r_ + 1] = c;
+        }
+        for (size_t r_ = 0; r_ < n_runs; ++r_) seg_off[r_ + 1] += seg_off[r_];
         GemmList r;
-        for (size_t q = 0; q < order.size();) {
-            Out o = gl.outs[order[q]];
-            int32_t sb = (int32_t)r.segs.size();
-            size_t q2 = q;
-            for (; q2 < order.size(); ++q2) {
-                Out const& x = gl.outs[order[q2]];
-                if (x.C.off != o.C.off) break;
+        r.outs.resize(n_runs); r.segs.resize((size_t)seg_off[n_runs]);
+#pragma omp parallel for schedule(static) if (n_runs > 4096)
+        for (long r_ = 0; r_ < (long)n_runs; ++r_) {
+            Out o = gl.outs[order[run_begin[(size_t)r_]]];
+            int64_t w = seg_off[(size_t)r_];
+            for (size_t q = run_begin[(size_t)r_]; q < run_begin[(size_t)r_ + 1]; ++q) {
+                Out const& x = gl.outs[order[q]];
                 o.m = std::max(o.m, x.m); o.n = std::max(o.n, x.n);
-                for (int32_t s = x.seg_begin; s < x.seg_end; ++s) r.segs.push_back(gl.segs[s]);
+                for (int32_t s_ = x.seg_begin; s_ < x.seg_end; ++s_) r.segs[(size_t)w++] = gl.segs[(size_t)s_];
             }
-            o.seg_begin = sb; o.seg_end = (int32_t)r.segs.size();
-            r.outs.push_back(o);
-            q = q2;
+            o.seg_begin = (int32_t)seg_off[(size_t)r_]; o.seg_end = (int32_t)seg_off[(size_t)r_ + 1];
+            r.outs[(size_t)r_] = o;
         }
         gl = std::move(r);
     }
