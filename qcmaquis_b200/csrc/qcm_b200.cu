@@ -621,6 +621,8 @@ static int plan_threads()
 {
     static const int n = []() {
         if (const char* e = getenv("QCM_PLAN_THREADS")) return std::max(1, atoi(e));
+        // one process per GPU: a rank takes its share of the host cores, the share the launcher gave its OpenMP runtime
+        if (const char* e = getenv("OMP_NUM_THREADS")) { int n = atoi(e); if (n >= 1) return std::min(16, n); }
         unsigned hc = std::thread::hardware_concurrency();
         return (int)std::min<unsigned>(16u, std::max<unsigned>(1u, hc));
     }();
